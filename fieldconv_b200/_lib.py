@@ -1,0 +1,110 @@
+"""ctypes binding of libfieldconv_b200.so (the C ABI in include/fieldconv_b200.h).
+
+The product path has no CPU fallback: if the library is missing or a call fails this raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfieldconv_b200.so")
+
+GEMM_SIMT_FP32 = 0
+GEMM_TC_3XTF32 = 1
+GEMM_TC_TF32 = 2
+
+_P = ctypes.c_void_p
+_I64 = ctypes.c_int64
+_I = ctypes.c_int
+_F = ctypes.c_float
+_SZ = ctypes.c_size_t
+_PSZ = ctypes.POINTER(ctypes.c_size_t)
+
+# name -> argtypes (all return int unless noted); mirrors include/fieldconv_b200.h
+SIGNATURES = {
+    "fcb_version": [],
+    "fcb_plan_workspace_bytes": [_I64, _I64, _I, _PSZ],
+    "fcb_plan_build": [_P, _P, _P, _P, _P, _P, _F, _I64, _I64, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P],
+    "fcb_plan_dense_workspace_bytes": [_I64, _I64, _PSZ],
+    "fcb_plan_build_dense": [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P],
+    "fcb_fwd_workspace_bytes": [_I64, _I, _I, _I, _I, _I, _PSZ],
+    "fcb_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_bwd_workspace_bytes": [_I64, _I, _I, _I, _I, _I, _PSZ],
+    "fcb_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_fwd_dense_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_bwd_dense_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_aggregate_f32": [_P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _P],
+    "fcb_gemm_f32": [_P, _P, _P, _I64, _I, _I64, _I64, _I64, _I64, _I, _I, _I64, _I64, _I64, _I, _P, _I, _P],
+    "fcb_sort_workspace_bytes": [_I64, _PSZ],
+    "fcb_sort_pairs_u32": [_P, _P, _P, _P, _I64, _I, _P, _SZ, _P],
+    "fcb_modrelu_fwd_f32": [_P, _P, _P, _I64, _I, _P],
+    "fcb_modrelu_bwd_workspace_bytes": [_I64, _I, _PSZ],
+    "fcb_modrelu_bwd_f32": [_P, _P, _P, _P, _P, _I64, _I, _P, _SZ, _P],
+    "fcb_profile_enable": [_I],
+    "fcb_profile_disable": [],
+    "fcb_profile_collect": [ctypes.c_char_p, _SZ, ctypes.POINTER(ctypes.c_float), _I, ctypes.POINTER(_I)],
+}
+
+_lib = None
+
+
+def launch_count():
+    """Kernels launched by the library so far in this process (fcb_launch_count)."""
+    return int(load().fcb_launch_count())
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "fieldconv_b200: %s is missing — build it with `python -m fieldconv_b200.build` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = ctypes.c_int
+        lib.fcb_last_error.argtypes = []
+        lib.fcb_last_error.restype = ctypes.c_char_p
+        lib.fcb_launch_count.argtypes = []
+        lib.fcb_launch_count.restype = ctypes.c_ulonglong
+        _lib = lib
+    return _lib
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; raise with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.fcb_last_error().decode()))
+    return rc
+
+
+def query_bytes(name, *args):
+    out = ctypes.c_size_t(0)
+    call(name, *args, ctypes.byref(out))
+    return int(out.value)
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def profile_enable(max_records=65536):
+    call("fcb_profile_enable", max_records)
+
+
+def profile_collect(max_records=65536):
+    """-> list of (kernel name, ms) in launch order; call after torch.cuda.synchronize()."""
+    names = ctypes.create_string_buffer(max_records * 24)
+    ms = (ctypes.c_float * max_records)()
+    cnt = ctypes.c_int(0)
+    call("fcb_profile_collect", names, len(names), ms, max_records, ctypes.byref(cnt))
+    call("fcb_profile_disable")
+    lst = names.value.decode().split("\n")[:cnt.value]
+    return [(lst[i], float(ms[i])) for i in range(cnt.value)]

@@ -1,0 +1,515 @@
+// C ABI glue: weight packing, the softAngle chain rule, modReLU, and the fwd / bwd drivers that
+// chain K1 (aggregate) -> K2 (contract) and K4 / K5 for one FieldConv layer.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace fcb {
+
+static thread_local char g_err[512] = "";
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional per-launch timing (debug/bench facility; not thread-safe, creates CUDA events)
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static ProfRec* g_prof = nullptr;
+static int g_prof_cap = 0, g_prof_n = 0;
+static bool g_prof_on = false;
+
+void prof_begin(const char* name, cudaStream_t st) {
+    if (!g_prof_on || g_prof_n >= g_prof_cap) return;
+    g_prof[g_prof_n].name = name;
+    cudaEventRecord(g_prof[g_prof_n].a, st);
+}
+void prof_end(cudaStream_t st) {
+    if (!g_prof_on || g_prof_n >= g_prof_cap) return;
+    cudaEventRecord(g_prof[g_prof_n].b, st);
+    ++g_prof_n;
+}
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ----------------------------------------------------------------------------- weight packing
+// W is complex (Co,Ci,R,M) as folded by the host from (zonal, spherical, phase) — nn/field_conv.py:10-33.
+// Forward operand: Bw[2k+a][2o+b], k = (r*Ci + c)*M + m (ring-major, matching contrib's layout).
+__global__ void k_pack_w_fwd(const float2* __restrict__ W, float* __restrict__ Bw, int Ci, int Co, int R, int M) {
+    const int64_t K = (int64_t)R * Ci * M;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * Co) return;
+    const int o = (int)(i % Co);
+    const int64_t k = i / Co;
+    const int m = (int)(k % M);
+    const int c = (int)((k / M) % Ci);
+    const int r = (int)(k / ((int64_t)M * Ci));
+    const float2 w = W[(((int64_t)o * Ci + c) * R + r) * M + m];
+    float* row0 = Bw + (2 * k) * (2 * (int64_t)Co) + 2 * o;
+    float* row1 = row0 + 2 * (int64_t)Co;
+    row0[0] = w.x;  row0[1] = w.y;
+    row1[0] = -w.y; row1[1] = w.x;
+}
+
+// Backward (grad x) operand, one matrix per m: Bt[m][2q+a][2c+b], q = r*Co + o, value conj(W[o,c,r,m]).
+__global__ void k_pack_w_bwd(const float2* __restrict__ W, float* __restrict__ Bt, int Ci, int Co, int R, int M) {
+    const int64_t Q = (int64_t)R * Co;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q * Ci * M) return;
+    const int c = (int)(i % Ci);
+    const int64_t q = (i / Ci) % Q;
+    const int m = (int)(i / (Ci * Q));
+    const int o = (int)(q % Co), r = (int)(q / Co);
+    const float2 w = W[(((int64_t)o * Ci + c) * R + r) * M + m];
+    float* base = Bt + (int64_t)m * (2 * Q) * (2 * Ci);
+    float* row0 = base + (2 * q) * (2 * (int64_t)Ci) + 2 * c;
+    float* row1 = row0 + 2 * (int64_t)Ci;
+    row0[0] = w.x; row0[1] = -w.y;
+    row1[0] = w.y; row1[1] = w.x;
+}
+
+// P = contrib_real^T @ gy_real  ([2K x 2Co])  ->  gW[o,c,r,m] = sum_n conj(contrib) * gy
+__global__ void k_combine_gw(const float* __restrict__ P, float2* __restrict__ gW, int Ci, int Co, int R, int M) {
+    const int64_t K = (int64_t)R * Ci * M;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * Co) return;
+    const int o = (int)(i % Co);
+    const int64_t k = i / Co;
+    const int m = (int)(k % M);
+    const int c = (int)((k / M) % Ci);
+    const int r = (int)(k / ((int64_t)M * Ci));
+    const float* row0 = P + (2 * k) * (2 * (int64_t)Co) + 2 * o;
+    const float* row1 = row0 + 2 * (int64_t)Co;
+    gW[(((int64_t)o * Ci + c) * R + r) * M + m] = make_float2(row0[0] + row1[1], row0[1] - row1[0]);
+}
+
+// ----------------------------------------------------------------------------- softAngle chain rule
+// gxh is [N][M][Ci] complex (gradient w.r.t. xhat[n,c,m] = x conj(u)^m).  SURVEY.md appendix A.3:
+//   non-origin: h_m = conj(g_m) u^(1-m);  gx = u * ( sum_m Re h_m  - i sum_m (1-m) Im h_m )
+//   origin    : gx = sum_m g_m            (phi is the constant 0 there: utils/field.py:42-46)
+template <int B>
+__global__ void k_softangle_bwd(const float2* __restrict__ x, const float2* __restrict__ gxh, float2* __restrict__ gx,
+                                int64_t N, int Ci) {
+    constexpr int M = 2 * B + 1;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * Ci) return;
+    const int64_t n = i / Ci;
+    const int c = (int)(i - n * Ci);
+    const float2 z = x[i];
+    float2 g[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) g[m] = gxh[(n * M + m) * Ci + c];
+    const bool origin = (fabsf(z.x) < 1e-7f) && (fabsf(z.y) < 1e-7f);
+    float2 out;
+    if (origin) {
+        out = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < M; ++m) { out.x += g[m].x; out.y += g[m].y; }
+    } else {
+        const float ri = rsqrtf(z.x * z.x + z.y * z.y);
+        const float2 u = make_float2(z.x * ri, z.y * ri);
+        // pw[j] = u^(j - B) ... we need u^(1-m) for m = -B..B, i.e. exponents 1+B .. 1-B
+        float2 up = u;   // u^1
+        float a = 0.f, b = 0.f;
+        // m = 0: exponent 1
+        {
+            const float2 h = cmul(make_float2(g[B].x, -g[B].y), u);
+            a += h.x; b -= h.y;
+        }
+        float2 pos = u;                      // u^(1+k) built upward for m = -k
+        float2 neg = u;                      // u^(1-k) built downward for m = +k
+#pragma unroll
+        for (int k = 1; k <= B; ++k) {
+            pos = cmul(pos, u);              // u^(1+k)
+            neg = cmul_conj(neg, u);         // u^(1-k)
+            const float2 hm = cmul(make_float2(g[B - k].x, -g[B - k].y), pos);   // m = -k, (1-m) = 1+k
+            const float2 hp = cmul(make_float2(g[B + k].x, -g[B + k].y), neg);   // m = +k, (1-m) = 1-k
+            a += hm.x + hp.x;
+            b -= (float)(1 + k) * hm.y + (float)(1 - k) * hp.y;
+        }
+        (void)up;
+        out = cmul(u, make_float2(a, b));
+    }
+    gx[i] = out;
+}
+
+// ----------------------------------------------------------------------------- modReLU (TangentNonLin)
+// nn/tangent_nonlin.py:24-35: y = relu(|x| + b_c) * x/|x|, origin entries passed through.
+__global__ void k_modrelu_fwd(const float2* __restrict__ x, const float* __restrict__ bias, float2* __restrict__ y,
+                              int64_t total, int C) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float2 z = x[i];
+    const bool origin = (fabsf(z.x) < 1e-7f) && (fabsf(z.y) < 1e-7f);
+    float2 out = z;
+    if (!origin) {
+        const float n2 = z.x * z.x + z.y * z.y;
+        const float ri = rsqrtf(n2);
+        const float mag = n2 * ri;
+        const float s = fmaxf(mag + bias[i % C], 0.f);
+        out = make_float2(s * z.x * ri, s * z.y * ri);
+    }
+    y[i] = out;
+}
+
+constexpr int MR_ROWS = 256;  // rows per block slab in the backward bias reduction
+
+// gx = u (s' Re t + i (s/rho) Im t), t = conj(u) g ; gb_c = sum_n s' Re t   
+__global__ void __launch_bounds__(256) k_modrelu_bwd(const float2* __restrict__ x, const float* __restrict__ bias,
+                                                     const float2* __restrict__ gy, float2* __restrict__ gx,
+                                                     float* __restrict__ gb_part, int64_t N, int C) {
+    extern __shared__ float red[];   // [lanes_per_col][C]
+    const int rl_count = max(1, 256 / C);
+    const int rl = threadIdx.x / C, c = threadIdx.x - rl * C;
+    const int64_t r0 = (int64_t)blockIdx.x * MR_ROWS;
+    float part = 0.f;
+    if (rl < rl_count) {
+        for (int cc = c; cc < C; cc += 256) {   // C > 256: a thread strides channels
+            const float bc = bias[cc];
+            float acc = 0.f;
+            for (int64_t r = r0 + rl; r < min(N, r0 + MR_ROWS); r += rl_count) {
+                const int64_t i = r * C + cc;
+                const float2 z = x[i];
+                const float2 g = gy[i];
+                const bool origin = (fabsf(z.x) < 1e-7f) && (fabsf(z.y) < 1e-7f);
+                float2 out = g;
+                if (!origin) {
+                    const float n2 = z.x * z.x + z.y * z.y;
+                    const float ri = rsqrtf(n2);
+                    const float mag = n2 * ri;
+                    const float2 u = make_float2(z.x * ri, z.y * ri);
+                    const float2 t = cmul_conj(g, u);  // g * conj(u)
+                    const float pre = mag + bc;
+                    const float sp = pre > 0.f ? 1.f : 0.f;
+                    const float s = fmaxf(pre, 0.f);
+                    out = cmul(u, make_float2(sp * t.x, s * ri * t.y));
+                    acc += sp * t.x;
+                }
+                gx[i] = out;
+            }
+            if (C > 256) gb_part[(int64_t)blockIdx.x * C + cc] = acc; else part = acc;
+        }
+    }
+    if (C <= 256) {
+        if (rl < rl_count) red[rl * C + c] = part;
+        __syncthreads();
+        if (threadIdx.x < C) {
+            float s = 0.f;
+            for (int k = 0; k < rl_count; ++k) s += red[k * C + threadIdx.x];
+            gb_part[(int64_t)blockIdx.x * C + threadIdx.x] = s;
+        }
+    }
+}
+
+__global__ void k_colsum_parts(const float* __restrict__ part, float* __restrict__ out, int64_t nparts, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int64_t p = 0; p < nparts; ++p) s += part[p * C + c];
+    out[c] = s;
+}
+
+// ----------------------------------------------------------------------------- layer drivers
+struct Dims {
+    int64_t N;
+    int Ci, Co, B, R, M;
+    int64_t K;    // complex contraction length R*Ci*M
+    int64_t Kt;   // complex length of the transposed gather R*Co*M
+};
+
+static int check_dims(const char* who, int64_t N, int Ci, int Co, int B, int R, Dims* d) {
+    FCB_REQUIRE(N >= 0 && Ci > 0 && Co > 0, FCB_E_ARG, "%s: bad sizes", who);
+    FCB_REQUIRE(B >= 0 && B <= FCB_MAX_BAND_LIMIT, FCB_E_UNSUPPORTED, "%s: band_limit %d unsupported (max %d)", who, B, FCB_MAX_BAND_LIMIT);
+    FCB_REQUIRE(R >= 1 && R <= FCB_MAX_RINGS, FCB_E_UNSUPPORTED, "%s: n_rings %d unsupported", who, R);
+    FCB_REQUIRE((Ci & 1) == 0 && (Co & 1) == 0, FCB_E_ALIGN, "%s: channel counts must be even (pad with a zero channel)", who);
+    FCB_REQUIRE(N <= FCB_MAX_VERTICES, FCB_E_UNSUPPORTED, "%s: N too large", who);
+    d->N = N; d->Ci = Ci; d->Co = Co; d->B = B; d->R = R; d->M = 2 * B + 1;
+    d->K = (int64_t)R * Ci * d->M;
+    d->Kt = (int64_t)R * Co * d->M;
+    return FCB_OK;
+}
+
+static int choose_split(int64_t rows_m, int64_t kdim) {
+    const int64_t tiles = (rows_m + 127) / 128;
+    int64_t s = (4 * 148 + tiles - 1) / tiles;
+    const int64_t cap = kdim / 512;
+    if (s > cap) s = cap;
+    if (s > 64) s = 64;
+    if (s < 1) s = 1;
+    return (int)s;
+}
+
+static size_t fwd_ws(const Dims& d) { return align_up((size_t)(4 * d.K * d.Co) * 4, 256) + 256; }
+
+static size_t bwd_ws(const Dims& d, bool need_contrib) {
+    size_t s = 0;
+    s += align_up((size_t)(4 * d.K * d.Co) * 4, 256);                       // Bt
+    s += align_up((size_t)(4 * d.K * d.Co) * 4, 256);                       // P
+    s += align_up((size_t)(4 * d.K * d.Co) * 4 * choose_split(2 * d.K, d.N), 256);  // split-K partials
+    s += align_up((size_t)d.N * d.Kt * 8, 256);                             // G
+    s += align_up((size_t)d.N * d.M * d.Ci * 8, 256);                       // gxh
+    if (need_contrib) s += align_up((size_t)d.N * d.K * 8, 256);            // recomputed contrib
+    return s + 1024;
+}
+
+static int contract_fwd(const Dims& d, const float* contrib, const float* W, float* y, void* ws, size_t ws_bytes, int flags,
+                        cudaStream_t st) {
+    FCB_REQUIRE(ws_bytes >= fwd_ws(d), FCB_E_WORKSPACE, "fwd: workspace too small");
+    Arena ar(ws, ws_bytes);
+    float* Bw = ar.take<float>((size_t)(4 * d.K * d.Co));
+    const int64_t tot = d.K * d.Co;
+    FCB_LAUNCH("pack_w_fwd", st, k_pack_w_fwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bw, d.Ci, d.Co, d.R, d.M));
+    return launch_gemm(contrib, Bw, y, d.N, 2 * d.Co, 2 * d.K, 2 * d.K, 2 * d.Co, 2 * d.Co, 0, 1, 0, 0, 0, 1, nullptr, flags, st);
+}
+
+template <typename GatherT>
+static int backward_common(const Dims& d, const float* x, const float* W, const float* gy, const float* contrib,
+                           GatherT&& gather_transpose, float* gx, float* gW, Arena& ar, int flags, cudaStream_t st) {
+    float* Bt = ar.take<float>((size_t)(4 * d.K * d.Co));
+    float* P = ar.take<float>((size_t)(4 * d.K * d.Co));
+    float* parts = ar.take<float>((size_t)(4 * d.K * d.Co) * choose_split(2 * d.K, d.N));
+    float* G = ar.take<float>((size_t)d.N * d.Kt * 2);
+    float* gxh = ar.take<float>((size_t)d.N * d.M * d.Ci * 2);
+    const int64_t tot = d.K * d.Co;
+    if (gW) {
+        // K4: P[2K x 2Co] = contrib_real^T @ gy_real, split over vertices, fixed-order reduction
+        const int split = choose_split(2 * d.K, d.N);
+        int rc = launch_gemm(contrib, gy, P, 2 * d.K, 2 * d.Co, d.N, 2 * d.K, 2 * d.Co, 2 * d.Co, 1, 1, 0, 0, 0, split, parts, flags, st);
+        if (rc) return rc;
+        FCB_LAUNCH("combine_gw", st, k_combine_gw<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, reinterpret_cast<float2*>(gW), d.Ci, d.Co, d.R, d.M));
+    }
+    if (gx) {
+        // K5a: G[j][m][r][o] = sum_{e: src=j} conj(sten) gy[tgt]
+        int rc = gather_transpose(G);
+        if (rc) return rc;
+        // K5b: gxh[:, m, :] = G[:, m, :] @ conj(W)[m]  (one real GEMM per m, batched)
+        FCB_LAUNCH("pack_w_bwd", st, k_pack_w_bwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bt, d.Ci, d.Co, d.R, d.M));
+        const int64_t Q2 = 2 * (int64_t)d.R * d.Co;
+        rc = launch_gemm(G, Bt, gxh, d.N, 2 * d.Ci, Q2, (int64_t)d.M * Q2, 2 * d.Ci, (int64_t)d.M * 2 * d.Ci, 0, d.M, Q2,
+                         Q2 * 2 * d.Ci, 2 * d.Ci, 1, nullptr, flags, st);
+        if (rc) return rc;
+        const int64_t el = d.N * d.Ci;
+        const unsigned blocks = (unsigned)((el + 255) / 256);
+        const float2* x2 = reinterpret_cast<const float2*>(x);
+        const float2* g2 = reinterpret_cast<const float2*>(gxh);
+        float2* o2 = reinterpret_cast<float2*>(gx);
+        if (el > 0) {
+            prof_begin("softangle_bwd", st);
+            switch (d.B) {
+                case 0: k_softangle_bwd<0><<<blocks, 256, 0, st>>>(x2, g2, o2, d.N, d.Ci); break;
+                case 1: k_softangle_bwd<1><<<blocks, 256, 0, st>>>(x2, g2, o2, d.N, d.Ci); break;
+                case 2: k_softangle_bwd<2><<<blocks, 256, 0, st>>>(x2, g2, o2, d.N, d.Ci); break;
+                case 3: k_softangle_bwd<3><<<blocks, 256, 0, st>>>(x2, g2, o2, d.N, d.Ci); break;
+                case 4: k_softangle_bwd<4><<<blocks, 256, 0, st>>>(x2, g2, o2, d.N, d.Ci); break;
+            }
+            prof_end(st);
+            FCB_CUDA_LAUNCH_CHECK("softangle_bwd");
+        }
+    }
+    return FCB_OK;
+}
+
+}  // namespace fcb
+
+using namespace fcb;
+
+extern "C" int fcb_profile_enable(int max_records) {
+    FCB_REQUIRE(max_records > 0 && max_records <= (1 << 20), FCB_E_ARG, "profile_enable: bad record count");
+    if (g_prof_cap < max_records) {
+        for (int i = 0; i < g_prof_cap; ++i) { cudaEventDestroy(g_prof[i].a); cudaEventDestroy(g_prof[i].b); }
+        delete[] g_prof;
+        g_prof = new ProfRec[max_records];
+        g_prof_cap = max_records;
+        for (int i = 0; i < g_prof_cap; ++i) {
+            if (cudaEventCreate(&g_prof[i].a) != cudaSuccess || cudaEventCreate(&g_prof[i].b) != cudaSuccess) {
+                set_error("profile_enable: cudaEventCreate failed");
+                g_prof_cap = i;
+                return FCB_E_CUDA;
+            }
+        }
+    }
+    g_prof_n = 0;
+    g_prof_on = true;
+    return FCB_OK;
+}
+
+extern "C" int fcb_profile_disable(void) {
+    g_prof_on = false;
+    return FCB_OK;
+}
+
+// After the caller synchronised the stream(s): writes up to `capacity` durations (ms) and the kernel names
+// joined by '\n' into names_buf; *count = number of records; resets the record list.
+extern "C" int fcb_profile_collect(char* names_buf, size_t names_bytes, float* ms, int capacity, int* count) {
+    FCB_REQUIRE(names_buf && ms && count && names_bytes > 0, FCB_E_ARG, "profile_collect: null argument");
+    size_t off = 0;
+    int n = g_prof_n < capacity ? g_prof_n : capacity;
+    names_buf[0] = 0;
+    for (int i = 0; i < n; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b) != cudaSuccess) {
+            set_error("profile_collect: events not complete (synchronise first)");
+            cudaGetLastError();
+            return FCB_E_CUDA;
+        }
+        ms[i] = t;
+        const size_t len = strlen(g_prof[i].name);
+        if (off + len + 2 > names_bytes) { n = i; break; }
+        memcpy(names_buf + off, g_prof[i].name, len);
+        off += len;
+        names_buf[off++] = '\n';
+        names_buf[off] = 0;
+    }
+    *count = n;
+    g_prof_n = 0;
+    return FCB_OK;
+}
+
+extern "C" const char* fcb_last_error(void) { return g_err; }
+extern "C" int fcb_version(void) { return 100; }
+extern "C" unsigned long long fcb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int fcb_fwd_workspace_bytes(int64_t N, int Ci, int Co, int band_limit, int R, int flags, size_t* bytes) {
+    Dims d;
+    (void)flags;
+    FCB_REQUIRE(bytes, FCB_E_ARG, "fwd_workspace: null");
+    int rc = check_dims("fwd_workspace", N, Ci, Co, band_limit, R, &d);
+    if (rc) return rc;
+    *bytes = fwd_ws(d);
+    return FCB_OK;
+}
+
+extern "C" int fcb_bwd_workspace_bytes(int64_t N, int Ci, int Co, int band_limit, int R, int flags, size_t* bytes) {
+    Dims d;
+    FCB_REQUIRE(bytes, FCB_E_ARG, "bwd_workspace: null");
+    int rc = check_dims("bwd_workspace", N, Ci, Co, band_limit, R, &d);
+    if (rc) return rc;
+    *bytes = bwd_ws(d, !(flags & FCB_FLAG_HAVE_CONTRIB));
+    return FCB_OK;
+}
+
+extern "C" int fcb_fwd_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
+                           const float* rot_tgt, float* y, float* contrib, int64_t N, int Ci, int Co, int band_limit,
+                           int R, int flags, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Dims d;
+    int rc = check_dims("fwd", N, Ci, Co, band_limit, R, &d);
+    if (rc) return rc;
+    FCB_REQUIRE(R >= 2, FCB_E_UNSUPPORTED, "fwd: n_rings must be >= 2 (reference divides by n_rings-1)");
+    FCB_REQUIRE(x && W && rowptr_tgt && rec_tgt && rot_tgt && y && ws, FCB_E_ARG, "fwd: null pointer");
+    FCB_REQUIRE(contrib, FCB_E_UNSUPPORTED, "fwd: this path needs a contrib buffer (N*R*Ci*M complex)");
+    FCB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(W) && aligned16(contrib), FCB_E_ALIGN, "fwd: pointers must be 16-byte aligned");
+    if (N == 0) return FCB_OK;
+    rc = launch_aggregate(x, rowptr_tgt, rec_tgt, rot_tgt, contrib, N, Ci, band_limit, R, 0, st);
+    if (rc) return rc;
+    return contract_fwd(d, contrib, W, y, ws, ws_bytes, flags, st);
+}
+
+extern "C" int fcb_bwd_f32(const float* x, const float* W, const float* gy, const float* contrib,
+                           const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
+                           const int32_t* rowptr_src, const void* rec_src, const float* rot_src, float* gx, float* gW,
+                           int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws, size_t ws_bytes,
+                           void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Dims d;
+    int rc = check_dims("bwd", N, Ci, Co, band_limit, R, &d);
+    if (rc) return rc;
+    FCB_REQUIRE(R >= 2, FCB_E_UNSUPPORTED, "bwd: n_rings must be >= 2");
+    FCB_REQUIRE(x && W && gy && ws, FCB_E_ARG, "bwd: null pointer");
+    FCB_REQUIRE(!gx || (rowptr_src && rec_src && rot_src), FCB_E_ARG, "bwd: grad x needs the by-source plan");
+    FCB_REQUIRE(!gW || contrib || (rowptr_tgt && rec_tgt && rot_tgt), FCB_E_ARG, "bwd: grad W needs contrib or the by-target plan");
+    FCB_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(W), FCB_E_ALIGN, "bwd: pointers must be 16-byte aligned");
+    const bool recompute = gW && !contrib;
+    FCB_REQUIRE(ws_bytes >= bwd_ws(d, recompute), FCB_E_WORKSPACE, "bwd: workspace too small");
+    if (N == 0) {
+        if (gW) cudaMemsetAsync(gW, 0, (size_t)d.K * d.Co * 8, st);
+        return FCB_OK;
+    }
+    Arena ar(ws, ws_bytes);
+    if (recompute) {
+        float* c2 = ar.take<float>((size_t)d.N * d.K * 2);
+        rc = launch_aggregate(x, rowptr_tgt, rec_tgt, rot_tgt, c2, N, Ci, band_limit, R, 0, st);
+        if (rc) return rc;
+        contrib = c2;
+    }
+    auto gather = [&](float* G) { return launch_aggregate(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, st); };
+    return backward_common(d, x, W, gy, contrib, gather, gx, gW, ar, flags, st);
+}
+
+extern "C" int fcb_fwd_dense_f32(const float* x, const float* W, const float* sten, const int32_t* rowptr_tgt,
+                                 const int32_t* nbr_tgt, const int32_t* perm_tgt, float* y, float* contrib, int64_t N,
+                                 int Ci, int Co, int band_limit, int R, int flags, void* ws, size_t ws_bytes,
+                                 void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Dims d;
+    int rc = check_dims("fwd_dense", N, Ci, Co, band_limit, R, &d);
+    if (rc) return rc;
+    FCB_REQUIRE(x && W && rowptr_tgt && nbr_tgt && perm_tgt && y && contrib && ws, FCB_E_ARG, "fwd_dense: null pointer");
+    FCB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(W) && aligned16(contrib), FCB_E_ALIGN, "fwd_dense: pointers must be 16-byte aligned");
+    if (N == 0) return FCB_OK;
+    rc = launch_aggregate_dense(x, sten, rowptr_tgt, nbr_tgt, perm_tgt, contrib, N, Ci, band_limit, R, 0, st);
+    if (rc) return rc;
+    return contract_fwd(d, contrib, W, y, ws, ws_bytes, flags, st);
+}
+
+extern "C" int fcb_bwd_dense_f32(const float* x, const float* W, const float* gy, const float* contrib,
+                                 const float* sten, const int32_t* rowptr_src, const int32_t* nbr_src,
+                                 const int32_t* perm_src, float* gx, float* gW, int64_t N, int Ci, int Co,
+                                 int band_limit, int R, int flags, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Dims d;
+    int rc = check_dims("bwd_dense", N, Ci, Co, band_limit, R, &d);
+    if (rc) return rc;
+    FCB_REQUIRE(x && W && gy && ws, FCB_E_ARG, "bwd_dense: null pointer");
+    FCB_REQUIRE(!gW || contrib, FCB_E_ARG, "bwd_dense: grad W needs the contrib saved by the forward");
+    FCB_REQUIRE(!gx || (sten && rowptr_src && nbr_src && perm_src), FCB_E_ARG, "bwd_dense: grad x needs the by-source plan");
+    FCB_REQUIRE(ws_bytes >= bwd_ws(d, false), FCB_E_WORKSPACE, "bwd_dense: workspace too small");
+    if (N == 0) {
+        if (gW) cudaMemsetAsync(gW, 0, (size_t)d.K * d.Co * 8, st);
+        return FCB_OK;
+    }
+    Arena ar(ws, ws_bytes);
+    auto gather = [&](float* G) {
+        return launch_aggregate_dense(gy, sten, rowptr_src, nbr_src, perm_src, G, N, Co, band_limit, R, 1, st);
+    };
+    return backward_common(d, x, W, gy, contrib, gather, gx, gW, ar, flags, st);
+}
+
+extern "C" int fcb_modrelu_fwd_f32(const float* x, const float* bias, float* y, int64_t N, int C, void* stream) {
+    FCB_REQUIRE(x && bias && y && N >= 0 && C > 0, FCB_E_ARG, "modrelu_fwd: bad arguments");
+    const int64_t tot = N * C;
+    if (tot == 0) return FCB_OK;
+    FCB_LAUNCH("modrelu_fwd", static_cast<cudaStream_t>(stream), k_modrelu_fwd<<<(unsigned)((tot + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2*>(x), bias, reinterpret_cast<float2*>(y), tot, C));
+    return FCB_OK;
+}
+
+extern "C" int fcb_modrelu_bwd_workspace_bytes(int64_t N, int C, size_t* bytes) {
+    FCB_REQUIRE(bytes && N >= 0 && C > 0, FCB_E_ARG, "modrelu_bwd_workspace: bad arguments");
+    *bytes = align_up((size_t)((N + MR_ROWS - 1) / MR_ROWS + 1) * C * 4, 256);
+    return FCB_OK;
+}
+
+extern "C" int fcb_modrelu_bwd_f32(const float* x, const float* bias, const float* gy, float* gx, float* gb, int64_t N,
+                                   int C, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FCB_REQUIRE(x && bias && gy && gx && gb && ws && N >= 0 && C > 0, FCB_E_ARG, "modrelu_bwd: bad arguments");
+    const int64_t slabs = (N + MR_ROWS - 1) / MR_ROWS;
+    FCB_REQUIRE(ws_bytes >= (size_t)(slabs + 1) * C * 4, FCB_E_WORKSPACE, "modrelu_bwd: workspace too small");
+    float* parts = static_cast<float*>(ws);
+    if (slabs > 0) {
+        const int rl_count = C <= 256 ? (256 / C > 0 ? 256 / C : 1) : 1;
+        const size_t smem = C <= 256 ? (size_t)rl_count * C * 4 : 0;
+        FCB_LAUNCH("modrelu_bwd", st, k_modrelu_bwd<<<(unsigned)slabs, 256, smem, st>>>(reinterpret_cast<const float2*>(x), bias,
+                                                          reinterpret_cast<const float2*>(gy),
+                                                          reinterpret_cast<float2*>(gx), parts, N, C));
+    }
+    FCB_LAUNCH("colsum_parts", st, k_colsum_parts<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(parts, gb, slabs, C));
+    return FCB_OK;
+}

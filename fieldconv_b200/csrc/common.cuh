@@ -1,0 +1,85 @@
+// Shared helpers for libfieldconv_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/fieldconv_b200.h"
+
+namespace fcb {
+
+void set_error(const char* fmt, ...);
+void count_launch();   // bumps the process-wide kernel-launch counter read by fcb_launch_count()
+// optional per-launch CUDA-event timing (fcb_profile_*): no-ops unless enabled
+void prof_begin(const char* name, cudaStream_t st);
+void prof_end(cudaStream_t st);
+
+// FCB_LAUNCH("name", stream, kernel<<<grid, block, smem, stream>>>(args...));
+#define FCB_LAUNCH(name, st, ...)            \
+    do {                                     \
+        fcb::prof_begin((name), (st));       \
+        __VA_ARGS__;                         \
+        fcb::prof_end((st));                 \
+        FCB_CUDA_LAUNCH_CHECK(name);         \
+    } while (0)
+
+#define FCB_REQUIRE(cond, code, ...)            \
+    do {                                        \
+        if (!(cond)) {                          \
+            fcb::set_error(__VA_ARGS__);        \
+            return (code);                      \
+        }                                       \
+    } while (0)
+
+#define FCB_CUDA_LAUNCH_CHECK(what)                                                   \
+    do {                                                                              \
+        cudaError_t e__ = cudaGetLastError();                                         \
+        fcb::count_launch();                                                          \
+        if (e__ != cudaSuccess) {                                                     \
+            fcb::set_error("%s: %s", (what), cudaGetErrorString(e__));                \
+            return FCB_E_CUDA;                                                        \
+        }                                                                             \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Bump allocator over a caller-provided workspace.
+struct Arena {
+    char* base;
+    size_t cap, off;
+    Arena(void* p, size_t n) : base(static_cast<char*>(p)), cap(n), off(0) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = align_up(off, 256);
+        T* r = reinterpret_cast<T*>(base + off);
+        off += count * sizeof(T);
+        return r;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+constexpr int NBR_BITS = 27;
+constexpr uint32_t NBR_MASK = (1u << NBR_BITS) - 1u;
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+
+// internal entry points shared between translation units
+int sort_pairs(uint32_t* k_in, uint32_t* v_in, uint32_t* k_out, uint32_t* v_out, int64_t n, int bits,
+               void* ws, size_t ws_bytes, cudaStream_t st);
+size_t sort_workspace(int64_t n);
+int launch_aggregate(const float* feat, const int32_t* rowptr, const void* rec, const float* rot, float* out,
+                     int64_t N, int C, int B, int R, int transpose, cudaStream_t st);
+int launch_aggregate_dense(const float* feat, const float* sten, const int32_t* rowptr, const int32_t* nbr,
+                           const int32_t* perm, float* out, int64_t N, int C, int B, int R, int transpose,
+                           cudaStream_t st);
+int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
+                int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k,
+                float* partials, int flags, cudaStream_t st);
+
+}  // namespace fcb

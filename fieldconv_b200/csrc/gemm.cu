@@ -1,0 +1,221 @@
+// K2 / K4 / K5b (FP32 FMA path) — real fp32 GEMM used for the three dense contractions of
+// the layer.  The complex contraction y = contrib (N x K) @ W (K x Co) (nn/field_conv.py:10-33,137)
+// is carried as a real GEMM on the interleaved (re,im) storage:
+//   [N x 2K] @ [2K x 2Co],  B[(k,re),(o,re)] = Wr, B[(k,re),(o,im)] = Wi,
+//                           B[(k,im),(o,re)] = -Wi, B[(k,im),(o,im)] = Wr
+// which costs exactly the 8 K Co real flops per vertex of the complex product.
+//
+// Tiling: 128 x (16*TN) output tile per 256-thread CTA, 8 x TN register tile per thread,
+// BK = 8 slices staged through shared memory with register prefetch of the next slice.
+// trans_a = 1 reads A as (K x M) row-major (used for gW = contrib^H gy, reduction over vertices),
+// split_k > 1 writes per-split partial tiles that are then summed in split order (deterministic).
+#include "common.cuh"
+
+namespace fcb {
+
+constexpr int G_BM = 128;
+constexpr int G_BK = 8;
+constexpr int G_PAD = 4;
+
+template <int TN, bool TRANS_A>
+__global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, const float* __restrict__ Bm,
+                                              float* __restrict__ C, int64_t M, int N, int64_t K, int64_t lda,
+                                              int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int split_k,
+                                              int64_t k_per_split, int64_t part_stride) {
+    constexpr int BN = 16 * TN;
+    __shared__ __align__(16) float As[G_BK][G_BM + G_PAD];
+    __shared__ __align__(16) float Bs[G_BK][BN];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int batch = blockIdx.z / split_k;
+    const int split = blockIdx.z - batch * split_k;
+    const int64_t m0 = (int64_t)blockIdx.x * G_BM;
+    const int n0 = blockIdx.y * BN;
+    A += batch * sa;
+    Bm += batch * sb;
+    if (split_k > 1) C += ((int64_t)split * gridDim.z / split_k + batch) * part_stride;  // partial buffer [split][batch]
+    else C += batch * sc;
+    const int64_t kb = (int64_t)split * k_per_split;
+    const int64_t ke = min(K, kb + k_per_split);
+
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    // global->register staging
+    float4 ra;          // A: one float4 per thread per slice
+    float4 rb;          // B: one float4 per thread (threads < BK*BN/4)
+    constexpr int B_F4 = G_BK * BN / 4;
+    const int a_row = TRANS_A ? (tid >> 5) : (tid >> 1);        // TRANS_A: k index 0..7 ; else m index 0..127
+    const int a_col = TRANS_A ? ((tid & 31) << 2) : ((tid & 1) << 2);  // TRANS_A: m offset ; else k offset
+    const int b_k = tid / (BN / 4), b_n = (tid % (BN / 4)) << 2;
+
+    auto load_slice = [&](int64_t k0) {
+        ra = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (TRANS_A) {
+            const int64_t k = k0 + a_row;
+            const int64_t m = m0 + a_col;
+            if (k < ke) {
+                const float* p = A + k * lda + m;
+                if (m + 3 < M) ra = *reinterpret_cast<const float4*>(p);
+                else {
+                    if (m < M) ra.x = p[0];
+                    if (m + 1 < M) ra.y = p[1];
+                    if (m + 2 < M) ra.z = p[2];
+                }
+            }
+        } else {
+            const int64_t m = m0 + a_row;
+            const int64_t k = k0 + a_col;
+            if (m < M) {
+                const float* p = A + m * lda + k;
+                if (k + 3 < ke) ra = *reinterpret_cast<const float4*>(p);
+                else {
+                    if (k < ke) ra.x = p[0];
+                    if (k + 1 < ke) ra.y = p[1];
+                    if (k + 2 < ke) ra.z = p[2];
+                }
+            }
+        }
+        rb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < B_F4) {
+            const int64_t k = k0 + b_k;
+            const int n = n0 + b_n;
+            if (k < ke && n < N) {
+                const float* p = Bm + k * ldb + n;
+                if (n + 3 < N) rb = *reinterpret_cast<const float4*>(p);
+                else {
+                    rb.x = p[0];
+                    if (n + 1 < N) rb.y = p[1];
+                    if (n + 2 < N) rb.z = p[2];
+                }
+            }
+        }
+    };
+    auto store_slice = [&]() {
+        if (TRANS_A) {
+            *reinterpret_cast<float4*>(&As[a_row][a_col]) = ra;
+        } else {
+            As[a_col + 0][a_row] = ra.x;
+            As[a_col + 1][a_row] = ra.y;
+            As[a_col + 2][a_row] = ra.z;
+            As[a_col + 3][a_row] = ra.w;
+        }
+        if (tid < B_F4) *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = rb;
+    };
+
+    if (kb < ke) load_slice(kb);
+    for (int64_t k0 = kb; k0 < ke; k0 += G_BK) {
+        store_slice();
+        __syncthreads();
+        if (k0 + G_BK < ke) load_slice(k0 + G_BK);
+#pragma unroll
+        for (int kk = 0; kk < G_BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float b[TN];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t m = m0 + ty * 8 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx + 16 * j;
+            if (n < N) C[m * ldc + n] = acc[i][j];
+        }
+    }
+}
+
+// C[b][m][n] = sum_s partials[s][b][m][n], fixed order
+__global__ void k_reduce_splits(const float* __restrict__ partials, float* __restrict__ C, int64_t M, int N, int64_t ldc,
+                                int64_t sc, int batch, int split_k) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = M * N;
+    if (i >= per * batch) return;
+    const int b = (int)(i / per);
+    const int64_t r = i - (int64_t)b * per;
+    const int64_t m = r / N;
+    const int n = (int)(r - m * N);
+    float s = 0.f;
+    for (int k = 0; k < split_k; ++k) s += partials[((int64_t)k * batch + b) * per + r];
+    C[b * sc + m * ldc + n] = s;
+}
+
+template <bool TRANS_A>
+static int dispatch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
+                         int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k, int64_t kps,
+                         int64_t part_stride, cudaStream_t st) {
+    int tn = (N + 15) / 16;
+    if (tn > 8) tn = 8;
+    if (tn == 5) tn = 6;
+    if (tn == 7) tn = 8;
+    if (tn == 3) tn = 4;
+    const int bn = 16 * tn;
+    dim3 grid((unsigned)((M + G_BM - 1) / G_BM), (unsigned)((N + bn - 1) / bn), (unsigned)(batch * split_k));
+#define FCB_GEMM_CASE(T) \
+    case T: k_gemm<T, TRANS_A><<<grid, 256, 0, st>>>(A, Bm, C, M, N, K, lda, ldb, ldc, sa, sb, sc, split_k, kps, part_stride); break;
+    prof_begin(TRANS_A ? "gemm_tn" : "gemm_nn", st);
+    switch (tn) {
+        FCB_GEMM_CASE(1)
+        FCB_GEMM_CASE(2)
+        FCB_GEMM_CASE(4)
+        FCB_GEMM_CASE(6)
+        FCB_GEMM_CASE(8)
+        default: set_error("gemm: internal tile selection error"); return FCB_E_ARG;
+    }
+#undef FCB_GEMM_CASE
+    prof_end(st);
+    FCB_CUDA_LAUNCH_CHECK("gemm");
+    return FCB_OK;
+}
+
+int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
+                int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k, float* partials,
+                int flags, cudaStream_t st) {
+    (void)flags;
+    FCB_REQUIRE(A && Bm && C, FCB_E_ARG, "gemm: null pointer");
+    FCB_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 1 && split_k >= 1, FCB_E_ARG, "gemm: bad sizes");
+    FCB_REQUIRE(split_k == 1 || partials, FCB_E_ARG, "gemm: split_k > 1 needs a partials buffer");
+    FCB_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (sa % 4) == 0 && (sb % 4) == 0 && aligned16(A) && aligned16(Bm),
+                FCB_E_ALIGN, "gemm: A/B leading dimensions and strides must be multiples of 4 floats, 16-byte aligned");
+    FCB_REQUIRE((int64_t)batch * split_k <= 65535, FCB_E_UNSUPPORTED, "gemm: batch*split_k too large");
+    if (M == 0 || N == 0) return FCB_OK;
+    int64_t kps = (K + split_k - 1) / split_k;
+    kps = (kps + G_BK - 1) / G_BK * G_BK;  // keep float4 alignment of the K offsets
+    float* out = split_k > 1 ? partials : C;
+    const int64_t part_stride = M * (int64_t)N;
+    int rc;
+    if (split_k > 1) {
+        rc = trans_a ? dispatch_gemm<true>(A, Bm, out, M, N, K, lda, ldb, N, batch, sa, sb, 0, split_k, kps, part_stride, st)
+                     : dispatch_gemm<false>(A, Bm, out, M, N, K, lda, ldb, N, batch, sa, sb, 0, split_k, kps, part_stride, st);
+        if (rc) return rc;
+        const int64_t tot = part_stride * batch;
+        FCB_LAUNCH("reduce_splits", st, k_reduce_splits<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(partials, C, M, N, ldc, sc, batch, split_k));
+        return FCB_OK;
+    }
+    rc = trans_a ? dispatch_gemm<true>(A, Bm, out, M, N, K, lda, ldb, ldc, batch, sa, sb, sc, 1, kps, 0, st)
+                 : dispatch_gemm<false>(A, Bm, out, M, N, K, lda, ldb, ldc, batch, sa, sb, sc, 1, kps, 0, st);
+    return rc;
+}
+
+}  // namespace fcb
+
+extern "C" int fcb_gemm_f32(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda,
+                            int64_t ldb, int64_t ldc, int trans_a, int batch, int64_t stride_a, int64_t stride_b,
+                            int64_t stride_c, int split_k, float* partials, int flags, void* stream) {
+    return fcb::launch_gemm(A, B, C, M, N, K, lda, ldb, ldc, trans_a, batch, stride_a, stride_b, stride_c, split_k,
+                            partials, flags, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,156 @@
+"""Drop-in modules mirroring the reference's operator interface for the hot path:
+
+    FieldConv(in_channels, out_channels, band_limit=1, n_rings=6, ftype=1)     nn/field_conv.py:62
+        .forward(x, supp_edges, supp_sten)                                       nn/field_conv.py:104
+    TangentLin, TangentNonLin, FCResNetBlock                                     nn/tangent_lin.py, nn/tangent_nonlin.py,
+                                                                                 nn/fc_resnet_block.py:43-88
+
+Parameter / buffer names, shapes and initialisation are the reference's (state_dicts interchange).
+Extra, keyword-only: ``precision=`` selects the contraction arithmetic, and ``forward(x, plan)`` accepts
+a compact ``fieldconv_b200.Plan`` instead of (supp_edges, supp_sten) — the fast path.
+"""
+import torch
+import torch.nn as nn
+from torch.nn import Parameter
+
+from . import _lib, ops
+from .plan import DensePlan, Plan, build_dense_plan
+
+_PRECISIONS = {"fp32": _lib.GEMM_SIMT_FP32, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32": _lib.GEMM_TC_TF32}
+
+
+def fold_weights(zonal, spherical, phase, ftype, band_limit):
+    """(zonal, spherical, phase) -> W (Co,Ci,R,2B+1) complex with y = sum contrib * W, i.e. the
+    coefficient tensors of weightContribReal / Offset / Complex divided by 2B+1
+    (nn/field_conv.py:12-14, :18-25, :31-33).  Differentiable torch code on tiny tensors."""
+    B = band_limit
+    sph = torch.view_as_complex(spherical.contiguous())
+    if ftype == 2:
+        zc = torch.view_as_complex(zonal.contiguous())
+        w = torch.cat((sph[..., :B], zc.unsqueeze(-1), sph[..., B:]), dim=-1)
+    else:
+        zc = torch.complex(zonal, torch.zeros_like(zonal)).unsqueeze(-1)
+        w = torch.cat((sph.conj().flip(-1), zc, sph), dim=-1)
+        if ftype == 1:
+            ph = torch.cat((phase[..., 1:].flip(-1), phase), dim=-1)          # |m| = B..1, 0, 1..B
+            w = w * torch.polar(torch.ones_like(ph), ph).unsqueeze(2)
+    return (w / (2 * B + 1)).resolve_conj().contiguous()
+
+
+class FieldConv(nn.Module):
+    def __init__(self, in_channels, out_channels, band_limit=1, n_rings=6, ftype=1, *, precision="fp32"):
+        super().__init__()
+        if precision not in _PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.R, self.B, self.ftype = n_rings, band_limit, ftype
+        self.precision = precision
+        if ftype == 0 or ftype == 1:
+            self.zonal = Parameter(torch.empty(out_channels, in_channels, n_rings))
+            self.spherical = Parameter(torch.empty(out_channels, in_channels, n_rings, band_limit, 2))
+            if ftype == 1:
+                self.phase = Parameter(torch.empty(out_channels, in_channels, band_limit + 1))
+                nn.init.xavier_uniform_(self.phase)
+            else:
+                self.register_buffer("phase", torch.zeros(out_channels, in_channels, band_limit + 1))
+        else:
+            self.zonal = Parameter(torch.empty(out_channels, in_channels, n_rings, 2))
+            self.spherical = Parameter(torch.empty(out_channels, in_channels, n_rings, 2 * band_limit, 2))
+            self.register_buffer("phase", torch.zeros(out_channels, in_channels, band_limit + 1))
+        nn.init.xavier_uniform_(self.zonal)
+        nn.init.xavier_uniform_(self.spherical)
+        self._dense_cache = None
+
+    def weight(self):
+        return fold_weights(self.zonal, self.spherical, self.phase, self.ftype, self.B)
+
+    def _dense_plan(self, supp_edges, n):
+        key = (supp_edges.data_ptr(), supp_edges.shape[0], supp_edges._version, n)
+        if self._dense_cache is None or self._dense_cache[0] != key:
+            self._dense_cache = (key, build_dense_plan(supp_edges, n))
+        return self._dense_cache[1]
+
+    def forward(self, x, supp_edges=None, supp_sten=None, *, plan=None):
+        if isinstance(supp_edges, (Plan, DensePlan)):
+            plan, supp_edges = supp_edges, None
+        if not x.is_cuda:
+            raise RuntimeError("fieldconv_b200.FieldConv runs on CUDA (sm_100a) only; there is no CPU fallback")
+        flags = _PRECISIONS[self.precision]
+        w = self.weight()
+        ci, co = self.in_channels, self.out_channels
+        if x.shape[1] != ci:
+            raise ValueError("expected %d input channels, got %d" % (ci, x.shape[1]))
+        if ci % 2:  # 16-byte feature rows: pad a zero channel (contributes nothing)
+            x = torch.cat((x, torch.zeros_like(x[:, :1])), dim=1)
+            w = torch.cat((w, torch.zeros_like(w[:, :1])), dim=1)
+        if co % 2:
+            w = torch.cat((w, torch.zeros_like(w[:1])), dim=0)
+        if plan is not None and not plan.dense:
+            if plan.n_rings != self.R:
+                raise ValueError("plan was built for n_rings=%d, layer has %d" % (plan.n_rings, self.R))
+            y = ops.field_conv(x, w, plan, self.B, flags)
+        else:
+            if supp_sten is None:
+                raise ValueError("forward needs (supp_edges, supp_sten) or a compact plan")
+            if tuple(supp_sten.shape[1:]) != (self.R, 2 * self.B + 1):
+                raise ValueError("supp_sten must be (E, %d, %d)" % (self.R, 2 * self.B + 1))
+            dplan = plan if plan is not None else self._dense_plan(supp_edges, x.shape[0])
+            y = ops.field_conv_dense(x, w, supp_sten, dplan, flags)
+        return y[:, :co] if co % 2 else y
+
+
+class TangentLin(nn.Module):
+    """nn/tangent_lin.py:12-29 — y = x @ (Re + i Im)^T, carried as one real GEMM on the interleaved storage."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.Re = Parameter(torch.empty(out_channels, in_channels))
+        self.Im = Parameter(torch.empty(out_channels, in_channels))
+        nn.init.xavier_uniform_(self.Re)
+        nn.init.xavier_uniform_(self.Im, gain=0.1)
+
+    def forward(self, x):
+        ci, co = self.in_channels, self.out_channels
+        re, im = self.Re.t(), self.Im.t()                       # (Ci, Co)
+        emb = torch.stack((torch.stack((re, im), -1), torch.stack((-im, re), -1)), 1)   # (Ci, 2, Co, 2)
+        emb = emb.reshape(2 * ci, 2 * co)
+        xr = torch.view_as_real(x.contiguous()).reshape(x.shape[0], 2 * ci)
+        if (2 * ci) % 4 or (2 * co) % 4:                         # GEMM wants 16-byte rows
+            pad_i, pad_o = (2 * ci) % 4, (2 * co) % 4
+            xr = torch.nn.functional.pad(xr, (0, pad_i))
+            emb = torch.nn.functional.pad(emb, (0, pad_o, 0, pad_i))
+        y = ops.gemm(xr, emb.contiguous(), False)[:, :2 * co]
+        return torch.view_as_complex(y.reshape(x.shape[0], co, 2).contiguous())
+
+
+class TangentNonLin(nn.Module):
+    """nn/tangent_nonlin.py:12-35 — modReLU."""
+
+    def __init__(self, in_channels):
+        super().__init__()
+        self.bias = Parameter(torch.zeros(1, in_channels))
+
+    def forward(self, x):
+        return ops.modrelu(x, self.bias)
+
+
+class FCResNetBlock(nn.Module):
+    """nn/fc_resnet_block.py:43-88 — nonlin2(res(x) + conv2(nonlin1(conv1(x))))."""
+
+    def __init__(self, in_channels, out_channels, band_limit=1, n_rings=6, ftype=1, frontload=False, *,
+                 precision="fp32"):
+        super().__init__()
+        mid = in_channels if frontload else out_channels
+        self.conv1 = FieldConv(in_channels, mid, band_limit=band_limit, n_rings=n_rings, ftype=ftype, precision=precision)
+        self.conv2 = FieldConv(mid, out_channels, band_limit=band_limit, n_rings=n_rings, ftype=ftype, precision=precision)
+        self.nonlin1 = TangentNonLin(mid)
+        self.nonlin2 = TangentNonLin(out_channels)
+        self.res = TangentLin(in_channels, out_channels)
+
+    def forward(self, x, supp_edges=None, supp_sten=None, *, plan=None):
+        if isinstance(supp_edges, (Plan, DensePlan)):
+            plan, supp_edges = supp_edges, None
+        h = self.nonlin1(self.conv1(x, supp_edges, supp_sten, plan=plan))
+        h = self.conv2(h, supp_edges, supp_sten, plan=plan)
+        return self.nonlin2(self.res(x) + h)

@@ -1,0 +1,300 @@
+"""PyTorch custom ops over the C ABI (torch is plumbing: device memory, streams, autograd graph).
+
+``fieldconv_b200::fc_fwd / fc_bwd``          compact plan (fast path)
+``fieldconv_b200::fc_fwd_dense / _bwd_dense`` dense supp_sten (E,R,M), exact drop-in for
+                                             nn/field_conv.py:104 of the reference
+``fieldconv_b200::modrelu(_bwd)``            TangentNonLin (nn/tangent_nonlin.py:24-35)
+``fieldconv_b200::gemm``                     real fp32 GEMM used by TangentLin (nn/tangent_lin.py:27-29)
+
+The folded filter W (Co,Ci,R,M) complex is an op INPUT: it is built from (zonal, spherical, phase)
+with ordinary differentiable torch ops (tiny tensors), so parameter gradients flow from the op's
+gW through autograd exactly as in the reference (nn/field_conv.py:10-33).
+"""
+import os
+from typing import Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+SAVE_CONTRIB_BYTES = int(os.environ.get("FIELDCONV_B200_SAVE_CONTRIB_BYTES", str(4 << 30)))
+
+
+def _real(t):
+    return torch.view_as_real(t)
+
+
+def _ws(nbytes, dev):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+
+
+def _check(x, name, dtype=torch.complex64):
+    if not x.is_cuda:
+        raise RuntimeError("fieldconv_b200: %s must be a CUDA tensor — there is no CPU path" % name)
+    if x.dtype != dtype:
+        raise TypeError("fieldconv_b200: %s must be %s, got %s" % (name, dtype, x.dtype))
+
+
+# --------------------------------------------------------------------------- compact plan ops
+@torch.library.custom_op("fieldconv_b200::fc_fwd", mutates_args=())
+def fc_fwd(x: Tensor, W: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: Tensor, rowptr_src: Tensor,
+           rec_src: Tensor, rot_src: Tensor, band_limit: int, n_rings: int, flags: int,
+           keep_contrib: bool) -> Tuple[Tensor, Tensor]:
+    # the by-source plan tensors are unused here; they are inputs so autograd can hand them to fc_bwd
+    _check(x, "x")
+    _check(W, "W")
+    x, W = x.contiguous(), W.contiguous()
+    n, ci = x.shape
+    co = W.shape[0]
+    k = n_rings * ci * (2 * band_limit + 1)
+    y = torch.empty(n, co, dtype=torch.complex64, device=x.device)
+    contrib = torch.empty(n, k, dtype=torch.complex64, device=x.device)
+    nbytes = _lib.query_bytes("fcb_fwd_workspace_bytes", n, ci, co, band_limit, n_rings, flags)
+    ws = _ws(nbytes, x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("fcb_fwd_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
+                  rot_tgt.data_ptr(), _real(y).data_ptr(), _real(contrib).data_ptr(), n, ci, co, band_limit, n_rings,
+                  flags, ws.data_ptr(), nbytes, _lib.stream_ptr())
+    if not keep_contrib:
+        contrib = torch.empty(0, dtype=torch.complex64, device=x.device)
+    return y, contrib
+
+
+@fc_fwd.register_fake
+def _(x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings, flags, keep_contrib):
+    n, ci = x.shape
+    k = n_rings * ci * (2 * band_limit + 1)
+    return x.new_empty(n, W.shape[0]), x.new_empty((n, k) if keep_contrib else (0,))
+
+
+@torch.library.custom_op("fieldconv_b200::fc_bwd", mutates_args=())
+def fc_bwd(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: Tensor,
+           rowptr_src: Tensor, rec_src: Tensor, rot_src: Tensor, band_limit: int, n_rings: int, flags: int,
+           need_gx: bool, need_gw: bool) -> Tuple[Tensor, Tensor]:
+    _check(gy, "grad_output")
+    x, W, gy = x.contiguous(), W.contiguous(), gy.contiguous()
+    n, ci = x.shape
+    co = W.shape[0]
+    gx = torch.empty_like(x) if need_gx else torch.empty(0, dtype=x.dtype, device=x.device)
+    gw = torch.empty_like(W) if need_gw else torch.empty(0, dtype=W.dtype, device=x.device)
+    have_contrib = contrib.numel() > 0
+    nbytes = _lib.query_bytes("fcb_bwd_workspace_bytes", n, ci, co, band_limit, n_rings,
+                              flags | (0x100 if have_contrib else 0))
+    ws = _ws(nbytes, x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("fcb_bwd_f32", _real(x).data_ptr(), _real(W).data_ptr(), _real(gy).data_ptr(),
+                  _real(contrib).data_ptr() if have_contrib else 0,
+                  rowptr_tgt.data_ptr(), rec_tgt.data_ptr(), rot_tgt.data_ptr(),
+                  rowptr_src.data_ptr(), rec_src.data_ptr(), rot_src.data_ptr(),
+                  _real(gx).data_ptr() if need_gx else 0, _real(gw).data_ptr() if need_gw else 0,
+                  n, ci, co, band_limit, n_rings, flags, ws.data_ptr(), nbytes, _lib.stream_ptr())
+    return gx, gw
+
+
+@fc_bwd.register_fake
+def _(x, W, gy, contrib, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings, flags,
+      need_gx, need_gw):
+    return (torch.empty_like(x) if need_gx else x.new_empty(0)), (torch.empty_like(W) if need_gw else W.new_empty(0))
+
+
+def _fc_setup(ctx, inputs, output):
+    x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings, flags, keep = inputs
+    _, contrib = output
+    ctx.save_for_backward(x, W, contrib, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src)
+    ctx.cfg = (band_limit, n_rings, flags)
+
+
+def _fc_backward(ctx, gy, _gcontrib):
+    x, W, contrib, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src = ctx.saved_tensors
+    band_limit, n_rings, flags = ctx.cfg
+    gx, gw = fc_bwd(x, W, gy, contrib, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings,
+                    flags, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+    return (gx if ctx.needs_input_grad[0] else None, gw if ctx.needs_input_grad[1] else None) + (None,) * 10
+
+
+fc_fwd.register_autograd(_fc_backward, setup_context=_fc_setup)
+
+
+def field_conv(x, W, plan, band_limit, flags=0, keep_contrib=None):
+    """y = FieldConv(x) for the compact plan; differentiable w.r.t. x and W."""
+    n, ci = x.shape
+    if keep_contrib is None:
+        keep_contrib = n * plan.n_rings * ci * (2 * band_limit + 1) * 8 <= SAVE_CONTRIB_BYTES
+    y, _ = fc_fwd(x, W, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src, plan.rot_src,
+                  band_limit, plan.n_rings, flags, bool(keep_contrib))
+    return y
+
+
+# --------------------------------------------------------------------------- dense-stencil ops
+@torch.library.custom_op("fieldconv_b200::fc_fwd_dense", mutates_args=())
+def fc_fwd_dense(x: Tensor, W: Tensor, sten: Tensor, rowptr_tgt: Tensor, nbr_tgt: Tensor, perm_tgt: Tensor,
+                 rowptr_src: Tensor, nbr_src: Tensor, perm_src: Tensor, flags: int) -> Tuple[Tensor, Tensor]:
+    _check(x, "x")
+    _check(W, "W")
+    _check(sten, "supp_sten")
+    x, W, sten = x.contiguous(), W.contiguous(), sten.contiguous()
+    n, ci = x.shape
+    co, _, r, m = W.shape
+    b = (m - 1) // 2
+    y = torch.empty(n, co, dtype=torch.complex64, device=x.device)
+    contrib = torch.empty(n, r * ci * m, dtype=torch.complex64, device=x.device)
+    nbytes = _lib.query_bytes("fcb_fwd_workspace_bytes", n, ci, co, b, r, flags)
+    ws = _ws(nbytes, x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("fcb_fwd_dense_f32", _real(x).data_ptr(), _real(W).data_ptr(), _real(sten).data_ptr(),
+                  rowptr_tgt.data_ptr(), nbr_tgt.data_ptr(), perm_tgt.data_ptr(), _real(y).data_ptr(),
+                  _real(contrib).data_ptr(), n, ci, co, b, r, flags, ws.data_ptr(), nbytes, _lib.stream_ptr())
+    return y, contrib
+
+
+@fc_fwd_dense.register_fake
+def _(x, W, sten, rowptr_tgt, nbr_tgt, perm_tgt, rowptr_src, nbr_src, perm_src, flags):
+    n, ci = x.shape
+    co, _, r, m = W.shape
+    return x.new_empty(n, co), x.new_empty(n, r * ci * m)
+
+
+@torch.library.custom_op("fieldconv_b200::fc_bwd_dense", mutates_args=())
+def fc_bwd_dense(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, sten: Tensor, rowptr_src: Tensor, nbr_src: Tensor,
+                 perm_src: Tensor, flags: int, need_gx: bool, need_gw: bool) -> Tuple[Tensor, Tensor]:
+    x, W, gy, sten = x.contiguous(), W.contiguous(), gy.contiguous(), sten.contiguous()
+    n, ci = x.shape
+    co, _, r, m = W.shape
+    b = (m - 1) // 2
+    gx = torch.empty_like(x) if need_gx else torch.empty(0, dtype=x.dtype, device=x.device)
+    gw = torch.empty_like(W) if need_gw else torch.empty(0, dtype=W.dtype, device=x.device)
+    nbytes = _lib.query_bytes("fcb_bwd_workspace_bytes", n, ci, co, b, r, flags | 0x100)
+    ws = _ws(nbytes, x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("fcb_bwd_dense_f32", _real(x).data_ptr(), _real(W).data_ptr(), _real(gy).data_ptr(),
+                  _real(contrib).data_ptr(), _real(sten).data_ptr(), rowptr_src.data_ptr(), nbr_src.data_ptr(),
+                  perm_src.data_ptr(), _real(gx).data_ptr() if need_gx else 0, _real(gw).data_ptr() if need_gw else 0,
+                  n, ci, co, b, r, flags, ws.data_ptr(), nbytes, _lib.stream_ptr())
+    return gx, gw
+
+
+@fc_bwd_dense.register_fake
+def _(x, W, gy, contrib, sten, rowptr_src, nbr_src, perm_src, flags, need_gx, need_gw):
+    return (torch.empty_like(x) if need_gx else x.new_empty(0)), (torch.empty_like(W) if need_gw else W.new_empty(0))
+
+
+def _fcd_setup(ctx, inputs, output):
+    x, W, sten, rowptr_tgt, nbr_tgt, perm_tgt, rowptr_src, nbr_src, perm_src, flags = inputs
+    ctx.save_for_backward(x, W, output[1], sten, rowptr_src, nbr_src, perm_src)
+    ctx.flags = flags
+
+
+def _fcd_backward(ctx, gy, _gc):
+    x, W, contrib, sten, rowptr_src, nbr_src, perm_src = ctx.saved_tensors
+    gx, gw = fc_bwd_dense(x, W, gy, contrib, sten, rowptr_src, nbr_src, perm_src, ctx.flags,
+                          ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+    return (gx if ctx.needs_input_grad[0] else None, gw if ctx.needs_input_grad[1] else None) + (None,) * 8
+
+
+fc_fwd_dense.register_autograd(_fcd_backward, setup_context=_fcd_setup)
+
+
+def field_conv_dense(x, W, supp_sten, plan, flags=0):
+    y, _ = fc_fwd_dense(x, W, supp_sten, plan.rowptr_tgt, plan.nbr_tgt, plan.perm_tgt, plan.rowptr_src, plan.nbr_src,
+                        plan.perm_src, flags)
+    return y
+
+
+# --------------------------------------------------------------------------- modReLU
+@torch.library.custom_op("fieldconv_b200::modrelu", mutates_args=())
+def modrelu(x: Tensor, bias: Tensor) -> Tensor:
+    _check(x, "x")
+    x = x.contiguous()
+    b = bias.reshape(-1).contiguous().float()
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.call("fcb_modrelu_fwd_f32", _real(x).data_ptr(), b.data_ptr(), _real(y).data_ptr(), x.shape[0], x.shape[1],
+                  _lib.stream_ptr())
+    return y
+
+
+@modrelu.register_fake
+def _(x, bias):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op("fieldconv_b200::modrelu_bwd", mutates_args=())
+def modrelu_bwd(x: Tensor, bias: Tensor, gy: Tensor) -> Tuple[Tensor, Tensor]:
+    x, gy = x.contiguous(), gy.contiguous()
+    b = bias.reshape(-1).contiguous().float()
+    n, c = x.shape
+    gx = torch.empty_like(x)
+    gb = torch.empty(c, dtype=torch.float32, device=x.device)
+    nbytes = _lib.query_bytes("fcb_modrelu_bwd_workspace_bytes", n, c)
+    ws = _ws(nbytes, x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("fcb_modrelu_bwd_f32", _real(x).data_ptr(), b.data_ptr(), _real(gy).data_ptr(), _real(gx).data_ptr(),
+                  gb.data_ptr(), n, c, ws.data_ptr(), nbytes, _lib.stream_ptr())
+    return gx, gb
+
+
+@modrelu_bwd.register_fake
+def _(x, bias, gy):
+    return torch.empty_like(x), x.new_empty(x.shape[1], dtype=torch.float32)
+
+
+def _mr_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1])
+
+
+def _mr_backward(ctx, gy):
+    x, bias = ctx.saved_tensors
+    gx, gb = modrelu_bwd(x, bias, gy)
+    return gx, gb.reshape(bias.shape)
+
+
+modrelu.register_autograd(_mr_backward, setup_context=_mr_setup)
+
+
+# --------------------------------------------------------------------------- real GEMM (TangentLin)
+@torch.library.custom_op("fieldconv_b200::gemm", mutates_args=())
+def gemm(a: Tensor, b: Tensor, trans_a: bool) -> Tensor:
+    """C = A @ B (trans_a False, A is MxK) or A^T @ B (trans_a True, A is KxM); fp32, row-major."""
+    _check(a, "a", torch.float32)
+    _check(b, "b", torch.float32)
+    a, b = a.contiguous(), b.contiguous()
+    if trans_a:
+        k, m = a.shape
+    else:
+        m, k = a.shape
+    n = b.shape[1]
+    c = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    split = 1
+    parts = None
+    if trans_a:
+        tiles = (m + 127) // 128
+        split = max(1, min(64, k // 512, (4 * 148 + tiles - 1) // tiles))
+        if split > 1:
+            parts = torch.empty(split * m * n, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call("fcb_gemm_f32", a.data_ptr(), b.data_ptr(), c.data_ptr(), m, n, k, a.shape[1], n, n,
+                  1 if trans_a else 0, 1, 0, 0, 0, split, _lib.ptr(parts), 0, _lib.stream_ptr())
+    return c
+
+
+@gemm.register_fake
+def _(a, b, trans_a):
+    return a.new_empty(a.shape[1] if trans_a else a.shape[0], b.shape[1])
+
+
+def _gemm_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1])
+    ctx.trans_a = inputs[2]
+
+
+def _gemm_backward(ctx, gc):
+    a, b = ctx.saved_tensors
+    if ctx.trans_a:
+        raise RuntimeError("fieldconv_b200::gemm: backward of the transposed form is not needed")
+    ga = gemm(gc, b.t().contiguous(), False) if ctx.needs_input_grad[0] else None
+    gb = gemm(a, gc, True) if ctx.needs_input_grad[1] else None
+    return ga, gb, None
+
+
+gemm.register_autograd(_gemm_backward, setup_context=_gemm_setup)

@@ -1,0 +1,165 @@
+/* fieldconv_b200 — C ABI of the B200-native FieldConv hot path (libfieldconv_b200.so).
+ *
+ * The reference (twmitchel/FieldConv) has NO native code on this path: the boundary it
+ * exposes is the Python operator `FieldConv.forward(x, supp_edges, supp_sten)`
+ * (nn/field_conv.py:104-137) built from ATen ops plus `torch_scatter.scatter_add`
+ * (nn/field_conv.py:134), fed by `FCPrecomp.__call__` (transforms/fc_precomp.py:53-97).
+ * Each entry point below names the reference lines it replaces.  INTEGRATION.md shows the
+ * ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless stated otherwise; complex = interleaved
+ *    (re, im) float pairs exactly like torch.complex64; all buffers are owned by the caller;
+ *  - the library allocates nothing, keeps no state except a thread-local error string, never
+ *    synchronises: all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *  - return 0 on success, a negative FCB_E_* code on failure (fcb_last_error() explains);
+ *  - feature rows must be 16-byte aligned: channel counts must be even (pad with a zero
+ *    channel otherwise — the Python layer does this).
+ *
+ * Edge record layout (16 bytes, "rec"): { int32 nbr | ring_floor << 27, float t, float wxp_re,
+ * float wxp_im } where nbr is the source (by-target plan) or the target (by-source plan),
+ * ring_floor = f and t the two-tap radial weights (1-t on ring f, t on ring f+1) of
+ * fc_precomp.py:10-27, and wxp the normalised integration weight times transport
+ * (fc_precomp.py:87,92).  "rot" = (cos theta, sin theta) of the log-map angle (fc_precomp.py:83).
+ */
+#ifndef FIELDCONV_B200_H
+#define FIELDCONV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCB_OK 0
+#define FCB_E_ARG (-1)       /* bad shape / size / null pointer */
+#define FCB_E_ALIGN (-2)     /* pointer or channel-count alignment */
+#define FCB_E_WORKSPACE (-3) /* workspace too small */
+#define FCB_E_CUDA (-4)      /* a CUDA runtime call failed (message has the CUDA error) */
+#define FCB_E_UNSUPPORTED (-5)
+
+#define FCB_MAX_BAND_LIMIT 4
+#define FCB_MAX_RINGS 32
+#define FCB_MAX_VERTICES (1 << 27)
+
+/* flags for fcb_fwd_f32 / fcb_bwd_f32 */
+#define FCB_GEMM_SIMT_FP32 0  /* contraction on FP32 FMA (bit-for-bit fp32 semantics) */
+#define FCB_GEMM_TC_3XTF32 1  /* tcgen05 tensor cores, error-compensated 3xTF32 (fp32-grade) */
+#define FCB_GEMM_TC_TF32 2    /* tcgen05 tensor cores, plain TF32 (looser tolerance) */
+#define FCB_GEMM_MASK 0xff
+#define FCB_FLAG_HAVE_CONTRIB 0x100 /* fcb_bwd_workspace_bytes: contrib will be supplied, no recompute buffer */
+
+const char* fcb_last_error(void);
+int fcb_version(void);
+/* number of CUDA kernels this library has launched in this process (monotonic counter; the only
+ * other process-wide state besides the thread-local error string) */
+unsigned long long fcb_launch_count(void);
+
+/* Optional per-launch timing used by bench.py for the roofline numbers: between enable and
+ * disable every kernel launch of this library is bracketed by CUDA events on its stream.
+ * Debug facility: not thread-safe, owns its events (the one exception to "allocates nothing").
+ * Collect after synchronising: names are '\n'-joined in launch order, ms[i] the durations. */
+int fcb_profile_enable(int max_records);
+int fcb_profile_disable(void);
+int fcb_profile_collect(char* names_buf, size_t names_bytes, float* ms, int capacity, int* count);
+
+/* ------------------------------------------------------------------ plan (K0)
+ * Replaces, on the device and without host synchronisation:
+ *   transforms/fc_precomp.py:67-74  r = logMag/epsilon, drop edges with r > 1
+ *   transforms/fc_precomp.py:10-27  radial two-tap interpolation (ring floor f, weight t)
+ *   transforms/fc_precomp.py:87,92  w_j / (1e-12 + sum_{e'->i} w_j') * xp
+ *   the implicit grouping that scatter_add's index performs (nn/field_conv.py:134) and that
+ *   autograd's gather-backward performs for grad x — as two CSR orders of the kept edges:
+ *   by (target, ring floor) and by (source, ring floor), both STABLE in the input order.
+ * rowptr_*[N] holds the number of kept edges; rec/rot/perm entries beyond it are untouched.
+ * perm_*[p] is the index into the caller's edge list of sorted edge p.
+ * ring_radii: R floats = sqrt(k/(R-1)) computed by the caller exactly as fc_precomp.py:12. */
+int fcb_plan_workspace_bytes(int64_t E, int64_t N, int R, size_t* bytes);
+int fcb_plan_build(const int64_t* edges_ji, const float* log_mag, const float* log_ang,
+                   const float* xp /*complex (E)*/, const float* w /*(N)*/,
+                   const float* ring_radii, float epsilon, int64_t E, int64_t N, int R,
+                   int32_t* rowptr_tgt, void* rec_tgt, float* rot_tgt, int32_t* perm_tgt,
+                   int32_t* rowptr_src, void* rec_src, float* rot_src, int32_t* perm_src,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Plan for the dense-stencil drop-in signature forward(x, supp_edges, supp_sten)
+ * (nn/field_conv.py:104): CSR by target and by source only; stencil rows are addressed through
+ * perm_*.  nbr_*[p] = source (by-target order) / target (by-source order) of sorted edge p. */
+int fcb_plan_dense_workspace_bytes(int64_t E, int64_t N, size_t* bytes);
+int fcb_plan_build_dense(const int64_t* edges_ji, int64_t E, int64_t N,
+                         int32_t* rowptr_tgt, int32_t* nbr_tgt, int32_t* perm_tgt,
+                         int32_t* rowptr_src, int32_t* nbr_src, int32_t* perm_src,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ forward (K1 + K2)
+ * Replaces nn/field_conv.py:128-137 (+ utils/field.py:40-48, + the weightContrib* reduction
+ * :10-33 given the folded weight W[o,c,r,m] = coeff/(2B+1)):
+ *   contrib[i, r, c, m] = sum_{e: tgt(e)=i} x[src(e),c] conj(u)^m * sten[e,r,m]   (deterministic
+ *                         segmented reduction over the CSR row, fixed order)
+ *   y[i, o]             = sum_{c,r,m} contrib[i,r,c,m] * W[o,c,r,m]
+ * contrib (N x R*Ci*M complex, ring-major) is an OUTPUT the caller may keep for backward, or
+ * NULL on the fused tensor-core path that never materialises it.
+ * W is complex (Co,Ci,R,M) contiguous.  M = 2*band_limit+1. */
+int fcb_fwd_workspace_bytes(int64_t N, int Ci, int Co, int band_limit, int R, int flags, size_t* bytes);
+int fcb_fwd_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
+                const float* rot_tgt, float* y, float* contrib, int64_t N, int Ci, int Co,
+                int band_limit, int R, int flags, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ backward (K4 + K5)
+ * Replaces torch autograd through nn/field_conv.py:128-137 (PyTorch complex convention
+ * g = dL/dRe + i dL/dIm):
+ *   gW[o,c,r,m] = sum_n conj(contrib[n,r,c,m]) gy[n,o]     (deterministic split reduction)
+ *   gx          = softAngle chain rule applied to the transposed gather over the by-source
+ *                 CSR of gy Wh conj(sten)                   
+ * contrib may be NULL: it is then recomputed from x with the by-target plan (which must be
+ * given).  gW is complex (Co,Ci,R,M); either of gx / gW may be NULL to skip it. */
+int fcb_bwd_workspace_bytes(int64_t N, int Ci, int Co, int band_limit, int R, int flags, size_t* bytes);
+int fcb_bwd_f32(const float* x, const float* W, const float* gy, const float* contrib,
+                const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
+                const int32_t* rowptr_src, const void* rec_src, const float* rot_src,
+                float* gx, float* gW, int64_t N, int Ci, int Co, int band_limit, int R, int flags,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ dense-stencil forward/backward
+ * Exact drop-in for arbitrary supp_sten (E,R,M) complex (nn/field_conv.py:114-116), any number
+ * of non-zero rings per edge.  Same outputs as above. */
+int fcb_fwd_dense_f32(const float* x, const float* W, const float* sten, const int32_t* rowptr_tgt,
+                      const int32_t* nbr_tgt, const int32_t* perm_tgt, float* y, float* contrib,
+                      int64_t N, int Ci, int Co, int band_limit, int R, int flags,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int fcb_bwd_dense_f32(const float* x, const float* W, const float* gy, const float* contrib,
+                      const float* sten, const int32_t* rowptr_src, const int32_t* nbr_src,
+                      const int32_t* perm_src, float* gx, float* gW, int64_t N, int Ci, int Co,
+                      int band_limit, int R, int flags, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* ------------------------------------------------------------------ building blocks (exported for tests)
+ * Gauge-aligned aggregation only (K1) / its transpose (first half of K5). */
+int fcb_aggregate_f32(const float* feat, const int32_t* rowptr, const void* rec, const float* rot,
+                      float* out, int64_t N, int C, int band_limit, int R, int transpose, void* stream);
+/* Real fp32 GEMM C[MxN] = A*B (trans_a=0: A is MxK row-major; trans_a=1: A is KxM row-major),
+ * B is KxN row-major; batch >= 1 with element strides; split_k >= 1 uses `partials`
+ * (split_k*batch*M*N floats) and a fixed-order final reduction (deterministic). */
+int fcb_gemm_f32(const float* A, const float* B, float* C, int64_t M, int N, int64_t K,
+                 int64_t lda, int64_t ldb, int64_t ldc, int trans_a, int batch, int64_t stride_a,
+                 int64_t stride_b, int64_t stride_c, int split_k, float* partials, int flags, void* stream);
+/* Stable LSD radix sort of (key,value) uint32 pairs on the low `bits` bits of the key.
+ * Result lands in keys_out/vals_out; keys_in/vals_in are clobbered. */
+int fcb_sort_workspace_bytes(int64_t n, size_t* bytes);
+int fcb_sort_pairs_u32(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                       int64_t n, int bits, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ block epilogue pieces
+ * TangentNonLin / modReLU, nn/tangent_nonlin.py:24-35: y = relu(|x|+b_c) x/|x|, origin entries
+ * passed through.  Backward returns gx and per-block partial bias gradients reduced in fixed
+ * order into gb (C floats). */
+int fcb_modrelu_fwd_f32(const float* x, const float* bias, float* y, int64_t N, int C, void* stream);
+int fcb_modrelu_bwd_workspace_bytes(int64_t N, int C, size_t* bytes);
+int fcb_modrelu_bwd_f32(const float* x, const float* bias, const float* gy, float* gx, float* gb,
+                        int64_t N, int C, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIELDCONV_B200_H */

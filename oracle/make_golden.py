@@ -1,0 +1,120 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference (build container only).
+
+    python -m oracle.make_golden
+
+Each file holds the inputs of one seeded case and what the reference produced for them:
+FCPrecomp outputs (transforms/fc_precomp.py:53-97), FieldConv forward output and the
+autograd gradients of x / zonal / spherical / phase (nn/field_conv.py:104-137), and for the
+block case FCResNetBlock (nn/fc_resnet_block.py:65-88).  The loss is Re<y, gy> with a seeded
+gy so that the x-gradient equals the vector-Jacobian product for upstream gradient gy.
+"""
+import importlib.util
+import os
+
+import numpy as np
+import torch
+
+from oracle import ref_loader
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_spec = importlib.util.spec_from_file_location("_syn", os.path.join(ROOT, "fieldconv_b200", "synthetic.py"))
+syn = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(syn)
+
+CASES = [
+    # name, n_side, deg, Ci, Co, B, R, ftype, eps_scale, tweaks
+    ("fc_b1r6_f1", 9, 14.0, 6, 4, 1, 6, 1, 0.93, ()),
+    ("fc_b2r6_f0", 8, 12.0, 4, 6, 2, 6, 0, 0.95, ()),
+    ("fc_b2r4_f2", 8, 12.0, 5, 3, 2, 4, 2, 1.0, ("dups", "shuffle")),
+    ("fc_b3r2_f1", 7, 10.0, 3, 5, 3, 2, 1, 0.9, ("isolated", "exact_eps")),
+    ("fc_b1r3_f2", 7, 16.0, 8, 8, 1, 3, 2, 1.0, ("shuffle",)),
+]
+
+
+def _np(t):
+    t = t.detach()
+    return t.numpy()
+
+
+def make_case(name, n_side, deg, ci, co, B, R, ftype, eps_scale, tweaks, seed):
+    ns = ref_loader.load()
+    d = syn.torus_mesh(n_side, deg=deg, seed=seed, tile=4)
+    g = torch.Generator().manual_seed(seed)
+    eps = float(d.epsilon * eps_scale)
+    if "dups" in tweaks:                      # duplicate edges are summed (field_conv.py:134)
+        pick = torch.randperm(d.supp_edges.shape[0], generator=g)[:7]
+        for k in ("supp_edges", "logMag", "logAng", "xp"):
+            setattr(d, k, torch.cat((getattr(d, k), getattr(d, k)[pick])))
+    if "isolated" in tweaks:                  # a target with no incoming edge -> y = 0
+        keep = d.supp_edges[:, 1] != 3
+        for k in ("supp_edges", "logMag", "logAng", "xp"):
+            setattr(d, k, getattr(d, k)[keep])
+    if "exact_eps" in tweaks:                 # r/eps == 1 exactly stays in the support
+        far = torch.nonzero(d.logMag > 0.5 * eps)[:2, 0]
+        d.logMag[far] = torch.tensor(eps, dtype=torch.float32)
+        eps = float(d.logMag[far[0]])
+    if "shuffle" in tweaks:                   # any edge order is accepted
+        perm = torch.randperm(d.supp_edges.shape[0], generator=g)
+        for k in ("supp_edges", "logMag", "logAng", "xp"):
+            setattr(d, k, getattr(d, k)[perm])
+    e, sten, ln, wxp = ns.FCPrecomp(B, R, eps)(d)
+    x = syn.random_features(d.num_nodes, ci, seed=seed, zero_frac=0.05)
+    torch.manual_seed(seed)
+    fc = ns.FieldConv(ci, co, B, R, ftype)
+    xr = x.clone().requires_grad_(True)
+    y = fc(xr, e, sten)
+    gy = torch.complex(torch.randn(y.shape, generator=g), torch.randn(y.shape, generator=g))
+    (y.real * gy.real + y.imag * gy.imag).sum().backward()
+    out = dict(
+        n=np.int64(d.num_nodes), ci=np.int64(ci), co=np.int64(co), B=np.int64(B), R=np.int64(R),
+        ftype=np.int64(ftype), epsilon=np.float64(eps),
+        raw_edges=_np(d.supp_edges), logMag=_np(d.logMag), logAng=_np(d.logAng), xp=_np(d.xp), w=_np(d.w),
+        supp_edges=_np(e), supp_sten=_np(sten), ln=_np(ln), wxp=_np(wxp),
+        x=_np(x), gy=_np(gy), zonal=_np(fc.zonal), spherical=_np(fc.spherical), phase=_np(fc.phase),
+        y=_np(y), gx=_np(xr.grad), g_zonal=_np(fc.zonal.grad), g_spherical=_np(fc.spherical.grad),
+    )
+    if ftype == 1:
+        out["g_phase"] = _np(fc.phase.grad)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+    print(name, "N", d.num_nodes, "E", e.shape[0], "|y|max", float(y.abs().max()))
+
+
+def make_block(seed=11):
+    ns = ref_loader.load()
+    d = syn.torus_mesh(8, deg=12.0, seed=seed, tile=4)
+    B, R, ci, co = 2, 6, 4, 6
+    e, sten, ln, wxp = ns.FCPrecomp(B, R, float(d.epsilon))(d)
+    x = syn.random_features(d.num_nodes, ci, seed=seed, zero_frac=0.05)
+    torch.manual_seed(seed)
+    blk = ns.FCResNetBlock(ci, co, B, R, 1)
+    with torch.no_grad():
+        blk.nonlin1.bias.uniform_(-0.3, 0.3)
+        blk.nonlin2.bias.uniform_(-0.3, 0.3)
+    xr = x.clone().requires_grad_(True)
+    y = blk(xr, e, sten)
+    g = torch.Generator().manual_seed(seed)
+    gy = torch.complex(torch.randn(y.shape, generator=g), torch.randn(y.shape, generator=g))
+    (y.real * gy.real + y.imag * gy.imag).sum().backward()
+    out = dict(n=np.int64(d.num_nodes), ci=np.int64(ci), co=np.int64(co), B=np.int64(B), R=np.int64(R),
+               epsilon=np.float64(d.epsilon), raw_edges=_np(d.supp_edges), logMag=_np(d.logMag),
+               logAng=_np(d.logAng), xp=_np(d.xp), w=_np(d.w),
+               supp_edges=_np(e), supp_sten=_np(sten), x=_np(x), gy=_np(gy), y=_np(y), gx=_np(xr.grad))
+    for k, v in blk.state_dict().items():
+        out["p." + k] = _np(v)
+    for k, v in blk.named_parameters():
+        out["g." + k] = _np(v.grad)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "block_b2r6.npz"), **out)
+    print("block_b2r6", "N", d.num_nodes, "E", e.shape[0])
+
+
+def main():
+    if not ref_loader.available():
+        raise SystemExit("reference tree not present; golden vectors can only be generated in the build container")
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    for i, c in enumerate(CASES):
+        make_case(*c, seed=100 + i)
+    make_block()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,63 @@
+"""CPU: the C-ABI library loads, exports every symbol include/fieldconv_b200.h declares, and its host-side
+argument checking / workspace queries behave (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from fieldconv_b200 import _lib
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "fieldconv_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fcb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = header_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+
+
+def test_binding_covers_header():
+    bound = set(_lib.SIGNATURES) | {"fcb_last_error", "fcb_launch_count"}
+    assert set(header_symbols()) <= bound
+
+
+def test_version_and_counter():
+    lib = _lib.load()
+    assert lib.fcb_version() >= 100
+    assert _lib.launch_count() >= 0
+
+
+def test_workspace_queries_and_errors():
+    n = _lib.query_bytes("fcb_fwd_workspace_bytes", 1000, 32, 32, 1, 6, 0)
+    assert n >= 4 * (6 * 32 * 3) * 32 * 4
+    big = _lib.query_bytes("fcb_bwd_workspace_bytes", 1000, 32, 32, 1, 6, 0)
+    small = _lib.query_bytes("fcb_bwd_workspace_bytes", 1000, 32, 32, 1, 6, 0x100)
+    assert big - small >= 1000 * 6 * 32 * 3 * 8
+    assert _lib.query_bytes("fcb_plan_workspace_bytes", 10000, 500, 6) > 7 * 10000 * 4
+    assert _lib.query_bytes("fcb_sort_workspace_bytes", 0) > 0
+    with pytest.raises(RuntimeError, match="even"):
+        _lib.query_bytes("fcb_fwd_workspace_bytes", 10, 3, 4, 1, 6, 0)          # odd channel count
+    with pytest.raises(RuntimeError, match="band_limit"):
+        _lib.query_bytes("fcb_fwd_workspace_bytes", 10, 4, 4, 9, 6, 0)
+    out = ctypes.c_size_t(0)
+    rc = _lib.load().fcb_plan_workspace_bytes(-1, 5, 6, ctypes.byref(out))
+    assert rc == -1 and b"bad arguments" in _lib.load().fcb_last_error()
+
+
+def test_null_pointer_calls_are_rejected_without_touching_the_gpu():
+    lib = _lib.load()
+    rc = lib.fcb_fwd_f32(None, None, None, None, None, None, None, 10, 4, 4, 1, 6, 0, None, 0, None)
+    assert rc == -1
+    rc = lib.fcb_plan_build(None, None, None, None, None, None, 1.0, 10, 10, 1, None, None, None, None,
+                            None, None, None, None, None, 0, None)
+    assert rc == -5      # n_rings = 1 is unsupported (the reference divides by n_rings-1)
+    rc = lib.fcb_gemm_f32(None, None, None, 4, 4, 4, 4, 4, 4, 0, 1, 0, 0, 0, 1, None, 0, None)
+    assert rc == -1

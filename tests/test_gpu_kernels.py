@@ -1,0 +1,178 @@
+"""GPU: building blocks of the C ABI (sort, plan, aggregation, GEMM, modReLU) against the oracle."""
+import pytest
+import torch
+
+import fieldconv_b200 as fcb
+from conftest import assert_close_normwise, golden_names, load_golden
+from fieldconv_b200 import _lib, ops
+from fieldconv_b200.synthetic import random_features, torus_mesh
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _sort(keys, vals, bits):
+    n = keys.numel()
+    k_in, v_in = keys.clone().int(), vals.clone().int()
+    k_out, v_out = torch.empty_like(k_in), torch.empty_like(v_in)
+    nbytes = _lib.query_bytes("fcb_sort_workspace_bytes", n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    _lib.call("fcb_sort_pairs_u32", k_in.data_ptr(), v_in.data_ptr(), k_out.data_ptr(), v_out.data_ptr(), n, bits,
+              ws.data_ptr(), nbytes, _lib.stream_ptr())
+    return k_out, v_out
+
+
+@pytest.mark.parametrize("n,bits", [(0, 8), (1, 8), (31, 3), (2048, 8), (2049, 9), (100003, 17), (1 << 20, 24), (300007, 31)])
+def test_radix_sort_is_stable_and_exact(n, bits):
+    g = torch.Generator(device="cpu").manual_seed(n + bits)
+    keys = torch.randint(0, 2 ** bits, (n,), generator=g, dtype=torch.int64).to(DEV)
+    if n > 10:
+        keys[: n // 3] = keys[n // 2]        # many duplicates -> stability matters
+    vals = torch.arange(n, device=DEV)
+    k_out, v_out = _sort(keys, vals, bits)
+    ref_k, ref_i = torch.sort(keys, stable=True)
+    assert torch.equal(k_out.long(), ref_k)
+    assert torch.equal(v_out.long(), ref_i)
+
+
+def _plan_from_golden(g):
+    return fcb.build_plan(g["raw_edges"].to(DEV), g["logMag"].to(DEV), g["logAng"].to(DEV), g["xp"].to(DEV),
+                          g["w"].to(DEV), g["R"], g["epsilon"])
+
+
+@pytest.mark.parametrize("name", golden_names("fc_") + ["block_b2r6"])
+def test_plan_matches_reference_fcprecomp(name):
+    g = load_golden(name)
+    R, B = g["R"], g["B"]
+    plan = _plan_from_golden(g)
+    e_ref = g["supp_edges"]                                     # reference FCPrecomp output (kept edges, input order)
+    E = e_ref.shape[0]
+    assert plan.num_edges == E
+    # oracle pieces (bit-exact restatement of the reference, see test_oracle.py)
+    _, sten, _, wxp, (keep, f, t) = restate.fc_precomp(g["logMag"], g["logAng"], g["w"], g["raw_edges"], g["xp"], B, R,
+                                                       g["epsilon"])
+    for side, col in (("tgt", 1), ("src", 0)):
+        perm = getattr(plan, "perm_" + side)[:E].long().cpu()
+        rec = getattr(plan, "rec_" + side)[:E].cpu()
+        rot = getattr(plan, "rot_" + side)[:E].cpu()
+        rowptr = getattr(plan, "rowptr_" + side).long().cpu()
+        # CSR order == stable sort of the kept edges by (vertex, ring floor): indices bit-exact
+        key = e_ref[:, col] * (R - 1) + f
+        order = torch.argsort(key, stable=True)
+        assert torch.equal(perm, keep[order]), side + ": permutation"
+        counts = torch.bincount(e_ref[:, col], minlength=g["n"])
+        assert torch.equal(rowptr[1:] - rowptr[:-1], counts), side + ": row pointers"
+        assert int(rowptr[0]) == 0 and int(rowptr[-1]) == E
+        nbr = (rec[:, 0] & ((1 << 27) - 1)).long()
+        ring = (rec[:, 0] >> 27) & 31
+        assert torch.equal(nbr, e_ref[order, 1 - col]), side + ": neighbour ids"
+        assert torch.equal(ring.long(), f[order]), side + ": ring floor"
+        assert torch.equal(rec[:, 1].view(torch.float32), t[order]), side + ": ring weight t bit-exact"
+        got_wxp = torch.view_as_complex(rec[:, 2:4].contiguous().view(torch.float32))
+        assert_close_normwise(got_wxp, wxp[order], 1e-6, side + ": wxp")
+        theta = g["logAng"][keep][order]
+        assert_close_normwise(rot, torch.stack((torch.cos(theta), torch.sin(theta)), 1), 1e-6, side + ": rot")
+    # expanded multiset of (j, i) equals the reference's edge list
+    got = plan.edges_by_target().cpu()
+    assert torch.equal(got[torch.argsort(got[:, 0] * g["n"] + got[:, 1], stable=True)],
+                       e_ref[torch.argsort(e_ref[:, 0] * g["n"] + e_ref[:, 1], stable=True)])
+
+
+def test_plan_empty_and_all_filtered():
+    w = torch.ones(7, 1, device=DEV)
+    p = fcb.build_plan(torch.zeros(0, 2, dtype=torch.long, device=DEV), torch.zeros(0, device=DEV), torch.zeros(0, device=DEV),
+                       torch.zeros(0, dtype=torch.complex64, device=DEV), w, 6, 1.0)
+    assert p.num_edges == 0 and int(p.rowptr_src[-1]) == 0
+    e = torch.tensor([[0, 1], [2, 3], [6, 6]], device=DEV)
+    p = fcb.build_plan(e, torch.full((3,), 5.0, device=DEV), torch.zeros(3, device=DEV),
+                       torch.ones(3, dtype=torch.complex64, device=DEV), w, 6, 1.0)
+    assert p.num_edges == 0
+    m = fcb.FieldConv(4, 6).to(DEV)
+    y = m(torch.randn(7, 4, dtype=torch.complex64, device=DEV), p)
+    assert y.shape == (7, 6) and float(y.abs().max()) == 0.0     # no in-edges -> y = 0 (field_conv.py:134 dim_size=N)
+
+
+@pytest.mark.parametrize("m,n,k,trans", [(1, 4, 4, 0), (130, 96, 72, 0), (257, 20, 1000, 0), (1000, 64, 36, 0),
+                                         (300, 96, 4000, 1), (2880, 96, 20000, 1), (64, 256, 515, 1), (5, 12, 7, 1)])
+def test_gemm_matches_fp64(m, n, k, trans):
+    g = torch.Generator(device="cpu").manual_seed(m * 7 + n)
+    k_pad = (k + 3) // 4 * 4 if not trans else k
+    m_pad = (m + 3) // 4 * 4 if trans else m
+    a = torch.randn((k, m_pad) if trans else (m, k_pad), generator=g).to(DEV)
+    if trans:
+        a[:, m:] = 0
+    else:
+        a[:, k:] = 0
+    b = torch.randn(k_pad if not trans else k, n, generator=g).to(DEV)
+    c = ops.gemm(a, b, bool(trans))
+    ref = (a.double().t() if trans else a.double()) @ b.double()
+    assert_close_normwise(c, ref.float(), 2e-6, "gemm")
+    c2 = ops.gemm(a, b, bool(trans))
+    assert torch.equal(c, c2), "split-K reduction must be deterministic"
+
+
+@pytest.mark.parametrize("name", golden_names("fc_"))
+def test_aggregate_matches_oracle(name):
+    g = load_golden(name)
+    B, R, ci = g["B"], g["R"], g["ci"]
+    plan = _plan_from_golden(g)
+    cpad = ci + (ci % 2)
+    x = torch.zeros(g["n"], cpad, dtype=torch.complex64)
+    x[:, :ci] = g["x"]
+    xd = x.to(DEV)
+    M = 2 * B + 1
+    out = torch.empty(g["n"], R * cpad * M, dtype=torch.complex64, device=DEV)
+    _lib.call("fcb_aggregate_f32", torch.view_as_real(xd).data_ptr(), plan.rowptr_tgt.data_ptr(), plan.rec_tgt.data_ptr(),
+              plan.rot_tgt.data_ptr(), torch.view_as_real(out).data_ptr(), g["n"], cpad, B, R, 0, _lib.stream_ptr())
+    ref = restate.aggregate(x, g["supp_edges"], g["supp_sten"], B)            # (N, C, R, M)
+    got = out.cpu().reshape(g["n"], R, cpad, M).permute(0, 2, 1, 3)
+    assert_close_normwise(got, ref, 3e-6, "contrib")
+    # transposed gather: G[j,m,r,o] = sum_{e: src=j} conj(sten[e,r,m]) gy[tgt(e), o]
+    gy = xd                                                                   # any complex field will do
+    outT = torch.empty_like(out)
+    _lib.call("fcb_aggregate_f32", torch.view_as_real(gy).data_ptr(), plan.rowptr_src.data_ptr(), plan.rec_src.data_ptr(),
+              plan.rot_src.data_ptr(), torch.view_as_real(outT).data_ptr(), g["n"], cpad, B, R, 1, _lib.stream_ptr())
+    e, sten = g["supp_edges"], g["supp_sten"]
+    per_edge = x[e[:, 1]][:, None, None, :] * sten.conj().permute(0, 2, 1)[..., None]   # (E, M, R, C)
+    refT = torch.zeros(g["n"], M, R, cpad, dtype=torch.complex64).index_add(0, e[:, 0], per_edge)
+    assert_close_normwise(outT.cpu().reshape(g["n"], M, R, cpad), refT, 3e-6, "transposed gather")
+
+
+def test_modrelu_matches_oracle():
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for n, c in ((1000, 48), (77, 5), (300, 300)):
+        x = random_features(n, c, seed=n, zero_frac=0.05)
+        bias = (torch.rand(1, c, generator=g) - 0.5)
+        gy = torch.complex(torch.randn(n, c, generator=g), torch.randn(n, c, generator=g))
+        xr = x.clone().requires_grad_(True)
+        br = bias.clone().requires_grad_(True)
+        y_ref = restate.tangent_nonlin(xr, br)
+        (y_ref.real * gy.real + y_ref.imag * gy.imag).sum().backward()
+        xd = x.to(DEV).requires_grad_(True)
+        bd = bias.to(DEV).requires_grad_(True)
+        y = ops.modrelu(xd, bd)
+        (y.real * gy.to(DEV).real + y.imag * gy.to(DEV).imag).sum().backward()
+        assert_close_normwise(y, y_ref, 2e-6, "modrelu y")
+        assert_close_normwise(xd.grad, xr.grad, 2e-6, "modrelu gx")
+        assert_close_normwise(bd.grad, br.grad, 5e-6, "modrelu gb")
+
+
+def test_tangent_lin_matches_oracle():
+    for ci, co in ((48, 48), (5, 7), (6, 3)):
+        lin = fcb.TangentLin(ci, co)
+        x = random_features(200, ci, seed=ci)
+        xr = x.clone().requires_grad_(True)
+        y_ref = restate.tangent_lin(xr, lin.Re, lin.Im)
+        gy = random_features(200, co, seed=co + 1, zero_frac=0)
+        (y_ref.real * gy.real + y_ref.imag * gy.imag).sum().backward()
+        g_re, g_im = lin.Re.grad.clone(), lin.Im.grad.clone()
+        lin.zero_grad()
+        lin_d = lin.to(DEV)
+        xd = x.to(DEV).requires_grad_(True)
+        y = lin_d(xd)
+        (y.real * gy.to(DEV).real + y.imag * gy.to(DEV).imag).sum().backward()
+        assert_close_normwise(y, y_ref, 2e-6, "TangentLin y")
+        assert_close_normwise(xd.grad, xr.grad, 2e-6, "TangentLin gx")
+        assert_close_normwise(lin_d.Re.grad, g_re, 2e-6, "TangentLin gRe")
+        assert_close_normwise(lin_d.Im.grad, g_im, 2e-6, "TangentLin gIm")

@@ -1,0 +1,199 @@
+"""GPU: parity of the CUDA FieldConv path (through the C ABI) with the reference.
+
+Tolerance (BASELINE.json north_star): fp32 path  max|a-b| <= 1e-5 max|b|  and
+||a-b||_2 <= 1e-5 ||b||_2  for y, grad x and every parameter gradient; indices bit-exact (test_gpu_kernels)."""
+import pytest
+import torch
+
+import fieldconv_b200 as fcb
+from conftest import assert_close_normwise, golden_names, load_golden
+from fieldconv_b200.synthetic import merge_meshes, random_features, torus_mesh
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5
+
+
+def _layer_from_golden(g, precision="fp32"):
+    m = fcb.FieldConv(g["ci"], g["co"], g["B"], g["R"], g["ftype"], precision=precision)
+    m.load_state_dict({"zonal": g["zonal"], "spherical": g["spherical"], "phase": g["phase"]})
+    return m.to(DEV)
+
+
+def _check_against_golden(g, m, y, x):
+    gy = g["gy"].to(DEV)
+    (y.real * gy.real + y.imag * gy.imag).sum().backward()
+    assert_close_normwise(y, g["y"], TOL, "y")
+    assert_close_normwise(x.grad, g["gx"], TOL, "grad x")
+    assert_close_normwise(m.zonal.grad, g["g_zonal"], TOL, "grad zonal")
+    assert_close_normwise(m.spherical.grad, g["g_spherical"], TOL, "grad spherical")
+    if g["ftype"] == 1:
+        assert_close_normwise(m.phase.grad, g["g_phase"], TOL, "grad phase")
+
+
+@pytest.mark.parametrize("name", golden_names("fc_"))
+def test_dropin_signature_dense_stencil(name):
+    """forward(x, supp_edges, supp_sten) with the reference's own FCPrecomp outputs."""
+    g = load_golden(name)
+    m = _layer_from_golden(g)
+    x = g["x"].to(DEV).requires_grad_(True)
+    y = m(x, g["supp_edges"].to(DEV), g["supp_sten"].to(DEV))
+    _check_against_golden(g, m, y, x)
+
+
+@pytest.mark.parametrize("name", golden_names("fc_"))
+def test_compact_plan_path(name):
+    """forward(x, plan): FCPrecomp arithmetic + CSR built on the device from the raw mesh attributes."""
+    g = load_golden(name)
+    m = _layer_from_golden(g)
+    plan = fcb.build_plan(g["raw_edges"].to(DEV), g["logMag"].to(DEV), g["logAng"].to(DEV), g["xp"].to(DEV),
+                          g["w"].to(DEV), g["R"], g["epsilon"])
+    x = g["x"].to(DEV).requires_grad_(True)
+    y = m(x, plan)
+    _check_against_golden(g, m, y, x)
+
+
+def test_recompute_contrib_path_matches():
+    g = load_golden("fc_b2r6_f0")
+    from fieldconv_b200 import ops
+    plan = fcb.build_plan(g["raw_edges"].to(DEV), g["logMag"].to(DEV), g["logAng"].to(DEV), g["xp"].to(DEV),
+                          g["w"].to(DEV), g["R"], g["epsilon"])
+    W = restate.fold_weights(g["zonal"], g["spherical"], g["phase"], g["ftype"], g["B"]).to(DEV)
+    outs = []
+    for keep in (True, False):
+        x = g["x"].to(DEV).requires_grad_(True)
+        w = W.clone().requires_grad_(True)
+        y = ops.field_conv(x, w, plan, g["B"], 0, keep_contrib=keep)
+        gy = g["gy"].to(DEV)
+        (y.real * gy.real + y.imag * gy.imag).sum().backward()
+        outs.append((y.detach(), x.grad, w.grad))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_block_matches_reference():
+    g = load_golden("block_b2r6")
+    blk = fcb.FCResNetBlock(g["ci"], g["co"], g["B"], g["R"], 1)
+    blk.load_state_dict({k[2:]: v for k, v in g.items() if k.startswith("p.")})
+    blk = blk.to(DEV)
+    plan = fcb.build_plan(g["raw_edges"].to(DEV), g["logMag"].to(DEV), g["logAng"].to(DEV), g["xp"].to(DEV),
+                          g["w"].to(DEV), g["R"], g["epsilon"])
+    for mode in ("plan", "dense"):
+        blk.zero_grad()
+        x = g["x"].to(DEV).requires_grad_(True)
+        y = blk(x, plan) if mode == "plan" else blk(x, g["supp_edges"].to(DEV), g["supp_sten"].to(DEV))
+        gy = g["gy"].to(DEV)
+        (y.real * gy.real + y.imag * gy.imag).sum().backward()
+        assert_close_normwise(y, g["y"], TOL, mode + ": block y")
+        assert_close_normwise(x.grad, g["gx"], TOL, mode + ": block grad x")
+        for k, p in blk.named_parameters():
+            assert_close_normwise(p.grad, g["g." + k], 2e-5 if "bias" in k else TOL, mode + ": grad " + k)
+
+
+def _oracle_layer(mesh, x, m, gy, dtype=torch.complex128):
+    """fp64 folded-form oracle on the CPU for a synthetic mesh."""
+    B, R = m.B, m.R
+    e, sten, _, _, _ = restate.fc_precomp(mesh.logMag.cpu(), mesh.logAng.cpu(), mesh.w.cpu(), mesh.supp_edges.cpu(),
+                                          mesh.xp.cpu(), B, R, mesh.epsilon)
+    ps = [p.detach().cpu().double().requires_grad_(True) for p in (m.zonal, m.spherical, m.phase)]
+    W = restate.fold_weights(ps[0], ps[1], ps[2], m.ftype, B)
+    xd = x.detach().cpu().to(dtype)
+    y = restate.field_conv_lean(xd, e, sten.to(dtype), W.detach(), B)
+    gx, gw = restate.field_conv_backward(xd, e, sten.to(dtype), W.detach(), B, gy.cpu().to(dtype))
+    (W.real * gw.real + W.imag * gw.imag).sum().backward()
+    return y, gx, [p.grad for p in ps]
+
+
+@pytest.mark.parametrize("n_side,ci,co,B,R,ftype", [(71, 32, 32, 1, 6, 1), (24, 48, 48, 2, 6, 1), (20, 18, 10, 3, 3, 2),
+                                                     (16, 128, 128, 2, 6, 0)])
+def test_synthetic_mesh_vs_fp64_oracle(n_side, ci, co, B, R, ftype):
+    """BASELINE config 1 (5k vertices, C=32, B=1, R=6) and cut-down configs 2/3 against the fp64 oracle."""
+    mesh = torus_mesh(n_side, deg=40.0, seed=1, device=DEV)
+    torch.manual_seed(0)
+    m = fcb.FieldConv(ci, co, B, R, ftype).to(DEV)
+    plan = fcb.build_plan(mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp, mesh.w, R, mesh.epsilon)
+    x = random_features(mesh.num_nodes, ci, seed=2, device=DEV).requires_grad_(True)
+    gy = random_features(mesh.num_nodes, co, seed=3, zero_frac=0, device=DEV)
+    y = m(x, plan)
+    (y.real * gy.real + y.imag * gy.imag).sum().backward()
+    y_ref, gx_ref, gp_ref = _oracle_layer(mesh, x, m, gy)
+    assert_close_normwise(y, y_ref.to(torch.complex64), TOL, "y")
+    assert_close_normwise(x.grad, gx_ref.to(torch.complex64), TOL, "grad x")
+    assert_close_normwise(m.zonal.grad, gp_ref[0].float(), TOL, "grad zonal")
+    assert_close_normwise(m.spherical.grad, gp_ref[1].float(), TOL, "grad spherical")
+    if ftype == 1:
+        assert_close_normwise(m.phase.grad, gp_ref[2].float(), TOL, "grad phase")
+
+
+def test_bitwise_determinism():
+    """The segmented reduction and the split reductions use fixed orders: two runs agree bit for bit
+    (the reference's scatter_add uses float atomics on CUDA and does not)."""
+    mesh = torus_mesh(40, deg=40.0, seed=4, device=DEV, permute=True)
+    torch.manual_seed(1)
+    m = fcb.FieldConv(32, 32, 1, 6, 1).to(DEV)
+    plan = fcb.build_plan(mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp, mesh.w, 6, mesh.epsilon)
+    gy = random_features(mesh.num_nodes, 32, seed=9, zero_frac=0, device=DEV)
+    res = []
+    for _ in range(2):
+        m.zero_grad()
+        x = random_features(mesh.num_nodes, 32, seed=8, device=DEV).requires_grad_(True)
+        y = m(x, plan)
+        (y.real * gy.real + y.imag * gy.imag).sum().backward()
+        res.append([y.detach().clone(), x.grad.clone()] + [p.grad.clone() for p in m.parameters()])
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+def test_full_size_properties_config2_layer():
+    """At BASELINE config-2 layer size (16 x 5k-vertex meshes merged, C=48, B=2, R=6) the oracle is too slow, so
+    check size-independent properties: (a) block-diagonal batching == per-mesh results, (b) linearity in W,
+    (c) <gy, J dx> == <J^T gy, dx> (adjoint identity between forward and backward, away from origin entries),
+    (d) gauge equivariance."""
+    B, R, C = 2, 6, 48
+    meshes = [torus_mesh(71, deg=40.0, seed=10 + i, device=DEV) for i in range(16)]
+    big = merge_meshes(meshes)
+    torch.manual_seed(3)
+    m = fcb.FieldConv(C, C, B, R, 1).to(DEV)
+    plan = fcb.build_plan(big.supp_edges, big.logMag, big.logAng, big.xp, big.w, R, big.epsilon)
+    x = random_features(big.num_nodes, C, seed=5, zero_frac=0.01, device=DEV)
+    with torch.no_grad():
+        y = m(x, plan)
+        # (a) one mesh alone
+        k = 3
+        n0 = sum(mm.num_nodes for mm in meshes[:k])
+        pk = fcb.build_plan(meshes[k].supp_edges, meshes[k].logMag, meshes[k].logAng, meshes[k].xp, meshes[k].w, R,
+                            meshes[k].epsilon)
+        yk = m(x[n0:n0 + meshes[k].num_nodes].contiguous(), pk)
+        assert torch.equal(yk, y[n0:n0 + meshes[k].num_nodes])
+        # (b) linearity in the filter: conv(W1 + 2 W2) = conv(W1) + 2 conv(W2)
+        from fieldconv_b200 import ops
+        w1 = m.weight()
+        w2 = torch.randn_like(w1) * 0.05
+        lhs = ops.field_conv(x, (w1 + 2 * w2).contiguous(), plan, B)
+        rhs = ops.field_conv(x, w1, plan, B) + 2 * ops.field_conv(x, w2.contiguous(), plan, B)
+        assert_close_normwise(lhs, rhs, 2e-6, "linearity in W")
+    # (c) adjoint identity with a finite perturbation along dx (away from the origin entries)
+    xg = random_features(big.num_nodes, C, seed=6, zero_frac=0.0, device=DEV).requires_grad_(True)
+    gy = random_features(big.num_nodes, C, seed=7, zero_frac=0.0, device=DEV)
+    yg = m(xg, plan)
+    (yg.real * gy.real + yg.imag * gy.imag).sum().backward()
+    dx = random_features(big.num_nodes, C, seed=8, zero_frac=0.0, device=DEV)
+    h = 1e-3
+    with torch.no_grad():
+        yp = m((xg + h * dx).detach(), plan).to(torch.complex128)
+        ym = m((xg - h * dx).detach(), plan).to(torch.complex128)
+        jdx = (yp - ym) / (2 * h)
+        lhs = (jdx.real * gy.real.double() + jdx.imag * gy.imag.double()).sum()
+        rhs = (xg.grad.real.double() * dx.real.double() + xg.grad.imag.double() * dx.imag.double()).sum()
+    assert abs(float(lhs - rhs)) <= 2e-3 * abs(float(rhs)), (float(lhs), float(rhs))
+    # (d) gauge equivariance on the full batch
+    g = torch.Generator(device="cpu").manual_seed(11)
+    alpha = ((torch.rand(big.num_nodes, generator=g) * 2 - 1) * 3.0).to(DEV)
+    src, tgt = big.supp_edges[:, 0], big.supp_edges[:, 1]
+    rot = torch.polar(torch.ones_like(alpha), -alpha)
+    plan2 = fcb.build_plan(big.supp_edges, big.logMag, big.logAng - alpha[src],
+                           big.xp * torch.polar(torch.ones_like(alpha[src]), alpha[src] - alpha[tgt]), big.w, R, big.epsilon)
+    with torch.no_grad():
+        y2 = m((x * rot[:, None]).contiguous(), plan2)
+    assert_close_normwise(y2, y * rot[:, None], 2e-5, "gauge equivariance")

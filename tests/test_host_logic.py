@@ -1,0 +1,61 @@
+"""CPU: host-side mirror of the reference interface (module surface, weight folding, input checks)."""
+import pytest
+import torch
+
+import fieldconv_b200 as fcb
+from conftest import assert_close_normwise, golden_names, load_golden
+from oracle import restate
+
+
+@pytest.mark.parametrize("name", golden_names("fc_"))
+def test_fold_weights_matches_oracle(name):
+    g = load_golden(name)
+    w = fcb.fold_weights(g["zonal"], g["spherical"], g["phase"], g["ftype"], g["B"])
+    w_ref = restate.fold_weights(g["zonal"], g["spherical"], g["phase"], g["ftype"], g["B"])
+    assert w.shape == (g["co"], g["ci"], g["R"], 2 * g["B"] + 1)
+    assert_close_normwise(w, w_ref, 1e-7, "fold_weights")
+
+
+@pytest.mark.parametrize("ftype", [0, 1, 2])
+def test_state_dict_contract(ftype):
+    """Parameter/buffer names, shapes and Parameter-vs-buffer status follow nn/field_conv.py:71-98."""
+    m = fcb.FieldConv(6, 4, 2, 5, ftype)
+    sd = m.state_dict()
+    assert set(sd) == {"zonal", "spherical", "phase"}
+    if ftype == 2:
+        assert sd["zonal"].shape == (4, 6, 5, 2) and sd["spherical"].shape == (4, 6, 5, 4, 2)
+    else:
+        assert sd["zonal"].shape == (4, 6, 5) and sd["spherical"].shape == (4, 6, 5, 2, 2)
+    assert sd["phase"].shape == (4, 6, 3)
+    params = dict(m.named_parameters())
+    assert ("phase" in params) == (ftype == 1)
+    assert (m.in_channels, m.out_channels, m.R, m.B, m.ftype) == (6, 4, 5, 2, ftype)
+
+
+def test_reference_state_dict_loads():
+    g = load_golden("block_b2r6")
+    blk = fcb.FCResNetBlock(g["ci"], g["co"], g["B"], g["R"], 1)
+    sd = {k[2:]: v for k, v in g.items() if k.startswith("p.")}
+    missing, unexpected = blk.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+
+
+def test_no_cpu_fallback():
+    m = fcb.FieldConv(4, 4)
+    x = torch.zeros(5, 4, dtype=torch.complex64)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(x, torch.zeros(3, 2, dtype=torch.long), torch.zeros(3, 6, 3, dtype=torch.complex64))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fcb.build_plan(torch.zeros(3, 2, dtype=torch.long), torch.zeros(3), torch.zeros(3),
+                       torch.zeros(3, dtype=torch.complex64), torch.ones(5, 1), 6, 1.0)
+
+
+def test_product_does_not_import_oracle():
+    import os
+    import re
+    from conftest import ROOT
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "fieldconv_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
