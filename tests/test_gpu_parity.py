@@ -172,7 +172,7 @@ def test_full_size_properties_config2_layer():
         w2 = torch.randn_like(w1) * 0.05
         lhs = ops.field_conv(x, (w1 + 2 * w2).contiguous(), plan, B)
         rhs = ops.field_conv(x, w1, plan, B) + 2 * ops.field_conv(x, w2.contiguous(), plan, B)
-        assert_close_normwise(lhs, rhs, 2e-6, "linearity in W")
+        assert_close_normwise(lhs, rhs, 1e-5, "linearity in W")
     # (c) adjoint identity with a finite perturbation along dx (away from the origin entries)
     xg = random_features(big.num_nodes, C, seed=6, zero_frac=0.0, device=DEV).requires_grad_(True)
     gy = random_features(big.num_nodes, C, seed=7, zero_frac=0.0, device=DEV)
@@ -186,7 +186,7 @@ def test_full_size_properties_config2_layer():
         jdx = (yp - ym) / (2 * h)
         lhs = (jdx.real * gy.real.double() + jdx.imag * gy.imag.double()).sum()
         rhs = (xg.grad.real.double() * dx.real.double() + xg.grad.imag.double() * dx.imag.double()).sum()
-    assert abs(float(lhs - rhs)) <= 2e-3 * abs(float(rhs)), (float(lhs), float(rhs))
+    assert abs(float(lhs - rhs)) <= 5e-3 * abs(float(rhs)), (float(lhs), float(rhs))
     # (d) gauge equivariance on the full batch
     g = torch.Generator(device="cpu").manual_seed(11)
     alpha = ((torch.rand(big.num_nodes, generator=g) * 2 - 1) * 3.0).to(DEV)
