@@ -103,9 +103,12 @@ def _fc_setup(ctx, inputs, output):
     _, contrib = output
     ctx.save_for_backward(x, W, contrib, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src)
     ctx.cfg = (band_limit, n_rings, flags)
+    ctx.set_materialize_grads(False)      # no N*K zero tensor for the unused contrib output
 
 
 def _fc_backward(ctx, gy, _gcontrib):
+    if gy is None:
+        return (None,) * 12
     x, W, contrib, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src = ctx.saved_tensors
     band_limit, n_rings, flags = ctx.cfg
     gx, gw = fc_bwd(x, W, gy, contrib, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings,
@@ -183,9 +186,12 @@ def _fcd_setup(ctx, inputs, output):
     x, W, sten, rowptr_tgt, nbr_tgt, perm_tgt, rowptr_src, nbr_src, perm_src, flags = inputs
     ctx.save_for_backward(x, W, output[1], sten, rowptr_src, nbr_src, perm_src)
     ctx.flags = flags
+    ctx.set_materialize_grads(False)
 
 
 def _fcd_backward(ctx, gy, _gc):
+    if gy is None:
+        return (None,) * 10
     x, W, contrib, sten, rowptr_src, nbr_src, perm_src = ctx.saved_tensors
     gx, gw = fc_bwd_dense(x, W, gy, contrib, sten, rowptr_src, nbr_src, perm_src, ctx.flags,
                           ctx.needs_input_grad[0], ctx.needs_input_grad[1])
