@@ -32,7 +32,8 @@ SIGNATURES = {
     "fcb_fwd_dense_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_bwd_dense_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_aggregate_f32": [_P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _P],
-    "fcb_gemm_f32": [_P, _P, _P, _I64, _I, _I64, _I64, _I64, _I64, _I, _I, _I64, _I64, _I64, _I, _P, _I, _P],
+    "fcb_gemm_workspace_bytes": [_I64, _I, _I64, _I, _I, _I, _I, _PSZ],
+    "fcb_gemm_f32": [_P, _P, _P, _I64, _I, _I64, _I64, _I64, _I64, _I, _I, _I64, _I64, _I64, _I, _P, _SZ, _I, _P],
     "fcb_sort_workspace_bytes": [_I64, _PSZ],
     "fcb_sort_pairs_u32": [_P, _P, _P, _P, _I64, _I, _P, _SZ, _P],
     "fcb_modrelu_fwd_f32": [_P, _P, _P, _I64, _I, _P],

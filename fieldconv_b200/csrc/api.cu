@@ -245,7 +245,9 @@ static int choose_split(int64_t rows_m, int64_t kdim) {
     return (int)s;
 }
 
-static size_t fwd_ws(const Dims& d) { return align_up((size_t)(4 * d.K * d.Co) * 4, 256) + 256; }
+static size_t fwd_ws(const Dims& d) {
+    return align_up((size_t)(4 * d.K * d.Co) * 4, 256) + gemm_tc_ws_bytes(2 * d.Co, 2 * d.K, 1) + 512;
+}
 
 static size_t bwd_ws(const Dims& d, bool need_contrib) {
     size_t s = 0;
@@ -255,7 +257,8 @@ static size_t bwd_ws(const Dims& d, bool need_contrib) {
     s += align_up((size_t)d.N * d.Kt * 8, 256);                             // G
     s += align_up((size_t)d.N * d.M * d.Ci * 8, 256);                       // gxh
     if (need_contrib) s += align_up((size_t)d.N * d.K * 8, 256);            // recomputed contrib
-    return s + 1024;
+    s += gemm_tc_ws_bytes(2 * d.Ci, 2 * (int64_t)d.R * d.Co, d.M);           // packed operand of the tensor-core grad-x GEMM
+    return s + 2048;
 }
 
 static int contract_fwd(const Dims& d, const float* contrib, const float* W, float* y, void* ws, size_t ws_bytes, int flags,
@@ -265,7 +268,9 @@ static int contract_fwd(const Dims& d, const float* contrib, const float* W, flo
     float* Bw = ar.take<float>((size_t)(4 * d.K * d.Co));
     const int64_t tot = d.K * d.Co;
     FCB_LAUNCH("pack_w_fwd", st, k_pack_w_fwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bw, d.Ci, d.Co, d.R, d.M));
-    return launch_gemm(contrib, Bw, y, d.N, 2 * d.Co, 2 * d.K, 2 * d.K, 2 * d.Co, 2 * d.Co, 0, 1, 0, 0, 0, 1, nullptr, flags, st);
+    const size_t tcb = gemm_tc_ws_bytes(2 * d.Co, 2 * d.K, 1);
+    void* tcw = ar.take<char>(tcb);
+    return launch_gemm(contrib, Bw, y, d.N, 2 * d.Co, 2 * d.K, 2 * d.K, 2 * d.Co, 2 * d.Co, 0, 1, 0, 0, 0, 1, tcw, tcb, flags, st);
 }
 
 template <typename GatherT>
@@ -280,7 +285,8 @@ static int backward_common(const Dims& d, const float* x, const float* W, const 
     if (gW) {
         // K4: P[2K x 2Co] = contrib_real^T @ gy_real, split over vertices, fixed-order reduction
         const int split = choose_split(2 * d.K, d.N);
-        int rc = launch_gemm(contrib, gy, P, 2 * d.K, 2 * d.Co, d.N, 2 * d.K, 2 * d.Co, 2 * d.Co, 1, 1, 0, 0, 0, split, parts, flags, st);
+        int rc = launch_gemm(contrib, gy, P, 2 * d.K, 2 * d.Co, d.N, 2 * d.K, 2 * d.Co, 2 * d.Co, 1, 1, 0, 0, 0, split, parts,
+                             (size_t)(4 * d.K * d.Co) * split * 4, flags, st);
         if (rc) return rc;
         FCB_LAUNCH("combine_gw", st, k_combine_gw<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, reinterpret_cast<float2*>(gW), d.Ci, d.Co, d.R, d.M));
     }
@@ -291,8 +297,10 @@ static int backward_common(const Dims& d, const float* x, const float* W, const 
         // K5b: gxh[:, m, :] = G[:, m, :] @ conj(W)[m]  (one real GEMM per m, batched)
         FCB_LAUNCH("pack_w_bwd", st, k_pack_w_bwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bt, d.Ci, d.Co, d.R, d.M));
         const int64_t Q2 = 2 * (int64_t)d.R * d.Co;
+        const size_t tcb = gemm_tc_ws_bytes(2 * d.Ci, Q2, d.M);
+        void* tcw = ar.take<char>(tcb);
         rc = launch_gemm(G, Bt, gxh, d.N, 2 * d.Ci, Q2, (int64_t)d.M * Q2, 2 * d.Ci, (int64_t)d.M * 2 * d.Ci, 0, d.M, Q2,
-                         Q2 * 2 * d.Ci, 2 * d.Ci, 1, nullptr, flags, st);
+                         Q2 * 2 * d.Ci, 2 * d.Ci, 1, tcw, tcb, flags, st);
         if (rc) return rc;
         const int64_t el = d.N * d.Ci;
         const unsigned blocks = (unsigned)((el + 255) / 256);

@@ -78,8 +78,15 @@ int launch_aggregate(const float* feat, const int32_t* rowptr, const void* rec, 
 int launch_aggregate_dense(const float* feat, const float* sten, const int32_t* rowptr, const int32_t* nbr,
                            const int32_t* perm, float* out, int64_t N, int C, int B, int R, int transpose,
                            cudaStream_t st);
+// Real GEMM dispatcher.  flags & FCB_GEMM_MASK selects FP32 FMA or the tcgen05 path (trans_a == 0, N <= 256 only;
+// anything else runs on the FMA path).  ws must hold gemm_ws_bytes(...) bytes.
+size_t gemm_ws_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags);
 int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                 int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k,
-                float* partials, int flags, cudaStream_t st);
+                void* ws, size_t ws_bytes, int flags, cudaStream_t st);
+size_t gemm_tc_ws_bytes(int N, int64_t K, int batch);
+int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
+                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int mode, void* ws, size_t ws_bytes,
+                      cudaStream_t st);
 
 }  // namespace fcb

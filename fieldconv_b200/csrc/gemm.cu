@@ -182,13 +182,26 @@ static int dispatch_gemm(const float* A, const float* Bm, float* C, int64_t M, i
     return FCB_OK;
 }
 
+static bool use_tc(int N, int64_t K, int trans_a, int flags) {
+    const int mode = flags & FCB_GEMM_MASK;
+    return (mode == FCB_GEMM_TC_3XTF32 || mode == FCB_GEMM_TC_TF32) && !trans_a && N <= 256 && N > 0 && K > 0;
+}
+
+size_t gemm_ws_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags) {
+    if (use_tc(N, K, trans_a, flags)) return gemm_tc_ws_bytes(N, K, batch);
+    return split_k > 1 ? align_up((size_t)split_k * batch * M * N * 4, 256) : 0;
+}
+
 int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
-                int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k, float* partials,
-                int flags, cudaStream_t st) {
-    (void)flags;
+                int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k, void* ws,
+                size_t ws_bytes, int flags, cudaStream_t st) {
     FCB_REQUIRE(A && Bm && C, FCB_E_ARG, "gemm: null pointer");
     FCB_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 1 && split_k >= 1, FCB_E_ARG, "gemm: bad sizes");
-    FCB_REQUIRE(split_k == 1 || partials, FCB_E_ARG, "gemm: split_k > 1 needs a partials buffer");
+    if (use_tc(N, K, trans_a, flags) && (ldc % 4) == 0 && (sc % 4) == 0 && aligned16(C))
+        return launch_gemm_tc_nn(A, Bm, C, M, N, K, lda, ldb, ldc, batch, sa, sb, sc, flags & FCB_GEMM_MASK, ws, ws_bytes, st);
+    float* partials = static_cast<float*>(ws);
+    FCB_REQUIRE(split_k == 1 || (partials && ws_bytes >= (size_t)split_k * batch * M * N * 4), FCB_E_WORKSPACE,
+                "gemm: split_k > 1 needs a workspace of split_k*batch*M*N floats");
     FCB_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (sa % 4) == 0 && (sb % 4) == 0 && aligned16(A) && aligned16(Bm),
                 FCB_E_ALIGN, "gemm: A/B leading dimensions and strides must be multiples of 4 floats, 16-byte aligned");
     FCB_REQUIRE((int64_t)batch * split_k <= 65535, FCB_E_UNSUPPORTED, "gemm: batch*split_k too large");
@@ -213,9 +226,17 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
 
 }  // namespace fcb
 
+extern "C" int fcb_gemm_workspace_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags,
+                                        size_t* bytes) {
+    FCB_REQUIRE(bytes && M >= 0 && N >= 0 && K >= 0 && batch >= 1 && split_k >= 1, FCB_E_ARG, "gemm_workspace: bad arguments");
+    *bytes = fcb::gemm_ws_bytes(M, N, K, trans_a, batch, split_k, flags);
+    return FCB_OK;
+}
+
 extern "C" int fcb_gemm_f32(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda,
                             int64_t ldb, int64_t ldc, int trans_a, int batch, int64_t stride_a, int64_t stride_b,
-                            int64_t stride_c, int split_k, float* partials, int flags, void* stream) {
+                            int64_t stride_c, int split_k, void* workspace, size_t workspace_bytes, int flags,
+                            void* stream) {
     return fcb::launch_gemm(A, B, C, M, N, K, lda, ldb, ldc, trans_a, batch, stride_a, stride_b, stride_c, split_k,
-                            partials, flags, static_cast<cudaStream_t>(stream));
+                            workspace, workspace_bytes, flags, static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,361 @@
+// K2 / K5b on the 5th-generation tensor cores: C[M x N] = A[M x K] * B[K x N], fp32 in / fp32 out, computed
+// with tcgen05.mma kind::tf32 and fp32 accumulators in TMEM.
+//
+// Accuracy modes
+//   3xTF32 (default tensor-core mode): every operand is split into hi = tf32(x) and lo = x - hi and the
+//   product is accumulated as  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is ~2^-22 relative),
+//   which keeps the contraction inside the 1e-5 parity budget of the fp32 path.
+//   TF32: hi planes only (~1e-3 relative; looser tolerance, stated separately in the tests).
+//
+// Structure of one CTA (one 128-row tile of A, all N <= 256 columns), 10 warps:
+//   warps 0-7  producers: 128-bit coalesced loads of the fp32 A tile (32 reals = 128 B per row and stage),
+//              hi/lo split in registers, stores into the canonical 128B-swizzled K-major UMMA layout,
+//              fence.proxy.async, mbarrier arrive.  After the K loop the same warps run the epilogue
+//              (tcgen05.ld 32x32b -> registers -> 128-bit global stores).
+//   warp 8     single-thread MMA issue (tcgen05.mma, tcgen05.commit), TMEM alloc / dealloc.
+//   warp 9     B operand: the weights are pre-packed (k_pack_b_tc) into the exact shared-memory image of every
+//              stage, so one cp.async.bulk (TMA engine, mbarrier complete_tx) per stage brings hi and lo planes in.
+// Shared-memory ring of S stages: {A_hi 16 KB, A_lo 16 KB, B_hi, B_lo (Npad*128 B each)}.
+#include "common.cuh"
+
+namespace fcb {
+namespace tc {
+
+constexpr int BM = 128;        // rows per CTA tile == UMMA M
+constexpr int KC = 32;         // reals per stage == one 128-byte swizzle row
+constexpr int N_PROD_WARPS = 8;
+constexpr int THREADS = (N_PROD_WARPS + 2) * 32;
+constexpr uint32_t A_PLANE = BM * KC * 4;   // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO), LBO unused (=1),
+// descriptor version 1 (Blackwell).  Field layout follows the PTX ISA "tcgen05 shared memory descriptor".
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                  // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset between 8-row core-matrix groups
+    d |= (uint64_t)1 << 46;                  // version
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=n.
+__host__ __device__ inline uint32_t make_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+struct Params {
+    const float* A;
+    const float* Bp;   // packed B: [batch][chunk][plane(hi,lo)][Npad][32] swizzled
+    float* C;
+    int64_t M, K, lda, ldc, sa, sc;
+    int64_t bp_batch_stride;   // floats
+    int N, Npad, nchunks, stages, mode;
+    uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw);
+    const int S = p.stages;
+    const uint32_t b_plane = (uint32_t)p.Npad * 128u;
+    // layout: A_hi[S] | A_lo[S] | B[S] (hi,lo) | barriers
+    const uint32_t a_hi0 = base, a_lo0 = base + S * A_PLANE, b0 = base + 2 * S * A_PLANE;
+    const uint32_t bars = b0 + S * 2 * b_plane;
+    auto full_a = [&](int s) { return bars + 8u * s; };
+    auto full_b = [&](int s) { return bars + 8u * (S + s); };
+    auto empty = [&](int s) { return bars + 8u * (2 * S + s); };
+    const uint32_t tmem_full = bars + 8u * (3 * S);
+    const uint32_t tmem_slot = bars + 8u * (3 * S + 1);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(sm + (tmem_slot - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int batch = blockIdx.y;
+    const float* A = p.A + batch * p.sa;
+    const float* Bp = p.Bp + batch * p.bp_batch_stride;
+    float* C = p.C + batch * p.sc;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_a(s), N_PROD_WARPS);
+            mbar_init(full_b(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == N_PROD_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot_ptr;
+
+    if (warp < N_PROD_WARPS) {
+        // ------------------------------------------------------------------ producers
+        const int t = threadIdx.x;   // 0..255
+        for (int kc = 0; kc < p.nchunks; ++kc) {
+            const int s = kc % S;
+            const uint32_t ph = (uint32_t)(kc / S) & 1u;
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = t + 256 * i;
+                const int row = idx >> 3, j = idx & 7;
+                const int64_t m = m0 + row;
+                const int64_t k = (int64_t)kc * KC + 4 * j;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < p.M) {
+                    const float* src = A + m * p.lda + k;
+                    if (k + 3 < p.K) v[i] = __ldg(reinterpret_cast<const float4*>(src));
+                    else {
+                        if (k < p.K) v[i].x = src[0];
+                        if (k + 1 < p.K) v[i].y = src[1];
+                        if (k + 2 < p.K) v[i].z = src[2];
+                    }
+                }
+            }
+            mbar_wait(empty(s), ph ^ 1u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = t + 256 * i;
+                const int row = idx >> 3, j = idx & 7;
+                const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
+                float4 hi = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
+                *reinterpret_cast<float4*>(sm + (a_hi0 - base) + s * A_PLANE + off) = hi;
+                if (p.mode == FCB_GEMM_TC_3XTF32) {
+                    float4 lo = make_float4(v[i].x - hi.x, v[i].y - hi.y, v[i].z - hi.z, v[i].w - hi.w);
+                    *reinterpret_cast<float4*>(sm + (a_lo0 - base) + s * A_PLANE + off) = lo;
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_a(s));
+        }
+        // ------------------------------------------------------------------ epilogue
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3, half = warp >> 2;
+        const int64_t m = m0 + 32 * q + lane;
+        const int groups = p.Npad / 16;
+        for (int g = half; g < groups; g += 2) {
+            uint32_t r[16];
+            tc_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * g), r);
+            tc_ld_wait();
+            if (m < p.M) {
+                float* dst = C + m * p.ldc + 16 * g;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int n = 16 * g + 4 * c4;
+                    if (n + 3 < p.N) {
+                        *reinterpret_cast<float4*>(dst + 4 * c4) =
+                            make_float4(__uint_as_float(r[4 * c4]), __uint_as_float(r[4 * c4 + 1]),
+                                        __uint_as_float(r[4 * c4 + 2]), __uint_as_float(r[4 * c4 + 3]));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (n + e < p.N) dst[4 * c4 + e] = __uint_as_float(r[4 * c4 + e]);
+                    }
+                }
+            }
+        }
+    } else if (warp == N_PROD_WARPS) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(p.Npad);
+            for (int kc = 0; kc < p.nchunks; ++kc) {
+                const int s = kc % S;
+                const uint32_t ph = (uint32_t)(kc / S) & 1u;
+                mbar_wait(full_a(s), ph);
+                mbar_wait(full_b(s), ph);
+                tc_fence_after();
+                const uint64_t a_hi = make_desc_k_sw128(a_hi0 + s * A_PLANE);
+                const uint64_t a_lo = make_desc_k_sw128(a_lo0 + s * A_PLANE);
+                const uint64_t b_hi = make_desc_k_sw128(b0 + s * 2 * b_plane);
+                const uint64_t b_lo = make_desc_k_sw128(b0 + s * 2 * b_plane + b_plane);
+#pragma unroll
+                for (int ks = 0; ks < KC / 8; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 2);   // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzle row
+                    const uint32_t first = (kc > 0 || ks > 0) ? 1u : 0u;
+                    if (p.mode == FCB_GEMM_TC_3XTF32) {
+                        tc_mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, first);
+                        tc_mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                        tc_mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+                    } else {
+                        tc_mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, first);
+                    }
+                }
+                tc_commit(empty(s));      // frees the stage once these MMAs have read it
+            }
+            tc_commit(tmem_full);
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ B loader (one thread, TMA bulk copies)
+        if (lane == 0) {
+            const uint32_t bytes = (p.mode == FCB_GEMM_TC_3XTF32 ? 2u : 1u) * b_plane;
+            for (int kc = 0; kc < p.nchunks; ++kc) {
+                const int s = kc % S;
+                const uint32_t ph = (uint32_t)(kc / S) & 1u;
+                mbar_wait(empty(s), ph ^ 1u);
+                mbar_expect_tx(full_b(s), bytes);
+                bulk_copy_g2s(b0 + s * 2 * b_plane, Bp + (int64_t)kc * 2 * p.Npad * KC, bytes, full_b(s));
+            }
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == N_PROD_WARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// B[K x N] row-major (ldb) -> [chunk][plane][Npad][32] with the 128B swizzle applied (16-byte unit j of row n
+// stored at unit j ^ (n & 7)), hi = tf32(b), lo = b - hi; rows n >= N and k >= K are zero.
+__global__ void k_pack_b_tc(const float* __restrict__ B, float* __restrict__ Bp, int64_t K, int N, int Npad, int64_t ldb,
+                            int nchunks, int64_t sb, int64_t bp_batch_stride) {
+    const int64_t per = (int64_t)nchunks * Npad * KC;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per) return;
+    const int batch = blockIdx.y;
+    const int kk = (int)(i % KC);
+    const int n = (int)((i / KC) % Npad);
+    const int64_t c = i / ((int64_t)KC * Npad);
+    const int64_t k = c * KC + kk;
+    float v = 0.f;
+    if (n < N && k < K) v = B[batch * sb + k * ldb + n];
+    const float hi = tf32_hi(v);
+    const float lo = v - hi;
+    const int unit = (kk >> 2) ^ (n & 7);
+    float* dst = Bp + batch * bp_batch_stride + (c * 2) * (int64_t)Npad * KC + (int64_t)n * KC + unit * 4 + (kk & 3);
+    dst[0] = hi;
+    dst[(int64_t)Npad * KC] = lo;
+}
+
+}  // namespace tc
+
+size_t gemm_tc_ws_bytes(int N, int64_t K, int batch) {
+    const int npad = (N + 15) / 16 * 16;
+    const int64_t nchunks = (K + tc::KC - 1) / tc::KC;
+    return align_up((size_t)batch * nchunks * 2 * npad * tc::KC * 4, 256) + 256;
+}
+
+int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
+                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int mode, void* ws, size_t ws_bytes,
+                      cudaStream_t st) {
+    FCB_REQUIRE(A && B && C && ws, FCB_E_ARG, "gemm_tc: null pointer");
+    FCB_REQUIRE(M >= 0 && N > 0 && K > 0 && batch >= 1 && batch <= 65535, FCB_E_ARG, "gemm_tc: bad sizes");
+    FCB_REQUIRE(N <= 256, FCB_E_UNSUPPORTED, "gemm_tc: N=%d > 256 not supported by one accumulator tile", N);
+    FCB_REQUIRE(mode == FCB_GEMM_TC_3XTF32 || mode == FCB_GEMM_TC_TF32, FCB_E_ARG, "gemm_tc: bad mode");
+    FCB_REQUIRE((lda % 4) == 0 && (ldc % 4) == 0 && (sa % 4) == 0 && (sc % 4) == 0 && aligned16(A) && aligned16(C),
+                FCB_E_ALIGN, "gemm_tc: A/C leading dimensions and strides must be multiples of 4 floats, 16-byte aligned");
+    FCB_REQUIRE(ws_bytes >= gemm_tc_ws_bytes(N, K, batch), FCB_E_WORKSPACE, "gemm_tc: workspace too small");
+    if (M == 0) return FCB_OK;
+    const int npad = (N + 15) / 16 * 16;
+    const int nchunks = (int)((K + tc::KC - 1) / tc::KC);
+    float* Bp = static_cast<float*>(ws);
+    const int64_t bp_stride = (int64_t)nchunks * 2 * npad * tc::KC;
+    {
+        const int64_t per = (int64_t)nchunks * npad * tc::KC;
+        dim3 grid((unsigned)((per + 255) / 256), (unsigned)batch);
+        FCB_LAUNCH("pack_b_tc", st, tc::k_pack_b_tc<<<grid, 256, 0, st>>>(B, Bp, K, N, npad, ldb, nchunks, sb, bp_stride));
+    }
+    tc::Params p;
+    p.A = A; p.Bp = Bp; p.C = C;
+    p.M = M; p.K = K; p.lda = lda; p.ldc = ldc; p.sa = sa; p.sc = sc;
+    p.bp_batch_stride = bp_stride;
+    p.N = N; p.Npad = npad; p.nchunks = nchunks; p.mode = mode;
+    uint32_t cols = 32;
+    while ((int)cols < npad) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t stage_bytes = 2 * tc::A_PLANE + 2 * (size_t)npad * 128;
+    int stages = (int)((220 * 1024 - 2048) / stage_bytes);
+    if (stages > 4) stages = 4;
+    if (stages > nchunks) stages = nchunks < 1 ? 1 : nchunks;
+    FCB_REQUIRE(stages >= 1, FCB_E_UNSUPPORTED, "gemm_tc: tile does not fit shared memory");
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + 1024 /*align slack*/ + 8 * (3 * stages + 2) + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc::k_gemm_tc_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+            set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return FCB_E_CUDA;
+        }
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((M + tc::BM - 1) / tc::BM), (unsigned)batch);
+    FCB_LAUNCH("gemm_tc_nn", st, tc::k_gemm_tc_nn<<<grid, tc::THREADS, smem, st>>>(p));
+    return FCB_OK;
+}
+
+}  // namespace fcb

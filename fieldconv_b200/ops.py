@@ -260,7 +260,7 @@ modrelu.register_autograd(_mr_backward, setup_context=_mr_setup)
 
 # --------------------------------------------------------------------------- real GEMM (TangentLin)
 @torch.library.custom_op("fieldconv_b200::gemm", mutates_args=())
-def gemm(a: Tensor, b: Tensor, trans_a: bool) -> Tensor:
+def gemm(a: Tensor, b: Tensor, trans_a: bool, flags: int = 0) -> Tensor:
     """C = A @ B (trans_a False, A is MxK) or A^T @ B (trans_a True, A is KxM); fp32, row-major."""
     _check(a, "a", torch.float32)
     _check(b, "b", torch.float32)
@@ -272,35 +272,35 @@ def gemm(a: Tensor, b: Tensor, trans_a: bool) -> Tensor:
     n = b.shape[1]
     c = torch.empty(m, n, dtype=torch.float32, device=a.device)
     split = 1
-    parts = None
     if trans_a:
         tiles = (m + 127) // 128
         split = max(1, min(64, k // 512, (4 * 148 + tiles - 1) // tiles))
-        if split > 1:
-            parts = torch.empty(split * m * n, dtype=torch.float32, device=a.device)
+    nbytes = _lib.query_bytes("fcb_gemm_workspace_bytes", m, n, k, 1 if trans_a else 0, 1, split, flags)
+    ws = _ws(nbytes, a.device)
     with torch.cuda.device(a.device):
         _lib.call("fcb_gemm_f32", a.data_ptr(), b.data_ptr(), c.data_ptr(), m, n, k, a.shape[1], n, n,
-                  1 if trans_a else 0, 1, 0, 0, 0, split, _lib.ptr(parts), 0, _lib.stream_ptr())
+                  1 if trans_a else 0, 1, 0, 0, 0, split, ws.data_ptr(), nbytes, flags, _lib.stream_ptr())
     return c
 
 
 @gemm.register_fake
-def _(a, b, trans_a):
+def _(a, b, trans_a, flags=0):
     return a.new_empty(a.shape[1] if trans_a else a.shape[0], b.shape[1])
 
 
 def _gemm_setup(ctx, inputs, output):
     ctx.save_for_backward(inputs[0], inputs[1])
     ctx.trans_a = inputs[2]
+    ctx.flags = inputs[3]
 
 
 def _gemm_backward(ctx, gc):
     a, b = ctx.saved_tensors
     if ctx.trans_a:
         raise RuntimeError("fieldconv_b200::gemm: backward of the transposed form is not needed")
-    ga = gemm(gc, b.t().contiguous(), False) if ctx.needs_input_grad[0] else None
-    gb = gemm(a, gc, True) if ctx.needs_input_grad[1] else None
-    return ga, gb, None
+    ga = gemm(gc, b.t().contiguous(), False, ctx.flags) if ctx.needs_input_grad[0] else None
+    gb = gemm(a, gc, True, ctx.flags) if ctx.needs_input_grad[1] else None
+    return ga, gb, None, None
 
 
 gemm.register_autograd(_gemm_backward, setup_context=_gemm_setup)

@@ -139,11 +139,16 @@ int fcb_bwd_dense_f32(const float* x, const float* W, const float* gy, const flo
 int fcb_aggregate_f32(const float* feat, const int32_t* rowptr, const void* rec, const float* rot,
                       float* out, int64_t N, int C, int band_limit, int R, int transpose, void* stream);
 /* Real fp32 GEMM C[MxN] = A*B (trans_a=0: A is MxK row-major; trans_a=1: A is KxM row-major),
- * B is KxN row-major; batch >= 1 with element strides; split_k >= 1 uses `partials`
- * (split_k*batch*M*N floats) and a fixed-order final reduction (deterministic). */
+ * B is KxN row-major; batch >= 1 with element strides; split_k >= 1 writes per-split partials into
+ * the workspace and reduces them in a fixed order (deterministic).  flags & FCB_GEMM_MASK selects
+ * the FP32-FMA kernel or the tcgen05 tensor-core kernel (trans_a=0 and N<=256; otherwise FMA).
+ * The workspace size comes from fcb_gemm_workspace_bytes with the same arguments. */
+int fcb_gemm_workspace_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags,
+                             size_t* bytes);
 int fcb_gemm_f32(const float* A, const float* B, float* C, int64_t M, int N, int64_t K,
                  int64_t lda, int64_t ldb, int64_t ldc, int trans_a, int batch, int64_t stride_a,
-                 int64_t stride_b, int64_t stride_c, int split_k, float* partials, int flags, void* stream);
+                 int64_t stride_b, int64_t stride_c, int split_k, void* workspace, size_t workspace_bytes,
+                 int flags, void* stream);
 /* Stable LSD radix sort of (key,value) uint32 pairs on the low `bits` bits of the key.
  * Result lands in keys_out/vals_out; keys_in/vals_in are clobbered. */
 int fcb_sort_workspace_bytes(int64_t n, size_t* bytes);

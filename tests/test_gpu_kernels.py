@@ -176,3 +176,23 @@ def test_tangent_lin_matches_oracle():
         assert_close_normwise(xd.grad, xr.grad, 2e-6, "TangentLin gx")
         assert_close_normwise(lin_d.Re.grad, g_re, 2e-6, "TangentLin gRe")
         assert_close_normwise(lin_d.Im.grad, g_im, 2e-6, "TangentLin gIm")
+
+
+@pytest.mark.parametrize("mode,tol", [(1, 2e-6), (2, 3e-3)])
+@pytest.mark.parametrize("m,n,k", [(128, 96, 32), (128, 96, 2880), (1000, 96, 576), (80656, 96, 2880), (300, 64, 1152),
+                                   (257, 256, 520), (130, 20, 36), (5, 12, 8), (4096, 16, 64)])
+def test_tensor_core_gemm(m, n, k, mode, tol):
+    """tcgen05 kind::tf32 GEMM: 3xTF32 (mode 1) must sit at fp32-grade accuracy, plain TF32 (mode 2) at ~1e-3."""
+    g = torch.Generator(device="cpu").manual_seed(m + n + k)
+    k_pad = (k + 3) // 4 * 4
+    a = torch.randn(m, k_pad, generator=g).to(DEV)
+    a[:, k:] = 0
+    b = torch.randn(k_pad, n, generator=g).to(DEV)
+    c = ops.gemm(a, b, False, mode)
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double()
+    assert_close_normwise(c, ref.float(), tol, "tensor-core gemm mode %d" % mode)
+    assert torch.equal(c, ops.gemm(a, b, False, mode)), "deterministic"
+    if mode == 2:   # TF32 must actually be less accurate than fp32 (i.e. the tensor path really ran)
+        err = float((c.double() - ref).abs().max() / ref.abs().max())
+        assert err > 1e-6 or k <= 8
