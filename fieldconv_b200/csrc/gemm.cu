@@ -182,14 +182,23 @@ static int dispatch_gemm(const float* A, const float* Bm, float* C, int64_t M, i
     return FCB_OK;
 }
 
-static bool use_tc(int N, int64_t K, int trans_a, int flags) {
+static bool use_tc(int N, int64_t K, int trans_a, int batch, int flags) {
     const int mode = flags & FCB_GEMM_MASK;
-    return (mode == FCB_GEMM_TC_3XTF32 || mode == FCB_GEMM_TC_TF32) && !trans_a && N <= 256 && N > 0 && K > 0;
+    if (!(mode == FCB_GEMM_TC_3XTF32 || mode == FCB_GEMM_TC_TF32) || N > 256 || N <= 0 || K <= 0) return false;
+    return trans_a ? batch == 1 : true;
 }
 
 size_t gemm_ws_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags) {
-    if (use_tc(N, K, trans_a, flags)) return gemm_tc_ws_bytes(N, K, batch);
+    if (use_tc(N, K, trans_a, batch, flags) && !trans_a) return gemm_tc_ws_bytes(N, K, batch);
     return split_k > 1 ? align_up((size_t)split_k * batch * M * N * 4, 256) : 0;
+}
+
+int launch_reduce_splits(const float* partials, float* C, int64_t M, int N, int64_t ldc, int64_t sc, int batch, int split_k,
+                         cudaStream_t st) {
+    const int64_t tot = M * (int64_t)N * batch;
+    if (tot == 0) return FCB_OK;
+    FCB_LAUNCH("reduce_splits", st, k_reduce_splits<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(partials, C, M, N, ldc, sc, batch, split_k));
+    return FCB_OK;
 }
 
 int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
@@ -197,9 +206,18 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
                 size_t ws_bytes, int flags, cudaStream_t st) {
     FCB_REQUIRE(A && Bm && C, FCB_E_ARG, "gemm: null pointer");
     FCB_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 1 && split_k >= 1, FCB_E_ARG, "gemm: bad sizes");
-    if (use_tc(N, K, trans_a, flags) && (ldc % 4) == 0 && (sc % 4) == 0 && aligned16(C))
+    if (use_tc(N, K, trans_a, batch, flags) && !trans_a && (ldc % 4) == 0 && (sc % 4) == 0 && aligned16(C))
         return launch_gemm_tc_nn(A, Bm, C, M, N, K, lda, ldb, ldc, batch, sa, sb, sc, flags & FCB_GEMM_MASK, ws, ws_bytes, st);
     float* partials = static_cast<float*>(ws);
+    if (use_tc(N, K, trans_a, batch, flags) && trans_a && (lda % 4) == 0 && (ldb % 4) == 0 && aligned16(A) && aligned16(Bm)) {
+        FCB_REQUIRE(split_k == 1 || (partials && ws_bytes >= (size_t)split_k * M * N * 4), FCB_E_WORKSPACE,
+                    "gemm: split_k > 1 needs a workspace of split_k*M*N floats");
+        int64_t kps_tc = (K + split_k - 1) / split_k;
+        kps_tc = (kps_tc + 31) / 32 * 32;
+        int rc = launch_gemm_tc_tn(A, Bm, C, M, N, K, lda, ldb, ldc, split_k, kps_tc, partials, flags & FCB_GEMM_MASK, st);
+        if (rc || split_k == 1) return rc;
+        return launch_reduce_splits(partials, C, M, N, ldc, 0, 1, split_k, st);
+    }
     FCB_REQUIRE(split_k == 1 || (partials && ws_bytes >= (size_t)split_k * batch * M * N * 4), FCB_E_WORKSPACE,
                 "gemm: split_k > 1 needs a workspace of split_k*batch*M*N floats");
     FCB_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (sa % 4) == 0 && (sb % 4) == 0 && aligned16(A) && aligned16(Bm),

@@ -4,7 +4,11 @@
 // Accuracy modes
 //   3xTF32 (default tensor-core mode): every operand is split into hi = tf32(x) and lo = x - hi and the
 //   product is accumulated as  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is ~2^-22 relative),
-//   which keeps the contraction inside the 1e-5 parity budget of the fp32 path.
+//   which removes the operand-rounding error.  What remains is the tensor core's accumulator behaviour: the
+//   fp32 accumulate in TMEM truncates (measured: a systematic toward-zero drift of ~6e-8 per accumulating MMA,
+//   2e-5 after the 1080 MMAs of a K=2880 contraction).  So the small cross terms go to their OWN accumulator
+//   (their truncation error is 2^-11 smaller) and the hi*hi products are dealt round-robin over up to three
+//   more accumulators (TMEM has 512 columns); the epilogue adds the accumulators with ordinary fp32 adds.
 //   TF32: hi planes only (~1e-3 relative; looser tolerance, stated separately in the tests).
 //
 // Structure of one CTA (one 128-row tile of A, all N <= 256 columns), 10 warps:
@@ -113,6 +117,7 @@ struct Params {
     int64_t M, K, lda, ldc, sa, sc;
     int64_t bp_batch_stride;   // floats
     int N, Npad, nchunks, stages, mode;
+    int n_main;                // accumulators for the hi*hi products (3xTF32: + 1 for the cross terms)
     uint32_t tmem_cols;
 };
 
@@ -206,10 +211,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
         const int q = warp & 3, half = warp >> 2;
         const int64_t m = m0 + 32 * q + lane;
         const int groups = p.Npad / 16;
+        const int n_acc = p.n_main + (p.mode == FCB_GEMM_TC_3XTF32 ? 1 : 0);
         for (int g = half; g < groups; g += 2) {
             uint32_t r[16];
-            tc_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * g), r);
-            tc_ld_wait();
+            float acc[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+            for (int a = n_acc - 1; a >= 0; --a) {      // cross-term accumulator (last) first: small + large
+                tc_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(a * p.Npad + 16 * g), r);
+                tc_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(r[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(acc[e]);
             if (m < p.M) {
                 float* dst = C + m * p.ldc + 16 * g;
 #pragma unroll
@@ -244,13 +259,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
 #pragma unroll
                 for (int ks = 0; ks < KC / 8; ++ks) {
                     const uint64_t adv = (uint64_t)(ks * 2);   // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzle row
-                    const uint32_t first = (kc > 0 || ks > 0) ? 1u : 0u;
+                    const int step = kc * (KC / 8) + ks;
+                    const uint32_t d_main = tmem_d + (uint32_t)((step % p.n_main) * p.Npad);
+                    tc_mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, step >= p.n_main ? 1u : 0u);
                     if (p.mode == FCB_GEMM_TC_3XTF32) {
-                        tc_mma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, first);
-                        tc_mma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
-                        tc_mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
-                    } else {
-                        tc_mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, first);
+                        const uint32_t d_x = tmem_d + (uint32_t)(p.n_main * p.Npad);
+                        tc_mma_tf32(d_x, a_lo + adv, b_hi + adv, idesc, step > 0 ? 1u : 0u);
+                        tc_mma_tf32(d_x, a_hi + adv, b_lo + adv, idesc, 1u);
                     }
                 }
                 tc_commit(empty(s));      // frees the stage once these MMAs have read it
@@ -269,6 +284,217 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
                 mbar_expect_tx(full_b(s), bytes);
                 bulk_copy_g2s(b0 + s * 2 * b_plane, Bp + (int64_t)kc * 2 * p.Npad * KC, bytes, full_b(s));
             }
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == N_PROD_WARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// TN variant (K4, weight gradient): P[Mr x N] = A^T B with A = [Kv x Mr] and B = [Kv x N] row-major, i.e. both
+// operands are "MN-major" (the reduction index, vertices, is the slow one in memory).  The hardware transposes:
+// UMMA descriptors with a_major = b_major = MN over 128B-swizzled tiles whose 128-byte rows are 32 consecutive
+// features of one vertex — exactly a coalesced 128-byte piece of the global row.  Both operands are activations,
+// so the producer warps split both into hi/lo planes.  grid.z = split over vertex ranges; every split writes its
+// own partial tile, summed later in split order (k_reduce_splits) so the result is deterministic.
+struct ParamsTN {
+    const float* A;    // [Kv x Mr], lda
+    const float* B;    // [Kv x N], ldb
+    float* C;          // partials [split][Mr][N] or C itself when split == 1 (ldc)
+    int64_t Mr, Kv, lda, ldb, ldc, k_per_split, part_stride;
+    int N, Npad, nb_atoms, stages, mode, n_main;
+    uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // between 32-element MN atoms
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // between 8-row K groups
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+constexpr int KV = 32;   // vertices per stage (4 MMA K-steps of 8)
+
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw);
+    const int S = p.stages;
+    const uint32_t b_plane = (uint32_t)KV * (uint32_t)p.nb_atoms * 128u;   // 32 vertices x nb_atoms x 128 B
+    const uint32_t a_hi0 = base, a_lo0 = base + S * A_PLANE, b_hi0 = base + 2 * S * A_PLANE, b_lo0 = b_hi0 + S * b_plane;
+    const uint32_t bars = b_lo0 + S * b_plane;
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (S + s); };
+    const uint32_t tmem_full = bars + 8u * (2 * S);
+    const uint32_t tmem_slot = bars + 8u * (2 * S + 1);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(sm + (tmem_slot - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int split = blockIdx.z;
+    const int64_t kb = (int64_t)split * p.k_per_split;
+    const int64_t ke = min(p.Kv, kb + p.k_per_split);
+    const int nchunks = kb < ke ? (int)((ke - kb + KV - 1) / KV) : 0;
+    float* C = p.C + (int64_t)split * p.part_stride;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full(s), N_PROD_WARPS);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == N_PROD_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot_ptr;
+    const bool split3 = (p.mode == FCB_GEMM_TC_3XTF32);
+
+    if (warp < N_PROD_WARPS) {
+        const int t = threadIdx.x;
+        const int nf4_b = p.nb_atoms * 8;                 // float4 slots per vertex row of the B operand (padded)
+        const int b_items = KV * nf4_b;                   // <= 32 * 64 = 2048
+        for (int kc = 0; kc < nchunks; ++kc) {
+            const int s = kc % S;
+            const uint32_t ph = (uint32_t)(kc / S) & 1u;
+            const int64_t v0 = kb + (int64_t)kc * KV;
+            float4 va[4], vb[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {                 // A operand: 32 vertices x 128 features
+                const int idx = t + 256 * i;
+                const int v = idx >> 5, f4 = idx & 31;
+                const int64_t m = m0 + 4 * f4;
+                va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (v0 + v < ke) {
+                    const float* src = p.A + (v0 + v) * p.lda + m;
+                    if (m + 3 < p.Mr) va[i] = __ldg(reinterpret_cast<const float4*>(src));
+                    else {
+                        if (m < p.Mr) va[i].x = src[0];
+                        if (m + 1 < p.Mr) va[i].y = src[1];
+                        if (m + 2 < p.Mr) va[i].z = src[2];
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {                 // B operand: 32 vertices x Npad32 features
+                const int idx = t + 256 * i;
+                vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx < b_items) {
+                    const int v = idx / nf4_b, f4 = idx - v * nf4_b;
+                    const int n = 4 * f4;
+                    if (v0 + v < ke && n < p.N) {
+                        const float* src = p.B + (v0 + v) * p.ldb + n;
+                        if (n + 3 < p.N) vb[i] = __ldg(reinterpret_cast<const float4*>(src));
+                        else {
+                            vb[i].x = src[0];
+                            if (n + 1 < p.N) vb[i].y = src[1];
+                            if (n + 2 < p.N) vb[i].z = src[2];
+                        }
+                    }
+                }
+            }
+            mbar_wait(empty(s), ph ^ 1u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = t + 256 * i;
+                const int v = idx >> 5, f4 = idx & 31;
+                const int kg = v >> 3, row = v & 7, ma = f4 >> 3, unit = f4 & 7;
+                const uint32_t off = (uint32_t)((kg * 4 + ma) * 1024 + row * 128 + ((unit ^ row) << 4));
+                const float4 hi = make_float4(tf32_hi(va[i].x), tf32_hi(va[i].y), tf32_hi(va[i].z), tf32_hi(va[i].w));
+                *reinterpret_cast<float4*>(sm + (a_hi0 - base) + s * A_PLANE + off) = hi;
+                if (split3)
+                    *reinterpret_cast<float4*>(sm + (a_lo0 - base) + s * A_PLANE + off) =
+                        make_float4(va[i].x - hi.x, va[i].y - hi.y, va[i].z - hi.z, va[i].w - hi.w);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = t + 256 * i;
+                if (idx < b_items) {
+                    const int v = idx / nf4_b, f4 = idx - v * nf4_b;
+                    const int kg = v >> 3, row = v & 7, na = f4 >> 3, unit = f4 & 7;
+                    const uint32_t off = (uint32_t)((kg * p.nb_atoms + na) * 1024 + row * 128 + ((unit ^ row) << 4));
+                    const float4 hi = make_float4(tf32_hi(vb[i].x), tf32_hi(vb[i].y), tf32_hi(vb[i].z), tf32_hi(vb[i].w));
+                    *reinterpret_cast<float4*>(sm + (b_hi0 - base) + s * b_plane + off) = hi;
+                    if (split3)
+                        *reinterpret_cast<float4*>(sm + (b_lo0 - base) + s * b_plane + off) =
+                            make_float4(vb[i].x - hi.x, vb[i].y - hi.y, vb[i].z - hi.z, vb[i].w - hi.w);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full(s));
+        }
+        // epilogue
+        const int q = warp & 3, half = warp >> 2;
+        const int64_t m = m0 + 32 * q + lane;
+        const int groups = p.Npad / 16;
+        const int n_acc = p.n_main + (split3 ? 1 : 0);
+        if (nchunks > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        for (int g = half; g < groups; g += 2) {
+            uint32_t r[16];
+            float acc[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+            if (nchunks > 0) {
+                for (int a = n_acc - 1; a >= 0; --a) {
+                    tc_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(a * p.Npad + 16 * g), r);
+                    tc_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(r[e]);
+                }
+            }
+            if (m < p.Mr) {
+                float* dst = C + m * p.ldc + 16 * g;
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (16 * g + e < p.N) dst[e] = acc[e];
+            }
+        }
+    } else if (warp == N_PROD_WARPS) {
+        if (lane == 0 && nchunks > 0) {
+            // D=f32, A=B=tf32, both MN-major (bits 15, 16), M=128, N=Npad
+            const uint32_t idesc = make_idesc_tf32(p.Npad) | (1u << 15) | (1u << 16);
+            const uint32_t sbo_a = 4 * 1024, sbo_b = (uint32_t)p.nb_atoms * 1024;
+            for (int kc = 0; kc < nchunks; ++kc) {
+                const int s = kc % S;
+                const uint32_t ph = (uint32_t)(kc / S) & 1u;
+                mbar_wait(full(s), ph);
+                tc_fence_after();
+#pragma unroll
+                for (int kg = 0; kg < KV / 8; ++kg) {
+                    const uint64_t a_hi = make_desc_mn_sw128(a_hi0 + s * A_PLANE + kg * sbo_a, 1024, sbo_a);
+                    const uint64_t a_lo = make_desc_mn_sw128(a_lo0 + s * A_PLANE + kg * sbo_a, 1024, sbo_a);
+                    const uint64_t b_hi = make_desc_mn_sw128(b_hi0 + s * b_plane + kg * sbo_b, 1024, sbo_b);
+                    const uint64_t b_lo = make_desc_mn_sw128(b_lo0 + s * b_plane + kg * sbo_b, 1024, sbo_b);
+                    const int step = kc * (KV / 8) + kg;
+                    const uint32_t d_main = tmem_d + (uint32_t)((step % p.n_main) * p.Npad);
+                    tc_mma_tf32(d_main, a_hi, b_hi, idesc, step >= p.n_main ? 1u : 0u);
+                    if (split3) {
+                        const uint32_t d_x = tmem_d + (uint32_t)(p.n_main * p.Npad);
+                        tc_mma_tf32(d_x, a_lo, b_hi, idesc, step > 0 ? 1u : 0u);
+                        tc_mma_tf32(d_x, a_hi, b_lo, idesc, 1u);
+                    }
+                }
+                tc_commit(empty(s));
+            }
+            tc_commit(tmem_full);
         }
         __syncwarp();
     }
@@ -334,8 +560,17 @@ int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N
     p.M = M; p.K = K; p.lda = lda; p.ldc = ldc; p.sa = sa; p.sc = sc;
     p.bp_batch_stride = bp_stride;
     p.N = N; p.Npad = npad; p.nchunks = nchunks; p.mode = mode;
+    int n_main = 1;
+    if (mode == FCB_GEMM_TC_3XTF32) {
+        n_main = 512 / npad - 1;
+        if (n_main > 3) n_main = 3;
+        if (n_main < 1) n_main = 1;
+    }
+    const int64_t ksteps = (int64_t)nchunks * (tc::KC / 8);
+    if (n_main > ksteps) n_main = (int)ksteps;
+    p.n_main = n_main;
     uint32_t cols = 32;
-    while ((int)cols < npad) cols <<= 1;
+    while ((int)cols < npad * (n_main + (mode == FCB_GEMM_TC_3XTF32 ? 1 : 0))) cols <<= 1;
     p.tmem_cols = cols;
     const size_t stage_bytes = 2 * tc::A_PLANE + 2 * (size_t)npad * 128;
     int stages = (int)((220 * 1024 - 2048) / stage_bytes);
@@ -355,6 +590,55 @@ int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N
     }
     dim3 grid((unsigned)((M + tc::BM - 1) / tc::BM), (unsigned)batch);
     FCB_LAUNCH("gemm_tc_nn", st, tc::k_gemm_tc_nn<<<grid, tc::THREADS, smem, st>>>(p));
+    return FCB_OK;
+}
+
+// P[Mr x N] = A^T B on the tensor cores; split >= 1 vertex ranges; `parts` (split*Mr*N floats) is used when split > 1.
+int launch_gemm_tc_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
+                      int64_t ldc, int split, int64_t k_per_split, float* parts, int mode, cudaStream_t st) {
+    FCB_REQUIRE(A && B && C, FCB_E_ARG, "gemm_tc_tn: null pointer");
+    FCB_REQUIRE(N > 0 && N <= 256 && split >= 1 && split <= 65535, FCB_E_UNSUPPORTED, "gemm_tc_tn: unsupported shape");
+    FCB_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && aligned16(A) && aligned16(B), FCB_E_ALIGN, "gemm_tc_tn: alignment");
+    if (Mr == 0) return FCB_OK;
+    const int npad = (N + 15) / 16 * 16;
+    const int nb_atoms = (npad + 31) / 32;
+    tc::ParamsTN p;
+    p.A = A; p.B = B;
+    p.C = split > 1 ? parts : C;
+    p.Mr = Mr; p.Kv = Kv; p.lda = lda; p.ldb = ldb;
+    p.ldc = split > 1 ? N : ldc;
+    p.k_per_split = k_per_split;
+    p.part_stride = split > 1 ? Mr * (int64_t)N : 0;
+    p.N = N; p.Npad = npad; p.nb_atoms = nb_atoms; p.mode = mode;
+    int n_main = 1;
+    if (mode == FCB_GEMM_TC_3XTF32) {
+        n_main = 512 / npad - 1;
+        if (n_main > 3) n_main = 3;
+        if (n_main < 1) n_main = 1;
+    }
+    const int64_t ksteps = (k_per_split + 7) / 8;
+    if (n_main > ksteps) n_main = (int)(ksteps < 1 ? 1 : ksteps);
+    p.n_main = n_main;
+    uint32_t cols = 32;
+    while ((int)cols < npad * (n_main + (mode == FCB_GEMM_TC_3XTF32 ? 1 : 0))) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t stage_bytes = 2 * tc::A_PLANE + 2 * (size_t)tc::KV * nb_atoms * 128;
+    int stages = (int)((220 * 1024 - 2048) / stage_bytes);
+    if (stages > 4) stages = 4;
+    FCB_REQUIRE(stages >= 1, FCB_E_UNSUPPORTED, "gemm_tc_tn: tile does not fit shared memory");
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + 1024 + 8 * (2 * stages + 2) + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc::k_gemm_tc_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+            set_error("gemm_tc_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return FCB_E_CUDA;
+        }
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((Mr + tc::BM - 1) / tc::BM), 1, (unsigned)split);
+    FCB_LAUNCH("gemm_tc_tn", st, tc::k_gemm_tc_tn<<<grid, tc::THREADS, smem, st>>>(p));
     return FCB_OK;
 }
 

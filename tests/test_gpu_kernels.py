@@ -178,7 +178,7 @@ def test_tangent_lin_matches_oracle():
         assert_close_normwise(lin_d.Im.grad, g_im, 2e-6, "TangentLin gIm")
 
 
-@pytest.mark.parametrize("mode,tol", [(1, 2e-6), (2, 3e-3)])
+@pytest.mark.parametrize("mode,tol", [(1, 5e-6), (2, 3e-3)])
 @pytest.mark.parametrize("m,n,k", [(128, 96, 32), (128, 96, 2880), (1000, 96, 576), (80656, 96, 2880), (300, 64, 1152),
                                    (257, 256, 520), (130, 20, 36), (5, 12, 8), (4096, 16, 64)])
 def test_tensor_core_gemm(m, n, k, mode, tol):
@@ -196,3 +196,20 @@ def test_tensor_core_gemm(m, n, k, mode, tol):
     if mode == 2:   # TF32 must actually be less accurate than fp32 (i.e. the tensor path really ran)
         err = float((c.double() - ref).abs().max() / ref.abs().max())
         assert err > 1e-6 or k <= 8
+
+
+@pytest.mark.parametrize("mode,tol", [(1, 5e-6), (2, 3e-3)])
+@pytest.mark.parametrize("m,n,k", [(128, 96, 32), (2880, 96, 80656), (1152, 64, 5041), (300, 256, 1000), (36, 20, 77),
+                                   (7680, 256, 6889), (128, 16, 8)])
+def test_tensor_core_gemm_transposed(m, n, k, mode, tol):
+    """gW-shaped product P[m x n] = A^T B, A = (k x m), B = (k x n): MN-major UMMA operands + split reduction."""
+    g = torch.Generator(device="cpu").manual_seed(m + n + k + 1)
+    m_pad = (m + 3) // 4 * 4
+    a = torch.randn(k, m_pad, generator=g).to(DEV)
+    a[:, m:] = 0
+    b = torch.randn(k, n, generator=g).to(DEV)
+    c = ops.gemm(a, b, True, mode)[:m]
+    torch.cuda.synchronize()
+    ref = (a.double().t() @ b.double())[:m]
+    assert_close_normwise(c, ref.float(), tol, "tensor-core gemm^T mode %d" % mode)
+    assert torch.equal(c, ops.gemm(a, b, True, mode)[:m]), "deterministic"

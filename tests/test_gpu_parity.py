@@ -197,3 +197,43 @@ def test_full_size_properties_config2_layer():
     with torch.no_grad():
         y2 = m((x * rot[:, None]).contiguous(), plan2)
     assert_close_normwise(y2, y * rot[:, None], 2e-5, "gauge equivariance")
+
+
+# Tensor-core variants: tolerance stated separately from the fp32 path (BASELINE.json north_star).
+#   3xTF32 : operand rounding is compensated; what remains is the truncating fp32 accumulate of the tensor core,
+#            spread over several TMEM accumulators -> a few 1e-6 for K ~ 3k; bound used here 2e-5.
+#   TF32   : 10-bit mantissa operands, ~1e-3; bound 5e-3.
+@pytest.mark.parametrize("precision,tol", [("3xtf32", 2e-5), ("tf32", 5e-3)])
+@pytest.mark.parametrize("name", golden_names("fc_"))
+def test_tensor_core_precision_golden(name, precision, tol):
+    g = load_golden(name)
+    m = _layer_from_golden(g, precision)
+    plan = fcb.build_plan(g["raw_edges"].to(DEV), g["logMag"].to(DEV), g["logAng"].to(DEV), g["xp"].to(DEV),
+                          g["w"].to(DEV), g["R"], g["epsilon"])
+    x = g["x"].to(DEV).requires_grad_(True)
+    y = m(x, plan)
+    gy = g["gy"].to(DEV)
+    (y.real * gy.real + y.imag * gy.imag).sum().backward()
+    assert_close_normwise(y, g["y"], tol, precision + " y")
+    assert_close_normwise(x.grad, g["gx"], tol, precision + " grad x")
+    assert_close_normwise(m.zonal.grad, g["g_zonal"], tol, precision + " grad zonal")
+    assert_close_normwise(m.spherical.grad, g["g_spherical"], tol, precision + " grad spherical")
+
+
+@pytest.mark.parametrize("precision,tol", [("3xtf32", 2e-5), ("tf32", 5e-3)])
+@pytest.mark.parametrize("n_side,ci,co,B,R", [(71, 32, 32, 1, 6), (24, 48, 48, 2, 6), (16, 128, 128, 2, 6)])
+def test_tensor_core_precision_vs_fp64_oracle(n_side, ci, co, B, R, precision, tol):
+    mesh = torus_mesh(n_side, deg=40.0, seed=1, device=DEV)
+    torch.manual_seed(0)
+    m = fcb.FieldConv(ci, co, B, R, 1, precision=precision).to(DEV)
+    plan = fcb.build_plan(mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp, mesh.w, R, mesh.epsilon)
+    x = random_features(mesh.num_nodes, ci, seed=2, device=DEV).requires_grad_(True)
+    gy = random_features(mesh.num_nodes, co, seed=3, zero_frac=0, device=DEV)
+    y = m(x, plan)
+    (y.real * gy.real + y.imag * gy.imag).sum().backward()
+    y_ref, gx_ref, gp_ref = _oracle_layer(mesh, x, m, gy)
+    assert_close_normwise(y, y_ref.to(torch.complex64), tol, precision + " y")
+    assert_close_normwise(x.grad, gx_ref.to(torch.complex64), tol, precision + " grad x")
+    assert_close_normwise(m.zonal.grad, gp_ref[0].float(), tol, precision + " grad zonal")
+    assert_close_normwise(m.spherical.grad, gp_ref[1].float(), tol, precision + " grad spherical")
+    assert_close_normwise(m.phase.grad, gp_ref[2].float(), tol, precision + " grad phase")
