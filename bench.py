@@ -353,7 +353,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("FIELDCONV_B200_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("FIELDCONV_B200_PRECISION", "auto"))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

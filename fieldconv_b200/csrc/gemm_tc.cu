@@ -297,8 +297,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
 // ------------------------------------------------------------------------------------------------------------
 // TN variant (K4, weight gradient): P[Mr x N] = A^T B with A = [Kv x Mr] and B = [Kv x N] row-major, i.e. both
 // operands are "MN-major" (the reduction index, vertices, is the slow one in memory).  The hardware transposes:
-// UMMA descriptors with a_major = b_major = MN over 128B-swizzled tiles whose 128-byte rows are 32 consecutive
-// features of one vertex — exactly a coalesced 128-byte piece of the global row.  Both operands are activations,
+// UMMA descriptors with a_major = b_major = MN.  For 32-bit (tf32) MN-major operands the only legal shared
+// memory layout is SWIZZLE_128B_BASE32B: atoms of 4 K-rows x 128 bytes, a row = 32 consecutive features of one
+// vertex (exactly a coalesced 128-byte piece of the global row), 32-byte chunks XOR-permuted by the row index.  Both operands are activations,
 // so the producer warps split both into hi/lo planes.  grid.z = split over vertex ranges; every split writes its
 // own partial tile, summed later in split order (k_reduce_splits) so the result is deterministic.
 struct ParamsTN {
@@ -314,9 +315,9 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // between 32-element MN atoms
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // between 8-row K groups
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // between 4-row K groups
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;                             // SWIZZLE_128B_BASE32B
     return d;
 }
 
@@ -412,8 +413,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
             for (int i = 0; i < 4; ++i) {
                 const int idx = t + 256 * i;
                 const int v = idx >> 5, f4 = idx & 31;
-                const int kg = v >> 3, row = v & 7, ma = f4 >> 3, unit = f4 & 7;
-                const uint32_t off = (uint32_t)((kg * 4 + ma) * 1024 + row * 128 + ((unit ^ row) << 4));
+                const int kq = v >> 2, row = v & 3, ma = f4 >> 3, unit = f4 & 7;
+                const uint32_t off = (uint32_t)((kq * 4 + ma) * 512 + row * 128 + (((unit >> 1) ^ row) << 5) + ((unit & 1) << 4));
                 const float4 hi = make_float4(tf32_hi(va[i].x), tf32_hi(va[i].y), tf32_hi(va[i].z), tf32_hi(va[i].w));
                 *reinterpret_cast<float4*>(sm + (a_hi0 - base) + s * A_PLANE + off) = hi;
                 if (split3)
@@ -425,8 +426,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
                 const int idx = t + 256 * i;
                 if (idx < b_items) {
                     const int v = idx / nf4_b, f4 = idx - v * nf4_b;
-                    const int kg = v >> 3, row = v & 7, na = f4 >> 3, unit = f4 & 7;
-                    const uint32_t off = (uint32_t)((kg * p.nb_atoms + na) * 1024 + row * 128 + ((unit ^ row) << 4));
+                    const int kq = v >> 2, row = v & 3, na = f4 >> 3, unit = f4 & 7;
+                    const uint32_t off = (uint32_t)((kq * p.nb_atoms + na) * 512 + row * 128 + (((unit >> 1) ^ row) << 5) + ((unit & 1) << 4));
                     const float4 hi = make_float4(tf32_hi(vb[i].x), tf32_hi(vb[i].y), tf32_hi(vb[i].z), tf32_hi(vb[i].w));
                     *reinterpret_cast<float4*>(sm + (b_hi0 - base) + s * b_plane + off) = hi;
                     if (split3)
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
         if (lane == 0 && nchunks > 0) {
             // D=f32, A=B=tf32, both MN-major (bits 15, 16), M=128, N=Npad
             const uint32_t idesc = make_idesc_tf32(p.Npad) | (1u << 15) | (1u << 16);
-            const uint32_t sbo_a = 4 * 1024, sbo_b = (uint32_t)p.nb_atoms * 1024;
+            const uint32_t sbo_a = 4 * 512, sbo_b = (uint32_t)p.nb_atoms * 512;   // between 4-vertex K groups
             for (int kc = 0; kc < nchunks; ++kc) {
                 const int s = kc % S;
                 const uint32_t ph = (uint32_t)(kc / S) & 1u;
@@ -479,10 +480,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
                 tc_fence_after();
 #pragma unroll
                 for (int kg = 0; kg < KV / 8; ++kg) {
-                    const uint64_t a_hi = make_desc_mn_sw128(a_hi0 + s * A_PLANE + kg * sbo_a, 1024, sbo_a);
-                    const uint64_t a_lo = make_desc_mn_sw128(a_lo0 + s * A_PLANE + kg * sbo_a, 1024, sbo_a);
-                    const uint64_t b_hi = make_desc_mn_sw128(b_hi0 + s * b_plane + kg * sbo_b, 1024, sbo_b);
-                    const uint64_t b_lo = make_desc_mn_sw128(b_lo0 + s * b_plane + kg * sbo_b, 1024, sbo_b);
+                    const uint64_t a_hi = make_desc_mn_sw128(a_hi0 + s * A_PLANE + 2 * kg * sbo_a, 512, sbo_a);
+                    const uint64_t a_lo = make_desc_mn_sw128(a_lo0 + s * A_PLANE + 2 * kg * sbo_a, 512, sbo_a);
+                    const uint64_t b_hi = make_desc_mn_sw128(b_hi0 + s * b_plane + 2 * kg * sbo_b, 512, sbo_b);
+                    const uint64_t b_lo = make_desc_mn_sw128(b_lo0 + s * b_plane + 2 * kg * sbo_b, 512, sbo_b);
                     const int step = kc * (KV / 8) + kg;
                     const uint32_t d_main = tmem_d + (uint32_t)((step % p.n_main) * p.Npad);
                     tc_mma_tf32(d_main, a_hi, b_hi, idesc, step >= p.n_main ? 1u : 0u);

@@ -16,7 +16,26 @@ from torch.nn import Parameter
 from . import _lib, ops
 from .plan import DensePlan, Plan, build_dense_plan
 
-_PRECISIONS = {"fp32": _lib.GEMM_SIMT_FP32, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32": _lib.GEMM_TC_TF32}
+_PRECISIONS = {"fp32": _lib.GEMM_SIMT_FP32, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32": _lib.GEMM_TC_TF32, "auto": -1}
+_AUTO_MAX_ACCUMULATES = 400     # tcgen05 accumulates truncate: ~6e-8 drift per MMA and accumulator
+
+
+def _resolve_precision(precision, ci, co, n_rings, band_limit):
+    """"auto": error-compensated tensor cores (3xTF32) when every TMEM accumulator of the three contractions
+    receives few enough MMAs to stay inside the fp32 path's 1e-5 parity budget, else the FP32-FMA kernels."""
+    if precision != "auto":
+        return _PRECISIONS[precision]
+    m = 2 * band_limit + 1
+
+    def ok(n_cols, k_reals):
+        npad = (n_cols + 15) // 16 * 16
+        if npad > 256:
+            return False
+        n_main = max(1, min(3, 512 // npad - 1))
+        return (k_reals // 8) / n_main <= _AUTO_MAX_ACCUMULATES
+    fwd = ok(2 * co, 2 * n_rings * ci * m)
+    bwd = ok(2 * ci, 2 * n_rings * co)
+    return _lib.GEMM_TC_3XTF32 if (fwd and bwd) else _lib.GEMM_SIMT_FP32
 
 
 def fold_weights(zonal, spherical, phase, ftype, band_limit):
@@ -38,7 +57,7 @@ def fold_weights(zonal, spherical, phase, ftype, band_limit):
 
 
 class FieldConv(nn.Module):
-    def __init__(self, in_channels, out_channels, band_limit=1, n_rings=6, ftype=1, *, precision="fp32"):
+    def __init__(self, in_channels, out_channels, band_limit=1, n_rings=6, ftype=1, *, precision="auto"):
         super().__init__()
         if precision not in _PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
@@ -75,9 +94,9 @@ class FieldConv(nn.Module):
             plan, supp_edges = supp_edges, None
         if not x.is_cuda:
             raise RuntimeError("fieldconv_b200.FieldConv runs on CUDA (sm_100a) only; there is no CPU fallback")
-        flags = _PRECISIONS[self.precision]
-        w = self.weight()
         ci, co = self.in_channels, self.out_channels
+        flags = _resolve_precision(self.precision, ci + ci % 2, co + co % 2, self.R, self.B)
+        w = self.weight()
         if x.shape[1] != ci:
             raise ValueError("expected %d input channels, got %d" % (ci, x.shape[1]))
         if ci % 2:  # 16-byte feature rows: pad a zero channel (contributes nothing)
@@ -139,7 +158,7 @@ class FCResNetBlock(nn.Module):
     """nn/fc_resnet_block.py:43-88 — nonlin2(res(x) + conv2(nonlin1(conv1(x))))."""
 
     def __init__(self, in_channels, out_channels, band_limit=1, n_rings=6, ftype=1, frontload=False, *,
-                 precision="fp32"):
+                 precision="auto"):
         super().__init__()
         mid = in_channels if frontload else out_channels
         self.conv1 = FieldConv(in_channels, mid, band_limit=band_limit, n_rings=n_rings, ftype=ftype, precision=precision)

@@ -15,7 +15,7 @@ DEV = "cuda:0"
 TOL = 1e-5
 
 
-def _layer_from_golden(g, precision="fp32"):
+def _layer_from_golden(g, precision="auto"):
     m = fcb.FieldConv(g["ci"], g["co"], g["B"], g["R"], g["ftype"], precision=precision)
     m.load_state_dict({"zonal": g["zonal"], "spherical": g["spherical"], "phase": g["phase"]})
     return m.to(DEV)
@@ -42,11 +42,14 @@ def test_dropin_signature_dense_stencil(name):
     _check_against_golden(g, m, y, x)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "auto"])
 @pytest.mark.parametrize("name", golden_names("fc_"))
-def test_compact_plan_path(name):
-    """forward(x, plan): FCPrecomp arithmetic + CSR built on the device from the raw mesh attributes."""
+def test_compact_plan_path(name, precision):
+    """forward(x, plan): FCPrecomp arithmetic + CSR built on the device from the raw mesh attributes.
+    "fp32" = FP32-FMA contraction kernels; "auto" (module default) = 3xTF32 tensor cores where they stay
+    inside the same 1e-5 budget.  Both are held to the fp32-path tolerance."""
     g = load_golden(name)
-    m = _layer_from_golden(g)
+    m = _layer_from_golden(g, precision)
     plan = fcb.build_plan(g["raw_edges"].to(DEV), g["logMag"].to(DEV), g["logAng"].to(DEV), g["xp"].to(DEV),
                           g["w"].to(DEV), g["R"], g["epsilon"])
     x = g["x"].to(DEV).requires_grad_(True)
@@ -105,13 +108,14 @@ def _oracle_layer(mesh, x, m, gy, dtype=torch.complex128):
     return y, gx, [p.grad for p in ps]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "auto"])
 @pytest.mark.parametrize("n_side,ci,co,B,R,ftype", [(71, 32, 32, 1, 6, 1), (24, 48, 48, 2, 6, 1), (20, 18, 10, 3, 3, 2),
                                                      (16, 128, 128, 2, 6, 0)])
-def test_synthetic_mesh_vs_fp64_oracle(n_side, ci, co, B, R, ftype):
+def test_synthetic_mesh_vs_fp64_oracle(n_side, ci, co, B, R, ftype, precision):
     """BASELINE config 1 (5k vertices, C=32, B=1, R=6) and cut-down configs 2/3 against the fp64 oracle."""
     mesh = torus_mesh(n_side, deg=40.0, seed=1, device=DEV)
     torch.manual_seed(0)
-    m = fcb.FieldConv(ci, co, B, R, ftype).to(DEV)
+    m = fcb.FieldConv(ci, co, B, R, ftype, precision=precision).to(DEV)
     plan = fcb.build_plan(mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp, mesh.w, R, mesh.epsilon)
     x = random_features(mesh.num_nodes, ci, seed=2, device=DEV).requires_grad_(True)
     gy = random_features(mesh.num_nodes, co, seed=3, zero_frac=0, device=DEV)
