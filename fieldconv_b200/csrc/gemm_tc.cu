@@ -167,43 +167,58 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
     if (warp < N_PROD_WARPS) {
         // ------------------------------------------------------------------ producers
         const int t = threadIdx.x;   // 0..255
-        for (int kc = 0; kc < p.nchunks; ++kc) {
-            const int s = kc % S;
-            const uint32_t ph = (uint32_t)(kc / S) & 1u;
-            float4 v[4];
+        // Software pipeline: the global loads of chunks kc+1 and kc+2 are in flight (registers) while chunk kc is
+        // split and stored, so one CTA per SM still keeps ~48 KB of loads outstanding.
+        float4 v[3][4];
+        auto issue = [&](int kc, float4(&dst)[4]) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int idx = t + 256 * i;
                 const int row = idx >> 3, j = idx & 7;
                 const int64_t m = m0 + row;
                 const int64_t k = (int64_t)kc * KC + 4 * j;
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (m < p.M) {
                     const float* src = A + m * p.lda + k;
-                    if (k + 3 < p.K) v[i] = __ldg(reinterpret_cast<const float4*>(src));
+                    if (k + 3 < p.K) dst[i] = __ldg(reinterpret_cast<const float4*>(src));
                     else {
-                        if (k < p.K) v[i].x = src[0];
-                        if (k + 1 < p.K) v[i].y = src[1];
-                        if (k + 2 < p.K) v[i].z = src[2];
+                        if (k < p.K) dst[i].x = src[0];
+                        if (k + 1 < p.K) dst[i].y = src[1];
+                        if (k + 2 < p.K) dst[i].z = src[2];
                     }
                 }
             }
+        };
+        auto commit = [&](int kc, const float4(&src)[4]) {
+            const int s = kc % S;
+            const uint32_t ph = (uint32_t)(kc / S) & 1u;
             mbar_wait(empty(s), ph ^ 1u);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int idx = t + 256 * i;
                 const int row = idx >> 3, j = idx & 7;
                 const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
-                float4 hi = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
+                const float4 hi = make_float4(tf32_hi(src[i].x), tf32_hi(src[i].y), tf32_hi(src[i].z), tf32_hi(src[i].w));
                 *reinterpret_cast<float4*>(sm + (a_hi0 - base) + s * A_PLANE + off) = hi;
-                if (p.mode == FCB_GEMM_TC_3XTF32) {
-                    float4 lo = make_float4(v[i].x - hi.x, v[i].y - hi.y, v[i].z - hi.z, v[i].w - hi.w);
-                    *reinterpret_cast<float4*>(sm + (a_lo0 - base) + s * A_PLANE + off) = lo;
-                }
+                if (p.mode == FCB_GEMM_TC_3XTF32)
+                    *reinterpret_cast<float4*>(sm + (a_lo0 - base) + s * A_PLANE + off) =
+                        make_float4(src[i].x - hi.x, src[i].y - hi.y, src[i].z - hi.z, src[i].w - hi.w);
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(full_a(s));
+        };
+        if (p.nchunks > 0) issue(0, v[0]);
+        if (p.nchunks > 1) issue(1, v[1]);
+        for (int kc = 0; kc < p.nchunks; kc += 3) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int k = kc + u;
+                if (k < p.nchunks) {
+                    if (k + 2 < p.nchunks) issue(k + 2, v[(u + 2) % 3]);
+                    commit(k, v[u]);
+                }
+            }
         }
         // ------------------------------------------------------------------ epilogue
         mbar_wait(tmem_full, 0);
@@ -323,6 +338,7 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
 
 constexpr int KV = 32;   // vertices per stage (4 MMA K-steps of 8)
 
+template <int NB4>   // float4 of the B operand per producer thread and stage == number of 32-feature atoms
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -367,47 +383,46 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
 
     if (warp < N_PROD_WARPS) {
         const int t = threadIdx.x;
-        const int nf4_b = p.nb_atoms * 8;                 // float4 slots per vertex row of the B operand (padded)
-        const int b_items = KV * nf4_b;                   // <= 32 * 64 = 2048
-        for (int kc = 0; kc < nchunks; ++kc) {
-            const int s = kc % S;
-            const uint32_t ph = (uint32_t)(kc / S) & 1u;
+        constexpr int nf4_b = NB4 * 8;                    // float4 slots per vertex row of the B operand (padded)
+        float4 va[2][4], vb[2][NB4];
+        auto issue = [&](int kc, float4(&da)[4], float4(&db)[NB4]) {
             const int64_t v0 = kb + (int64_t)kc * KV;
-            float4 va[4], vb[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {                 // A operand: 32 vertices x 128 features
                 const int idx = t + 256 * i;
                 const int v = idx >> 5, f4 = idx & 31;
                 const int64_t m = m0 + 4 * f4;
-                va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                da[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (v0 + v < ke) {
                     const float* src = p.A + (v0 + v) * p.lda + m;
-                    if (m + 3 < p.Mr) va[i] = __ldg(reinterpret_cast<const float4*>(src));
+                    if (m + 3 < p.Mr) da[i] = __ldg(reinterpret_cast<const float4*>(src));
                     else {
-                        if (m < p.Mr) va[i].x = src[0];
-                        if (m + 1 < p.Mr) va[i].y = src[1];
-                        if (m + 2 < p.Mr) va[i].z = src[2];
+                        if (m < p.Mr) da[i].x = src[0];
+                        if (m + 1 < p.Mr) da[i].y = src[1];
+                        if (m + 2 < p.Mr) da[i].z = src[2];
                     }
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {                 // B operand: 32 vertices x Npad32 features
+            for (int i = 0; i < NB4; ++i) {               // B operand: 32 vertices x (32*NB4) features
                 const int idx = t + 256 * i;
-                vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (idx < b_items) {
-                    const int v = idx / nf4_b, f4 = idx - v * nf4_b;
-                    const int n = 4 * f4;
-                    if (v0 + v < ke && n < p.N) {
-                        const float* src = p.B + (v0 + v) * p.ldb + n;
-                        if (n + 3 < p.N) vb[i] = __ldg(reinterpret_cast<const float4*>(src));
-                        else {
-                            vb[i].x = src[0];
-                            if (n + 1 < p.N) vb[i].y = src[1];
-                            if (n + 2 < p.N) vb[i].z = src[2];
-                        }
+                const int v = idx / nf4_b, f4 = idx - v * nf4_b;
+                const int n = 4 * f4;
+                db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (v0 + v < ke && n < p.N) {
+                    const float* src = p.B + (v0 + v) * p.ldb + n;
+                    if (n + 3 < p.N) db[i] = __ldg(reinterpret_cast<const float4*>(src));
+                    else {
+                        db[i].x = src[0];
+                        if (n + 1 < p.N) db[i].y = src[1];
+                        if (n + 2 < p.N) db[i].z = src[2];
                     }
                 }
             }
+        };
+        auto commit = [&](int kc, const float4(&sa)[4], const float4(&sb)[NB4]) {
+            const int s = kc % S;
+            const uint32_t ph = (uint32_t)(kc / S) & 1u;
             mbar_wait(empty(s), ph ^ 1u);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -415,29 +430,38 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
                 const int v = idx >> 5, f4 = idx & 31;
                 const int kq = v >> 2, row = v & 3, ma = f4 >> 3, unit = f4 & 7;
                 const uint32_t off = (uint32_t)((kq * 4 + ma) * 512 + row * 128 + (((unit >> 1) ^ row) << 5) + ((unit & 1) << 4));
-                const float4 hi = make_float4(tf32_hi(va[i].x), tf32_hi(va[i].y), tf32_hi(va[i].z), tf32_hi(va[i].w));
+                const float4 hi = make_float4(tf32_hi(sa[i].x), tf32_hi(sa[i].y), tf32_hi(sa[i].z), tf32_hi(sa[i].w));
                 *reinterpret_cast<float4*>(sm + (a_hi0 - base) + s * A_PLANE + off) = hi;
                 if (split3)
                     *reinterpret_cast<float4*>(sm + (a_lo0 - base) + s * A_PLANE + off) =
-                        make_float4(va[i].x - hi.x, va[i].y - hi.y, va[i].z - hi.z, va[i].w - hi.w);
+                        make_float4(sa[i].x - hi.x, sa[i].y - hi.y, sa[i].z - hi.z, sa[i].w - hi.w);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < NB4; ++i) {
                 const int idx = t + 256 * i;
-                if (idx < b_items) {
-                    const int v = idx / nf4_b, f4 = idx - v * nf4_b;
-                    const int kq = v >> 2, row = v & 3, na = f4 >> 3, unit = f4 & 7;
-                    const uint32_t off = (uint32_t)((kq * p.nb_atoms + na) * 512 + row * 128 + (((unit >> 1) ^ row) << 5) + ((unit & 1) << 4));
-                    const float4 hi = make_float4(tf32_hi(vb[i].x), tf32_hi(vb[i].y), tf32_hi(vb[i].z), tf32_hi(vb[i].w));
-                    *reinterpret_cast<float4*>(sm + (b_hi0 - base) + s * b_plane + off) = hi;
-                    if (split3)
-                        *reinterpret_cast<float4*>(sm + (b_lo0 - base) + s * b_plane + off) =
-                            make_float4(vb[i].x - hi.x, vb[i].y - hi.y, vb[i].z - hi.z, vb[i].w - hi.w);
-                }
+                const int v = idx / nf4_b, f4 = idx - v * nf4_b;
+                const int kq = v >> 2, row = v & 3, na = f4 >> 3, unit = f4 & 7;
+                const uint32_t off = (uint32_t)((kq * NB4 + na) * 512 + row * 128 + (((unit >> 1) ^ row) << 5) + ((unit & 1) << 4));
+                const float4 hi = make_float4(tf32_hi(sb[i].x), tf32_hi(sb[i].y), tf32_hi(sb[i].z), tf32_hi(sb[i].w));
+                *reinterpret_cast<float4*>(sm + (b_hi0 - base) + s * b_plane + off) = hi;
+                if (split3)
+                    *reinterpret_cast<float4*>(sm + (b_lo0 - base) + s * b_plane + off) =
+                        make_float4(sb[i].x - hi.x, sb[i].y - hi.y, sb[i].z - hi.z, sb[i].w - hi.w);
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(full(s));
+        };
+        if (nchunks > 0) issue(0, va[0], vb[0]);
+        for (int kc = 0; kc < nchunks; kc += 2) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int k = kc + u;
+                if (k < nchunks) {
+                    if (k + 1 < nchunks) issue(k + 1, va[u ^ 1], vb[u ^ 1]);
+                    commit(k, va[u], vb[u]);
+                }
+            }
         }
         // epilogue
         const int q = warp & 3, half = warp >> 2;
@@ -629,17 +653,28 @@ int launch_gemm_tc_tn(const float* A, const float* B, float* C, int64_t Mr, int 
     FCB_REQUIRE(stages >= 1, FCB_E_UNSUPPORTED, "gemm_tc_tn: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = stages * stage_bytes + 1024 + 8 * (2 * stages + 2) + 64;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc::k_gemm_tc_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) {
-            set_error("gemm_tc_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return FCB_E_CUDA;
-        }
-        attr_set = true;
-    }
     dim3 grid((unsigned)((Mr + tc::BM - 1) / tc::BM), 1, (unsigned)split);
-    FCB_LAUNCH("gemm_tc_tn", st, tc::k_gemm_tc_tn<<<grid, tc::THREADS, smem, st>>>(p));
+    static bool attr_set[9] = {false};
+#define FCB_TN_CASE(NB)                                                                                                  \
+    case NB: {                                                                                                           \
+        if (!attr_set[NB]) {                                                                                             \
+            cudaError_t e = cudaFuncSetAttribute(tc::k_gemm_tc_tn<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+            if (e != cudaSuccess) {                                                                                      \
+                set_error("gemm_tc_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                                \
+                return FCB_E_CUDA;                                                                                       \
+            }                                                                                                            \
+            attr_set[NB] = true;                                                                                         \
+        }                                                                                                                \
+        tc::k_gemm_tc_tn<NB><<<grid, tc::THREADS, smem, st>>>(p);                                                        \
+    } break;
+    prof_begin("gemm_tc_tn", st);
+    switch (nb_atoms) {
+        FCB_TN_CASE(1) FCB_TN_CASE(2) FCB_TN_CASE(3) FCB_TN_CASE(4) FCB_TN_CASE(5) FCB_TN_CASE(6) FCB_TN_CASE(7) FCB_TN_CASE(8)
+        default: set_error("gemm_tc_tn: bad atom count"); return FCB_E_ARG;
+    }
+#undef FCB_TN_CASE
+    prof_end(st);
+    FCB_CUDA_LAUNCH_CHECK("gemm_tc_tn");
     return FCB_OK;
 }
 
