@@ -124,9 +124,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -136,7 +136,11 @@ class ClockSampler:
             pass
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= t1 + 0.15)]
+        window = "timed region"
+        if len(inside) < 2:          # very short timed region: fall back to every sample taken under load (warm-up on)
+            inside, window = [r for (_, r) in self.rows], "warm-up + timed region"
+        for r in inside:
             if len(r) < 9:
                 continue
             try:
@@ -148,7 +152,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 def algorithmic_bytes_aggregate(n, e, c, transpose=False):
@@ -225,6 +230,10 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident leg
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
     for _ in range(args.warmup):
         step(x_dev, plan, labels)
     if os.environ.get("FIELDCONV_B200_NCU"):     # profiler capture of exactly one step (ncu --profile-from-start off)
@@ -234,10 +243,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
+    t_begin = time.perf_counter()
     l0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -247,7 +254,7 @@ def run_ours(args):
     barrier()
     launches = _lib.launch_count() - l0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * edges_per_step / (ms_step * 1e-3)
 
