@@ -11,13 +11,13 @@
 //   more accumulators (TMEM has 512 columns); the epilogue adds the accumulators with ordinary fp32 adds.
 //   TF32: hi planes only (~1e-3 relative; looser tolerance, stated separately in the tests).
 //
-// Structure of one CTA (one 128-row tile of A, all N <= 256 columns), 10 warps:
-//   warps 0-7  producers: 128-bit coalesced loads of the fp32 A tile (32 reals = 128 B per row and stage),
+// Structure of one CTA (one 128-row tile of A, all N <= 256 columns), 18 warps:
+//   warps 0-15 producers: 128-bit coalesced loads of the fp32 A tile (32 reals = 128 B per row and stage),
 //              hi/lo split in registers, stores into the canonical 128B-swizzled K-major UMMA layout,
 //              fence.proxy.async, mbarrier arrive.  After the K loop the same warps run the epilogue
 //              (tcgen05.ld 32x32b -> registers -> 128-bit global stores).
-//   warp 8     single-thread MMA issue (tcgen05.mma, tcgen05.commit), TMEM alloc / dealloc.
-//   warp 9     B operand: the weights are pre-packed (k_pack_b_tc) into the exact shared-memory image of every
+//   warp 16    single-thread MMA issue (tcgen05.mma, tcgen05.commit), TMEM alloc / dealloc.
+//   warp 17    B operand: the weights are pre-packed (k_pack_b_tc) into the exact shared-memory image of every
 //              stage, so one cp.async.bulk (TMA engine, mbarrier complete_tx) per stage brings hi and lo planes in.
 // Shared-memory ring of S stages: {A_hi 16 KB, A_lo 16 KB, B_hi, B_lo (Npad*128 B each)}.
 #include "common.cuh"
@@ -27,7 +27,9 @@ namespace tc {
 
 constexpr int BM = 128;        // rows per CTA tile == UMMA M
 constexpr int KC = 32;         // reals per stage == one 128-byte swizzle row
-constexpr int N_PROD_WARPS = 8;
+constexpr int N_PROD_WARPS = 16;
+constexpr int N_PROD = N_PROD_WARPS * 32;        // producer threads
+constexpr int A_F4 = BM * KC / 4 / N_PROD;        // float4 of the A tile per producer thread and stage (2)
 constexpr int THREADS = (N_PROD_WARPS + 2) * 32;
 constexpr uint32_t A_PLANE = BM * KC * 4;   // 16 KB
 
@@ -166,43 +168,56 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
 
     if (warp < N_PROD_WARPS) {
         // ------------------------------------------------------------------ producers
-        const int t = threadIdx.x;   // 0..255
+        const int t = threadIdx.x;   // 0..N_PROD-1
         // Software pipeline: the global loads of chunks kc+1 and kc+2 are in flight (registers) while chunk kc is
-        // split and stored, so one CTA per SM still keeps ~48 KB of loads outstanding.
-        float4 v[3][4];
-        auto issue = [&](int kc, float4(&dst)[4]) {
+        // split and stored.  All addressing is hoisted: per thread A_F4 source pointers and shared-memory offsets.
+        const float* src[A_F4];
+        uint32_t off[A_F4];
+        int kcol[A_F4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int idx = t + 256 * i;
-                const int row = idx >> 3, j = idx & 7;
-                const int64_t m = m0 + row;
-                const int64_t k = (int64_t)kc * KC + 4 * j;
-                dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m < p.M) {
-                    const float* src = A + m * p.lda + k;
-                    if (k + 3 < p.K) dst[i] = __ldg(reinterpret_cast<const float4*>(src));
-                    else {
-                        if (k < p.K) dst[i].x = src[0];
-                        if (k + 1 < p.K) dst[i].y = src[1];
-                        if (k + 2 < p.K) dst[i].z = src[2];
+        for (int i = 0; i < A_F4; ++i) {
+            const int idx = t + N_PROD * i;
+            const int row = idx >> 3, j = idx & 7;
+            const int64_t m = m0 + row;
+            src[i] = (m < p.M) ? (A + m * p.lda + 4 * j) : nullptr;
+            kcol[i] = 4 * j;
+            off[i] = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
+        }
+        uint8_t* const hi_base = sm + (a_hi0 - base);
+        uint8_t* const lo_base = sm + (a_lo0 - base);
+        const bool split3 = (p.mode == FCB_GEMM_TC_3XTF32);
+        float4 v[3][A_F4];
+        auto issue = [&](int kc, float4(&dst)[A_F4]) {
+            const int64_t k0 = (int64_t)kc * KC;
+            if (k0 + KC <= p.K) {                        // full chunk (warp-uniform)
+#pragma unroll
+                for (int i = 0; i < A_F4; ++i)
+                    dst[i] = src[i] ? __ldg(reinterpret_cast<const float4*>(src[i] + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+#pragma unroll
+                for (int i = 0; i < A_F4; ++i) {
+                    dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int64_t k = k0 + kcol[i];
+                    if (src[i]) {
+                        if (k < p.K) dst[i].x = src[i][k0];
+                        if (k + 1 < p.K) dst[i].y = src[i][k0 + 1];
+                        if (k + 2 < p.K) dst[i].z = src[i][k0 + 2];
+                        if (k + 3 < p.K) dst[i].w = src[i][k0 + 3];
                     }
                 }
             }
         };
-        auto commit = [&](int kc, const float4(&src)[4]) {
+        auto commit = [&](int kc, const float4(&sv)[A_F4]) {
             const int s = kc % S;
             const uint32_t ph = (uint32_t)(kc / S) & 1u;
             mbar_wait(empty(s), ph ^ 1u);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int idx = t + 256 * i;
-                const int row = idx >> 3, j = idx & 7;
-                const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
-                const float4 hi = make_float4(tf32_hi(src[i].x), tf32_hi(src[i].y), tf32_hi(src[i].z), tf32_hi(src[i].w));
-                *reinterpret_cast<float4*>(sm + (a_hi0 - base) + s * A_PLANE + off) = hi;
-                if (p.mode == FCB_GEMM_TC_3XTF32)
-                    *reinterpret_cast<float4*>(sm + (a_lo0 - base) + s * A_PLANE + off) =
-                        make_float4(src[i].x - hi.x, src[i].y - hi.y, src[i].z - hi.z, src[i].w - hi.w);
+            for (int i = 0; i < A_F4; ++i) {
+                const float4 hi = make_float4(tf32_hi(sv[i].x), tf32_hi(sv[i].y), tf32_hi(sv[i].z), tf32_hi(sv[i].w));
+                *reinterpret_cast<float4*>(hi_base + s * A_PLANE + off[i]) = hi;
+                if (split3)
+                    *reinterpret_cast<float4*>(lo_base + s * A_PLANE + off[i]) =
+                        make_float4(sv[i].x - hi.x, sv[i].y - hi.y, sv[i].z - hi.z, sv[i].w - hi.w);
             }
             fence_proxy_async();
             __syncwarp();
@@ -223,11 +238,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
         // ------------------------------------------------------------------ epilogue
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        const int q = warp & 3, half = warp >> 2;
+        const int q = warp & 3, part = warp >> 2;
         const int64_t m = m0 + 32 * q + lane;
         const int groups = p.Npad / 16;
         const int n_acc = p.n_main + (p.mode == FCB_GEMM_TC_3XTF32 ? 1 : 0);
-        for (int g = half; g < groups; g += 2) {
+        for (int g = part; g < groups; g += N_PROD_WARPS / 4) {
             uint32_t r[16];
             float acc[16];
 #pragma unroll
@@ -384,69 +399,87 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
     if (warp < N_PROD_WARPS) {
         const int t = threadIdx.x;
         constexpr int nf4_b = NB4 * 8;                    // float4 slots per vertex row of the B operand (padded)
-        float4 va[2][4], vb[2][NB4];
-        auto issue = [&](int kc, float4(&da)[4], float4(&db)[NB4]) {
-            const int64_t v0 = kb + (int64_t)kc * KV;
+        constexpr int B_ITEMS = KV * nf4_b;               // 256 * NB4
+        constexpr int B_F4 = (B_ITEMS + N_PROD - 1) / N_PROD;
+        // hoisted addressing: element pointers at the split's first vertex, advanced by kc*KV rows per stage
+        const float* a_src[A_F4];
+        uint32_t a_off[A_F4];
+        int a_v[A_F4], a_cnt[A_F4];                       // vertex within the stage, valid floats (0..4)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {                 // A operand: 32 vertices x 128 features
-                const int idx = t + 256 * i;
-                const int v = idx >> 5, f4 = idx & 31;
-                const int64_t m = m0 + 4 * f4;
-                da[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (v0 + v < ke) {
-                    const float* src = p.A + (v0 + v) * p.lda + m;
-                    if (m + 3 < p.Mr) da[i] = __ldg(reinterpret_cast<const float4*>(src));
-                    else {
-                        if (m < p.Mr) da[i].x = src[0];
-                        if (m + 1 < p.Mr) da[i].y = src[1];
-                        if (m + 2 < p.Mr) da[i].z = src[2];
-                    }
-                }
+        for (int i = 0; i < A_F4; ++i) {
+            const int idx = t + N_PROD * i;
+            const int v = idx >> 5, f4 = idx & 31;
+            const int64_t m = m0 + 4 * f4;
+            a_v[i] = v;
+            a_cnt[i] = (int)max((int64_t)0, min((int64_t)4, p.Mr - m));
+            a_src[i] = p.A + (kb + v) * p.lda + m;
+            const int kq = v >> 2, row = v & 3, ma = f4 >> 3, unit = f4 & 7;
+            a_off[i] = (uint32_t)((kq * 4 + ma) * 512 + row * 128 + (((unit >> 1) ^ row) << 5) + ((unit & 1) << 4));
+        }
+        const float* b_src[B_F4];
+        uint32_t b_off[B_F4];
+        int b_v[B_F4], b_cnt[B_F4];
+#pragma unroll
+        for (int i = 0; i < B_F4; ++i) {
+            const int idx = t + N_PROD * i;
+            const int v = idx / nf4_b, f4 = idx - v * nf4_b;
+            const int n = 4 * f4;
+            b_v[i] = v;
+            b_cnt[i] = idx < B_ITEMS ? max(0, min(4, p.N - n)) : -1;      // -1: this thread has no such item
+            b_src[i] = p.B + (kb + v) * p.ldb + n;
+            const int kq = v >> 2, row = v & 3, na = f4 >> 3, unit = f4 & 7;
+            b_off[i] = (uint32_t)((kq * NB4 + na) * 512 + row * 128 + (((unit >> 1) ^ row) << 5) + ((unit & 1) << 4));
+        }
+        auto load4 = [&](const float* q, int cnt) {
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cnt == 4) r = __ldg(reinterpret_cast<const float4*>(q));
+            else {
+                if (cnt > 0) r.x = q[0];
+                if (cnt > 1) r.y = q[1];
+                if (cnt > 2) r.z = q[2];
+            }
+            return r;
+        };
+        float4 va[2][A_F4], vb[2][B_F4];
+        auto issue = [&](int kc, float4(&da)[A_F4], float4(&db)[B_F4]) {
+            const int64_t v0 = kb + (int64_t)kc * KV;
+            const bool full_chunk = (v0 + KV <= ke);
+#pragma unroll
+            for (int i = 0; i < A_F4; ++i) {
+                const bool ok = full_chunk || (v0 + a_v[i] < ke);
+                da[i] = ok ? load4(a_src[i] + (int64_t)kc * KV * p.lda, a_cnt[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int i = 0; i < NB4; ++i) {               // B operand: 32 vertices x (32*NB4) features
-                const int idx = t + 256 * i;
-                const int v = idx / nf4_b, f4 = idx - v * nf4_b;
-                const int n = 4 * f4;
-                db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (v0 + v < ke && n < p.N) {
-                    const float* src = p.B + (v0 + v) * p.ldb + n;
-                    if (n + 3 < p.N) db[i] = __ldg(reinterpret_cast<const float4*>(src));
-                    else {
-                        db[i].x = src[0];
-                        if (n + 1 < p.N) db[i].y = src[1];
-                        if (n + 2 < p.N) db[i].z = src[2];
-                    }
-                }
+            for (int i = 0; i < B_F4; ++i) {
+                const bool ok = b_cnt[i] > 0 && (full_chunk || (v0 + b_v[i] < ke));
+                db[i] = ok ? load4(b_src[i] + (int64_t)kc * KV * p.ldb, b_cnt[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        auto commit = [&](int kc, const float4(&sa)[4], const float4(&sb)[NB4]) {
+        uint8_t* const ahi = sm + (a_hi0 - base);
+        uint8_t* const alo = sm + (a_lo0 - base);
+        uint8_t* const bhi = sm + (b_hi0 - base);
+        uint8_t* const blo = sm + (b_lo0 - base);
+        auto commit = [&](int kc, const float4(&sa)[A_F4], const float4(&sb)[B_F4]) {
             const int s = kc % S;
             const uint32_t ph = (uint32_t)(kc / S) & 1u;
             mbar_wait(empty(s), ph ^ 1u);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int idx = t + 256 * i;
-                const int v = idx >> 5, f4 = idx & 31;
-                const int kq = v >> 2, row = v & 3, ma = f4 >> 3, unit = f4 & 7;
-                const uint32_t off = (uint32_t)((kq * 4 + ma) * 512 + row * 128 + (((unit >> 1) ^ row) << 5) + ((unit & 1) << 4));
+            for (int i = 0; i < A_F4; ++i) {
                 const float4 hi = make_float4(tf32_hi(sa[i].x), tf32_hi(sa[i].y), tf32_hi(sa[i].z), tf32_hi(sa[i].w));
-                *reinterpret_cast<float4*>(sm + (a_hi0 - base) + s * A_PLANE + off) = hi;
+                *reinterpret_cast<float4*>(ahi + s * A_PLANE + a_off[i]) = hi;
                 if (split3)
-                    *reinterpret_cast<float4*>(sm + (a_lo0 - base) + s * A_PLANE + off) =
+                    *reinterpret_cast<float4*>(alo + s * A_PLANE + a_off[i]) =
                         make_float4(sa[i].x - hi.x, sa[i].y - hi.y, sa[i].z - hi.z, sa[i].w - hi.w);
             }
 #pragma unroll
-            for (int i = 0; i < NB4; ++i) {
-                const int idx = t + 256 * i;
-                const int v = idx / nf4_b, f4 = idx - v * nf4_b;
-                const int kq = v >> 2, row = v & 3, na = f4 >> 3, unit = f4 & 7;
-                const uint32_t off = (uint32_t)((kq * NB4 + na) * 512 + row * 128 + (((unit >> 1) ^ row) << 5) + ((unit & 1) << 4));
-                const float4 hi = make_float4(tf32_hi(sb[i].x), tf32_hi(sb[i].y), tf32_hi(sb[i].z), tf32_hi(sb[i].w));
-                *reinterpret_cast<float4*>(sm + (b_hi0 - base) + s * b_plane + off) = hi;
-                if (split3)
-                    *reinterpret_cast<float4*>(sm + (b_lo0 - base) + s * b_plane + off) =
-                        make_float4(sb[i].x - hi.x, sb[i].y - hi.y, sb[i].z - hi.z, sb[i].w - hi.w);
+            for (int i = 0; i < B_F4; ++i) {
+                if (b_cnt[i] >= 0) {
+                    const float4 hi = make_float4(tf32_hi(sb[i].x), tf32_hi(sb[i].y), tf32_hi(sb[i].z), tf32_hi(sb[i].w));
+                    *reinterpret_cast<float4*>(bhi + s * b_plane + b_off[i]) = hi;
+                    if (split3)
+                        *reinterpret_cast<float4*>(blo + s * b_plane + b_off[i]) =
+                            make_float4(sb[i].x - hi.x, sb[i].y - hi.y, sb[i].z - hi.z, sb[i].w - hi.w);
+                }
             }
             fence_proxy_async();
             __syncwarp();
@@ -464,7 +497,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
             }
         }
         // epilogue
-        const int q = warp & 3, half = warp >> 2;
+        const int q = warp & 3, part = warp >> 2;
         const int64_t m = m0 + 32 * q + lane;
         const int groups = p.Npad / 16;
         const int n_acc = p.n_main + (split3 ? 1 : 0);
@@ -472,7 +505,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
             mbar_wait(tmem_full, 0);
             tc_fence_after();
         }
-        for (int g = half; g < groups; g += 2) {
+        for (int g = part; g < groups; g += N_PROD_WARPS / 4) {
             uint32_t r[16];
             float acc[16];
 #pragma unroll
