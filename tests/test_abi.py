@@ -59,5 +59,5 @@ def test_null_pointer_calls_are_rejected_without_touching_the_gpu():
     rc = lib.fcb_plan_build(None, None, None, None, None, None, 1.0, 10, 10, 1, None, None, None, None,
                             None, None, None, None, None, 0, None)
     assert rc == -5      # n_rings = 1 is unsupported (the reference divides by n_rings-1)
-    rc = lib.fcb_gemm_f32(None, None, None, 4, 4, 4, 4, 4, 4, 0, 1, 0, 0, 0, 1, None, 0, None)
+    rc = lib.fcb_gemm_f32(None, None, None, 4, 4, 4, 4, 4, 4, 0, 1, 0, 0, 0, 1, None, 0, 0, None)
     assert rc == -1
