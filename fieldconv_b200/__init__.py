@@ -3,6 +3,7 @@
     from fieldconv_b200 import FieldConv, FCResNetBlock, build_plan
 """
 from .plan import DensePlan, Plan, build_dense_plan, build_plan  # noqa: F401
+from .partition import MeshPartition, allreduce_gradients, partition_mesh  # noqa: F401
 from .nn import FCResNetBlock, FieldConv, TangentLin, TangentNonLin, fold_weights  # noqa: F401
 
 __version__ = "0.1.0"

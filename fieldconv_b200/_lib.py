@@ -33,6 +33,7 @@ SIGNATURES = {
     "fcb_bwd_dense_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_aggregate_f32": [_P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _P],
     "fcb_gemm_workspace_bytes": [_I64, _I, _I64, _I, _I, _I, _I, _PSZ],
+    "fcb_gemm_tc_feasible": [_I, _I64, _I, _I, _I],
     "fcb_gemm_f32": [_P, _P, _P, _I64, _I, _I64, _I64, _I64, _I64, _I, _I, _I64, _I64, _I64, _I, _P, _SZ, _I, _P],
     "fcb_sort_workspace_bytes": [_I64, _PSZ],
     "fcb_sort_pairs_u32": [_P, _P, _P, _P, _I64, _I, _P, _SZ, _P],
@@ -85,6 +86,10 @@ def query_bytes(name, *args):
     out = ctypes.c_size_t(0)
     call(name, *args, ctypes.byref(out))
     return int(out.value)
+
+
+def tc_feasible(n, k, trans_a=0, split_k=1, flags=GEMM_TC_3XTF32):
+    return bool(load().fcb_gemm_tc_feasible(int(n), int(k), int(trans_a), int(split_k), int(flags)))
 
 
 def ptr(t):

@@ -1,7 +1,7 @@
 // K1 / K5a — gauge-aligned gather + deterministic segmented reduction over CSR rows.
 //
 // Forward (transpose = 0), nn/field_conv.py:128-134 + utils/field.py:40-48 of the reference:
-//   contrib[i, r, c, m] = sum_{e in row i} sten[e,r,m] * x[src(e),c] * conj(u[src(e),c])^m
+//   contrib[i, r, m, c] = sum_{e in row i} sten[e,r,m] * x[src(e),c] * conj(u[src(e),c])^m
 // Backward gather (transpose = 1), the adjoint of the same sparse operator applied to gy:
 //   G[j, m, r, o]       = sum_{e in row j (by-source)} conj(sten[e,r,m]) * gy[tgt(e),o]
 // with sten[e,r,m] = w_r(e) * wxp_e * exp(i m theta_e), only rings f and f+1 non-zero
@@ -16,26 +16,39 @@
 
 namespace fcb {
 
-template <int B>
-struct Coef {
-    static constexpr int M = 2 * B + 1;
-    float2 a[M];
-    // a[B+m] = wxp * exp(i m theta), built by recurrence from rot = exp(i theta)
-    __device__ __forceinline__ void build(float2 wxp, float2 rot, bool conj_all) {
-        a[B] = wxp;
-#pragma unroll
-        for (int m = 1; m <= B; ++m) {
-            a[B + m] = cmul(a[B + m - 1], rot);
-            a[B - m] = cmul_conj(a[B - m + 1], rot);
-        }
-        if (conj_all) {
-#pragma unroll
-            for (int m = 0; m < M; ++m) a[m].y = -a[m].y;
-        }
-    }
-};
+// p[B+m] = conj?(wxp) * z * q^m for m = -B..B, by recurrence on the (unit-modulus) per-edge, per-channel
+// rotation q.  Forward: q = e^{i theta} conj(u) with u = z/|z| (1 at origin entries: utils/field.py:14-16,42-46),
+// so p[B+m] = sten-factor a_{e,m} * xhat[src,c,m] (nn/field_conv.py:128-130 folded with fc_precomp.py:83-95);
+// transposed: q = e^{-i theta}, p[B+m] = conj(a_{e,m}) * gy.  2 + 2B complex products per (edge, channel).
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
-// xh[B+m] = z * conj(u)^m, u = z/|z| (1 at origin entries: utils/field.py:14-16,42-46)
+template <int B, bool TRANSPOSE>
+__device__ __forceinline__ void edge_products(float2 z, float2 wxp, float2 rot, float2* p) {
+    float2 q;
+    if (!TRANSPOSE) {
+        // branch-free: at origin entries (|re|,|im| < 1e-7) the selects discard the inf/NaN of rsqrt(0)
+        const bool origin = (fabsf(z.x) < 1e-7f) && (fabsf(z.y) < 1e-7f);
+        const float ri = rsqrt_ftz(fmaf(z.x, z.x, z.y * z.y));
+        const float ux = origin ? 1.f : z.x * ri;
+        const float uy = origin ? 0.f : z.y * ri;
+        q = cmul_conj(rot, make_float2(ux, uy));
+        p[B] = cmul(wxp, z);
+    } else {
+        q = make_float2(rot.x, -rot.y);
+        p[B] = cmul_conj(z, wxp);
+    }
+#pragma unroll
+    for (int m = 1; m <= B; ++m) {
+        p[B + m] = cmul(p[B + m - 1], q);
+        p[B - m] = cmul_conj(p[B - m + 1], q);
+    }
+}
+
+// xh[B+m] = z * conj(u)^m (dense-stencil path)
 template <int B>
 __device__ __forceinline__ void gauge_align(float2 z, float2* xh) {
     const bool origin = (fabsf(z.x) < 1e-7f) && (fabsf(z.y) < 1e-7f);
@@ -50,35 +63,21 @@ __device__ __forceinline__ void gauge_align(float2 z, float2* xh) {
     }
 }
 
-// store the 2 x M complex values a lane holds for one ring
-template <int M, bool TRANSPOSE>
-__device__ __forceinline__ void store_ring(float4* __restrict__ orow, const float2 (&acc)[2][M], int ring, int cp, int C,
-                                           int R) {
-    if (!TRANSPOSE) {
-        // out[row][ring][c][m]: channels 2cp, 2cp+1 -> 2M consecutive complex = M float4
-        float4* dst = orow + ((int64_t)ring * C + 2 * cp) * M / 2;
-        float tmp[4 * M];
+// store the 2 x M complex values a lane holds for one ring: one float4 (channels 2cp, 2cp+1) per m, `m_stride`
+// float4 apart.  Forward layout out[row][ring][m][c] (m_stride = C/2), transposed layout out[row][m][ring][o]
+// (m_stride = R*C/2): in both, consecutive lanes write consecutive 16-byte pieces -> full-line coalesced stores.
+template <int M>
+__device__ __forceinline__ void store_ring(float4* __restrict__ dst, const float2 (&acc)[2][M], int64_t m_stride) {
 #pragma unroll
-        for (int m = 0; m < M; ++m) {
-            tmp[2 * m] = acc[0][m].x;
-            tmp[2 * m + 1] = acc[0][m].y;
-            tmp[2 * M + 2 * m] = acc[1][m].x;
-            tmp[2 * M + 2 * m + 1] = acc[1][m].y;
-        }
-#pragma unroll
-        for (int q = 0; q < M; ++q) dst[q] = make_float4(tmp[4 * q], tmp[4 * q + 1], tmp[4 * q + 2], tmp[4 * q + 3]);
-    } else {
-        // out[row][m][ring][o]: one float4 (channels 2cp, 2cp+1) per m
-#pragma unroll
-        for (int m = 0; m < M; ++m)
-            orow[((int64_t)(m * R + ring) * C) / 2 + cp] = make_float4(acc[0][m].x, acc[0][m].y, acc[1][m].x, acc[1][m].y);
-    }
+    for (int m = 0; m < M; ++m) dst[m * m_stride] = make_float4(acc[0][m].x, acc[0][m].y, acc[1][m].x, acc[1][m].y);
 }
 
+// The two live rings sit in two fixed accumulator sets selected by ring
+// parity (ring r lives in acc[r & 1]), so sliding the two-ring window costs one store + one clear, no moves.
 template <int B, bool TRANSPOSE>
-__global__ void __launch_bounds__(256) k_aggregate(const float4* __restrict__ feat, const int32_t* __restrict__ rowptr,
-                                                   const int4* __restrict__ rec, const float2* __restrict__ rot,
-                                                   float4* __restrict__ out, int64_t N, int C, int R) {
+__global__ void __launch_bounds__(256, 2) k_aggregate(const float4* __restrict__ feat, const int32_t* __restrict__ rowptr,
+                                                      const int4* __restrict__ rec, const float2* __restrict__ rot,
+                                                      float4* __restrict__ out, int64_t N, int C, int R) {
     constexpr int M = 2 * B + 1;
     const int P = C >> 1;
     const int64_t lane_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -86,62 +85,82 @@ __global__ void __launch_bounds__(256) k_aggregate(const float4* __restrict__ fe
     if (row >= N) return;
     const int cp = (int)(lane_id - row * P);
 
-    float2 accF[2][M], accC[2][M];
+    float2 acc0[2][M], acc1[2][M];   // even rings / odd rings
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-        accF[0][m] = accF[1][m] = make_float2(0.f, 0.f);
-        accC[0][m] = accC[1][m] = make_float2(0.f, 0.f);
+        acc0[0][m] = acc0[1][m] = make_float2(0.f, 0.f);
+        acc1[0][m] = acc1[1][m] = make_float2(0.f, 0.f);
     }
-    float4* orow = out + row * ((int64_t)R * C * M / 2);
+    // where ring 0 of this lane goes, and how far apart rings are (float4 units)
+    float4* dst = out + row * ((int64_t)R * C * M / 2) + cp;
+    const int ring_stride = TRANSPOSE ? P : P * M;
+    const int64_t m_stride = TRANSPOSE ? (int64_t)R * P : (int64_t)P;
+    const float4* fbase = feat + cp;
+
+    // ring fcur is complete: write it once and clear its accumulator set (it becomes ring fcur + 2)
+    auto retire = [&](int ring) {
+        if (ring & 1) {
+            store_ring<M>(dst, acc1, m_stride);
+#pragma unroll
+            for (int m = 0; m < M; ++m) acc1[0][m] = acc1[1][m] = make_float2(0.f, 0.f);
+        } else {
+            store_ring<M>(dst, acc0, m_stride);
+#pragma unroll
+            for (int m = 0; m < M; ++m) acc0[0][m] = acc0[1][m] = make_float2(0.f, 0.f);
+        }
+        dst += ring_stride;
+    };
 
     int fcur = 0;
     const int p0 = rowptr[row], p1 = rowptr[row + 1];
-    for (int p = p0; p < p1; ++p) {
-        const int4 rc = __ldg(rec + p);
-        const float2 rt = __ldg(rot + p);
-        const int f = (int)((uint32_t)rc.x >> NBR_BITS);
-        const int64_t nbr = (int64_t)((uint32_t)rc.x & NBR_MASK);
-        while (fcur < f) {  // ring fcur is complete: write it once, slide the two-ring window
-            store_ring<M, TRANSPOSE>(orow, accF, fcur, cp, C, R);
+    if (p0 < p1) {
+        // Software pipeline, two deep: while edge p is accumulated the feature row of edge p+1 and the plan record
+        // of edge p+2 are in flight, so the dependent chain record -> neighbour id -> feature row stays off the
+        // FMA pipe's critical path.  All prefetches are unconditional (indices clamped to the row's last edge) so
+        // the register rotation unrolls away.  (Measured alternatives that were slower: an explicit L1 prefetch of
+        // the record stream 8 edges ahead plus a two-deep feature gather — more registers, same stalls.)
+        const int last = p1 - 1;
+        int4 rcA = __ldg(rec + p0);
+        float2 rtA = __ldg(rot + p0);
+        const int pb = min(p0 + 1, last);
+        int4 rcB = __ldg(rec + pb);
+        float2 rtB = __ldg(rot + pb);
+        float4 vA = __ldg(fbase + ((uint32_t)rcA.x & NBR_MASK) * (uint32_t)P);
+#pragma unroll 2
+        for (int p = p0; p < p1; ++p) {
+            const int4 rc = rcA;
+            const float2 rt = rtA;
+            const float4 v = vA;
+            rcA = rcB;
+            rtA = rtB;
+            vA = __ldg(fbase + ((uint32_t)rcA.x & NBR_MASK) * (uint32_t)P);
+            const int pn = min(p + 2, last);
+            rcB = __ldg(rec + pn);
+            rtB = __ldg(rot + pn);
+
+            const int f = (int)((uint32_t)rc.x >> NBR_BITS);
+            while (fcur < f) retire(fcur++);
+            const float t = __int_as_float(rc.y);
+            const float omt = 1.0f - t;  // fc_precomp.py:25
+            const float w0 = (f & 1) ? t : omt;   // weight of the even-ring set
+            const float w1 = (f & 1) ? omt : t;   // weight of the odd-ring set
+            const float2 wxp = make_float2(__int_as_float(rc.z), __int_as_float(rc.w));
 #pragma unroll
-            for (int m = 0; m < M; ++m) {
-                accF[0][m] = accC[0][m];
-                accF[1][m] = accC[1][m];
-                accC[0][m] = accC[1][m] = make_float2(0.f, 0.f);
-            }
-            ++fcur;
-        }
-        const float4 v = __ldg(feat + nbr * P + cp);
-        const float t = __int_as_float(rc.y);
-        const float omt = 1.0f - t;  // fc_precomp.py:25
-        Coef<B> cf;
-        cf.build(make_float2(__int_as_float(rc.z), __int_as_float(rc.w)), rt, TRANSPOSE);
+            for (int ch = 0; ch < 2; ++ch) {
+                const float2 z = ch ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+                float2 pr[M];
+                edge_products<B, TRANSPOSE>(z, wxp, rt, pr);
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            const float2 z = ch ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
-            float2 xh[M];
-            if (!TRANSPOSE) gauge_align<B>(z, xh);
-#pragma unroll
-            for (int m = 0; m < M; ++m) {
-                const float2 pr = cmul(cf.a[m], TRANSPOSE ? z : xh[m]);
-                accF[ch][m].x = fmaf(omt, pr.x, accF[ch][m].x);
-                accF[ch][m].y = fmaf(omt, pr.y, accF[ch][m].y);
-                accC[ch][m].x = fmaf(t, pr.x, accC[ch][m].x);
-                accC[ch][m].y = fmaf(t, pr.y, accC[ch][m].y);
+                for (int m = 0; m < M; ++m) {
+                    acc0[ch][m].x = fmaf(w0, pr[m].x, acc0[ch][m].x);
+                    acc0[ch][m].y = fmaf(w0, pr[m].y, acc0[ch][m].y);
+                    acc1[ch][m].x = fmaf(w1, pr[m].x, acc1[ch][m].x);
+                    acc1[ch][m].y = fmaf(w1, pr[m].y, acc1[ch][m].y);
+                }
             }
         }
     }
-    while (fcur < R - 1) {
-        store_ring<M, TRANSPOSE>(orow, accF, fcur, cp, C, R);
-#pragma unroll
-        for (int m = 0; m < M; ++m) {
-            accF[0][m] = accC[0][m];
-            accF[1][m] = accC[1][m];
-            accC[0][m] = accC[1][m] = make_float2(0.f, 0.f);
-        }
-        ++fcur;
-    }
-    store_ring<M, TRANSPOSE>(orow, accF, R - 1, cp, C, R);
+    while (fcur < R) retire(fcur++);
 }
 
 // Dense-stencil variant: arbitrary supp_sten (E,R,M), one lane per (row, ring, channel pair).
@@ -186,7 +205,7 @@ __global__ void __launch_bounds__(256) k_aggregate_dense(const float4* __restric
         }
     }
     float4* orow = out + row * ((int64_t)R * C * M / 2);
-    store_ring<M, TRANSPOSE>(orow, acc, ring, cp, C, R);
+    store_ring<M>(orow + (TRANSPOSE ? (int64_t)ring * P : (int64_t)ring * M * P) + cp, acc, TRANSPOSE ? (int64_t)R * P : (int64_t)P);
 }
 
 template <bool TRANSPOSE>
@@ -219,7 +238,7 @@ int launch_aggregate(const float* feat, const int32_t* rowptr, const void* rec, 
     FCB_REQUIRE(B >= 0 && B <= FCB_MAX_BAND_LIMIT, FCB_E_UNSUPPORTED, "aggregate: band_limit %d unsupported", B);
     FCB_REQUIRE((C & 1) == 0, FCB_E_ALIGN, "aggregate: channel count must be even (16-byte feature rows)");
     FCB_REQUIRE(aligned16(feat) && aligned16(out) && aligned16(rec), FCB_E_ALIGN, "aggregate: pointers must be 16-byte aligned");
-    FCB_REQUIRE(N * (int64_t)(C / 2) / 256 < 0x7fffffffLL, FCB_E_UNSUPPORTED, "aggregate: grid too large");
+    FCB_REQUIRE(N * (int64_t)(C / 2) < 0xffffffffLL, FCB_E_UNSUPPORTED, "aggregate: N*C/2 must fit 32 bits");
     return transpose ? dispatch_aggregate<true>(feat, rowptr, rec, rot, out, N, C, B, R, st)
                      : dispatch_aggregate<false>(feat, rowptr, rec, rot, out, N, C, B, R, st);
 }

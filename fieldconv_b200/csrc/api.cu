@@ -40,15 +40,15 @@ void set_error(const char* fmt, ...) {
 
 // ----------------------------------------------------------------------------- weight packing
 // W is complex (Co,Ci,R,M) as folded by the host from (zonal, spherical, phase) — nn/field_conv.py:10-33.
-// Forward operand: Bw[2k+a][2o+b], k = (r*Ci + c)*M + m (ring-major, matching contrib's layout).
+// Forward operand: Bw[2k+a][2o+b], k = (r*M + m)*Ci + c (ring-major, channel fastest: contrib's layout).
 __global__ void k_pack_w_fwd(const float2* __restrict__ W, float* __restrict__ Bw, int Ci, int Co, int R, int M) {
     const int64_t K = (int64_t)R * Ci * M;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= K * Co) return;
     const int o = (int)(i % Co);
     const int64_t k = i / Co;
-    const int m = (int)(k % M);
-    const int c = (int)((k / M) % Ci);
+    const int c = (int)(k % Ci);
+    const int m = (int)((k / Ci) % M);
     const int r = (int)(k / ((int64_t)M * Ci));
     const float2 w = W[(((int64_t)o * Ci + c) * R + r) * M + m];
     float* row0 = Bw + (2 * k) * (2 * (int64_t)Co) + 2 * o;
@@ -81,8 +81,8 @@ __global__ void k_combine_gw(const float* __restrict__ P, float2* __restrict__ g
     if (i >= K * Co) return;
     const int o = (int)(i % Co);
     const int64_t k = i / Co;
-    const int m = (int)(k % M);
-    const int c = (int)((k / M) % Ci);
+    const int c = (int)(k % Ci);
+    const int m = (int)((k / Ci) % M);
     const int r = (int)(k / ((int64_t)M * Ci));
     const float* row0 = P + (2 * k) * (2 * (int64_t)Co) + 2 * o;
     const float* row1 = row0 + 2 * (int64_t)Co;

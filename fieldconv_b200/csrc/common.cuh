@@ -85,12 +85,14 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
                 int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k,
                 void* ws, size_t ws_bytes, int flags, cudaStream_t st);
 size_t gemm_tc_ws_bytes(int N, int64_t K, int batch);
+// column-chunk width + number of hi*hi accumulators for `ksteps` accumulating MMA steps (0: tensor cores not usable)
+int gemm_tc_plan(int N, int64_t ksteps, int mode, int* n_main);
 int launch_gemm_tc_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
-                      int64_t ldc, int split, int64_t k_per_split, float* parts, int mode, cudaStream_t st);
+                      int64_t ldc, int split, int64_t k_per_split, float* parts, int mode, int n_main, cudaStream_t st);
 int launch_reduce_splits(const float* partials, float* C, int64_t M, int N, int64_t ldc, int64_t sc, int batch, int split_k,
                          cudaStream_t st);
 int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
-                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int mode, void* ws, size_t ws_bytes,
-                      cudaStream_t st);
+                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int mode, int n_main, void* ws,
+                      size_t ws_bytes, cudaStream_t st);
 
 }  // namespace fcb

@@ -182,14 +182,24 @@ static int dispatch_gemm(const float* A, const float* Bm, float* C, int64_t M, i
     return FCB_OK;
 }
 
-static bool use_tc(int N, int64_t K, int trans_a, int batch, int flags) {
+static int64_t tc_ksteps(int64_t K, int trans_a, int split_k) {
+    if (!trans_a) return (K + 31) / 32 * 4;
+    int64_t kps = (K + split_k - 1) / split_k;
+    kps = (kps + 31) / 32 * 32;
+    return kps / 8;
+}
+
+// tensor cores are used when the mode asks for them and the accumulation plan fits TMEM (gemm_tc_plan)
+static bool use_tc(int N, int64_t K, int trans_a, int batch, int split_k, int flags) {
     const int mode = flags & FCB_GEMM_MASK;
-    if (!(mode == FCB_GEMM_TC_3XTF32 || mode == FCB_GEMM_TC_TF32) || N > 256 || N <= 0 || K <= 0) return false;
-    return trans_a ? batch == 1 : true;
+    if (!(mode == FCB_GEMM_TC_3XTF32 || mode == FCB_GEMM_TC_TF32) || N <= 0 || K <= 0) return false;
+    if (trans_a && batch != 1) return false;
+    int n_main;
+    return gemm_tc_plan(N, tc_ksteps(K, trans_a, split_k), mode, &n_main) > 0;
 }
 
 size_t gemm_ws_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags) {
-    if (use_tc(N, K, trans_a, batch, flags) && !trans_a) return gemm_tc_ws_bytes(N, K, batch);
+    if (use_tc(N, K, trans_a, batch, split_k, flags) && !trans_a) return gemm_tc_ws_bytes(N, K, batch);
     return split_k > 1 ? align_up((size_t)split_k * batch * M * N * 4, 256) : 0;
 }
 
@@ -206,17 +216,37 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
                 size_t ws_bytes, int flags, cudaStream_t st) {
     FCB_REQUIRE(A && Bm && C, FCB_E_ARG, "gemm: null pointer");
     FCB_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 1 && split_k >= 1, FCB_E_ARG, "gemm: bad sizes");
-    if (use_tc(N, K, trans_a, batch, flags) && !trans_a && (ldc % 4) == 0 && (sc % 4) == 0 && aligned16(C))
-        return launch_gemm_tc_nn(A, Bm, C, M, N, K, lda, ldb, ldc, batch, sa, sb, sc, flags & FCB_GEMM_MASK, ws, ws_bytes, st);
+    const int mode = flags & FCB_GEMM_MASK;
+    if (use_tc(N, K, trans_a, batch, split_k, flags) && !trans_a && (ldc % 4) == 0 && (sc % 4) == 0 && aligned16(C)) {
+        int n_main = 1;
+        const int chunk = gemm_tc_plan(N, tc_ksteps(K, 0, 1), mode, &n_main);
+        for (int n0 = 0; n0 < N; n0 += chunk) {      // column chunks (one unless N is wide): same A, offset B and C
+            const int nc = N - n0 < chunk ? N - n0 : chunk;
+            int rc = launch_gemm_tc_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, mode, n_main, ws,
+                                       ws_bytes, st);
+            if (rc) return rc;
+        }
+        return FCB_OK;
+    }
     float* partials = static_cast<float*>(ws);
-    if (use_tc(N, K, trans_a, batch, flags) && trans_a && (lda % 4) == 0 && (ldb % 4) == 0 && aligned16(A) && aligned16(Bm)) {
+    if (use_tc(N, K, trans_a, batch, split_k, flags) && trans_a && (lda % 4) == 0 && (ldb % 4) == 0 && aligned16(A) &&
+        aligned16(Bm)) {
         FCB_REQUIRE(split_k == 1 || (partials && ws_bytes >= (size_t)split_k * M * N * 4), FCB_E_WORKSPACE,
                     "gemm: split_k > 1 needs a workspace of split_k*M*N floats");
         int64_t kps_tc = (K + split_k - 1) / split_k;
         kps_tc = (kps_tc + 31) / 32 * 32;
-        int rc = launch_gemm_tc_tn(A, Bm, C, M, N, K, lda, ldb, ldc, split_k, kps_tc, partials, flags & FCB_GEMM_MASK, st);
-        if (rc || split_k == 1) return rc;
-        return launch_reduce_splits(partials, C, M, N, ldc, 0, 1, split_k, st);
+        int n_main = 1;
+        const int chunk = gemm_tc_plan(N, kps_tc / 8, mode, &n_main);
+        for (int n0 = 0; n0 < N; n0 += chunk) {
+            const int nc = N - n0 < chunk ? N - n0 : chunk;
+            int rc = launch_gemm_tc_tn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, split_k, kps_tc, partials, mode, n_main, st);
+            if (rc) return rc;
+            if (split_k > 1) {
+                rc = launch_reduce_splits(partials, C + n0, M, nc, ldc, 0, 1, split_k, st);
+                if (rc) return rc;
+            }
+        }
+        return FCB_OK;
     }
     FCB_REQUIRE(split_k == 1 || (partials && ws_bytes >= (size_t)split_k * batch * M * N * 4), FCB_E_WORKSPACE,
                 "gemm: split_k > 1 needs a workspace of split_k*batch*M*N floats");
@@ -243,6 +273,10 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
 }
 
 }  // namespace fcb
+
+extern "C" int fcb_gemm_tc_feasible(int N, int64_t K, int trans_a, int split_k, int flags) {
+    return fcb::use_tc(N, K, trans_a, 1, split_k < 1 ? 1 : split_k, flags) ? 1 : 0;
+}
 
 extern "C" int fcb_gemm_workspace_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags,
                                         size_t* bytes) {

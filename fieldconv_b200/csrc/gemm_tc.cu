@@ -32,6 +32,7 @@ constexpr int N_PROD = N_PROD_WARPS * 32;        // producer threads
 constexpr int A_F4 = BM * KC / 4 / N_PROD;        // float4 of the A tile per producer thread and stage (2)
 constexpr int THREADS = (N_PROD_WARPS + 2) * 32;
 constexpr uint32_t A_PLANE = BM * KC * 4;   // 16 KB
+constexpr int PF = 6;          // producer prefetch depth: chunks of A in flight in registers (memory-level parallelism)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -112,6 +113,13 @@ __device__ __forceinline__ float tf32_hi(float x) {
     return __uint_as_float(r);
 }
 
+// debug timeline (tools/trace_gemm.py): when non-null, CTA 0 records clock64() at pipeline events
+__device__ long long* g_trace = nullptr;
+#define FCB_TRACE(slot, kc, cond)                                                          \
+    do {                                                                                   \
+        if (trace && (cond) && (kc) < 64) trace[(slot) * 64 + (kc)] = clock64();           \
+    } while (0)
+
 struct Params {
     const float* A;
     const float* Bp;   // packed B: [batch][chunk][plane(hi,lo)][Npad][32] swizzled
@@ -141,6 +149,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(sm + (tmem_slot - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long* const trace = (blockIdx.x == 0 && blockIdx.y == 0) ? g_trace : nullptr;
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int batch = blockIdx.y;
     const float* A = p.A + batch * p.sa;
@@ -169,8 +178,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
     if (warp < N_PROD_WARPS) {
         // ------------------------------------------------------------------ producers
         const int t = threadIdx.x;   // 0..N_PROD-1
-        // Software pipeline: the global loads of chunks kc+1 and kc+2 are in flight (registers) while chunk kc is
-        // split and stored.  All addressing is hoisted: per thread A_F4 source pointers and shared-memory offsets.
+        // Software pipeline: the global loads of chunks kc+1 .. kc+PF-1 are in flight (registers) while chunk kc is
+        // split and stored: with ~2 us of loaded HBM latency the bytes in flight per SM set the streaming rate.  All addressing is hoisted: per thread A_F4 source pointers and shared-memory offsets.
         const float* src[A_F4];
         uint32_t off[A_F4];
         int kcol[A_F4];
@@ -186,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
         uint8_t* const hi_base = sm + (a_hi0 - base);
         uint8_t* const lo_base = sm + (a_lo0 - base);
         const bool split3 = (p.mode == FCB_GEMM_TC_3XTF32);
-        float4 v[3][A_F4];
+        float4 v[PF][A_F4];
         auto issue = [&](int kc, float4(&dst)[A_F4]) {
             const int64_t k0 = (int64_t)kc * KC;
             if (k0 + KC <= p.K) {                        // full chunk (warp-uniform)
@@ -207,10 +216,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
                 }
             }
         };
+        uint32_t ps = 0, pph = 1;     // producer stage / parity of the `empty` barrier it waits for
         auto commit = [&](int kc, const float4(&sv)[A_F4]) {
-            const int s = kc % S;
-            const uint32_t ph = (uint32_t)(kc / S) & 1u;
-            mbar_wait(empty(s), ph ^ 1u);
+            const uint32_t s = ps;
+            FCB_TRACE(0, kc, t == 0);
+            mbar_wait(empty(s), pph);
+            FCB_TRACE(1, kc, t == 0);
 #pragma unroll
             for (int i = 0; i < A_F4; ++i) {
                 const float4 hi = make_float4(tf32_hi(sv[i].x), tf32_hi(sv[i].y), tf32_hi(sv[i].z), tf32_hi(sv[i].w));
@@ -222,15 +233,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(full_a(s));
+            FCB_TRACE(2, kc, t == 0);
+            if (++ps == (uint32_t)S) { ps = 0; pph ^= 1u; }
         };
-        if (p.nchunks > 0) issue(0, v[0]);
-        if (p.nchunks > 1) issue(1, v[1]);
-        for (int kc = 0; kc < p.nchunks; kc += 3) {
 #pragma unroll
-            for (int u = 0; u < 3; ++u) {
+        for (int u = 0; u < PF - 1; ++u)
+            if (u < p.nchunks) issue(u, v[u]);
+        for (int kc = 0; kc < p.nchunks; kc += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
                 const int k = kc + u;
                 if (k < p.nchunks) {
-                    if (k + 2 < p.nchunks) issue(k + 2, v[(u + 2) % 3]);
+                    if (k + PF - 1 < p.nchunks) issue(k + PF - 1, v[(u + PF - 1) % PF]);
                     commit(k, v[u]);
                 }
             }
@@ -274,31 +288,44 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
         }
     } else if (warp == N_PROD_WARPS) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
+        // Everything this thread needs per MMA is kept in counters / pre-built descriptors: a single thread
+        // issues dependent scalar instructions ~5 cycles apart, so divisions or descriptor rebuilds in this loop
+        // would cost more than the MMAs themselves (measured: ~270 cycles per k-step before, 48-cycle MMAs).
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(p.Npad);
+            const bool x3 = (p.mode == FCB_GEMM_TC_3XTF32);
+            const uint64_t a_hi_d = make_desc_k_sw128(a_hi0), a_lo_d = make_desc_k_sw128(a_lo0);
+            const uint64_t b_hi_d = make_desc_k_sw128(b0), b_lo_d = make_desc_k_sw128(b0 + b_plane);
+            const uint64_t a_step = (uint64_t)(A_PLANE >> 4), b_step = (uint64_t)((2 * b_plane) >> 4);
+            const uint32_t d_x = tmem_d + (uint32_t)(p.n_main * p.Npad);
+            const uint32_t n_main = (uint32_t)p.n_main, npad = (uint32_t)p.Npad;
+            uint32_t s = 0, ph = 0;          // stage, phase
+            uint32_t acc = 0, d_main = tmem_d, first = n_main;   // round-robin hi*hi accumulator; `first` MMAs overwrite
+            uint32_t x_acc = 0;              // 0 only for the very first cross-term MMA
             for (int kc = 0; kc < p.nchunks; ++kc) {
-                const int s = kc % S;
-                const uint32_t ph = (uint32_t)(kc / S) & 1u;
+                FCB_TRACE(3, kc, true);
                 mbar_wait(full_a(s), ph);
+                FCB_TRACE(4, kc, true);
                 mbar_wait(full_b(s), ph);
+                FCB_TRACE(5, kc, true);
                 tc_fence_after();
-                const uint64_t a_hi = make_desc_k_sw128(a_hi0 + s * A_PLANE);
-                const uint64_t a_lo = make_desc_k_sw128(a_lo0 + s * A_PLANE);
-                const uint64_t b_hi = make_desc_k_sw128(b0 + s * 2 * b_plane);
-                const uint64_t b_lo = make_desc_k_sw128(b0 + s * 2 * b_plane + b_plane);
+                const uint64_t a_hi = a_hi_d + s * a_step, a_lo = a_lo_d + s * a_step;
+                const uint64_t b_hi = b_hi_d + s * b_step, b_lo = b_lo_d + s * b_step;
 #pragma unroll
                 for (int ks = 0; ks < KC / 8; ++ks) {
                     const uint64_t adv = (uint64_t)(ks * 2);   // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzle row
-                    const int step = kc * (KC / 8) + ks;
-                    const uint32_t d_main = tmem_d + (uint32_t)((step % p.n_main) * p.Npad);
-                    tc_mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, step >= p.n_main ? 1u : 0u);
-                    if (p.mode == FCB_GEMM_TC_3XTF32) {
-                        const uint32_t d_x = tmem_d + (uint32_t)(p.n_main * p.Npad);
-                        tc_mma_tf32(d_x, a_lo + adv, b_hi + adv, idesc, step > 0 ? 1u : 0u);
+                    tc_mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, first ? 0u : 1u);
+                    if (first) --first;
+                    if (++acc == n_main) { acc = 0; d_main = tmem_d; } else d_main += npad;
+                    if (x3) {
+                        tc_mma_tf32(d_x, a_lo + adv, b_hi + adv, idesc, x_acc);
                         tc_mma_tf32(d_x, a_hi + adv, b_lo + adv, idesc, 1u);
+                        x_acc = 1u;
                     }
                 }
                 tc_commit(empty(s));      // frees the stage once these MMAs have read it
+                FCB_TRACE(6, kc, true);
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
             }
             tc_commit(tmem_full);
         }
@@ -307,12 +334,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
         // ------------------------------------------------------------------ B loader (one thread, TMA bulk copies)
         if (lane == 0) {
             const uint32_t bytes = (p.mode == FCB_GEMM_TC_3XTF32 ? 2u : 1u) * b_plane;
+            const float* src = Bp;
+            const int64_t src_step = (int64_t)2 * p.Npad * KC;
+            uint32_t s = 0, ph = 1;
             for (int kc = 0; kc < p.nchunks; ++kc) {
-                const int s = kc % S;
-                const uint32_t ph = (uint32_t)(kc / S) & 1u;
-                mbar_wait(empty(s), ph ^ 1u);
+                mbar_wait(empty(s), ph);
+                FCB_TRACE(7, kc, true);
                 mbar_expect_tx(full_b(s), bytes);
-                bulk_copy_g2s(b0 + s * 2 * b_plane, Bp + (int64_t)kc * 2 * p.Npad * KC, bytes, full_b(s));
+                bulk_copy_g2s(b0 + s * 2 * b_plane, src, bytes, full_b(s));
+                src += src_step;
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
             }
         }
         __syncwarp();
@@ -352,6 +383,8 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
 }
 
 constexpr int KV = 32;   // vertices per stage (4 MMA K-steps of 8)
+// producer prefetch depth of the TN kernel (chunks of both operands in flight in registers), bounded by registers
+__host__ __device__ constexpr int pft_for(int nb4) { return nb4 <= 3 ? 4 : (nb4 == 4 ? 3 : 2); }
 
 template <int NB4>   // float4 of the B operand per producer thread and stage == number of 32-feature atoms
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
@@ -440,7 +473,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
             }
             return r;
         };
-        float4 va[2][A_F4], vb[2][B_F4];
+        constexpr int PFT = pft_for(NB4);
+        float4 va[PFT][A_F4], vb[PFT][B_F4];
         auto issue = [&](int kc, float4(&da)[A_F4], float4(&db)[B_F4]) {
             const int64_t v0 = kb + (int64_t)kc * KV;
             const bool full_chunk = (v0 + KV <= ke);
@@ -459,10 +493,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
         uint8_t* const alo = sm + (a_lo0 - base);
         uint8_t* const bhi = sm + (b_hi0 - base);
         uint8_t* const blo = sm + (b_lo0 - base);
+        uint32_t ps = 0, pph = 1;
         auto commit = [&](int kc, const float4(&sa)[A_F4], const float4(&sb)[B_F4]) {
-            const int s = kc % S;
-            const uint32_t ph = (uint32_t)(kc / S) & 1u;
-            mbar_wait(empty(s), ph ^ 1u);
+            const uint32_t s = ps;
+            mbar_wait(empty(s), pph);
 #pragma unroll
             for (int i = 0; i < A_F4; ++i) {
                 const float4 hi = make_float4(tf32_hi(sa[i].x), tf32_hi(sa[i].y), tf32_hi(sa[i].z), tf32_hi(sa[i].w));
@@ -484,14 +518,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(full(s));
+            if (++ps == (uint32_t)S) { ps = 0; pph ^= 1u; }
         };
-        if (nchunks > 0) issue(0, va[0], vb[0]);
-        for (int kc = 0; kc < nchunks; kc += 2) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < PFT - 1; ++u)
+            if (u < nchunks) issue(u, va[u], vb[u]);
+        for (int kc = 0; kc < nchunks; kc += PFT) {
+#pragma unroll
+            for (int u = 0; u < PFT; ++u) {
                 const int k = kc + u;
                 if (k < nchunks) {
-                    if (k + 1 < nchunks) issue(k + 1, va[u ^ 1], vb[u ^ 1]);
+                    if (k + PFT - 1 < nchunks) issue(k + PFT - 1, va[(u + PFT - 1) % PFT], vb[(u + PFT - 1) % PFT]);
                     commit(k, va[u], vb[u]);
                 }
             }
@@ -527,30 +564,36 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
         }
     } else if (warp == N_PROD_WARPS) {
         if (lane == 0 && nchunks > 0) {
-            // D=f32, A=B=tf32, both MN-major (bits 15, 16), M=128, N=Npad
+            // D=f32, A=B=tf32, both MN-major (bits 15, 16), M=128, N=Npad.  Counters and pre-built descriptors
+            // only: see the NN issuer.
             const uint32_t idesc = make_idesc_tf32(p.Npad) | (1u << 15) | (1u << 16);
             const uint32_t sbo_a = 4 * 512, sbo_b = (uint32_t)p.nb_atoms * 512;   // between 4-vertex K groups
+            const uint64_t a_hi_d = make_desc_mn_sw128(a_hi0, 512, sbo_a), a_lo_d = make_desc_mn_sw128(a_lo0, 512, sbo_a);
+            const uint64_t b_hi_d = make_desc_mn_sw128(b_hi0, 512, sbo_b), b_lo_d = make_desc_mn_sw128(b_lo0, 512, sbo_b);
+            const uint64_t a_stage = (uint64_t)(A_PLANE >> 4), b_stage = (uint64_t)(b_plane >> 4);
+            const uint64_t a_kg = (uint64_t)((2 * sbo_a) >> 4), b_kg = (uint64_t)((2 * sbo_b) >> 4);   // 8 vertices
+            const uint32_t d_x = tmem_d + (uint32_t)(p.n_main * p.Npad);
+            const uint32_t n_main = (uint32_t)p.n_main, npad = (uint32_t)p.Npad;
+            uint32_t s = 0, ph = 0, acc = 0, d_main = tmem_d, first = n_main, x_acc = 0;
             for (int kc = 0; kc < nchunks; ++kc) {
-                const int s = kc % S;
-                const uint32_t ph = (uint32_t)(kc / S) & 1u;
                 mbar_wait(full(s), ph);
                 tc_fence_after();
+                uint64_t a_hi = a_hi_d + s * a_stage, a_lo = a_lo_d + s * a_stage;
+                uint64_t b_hi = b_hi_d + s * b_stage, b_lo = b_lo_d + s * b_stage;
 #pragma unroll
                 for (int kg = 0; kg < KV / 8; ++kg) {
-                    const uint64_t a_hi = make_desc_mn_sw128(a_hi0 + s * A_PLANE + 2 * kg * sbo_a, 512, sbo_a);
-                    const uint64_t a_lo = make_desc_mn_sw128(a_lo0 + s * A_PLANE + 2 * kg * sbo_a, 512, sbo_a);
-                    const uint64_t b_hi = make_desc_mn_sw128(b_hi0 + s * b_plane + 2 * kg * sbo_b, 512, sbo_b);
-                    const uint64_t b_lo = make_desc_mn_sw128(b_lo0 + s * b_plane + 2 * kg * sbo_b, 512, sbo_b);
-                    const int step = kc * (KV / 8) + kg;
-                    const uint32_t d_main = tmem_d + (uint32_t)((step % p.n_main) * p.Npad);
-                    tc_mma_tf32(d_main, a_hi, b_hi, idesc, step >= p.n_main ? 1u : 0u);
+                    tc_mma_tf32(d_main, a_hi, b_hi, idesc, first ? 0u : 1u);
+                    if (first) --first;
+                    if (++acc == n_main) { acc = 0; d_main = tmem_d; } else d_main += npad;
                     if (split3) {
-                        const uint32_t d_x = tmem_d + (uint32_t)(p.n_main * p.Npad);
-                        tc_mma_tf32(d_x, a_lo, b_hi, idesc, step > 0 ? 1u : 0u);
+                        tc_mma_tf32(d_x, a_lo, b_hi, idesc, x_acc);
                         tc_mma_tf32(d_x, a_hi, b_lo, idesc, 1u);
+                        x_acc = 1u;
                     }
+                    a_hi += a_kg; a_lo += a_kg; b_hi += b_kg; b_lo += b_kg;
                 }
                 tc_commit(empty(s));
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
             }
             tc_commit(tmem_full);
         }
@@ -587,6 +630,44 @@ __global__ void k_pack_b_tc(const float* __restrict__ B, float* __restrict__ Bp,
 
 }  // namespace tc
 
+}  // namespace fcb
+
+// debug: device buffer of 8*64 int64 receiving the pipeline timeline of CTA 0 of k_gemm_tc_nn (NULL = off)
+extern "C" int fcb_debug_trace(void* dev_buf) {
+    long long* p = static_cast<long long*>(dev_buf);
+    return cudaMemcpyToSymbol(fcb::tc::g_trace, &p, sizeof(p)) == cudaSuccess ? FCB_OK : FCB_E_CUDA;
+}
+
+namespace fcb {
+
+// tcgen05 accumulation into TMEM truncates (measured drift ~6e-8 per accumulating MMA), so no accumulator may
+// receive more than TC_MAX_ACC_MMAS of them inside the fp32 parity budget: the hi*hi products of a 3xTF32
+// contraction are dealt round-robin over n_main accumulators and wide outputs are cut into column chunks narrow
+// enough that n_main + 1 accumulators fit the 512 TMEM columns.  Returns the chunk width (0: not feasible).
+constexpr int64_t TC_MAX_ACC_MMAS = 400;
+int gemm_tc_plan(int N, int64_t ksteps, int mode, int* n_main_out) {
+    if (N <= 0) return 0;
+    if (mode == FCB_GEMM_TC_TF32) {
+        *n_main_out = 1;
+        return N < 256 ? N : 256;
+    }
+    const int64_t need = (ksteps + TC_MAX_ACC_MMAS - 1) / TC_MAX_ACC_MMAS;
+    const int widths[3] = {128, 64, 32};
+    for (int w : widths) {
+        const int nc = N < w ? N : w;
+        const int npad = (nc + 15) / 16 * 16;
+        const int avail = 512 / npad - 1;
+        if (avail >= 1 && need <= avail) {
+            int n_main = avail < 3 ? avail : 3;
+            if (n_main < need) n_main = (int)need;
+            if (n_main > ksteps) n_main = (int)(ksteps < 1 ? 1 : ksteps);
+            *n_main_out = n_main;
+            return nc;
+        }
+    }
+    return 0;
+}
+
 size_t gemm_tc_ws_bytes(int N, int64_t K, int batch) {
     const int npad = (N + 15) / 16 * 16;
     const int64_t nchunks = (K + tc::KC - 1) / tc::KC;
@@ -594,8 +675,8 @@ size_t gemm_tc_ws_bytes(int N, int64_t K, int batch) {
 }
 
 int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
-                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int mode, void* ws, size_t ws_bytes,
-                      cudaStream_t st) {
+                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int mode, int n_main, void* ws,
+                      size_t ws_bytes, cudaStream_t st) {
     FCB_REQUIRE(A && B && C && ws, FCB_E_ARG, "gemm_tc: null pointer");
     FCB_REQUIRE(M >= 0 && N > 0 && K > 0 && batch >= 1 && batch <= 65535, FCB_E_ARG, "gemm_tc: bad sizes");
     FCB_REQUIRE(N <= 256, FCB_E_UNSUPPORTED, "gemm_tc: N=%d > 256 not supported by one accumulator tile", N);
@@ -618,21 +699,15 @@ int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N
     p.M = M; p.K = K; p.lda = lda; p.ldc = ldc; p.sa = sa; p.sc = sc;
     p.bp_batch_stride = bp_stride;
     p.N = N; p.Npad = npad; p.nchunks = nchunks; p.mode = mode;
-    int n_main = 1;
-    if (mode == FCB_GEMM_TC_3XTF32) {
-        n_main = 512 / npad - 1;
-        if (n_main > 3) n_main = 3;
-        if (n_main < 1) n_main = 1;
-    }
-    const int64_t ksteps = (int64_t)nchunks * (tc::KC / 8);
-    if (n_main > ksteps) n_main = (int)ksteps;
+    FCB_REQUIRE(n_main >= 1 && npad * (n_main + (mode == FCB_GEMM_TC_3XTF32 ? 1 : 0)) <= 512, FCB_E_ARG,
+                "gemm_tc: accumulators do not fit TMEM");
     p.n_main = n_main;
     uint32_t cols = 32;
     while ((int)cols < npad * (n_main + (mode == FCB_GEMM_TC_3XTF32 ? 1 : 0))) cols <<= 1;
     p.tmem_cols = cols;
     const size_t stage_bytes = 2 * tc::A_PLANE + 2 * (size_t)npad * 128;
     int stages = (int)((220 * 1024 - 2048) / stage_bytes);
-    if (stages > 4) stages = 4;
+    if (stages > 8) stages = 8;
     if (stages > nchunks) stages = nchunks < 1 ? 1 : nchunks;
     FCB_REQUIRE(stages >= 1, FCB_E_UNSUPPORTED, "gemm_tc: tile does not fit shared memory");
     p.stages = stages;
@@ -653,7 +728,7 @@ int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N
 
 // P[Mr x N] = A^T B on the tensor cores; split >= 1 vertex ranges; `parts` (split*Mr*N floats) is used when split > 1.
 int launch_gemm_tc_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
-                      int64_t ldc, int split, int64_t k_per_split, float* parts, int mode, cudaStream_t st) {
+                      int64_t ldc, int split, int64_t k_per_split, float* parts, int mode, int n_main, cudaStream_t st) {
     FCB_REQUIRE(A && B && C, FCB_E_ARG, "gemm_tc_tn: null pointer");
     FCB_REQUIRE(N > 0 && N <= 256 && split >= 1 && split <= 65535, FCB_E_UNSUPPORTED, "gemm_tc_tn: unsupported shape");
     FCB_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && aligned16(A) && aligned16(B), FCB_E_ALIGN, "gemm_tc_tn: alignment");
@@ -668,21 +743,15 @@ int launch_gemm_tc_tn(const float* A, const float* B, float* C, int64_t Mr, int 
     p.k_per_split = k_per_split;
     p.part_stride = split > 1 ? Mr * (int64_t)N : 0;
     p.N = N; p.Npad = npad; p.nb_atoms = nb_atoms; p.mode = mode;
-    int n_main = 1;
-    if (mode == FCB_GEMM_TC_3XTF32) {
-        n_main = 512 / npad - 1;
-        if (n_main > 3) n_main = 3;
-        if (n_main < 1) n_main = 1;
-    }
-    const int64_t ksteps = (k_per_split + 7) / 8;
-    if (n_main > ksteps) n_main = (int)(ksteps < 1 ? 1 : ksteps);
+    FCB_REQUIRE(n_main >= 1 && npad * (n_main + (mode == FCB_GEMM_TC_3XTF32 ? 1 : 0)) <= 512, FCB_E_ARG,
+                "gemm_tc_tn: accumulators do not fit TMEM");
     p.n_main = n_main;
     uint32_t cols = 32;
     while ((int)cols < npad * (n_main + (mode == FCB_GEMM_TC_3XTF32 ? 1 : 0))) cols <<= 1;
     p.tmem_cols = cols;
     const size_t stage_bytes = 2 * tc::A_PLANE + 2 * (size_t)tc::KV * nb_atoms * 128;
     int stages = (int)((220 * 1024 - 2048) / stage_bytes);
-    if (stages > 4) stages = 4;
+    if (stages > 8) stages = 8;
     FCB_REQUIRE(stages >= 1, FCB_E_UNSUPPORTED, "gemm_tc_tn: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = stages * stage_bytes + 1024 + 8 * (2 * stages + 2) + 64;

@@ -14,27 +14,21 @@ import torch.nn as nn
 from torch.nn import Parameter
 
 from . import _lib, ops
+from .partition import MeshPartition, partitioned_field_conv
 from .plan import DensePlan, Plan, build_dense_plan
 
 _PRECISIONS = {"fp32": _lib.GEMM_SIMT_FP32, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32": _lib.GEMM_TC_TF32, "auto": -1}
-_AUTO_MAX_ACCUMULATES = 400     # tcgen05 accumulates truncate: ~6e-8 drift per MMA and accumulator
 
 
 def _resolve_precision(precision, ci, co, n_rings, band_limit):
-    """"auto": error-compensated tensor cores (3xTF32) when every TMEM accumulator of the three contractions
-    receives few enough MMAs to stay inside the fp32 path's 1e-5 parity budget, else the FP32-FMA kernels."""
+    """"auto": error-compensated tensor cores (3xTF32) when the library's accumulation plan (column chunks x TMEM
+    accumulators, at most 400 accumulating MMAs each — DESIGN.md §4) keeps the forward and the grad-x contractions
+    inside the fp32 path's 1e-5 parity budget, else the FP32-FMA kernels."""
     if precision != "auto":
         return _PRECISIONS[precision]
     m = 2 * band_limit + 1
-
-    def ok(n_cols, k_reals):
-        npad = (n_cols + 15) // 16 * 16
-        if npad > 256:
-            return False
-        n_main = max(1, min(3, 512 // npad - 1))
-        return (k_reals // 8) / n_main <= _AUTO_MAX_ACCUMULATES
-    fwd = ok(2 * co, 2 * n_rings * ci * m)
-    bwd = ok(2 * ci, 2 * n_rings * co)
+    fwd = _lib.tc_feasible(2 * co, 2 * n_rings * ci * m)
+    bwd = _lib.tc_feasible(2 * ci, 2 * n_rings * co)
     return _lib.GEMM_TC_3XTF32 if (fwd and bwd) else _lib.GEMM_SIMT_FP32
 
 
@@ -90,10 +84,12 @@ class FieldConv(nn.Module):
         return self._dense_cache[1]
 
     def forward(self, x, supp_edges=None, supp_sten=None, *, plan=None):
-        if isinstance(supp_edges, (Plan, DensePlan)):
+        if isinstance(supp_edges, (Plan, DensePlan, MeshPartition)):
             plan, supp_edges = supp_edges, None
         if not x.is_cuda:
             raise RuntimeError("fieldconv_b200.FieldConv runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if isinstance(plan, MeshPartition):      # one large mesh split across ranks: x holds this rank's owned rows
+            return partitioned_field_conv(self, x, plan)
         ci, co = self.in_channels, self.out_channels
         flags = _resolve_precision(self.precision, ci + ci % 2, co + co % 2, self.R, self.B)
         w = self.weight()
@@ -168,7 +164,7 @@ class FCResNetBlock(nn.Module):
         self.res = TangentLin(in_channels, out_channels)
 
     def forward(self, x, supp_edges=None, supp_sten=None, *, plan=None):
-        if isinstance(supp_edges, (Plan, DensePlan)):
+        if isinstance(supp_edges, (Plan, DensePlan, MeshPartition)):
             plan, supp_edges = supp_edges, None
         h = self.nonlin1(self.conv1(x, supp_edges, supp_sten, plan=plan))
         h = self.conv2(h, supp_edges, supp_sten, plan=plan)

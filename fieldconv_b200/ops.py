@@ -18,7 +18,18 @@ from torch import Tensor
 
 from . import _lib
 
-SAVE_CONTRIB_BYTES = int(os.environ.get("FIELDCONV_B200_SAVE_CONTRIB_BYTES", str(4 << 30)))
+# contrib (N x K complex) is kept for the weight gradient when it is at most this many bytes AND at most a quarter
+# of the device memory that is free at the time of the forward; otherwise the backward recomputes it.
+SAVE_CONTRIB_BYTES = int(os.environ.get("FIELDCONV_B200_SAVE_CONTRIB_BYTES", str(24 << 30)))
+
+
+def keep_contrib_default(nbytes, device):
+    if nbytes > SAVE_CONTRIB_BYTES:
+        return False
+    if nbytes <= (256 << 20):
+        return True
+    free, _ = torch.cuda.mem_get_info(device)
+    return nbytes <= free // 4
 
 
 def _real(t):
@@ -123,7 +134,7 @@ def field_conv(x, W, plan, band_limit, flags=0, keep_contrib=None):
     """y = FieldConv(x) for the compact plan; differentiable w.r.t. x and W."""
     n, ci = x.shape
     if keep_contrib is None:
-        keep_contrib = n * plan.n_rings * ci * (2 * band_limit + 1) * 8 <= SAVE_CONTRIB_BYTES
+        keep_contrib = keep_contrib_default(n * plan.n_rings * ci * (2 * band_limit + 1) * 8, x.device)
     y, _ = fc_fwd(x, W, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src, plan.rot_src,
                   band_limit, plan.n_rings, flags, bool(keep_contrib))
     return y

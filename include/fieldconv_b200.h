@@ -95,10 +95,10 @@ int fcb_plan_build_dense(const int64_t* edges_ji, int64_t E, int64_t N,
 /* ------------------------------------------------------------------ forward (K1 + K2)
  * Replaces nn/field_conv.py:128-137 (+ utils/field.py:40-48, + the weightContrib* reduction
  * :10-33 given the folded weight W[o,c,r,m] = coeff/(2B+1)):
- *   contrib[i, r, c, m] = sum_{e: tgt(e)=i} x[src(e),c] conj(u)^m * sten[e,r,m]   (deterministic
+ *   contrib[i, r, m, c] = sum_{e: tgt(e)=i} x[src(e),c] conj(u)^m * sten[e,r,m]   (deterministic
  *                         segmented reduction over the CSR row, fixed order)
- *   y[i, o]             = sum_{c,r,m} contrib[i,r,c,m] * W[o,c,r,m]
- * contrib (N x R*Ci*M complex, ring-major) is an OUTPUT the caller may keep for backward, or
+ *   y[i, o]             = sum_{c,r,m} contrib[i,r,m,c] * W[o,c,r,m]
+ * contrib (N x R*M*Ci complex, k = (r*M + m)*Ci + c) is an OUTPUT the caller may keep for backward, or
  * NULL on the fused tensor-core path that never materialises it.
  * W is complex (Co,Ci,R,M) contiguous.  M = 2*band_limit+1. */
 int fcb_fwd_workspace_bytes(int64_t N, int Ci, int Co, int band_limit, int R, int flags, size_t* bytes);
@@ -145,6 +145,9 @@ int fcb_aggregate_f32(const float* feat, const int32_t* rowptr, const void* rec,
  * The workspace size comes from fcb_gemm_workspace_bytes with the same arguments. */
 int fcb_gemm_workspace_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags,
                              size_t* bytes);
+/* 1 if fcb_gemm_f32 with these flags would run on the tensor cores inside the fp32 parity budget (the
+ * accumulation plan — column chunks x TMEM accumulators — fits), 0 if it would fall back to FP32 FMA. */
+int fcb_gemm_tc_feasible(int N, int64_t K, int trans_a, int split_k, int flags);
 int fcb_gemm_f32(const float* A, const float* B, float* C, int64_t M, int N, int64_t K,
                  int64_t lda, int64_t ldb, int64_t ldc, int trans_a, int batch, int64_t stride_a,
                  int64_t stride_b, int64_t stride_c, int split_k, void* workspace, size_t workspace_bytes,

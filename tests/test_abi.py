@@ -61,3 +61,13 @@ def test_null_pointer_calls_are_rejected_without_touching_the_gpu():
     assert rc == -5      # n_rings = 1 is unsupported (the reference divides by n_rings-1)
     rc = lib.fcb_gemm_f32(None, None, None, 4, 4, 4, 4, 4, 4, 0, 1, 0, 0, 0, 1, None, 0, 0, None)
     assert rc == -1
+
+
+def test_tensor_core_accumulation_plan():
+    """auto precision: tensor cores only where no TMEM accumulator would take more than 400 accumulating MMAs."""
+    assert _lib.tc_feasible(96, 2880)                 # cfg 2 forward (C=48, B=2, R=6)
+    assert _lib.tc_feasible(256, 7680)                # cfg 3 forward (C=128): two 128-column chunks
+    assert _lib.tc_feasible(512, 21504)               # C=256, B=3: 64-column chunks, 7 accumulators
+    assert not _lib.tc_feasible(96, 2880, flags=0)    # FP32-FMA mode never uses tensor cores
+    assert _lib.tc_feasible(96, 80000, trans_a=1, split_k=26)
+    assert not _lib.tc_feasible(64, 10 ** 6)          # too many accumulating steps for any plan

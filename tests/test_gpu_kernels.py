@@ -126,7 +126,7 @@ def test_aggregate_matches_oracle(name):
     _lib.call("fcb_aggregate_f32", torch.view_as_real(xd).data_ptr(), plan.rowptr_tgt.data_ptr(), plan.rec_tgt.data_ptr(),
               plan.rot_tgt.data_ptr(), torch.view_as_real(out).data_ptr(), g["n"], cpad, B, R, 0, _lib.stream_ptr())
     ref = restate.aggregate(x, g["supp_edges"], g["supp_sten"], B)            # (N, C, R, M)
-    got = out.cpu().reshape(g["n"], R, cpad, M).permute(0, 2, 1, 3)
+    got = out.cpu().reshape(g["n"], R, M, cpad).permute(0, 3, 1, 2)
     assert_close_normwise(got, ref, 3e-6, "contrib")
     # transposed gather: G[j,m,r,o] = sum_{e: src=j} conj(sten[e,r,m]) gy[tgt(e), o]
     gy = xd                                                                   # any complex field will do
