@@ -279,16 +279,17 @@ def run_ours(args):
     e2e_ms = max(e2e_ms, e2e_wall_ms)      # host-side work (copies are async, loss.item() syncs) is part of e2e
     e2e_value = world * edges_per_step / (e2e_ms * 1e-3)
 
+    # ---- per-kernel timing of one more step with CUDA events around every library launch (recorded on rank 0;
+    #      every rank runs the step because it contains the gradient all-reduce)
+    if rank == 0:
+        _lib.profile_enable(1 << 14)
+    step(x_dev, plan, labels)
+    barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-
-    # ---- per-kernel timing of one more step with CUDA events around every library launch (rank 0)
     hbm, tf_sus, which = peaks()
-    _lib.profile_enable(1 << 14)
-    step(x_dev, plan, labels)
-    torch.cuda.synchronize()
     recs = _lib.profile_collect(1 << 14)
     tot = {}
     for name, ms in recs:
@@ -354,6 +355,135 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- cfg 4: one large mesh, vertex partition
+def run_partitioned(args):
+    """BASELINE.json configs[3]: a single side^2-vertex torus mesh (64 support edges/vertex), C=64, band_limit=1,
+    n_rings=6, one FCResNetBlock (2 FieldConv layers) + |x| -> Linear -> CE; vertex-partitioned across the ranks,
+    halo rows exchanged over NCCL/NVLink and overlapped with the interior rows; strong scaling."""
+    import torch.distributed as dist
+    import fieldconv_b200 as fcb
+    from fieldconv_b200 import _lib
+    from fieldconv_b200.synthetic import random_features, torus_mesh
+    c4, b4, r4, deg4 = 64, 1, 6, 64.0
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mesh = torus_mesh(args.side, deg=deg4, seed=0, device=dev)
+    n_global = mesh.num_nodes
+    part = fcb.partition_mesh(mesh, world, rank)
+    del mesh
+    torch.cuda.empty_cache()
+    plan = part.build_plan(r4)
+    e_local = plan.num_edges
+    t = torch.tensor([e_local], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(t)
+    e_global = int(t.item())
+    torch.manual_seed(0)
+    blk = fcb.FCResNetBlock(c4, c4, b4, r4, 1, precision=args.precision).to(dev)
+    head = torch.nn.Linear(c4, N_CLASSES).to(dev)
+    params = list(blk.parameters()) + list(head.parameters())
+    opt = torch.optim.Adam(params, lr=0.01)
+    x_own = random_features(n_global, c4, seed=1, device=dev)[part.own_global].contiguous()
+    labels = torch.randint(0, N_CLASSES, (n_global,), device=dev, generator=torch.Generator(device=dev).manual_seed(0))
+    labels = labels[part.own_global].contiguous()
+    host_x, host_lab = x_own.cpu().pin_memory(), labels.cpu().pin_memory()
+    loss_fn = torch.nn.CrossEntropyLoss(reduction="sum")
+
+    def step(x, lab):
+        opt.zero_grad(set_to_none=True)
+        loss = loss_fn(head(blk(x, part).abs()), lab) / n_global
+        loss.backward()
+        fcb.allreduce_gradients(params)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        tt = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    for _ in range(args.warmup):
+        step(x_own, labels)
+    barrier()
+    t_begin = time.perf_counter()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step(x_own, labels)
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
+    value = e_global * 2 / (ms_step * 1e-3)
+
+    def e2e_step():
+        return float(step(host_x.to(dev, non_blocking=True), host_lab.to(dev, non_blocking=True)).item())
+    e2e_step()
+    barrier()
+    n_e2e = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_e2e
+    # one more step with per-launch CUDA events (every rank runs it: the step contains collectives)
+    if rank == 0:
+        _lib.profile_enable(1 << 12)
+    step(x_own, labels)
+    barrier()
+    if rank == 0:
+        hbm, _, which = peaks()
+        tot = {}
+        for name, ms in _lib.profile_collect(1 << 12):
+            a = tot.setdefault(name, [0, 0.0])
+            a[0] += 1
+            a[1] += ms
+        shares = {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1])}
+        n_own = part.n_own
+        agg = tot.get("aggregate", [1, 0.0])
+        per_launch = e_local * 24 + (n_own + 1) * 4 + part.n_ext * c4 * 8 + n_own * r4 * c4 * (2 * b4 + 1) * 8
+        avg_ms = agg[1] / max(agg[0], 1)
+        roof = {"kernel": "k_aggregate", "bound": "hbm", "achieved": per_launch / max(avg_ms, 1e-9) / 1e6, "peak": hbm,
+                "unit": "GB/s", "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms, "peak_source": which,
+                "traffic": None}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "partitioned_mesh_%dx%d_c64_b1_r6_deg64" % (args.side, args.side), "vertices": n_global,
+                           "edges": e_global, "fieldconv_layers": 2, "precision": args.precision,
+                           "parallelism": "vertex-partition x%d + NCCL halo exchange overlapped with interior rows" % world,
+                           "rank0": {"owned": part.n_own, "interior": part.n_interior, "halo": part.n_halo},
+                           "l2": "per-layer working set (>= 4 GB of contrib per rank) exceeds the 126 MB L2",
+                           "step": "forward + backward + halo exchanges + NCCL grad all-reduce + Adam"},
+                "e2e": {"value": e_global * 2 / (e2e_ms * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": host_x.numel() * 8 + host_lab.numel() * 8, "d2h_bytes_per_step": 4,
+                        "ms_per_step": e2e_ms, "includes": "H2D of this rank's features + labels (pinned), step, D2H loss; "
+                                                           "the static partition/plan is built once"},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_ms_rank0": shares}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -361,6 +491,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("FIELDCONV_B200_PRECISION", "auto"))
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"],
+                    help="cfg2 (default, the driver's line): FC-ResNet on a batch of 16 meshes per GPU, data parallel; "
+                         "cfg4: one large mesh vertex-partitioned across the GPUs with NVLink halo exchange (strong scaling)")
+    ap.add_argument("--side", type=int, default=2000, help="cfg4: the mesh has side^2 vertices (2000 -> 4M)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -368,7 +502,10 @@ def main():
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
-        run_ours(args)
+        if args.workload == "cfg4":
+            run_partitioned(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":

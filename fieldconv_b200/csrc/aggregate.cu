@@ -117,8 +117,10 @@ __global__ void __launch_bounds__(256, 2) k_aggregate(const float4* __restrict__
         // Software pipeline, two deep: while edge p is accumulated the feature row of edge p+1 and the plan record
         // of edge p+2 are in flight, so the dependent chain record -> neighbour id -> feature row stays off the
         // FMA pipe's critical path.  All prefetches are unconditional (indices clamped to the row's last edge) so
-        // the register rotation unrolls away.  (Measured alternatives that were slower: an explicit L1 prefetch of
-        // the record stream 8 edges ahead plus a two-deep feature gather — more registers, same stalls.)
+        // the register rotation unrolls away.  (Measured alternatives that were not faster: an explicit L1 prefetch
+        // of the record stream 8 edges ahead plus a two-deep feature gather — more registers, same stalls; packed
+        // FFMA2/FMUL2 arithmetic over the lane's two channels — halves the FMA-pipe instructions but nvcc 12.9 spends
+        // more than it saves on MOVs that build the aligned 64-bit register pairs.)
         const int last = p1 - 1;
         int4 rcA = __ldg(rec + p0);
         float2 rtA = __ldg(rot + p0);

@@ -235,12 +235,17 @@ static int check_dims(const char* who, int64_t N, int Ci, int Co, int B, int R, 
     return FCB_OK;
 }
 
+// Vertex ranges of the weight-gradient reduction: enough CTAs for (at most) four full waves on 148 SMs, and short
+// enough that each range's accumulating MMA steps fit three TMEM accumulators of the tensor-core plan (400 steps of
+// 8 vertices each: gemm_tc_plan) so the 3xTF32 kernel keeps its full 128-column tiles.
 static int choose_split(int64_t rows_m, int64_t kdim) {
     const int64_t tiles = (rows_m + 127) / 128;
-    int64_t s = (4 * 148 + tiles - 1) / tiles;
+    int64_t s = (4 * 148) / tiles;
+    const int64_t s_acc = (kdim + 3 * 400 * 8 - 1) / (3 * 400 * 8);
+    if (s < s_acc) s = s_acc;
     const int64_t cap = kdim / 512;
     if (s > cap) s = cap;
-    if (s > 64) s = 64;
+    if (s > 4096) s = 4096;
     if (s < 1) s = 1;
     return (int)s;
 }
@@ -299,9 +304,14 @@ static int backward_common(const Dims& d, const float* x, const float* W, const 
         const int64_t Q2 = 2 * (int64_t)d.R * d.Co;
         const size_t tcb = gemm_tc_ws_bytes(2 * d.Ci, Q2, d.M);
         void* tcw = ar.take<char>(tcb);
-        rc = launch_gemm(G, Bt, gxh, d.N, 2 * d.Ci, Q2, (int64_t)d.M * Q2, 2 * d.Ci, (int64_t)d.M * 2 * d.Ci, 0, d.M, Q2,
-                         Q2 * 2 * d.Ci, 2 * d.Ci, 1, tcw, tcb, flags, st);
+        int grouped = 0;     // all m in one pass over G (one long-K tensor-core pipeline) when the plan allows
+        rc = launch_gemm_grouped(G, Bt, gxh, d.N, 2 * d.Ci, Q2, d.M, flags, tcw, tcb, &grouped, st);
         if (rc) return rc;
+        if (!grouped) {
+            rc = launch_gemm(G, Bt, gxh, d.N, 2 * d.Ci, Q2, (int64_t)d.M * Q2, 2 * d.Ci, (int64_t)d.M * 2 * d.Ci, 0, d.M, Q2,
+                             Q2 * 2 * d.Ci, 2 * d.Ci, 1, tcw, tcb, flags, st);
+            if (rc) return rc;
+        }
         const int64_t el = d.N * d.Ci;
         const unsigned blocks = (unsigned)((el + 255) / 256);
         const float2* x2 = reinterpret_cast<const float2*>(x);

@@ -92,7 +92,11 @@ int launch_gemm_tc_tn(const float* A, const float* B, float* C, int64_t Mr, int 
 int launch_reduce_splits(const float* partials, float* C, int64_t M, int N, int64_t ldc, int64_t sc, int batch, int split_k,
                          cudaStream_t st);
 int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
-                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int mode, int n_main, void* ws,
-                      size_t ws_bytes, cudaStream_t st);
+                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int mode, int n_main, int kgroups,
+                      void* ws, size_t ws_bytes, cudaStream_t st);
+// grad-x contraction gxh[:, m, :] = G[:, m, :] @ Bt[m] for all m in one pass over G when the tensor-core plan allows
+// (returns FCB_OK and sets *done = 1), otherwise leaves *done = 0 for the caller to use the batched path
+int launch_gemm_grouped(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t Kg, int groups, int flags,
+                        void* ws, size_t ws_bytes, int* done, cudaStream_t st);
 
 }  // namespace fcb

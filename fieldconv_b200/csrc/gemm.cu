@@ -13,6 +13,7 @@
 
 namespace fcb {
 
+constexpr int64_t TC_MAX_ACC_MMAS_GROUPED = 400;   // same budget as gemm_tc_plan (gemm_tc.cu)
 constexpr int G_BM = 128;
 constexpr int G_BK = 8;
 constexpr int G_PAD = 4;
@@ -211,6 +212,24 @@ int launch_reduce_splits(const float* partials, float* C, int64_t M, int N, int6
     return FCB_OK;
 }
 
+// A = [M x groups*Kg] row-major (lda = groups*Kg), Bm = groups matrices [Kg x N] back to back, C = [M x groups*N].
+int launch_gemm_grouped(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t Kg, int groups, int flags,
+                        void* ws, size_t ws_bytes, int* done, cudaStream_t st) {
+    *done = 0;
+    const int mode = flags & FCB_GEMM_MASK;
+    if (!(mode == FCB_GEMM_TC_3XTF32 || mode == FCB_GEMM_TC_TF32) || groups < 2) return FCB_OK;
+    const int npad = (N + 15) / 16 * 16;
+    const int64_t chunks = Kg / 32;
+    const int64_t mmas = chunks * 4 * (mode == FCB_GEMM_TC_3XTF32 ? 3 : 1);     // accumulating MMAs per accumulator
+    if (Kg % 32 != 0 || npad * groups > 512 || mmas > TC_MAX_ACC_MMAS_GROUPED || ((groups * (int64_t)N) % 4) != 0 ||
+        ((groups * Kg) % 4) != 0 || !aligned16(A) || !aligned16(C) || ws_bytes < gemm_tc_ws_bytes(N, Kg, groups))
+        return FCB_OK;
+    int rc = launch_gemm_tc_nn(A, Bm, C, M, N, Kg, groups * Kg, N, groups * (int64_t)N, 1, 0, Kg * N, 0, mode, 1, groups, ws,
+                               ws_bytes, st);
+    if (rc == FCB_OK) *done = 1;
+    return rc;
+}
+
 int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                 int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k, void* ws,
                 size_t ws_bytes, int flags, cudaStream_t st) {
@@ -222,7 +241,7 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
         const int chunk = gemm_tc_plan(N, tc_ksteps(K, 0, 1), mode, &n_main);
         for (int n0 = 0; n0 < N; n0 += chunk) {      // column chunks (one unless N is wide): same A, offset B and C
             const int nc = N - n0 < chunk ? N - n0 : chunk;
-            int rc = launch_gemm_tc_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, mode, n_main, ws,
+            int rc = launch_gemm_tc_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, mode, n_main, 1, ws,
                                        ws_bytes, st);
             if (rc) return rc;
         }

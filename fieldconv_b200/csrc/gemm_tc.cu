@@ -128,6 +128,8 @@ struct Params {
     int64_t bp_batch_stride;   // floats
     int N, Npad, nchunks, stages, mode;
     int n_main;                // accumulators for the hi*hi products (3xTF32: + 1 for the cross terms)
+    int kgroups, cpg;          // grouped-K mode (kgroups > 1): K = kgroups * cpg chunks; group g accumulates (all three
+                               // product types) into its own TMEM accumulator and lands in C columns [g*N, (g+1)*N)
     uint32_t tmem_cols;
 };
 
@@ -255,14 +257,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
         const int q = warp & 3, part = warp >> 2;
         const int64_t m = m0 + 32 * q + lane;
         const int groups = p.Npad / 16;
-        const int n_acc = p.n_main + (p.mode == FCB_GEMM_TC_3XTF32 ? 1 : 0);
-        for (int g = part; g < groups; g += N_PROD_WARPS / 4) {
+        const bool grouped = p.kgroups > 1;
+        const int n_acc = grouped ? 1 : p.n_main + (p.mode == FCB_GEMM_TC_3XTF32 ? 1 : 0);
+        const int items = groups * (grouped ? p.kgroups : 1);       // (k-group, 16-column group) pairs
+        for (int it = part; it < items; it += N_PROD_WARPS / 4) {
+            const int kg = it / groups, g = it - kg * groups;
             uint32_t r[16];
             float acc[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) acc[e] = 0.f;
             for (int a = n_acc - 1; a >= 0; --a) {      // cross-term accumulator (last) first: small + large
-                tc_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(a * p.Npad + 16 * g), r);
+                tc_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)((a + kg) * p.Npad + 16 * g), r);
                 tc_ld_wait();
 #pragma unroll
                 for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(r[e]);
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(acc[e]);
             if (m < p.M) {
-                float* dst = C + m * p.ldc + 16 * g;
+                float* dst = C + m * p.ldc + (int64_t)kg * p.N + 16 * g;
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     const int n = 16 * g + 4 * c4;
@@ -302,6 +307,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
             uint32_t s = 0, ph = 0;          // stage, phase
             uint32_t acc = 0, d_main = tmem_d, first = n_main;   // round-robin hi*hi accumulator; `first` MMAs overwrite
             uint32_t x_acc = 0;              // 0 only for the very first cross-term MMA
+            const bool grouped = p.kgroups > 1;
+            uint32_t g_left = (uint32_t)p.cpg, d_grp = tmem_d;
             for (int kc = 0; kc < p.nchunks; ++kc) {
                 FCB_TRACE(3, kc, true);
                 mbar_wait(full_a(s), ph);
@@ -314,6 +321,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
 #pragma unroll
                 for (int ks = 0; ks < KC / 8; ++ks) {
                     const uint64_t adv = (uint64_t)(ks * 2);   // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzle row
+                    if (grouped) {
+                        tc_mma_tf32(d_grp, a_hi + adv, b_hi + adv, idesc, (ks == 0 && g_left == (uint32_t)p.cpg) ? 0u : 1u);
+                        if (x3) {
+                            tc_mma_tf32(d_grp, a_lo + adv, b_hi + adv, idesc, 1u);
+                            tc_mma_tf32(d_grp, a_hi + adv, b_lo + adv, idesc, 1u);
+                        }
+                        continue;
+                    }
                     tc_mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, first ? 0u : 1u);
                     if (first) --first;
                     if (++acc == n_main) { acc = 0; d_main = tmem_d; } else d_main += npad;
@@ -323,6 +338,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
                         x_acc = 1u;
                     }
                 }
+                if (grouped && --g_left == 0) { g_left = (uint32_t)p.cpg; d_grp += npad; }
                 tc_commit(empty(s));      // frees the stage once these MMAs have read it
                 FCB_TRACE(6, kc, true);
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
@@ -674,16 +690,20 @@ size_t gemm_tc_ws_bytes(int N, int64_t K, int batch) {
     return align_up((size_t)batch * nchunks * 2 * npad * tc::KC * 4, 256) + 256;
 }
 
+// kgroups == 1: `batch` independent GEMMs (grid.y).  kgroups > 1 (batch must be 1): ONE pass over A = [M x kgroups*K]
+// whose k-group g (K columns) is contracted with B_g = B + g*sb and written to C columns [g*N, (g+1)*N) — the
+// batched-over-m grad-x contraction as a single long-K pipeline instead of kgroups short ones.
 int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
-                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int mode, int n_main, void* ws,
-                      size_t ws_bytes, cudaStream_t st) {
+                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int mode, int n_main, int kgroups,
+                      void* ws, size_t ws_bytes, cudaStream_t st) {
     FCB_REQUIRE(A && B && C && ws, FCB_E_ARG, "gemm_tc: null pointer");
     FCB_REQUIRE(M >= 0 && N > 0 && K > 0 && batch >= 1 && batch <= 65535, FCB_E_ARG, "gemm_tc: bad sizes");
     FCB_REQUIRE(N <= 256, FCB_E_UNSUPPORTED, "gemm_tc: N=%d > 256 not supported by one accumulator tile", N);
     FCB_REQUIRE(mode == FCB_GEMM_TC_3XTF32 || mode == FCB_GEMM_TC_TF32, FCB_E_ARG, "gemm_tc: bad mode");
     FCB_REQUIRE((lda % 4) == 0 && (ldc % 4) == 0 && (sa % 4) == 0 && (sc % 4) == 0 && aligned16(A) && aligned16(C),
                 FCB_E_ALIGN, "gemm_tc: A/C leading dimensions and strides must be multiples of 4 floats, 16-byte aligned");
-    FCB_REQUIRE(ws_bytes >= gemm_tc_ws_bytes(N, K, batch), FCB_E_WORKSPACE, "gemm_tc: workspace too small");
+    FCB_REQUIRE(kgroups >= 1 && (kgroups == 1 || (batch == 1 && K % tc::KC == 0)), FCB_E_ARG, "gemm_tc: bad k-group shape");
+    FCB_REQUIRE(ws_bytes >= gemm_tc_ws_bytes(N, K, batch * kgroups), FCB_E_WORKSPACE, "gemm_tc: workspace too small");
     if (M == 0) return FCB_OK;
     const int npad = (N + 15) / 16 * 16;
     const int nchunks = (int)((K + tc::KC - 1) / tc::KC);
@@ -691,24 +711,29 @@ int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N
     const int64_t bp_stride = (int64_t)nchunks * 2 * npad * tc::KC;
     {
         const int64_t per = (int64_t)nchunks * npad * tc::KC;
-        dim3 grid((unsigned)((per + 255) / 256), (unsigned)batch);
+        dim3 grid((unsigned)((per + 255) / 256), (unsigned)(batch * kgroups));
         FCB_LAUNCH("pack_b_tc", st, tc::k_pack_b_tc<<<grid, 256, 0, st>>>(B, Bp, K, N, npad, ldb, nchunks, sb, bp_stride));
     }
     tc::Params p;
     p.A = A; p.Bp = Bp; p.C = C;
     p.M = M; p.K = K; p.lda = lda; p.ldc = ldc; p.sa = sa; p.sc = sc;
     p.bp_batch_stride = bp_stride;
-    p.N = N; p.Npad = npad; p.nchunks = nchunks; p.mode = mode;
-    FCB_REQUIRE(n_main >= 1 && npad * (n_main + (mode == FCB_GEMM_TC_3XTF32 ? 1 : 0)) <= 512, FCB_E_ARG,
+    p.N = N; p.Npad = npad; p.nchunks = nchunks * kgroups; p.mode = mode;
+    p.kgroups = kgroups; p.cpg = nchunks;
+    if (kgroups > 1) {
+        p.K = K * kgroups;
+        n_main = kgroups;      // TMEM columns: one accumulator per k-group, cross terms folded in
+    }
+    FCB_REQUIRE(n_main >= 1 && npad * (n_main + ((mode == FCB_GEMM_TC_3XTF32 && kgroups == 1) ? 1 : 0)) <= 512, FCB_E_ARG,
                 "gemm_tc: accumulators do not fit TMEM");
     p.n_main = n_main;
     uint32_t cols = 32;
-    while ((int)cols < npad * (n_main + (mode == FCB_GEMM_TC_3XTF32 ? 1 : 0))) cols <<= 1;
+    while ((int)cols < npad * (n_main + ((mode == FCB_GEMM_TC_3XTF32 && kgroups == 1) ? 1 : 0))) cols <<= 1;
     p.tmem_cols = cols;
     const size_t stage_bytes = 2 * tc::A_PLANE + 2 * (size_t)npad * 128;
     int stages = (int)((220 * 1024 - 2048) / stage_bytes);
     if (stages > 8) stages = 8;
-    if (stages > nchunks) stages = nchunks < 1 ? 1 : nchunks;
+    if (stages > p.nchunks) stages = p.nchunks < 1 ? 1 : p.nchunks;
     FCB_REQUIRE(stages >= 1, FCB_E_UNSUPPORTED, "gemm_tc: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = stages * stage_bytes + 1024 /*align slack*/ + 8 * (3 * stages + 2) + 64;

@@ -23,13 +23,18 @@ from . import _lib
 SAVE_CONTRIB_BYTES = int(os.environ.get("FIELDCONV_B200_SAVE_CONTRIB_BYTES", str(24 << 30)))
 
 
+_FREE_AT_FIRST_USE = {}
+
+
 def keep_contrib_default(nbytes, device):
     if nbytes > SAVE_CONTRIB_BYTES:
         return False
     if nbytes <= (256 << 20):
         return True
-    free, _ = torch.cuda.mem_get_info(device)
-    return nbytes <= free // 4
+    key = torch.device(device).index
+    if key not in _FREE_AT_FIRST_USE:            # queried once per device: cudaMemGetInfo is not free
+        _FREE_AT_FIRST_USE[key] = torch.cuda.mem_get_info(device)[0]
+    return nbytes <= _FREE_AT_FIRST_USE[key] // 4
 
 
 def _real(t):
@@ -285,7 +290,7 @@ def gemm(a: Tensor, b: Tensor, trans_a: bool, flags: int = 0) -> Tensor:
     split = 1
     if trans_a:
         tiles = (m + 127) // 128
-        split = max(1, min(64, k // 512, (4 * 148 + tiles - 1) // tiles))
+        split = max(1, min(k // 512, (4 * 148) // tiles))      # at most four full waves of CTAs on 148 SMs
     nbytes = _lib.query_bytes("fcb_gemm_workspace_bytes", m, n, k, 1 if trans_a else 0, 1, split, flags)
     ws = _ws(nbytes, a.device)
     with torch.cuda.device(a.device):
