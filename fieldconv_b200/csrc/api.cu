@@ -258,7 +258,12 @@ static size_t bwd_ws(const Dims& d, bool need_contrib) {
     size_t s = 0;
     s += align_up((size_t)(4 * d.K * d.Co) * 4, 256);                       // Bt
     s += align_up((size_t)(4 * d.K * d.Co) * 4, 256);                       // P
-    s += align_up((size_t)(4 * d.K * d.Co) * 4 * choose_split(2 * d.K, d.N), 256);  // split-K partials
+    {   // split-K partials (+ the packed gy operand of the tensor-core weight-gradient GEMM)
+        const int sp = choose_split(2 * d.K, d.N);
+        size_t b = gemm_ws_bytes(2 * d.K, 2 * d.Co, d.N, 1, 1, sp, FCB_GEMM_TC_3XTF32);
+        const size_t fp32_parts = (size_t)(4 * d.K * d.Co) * 4 * sp;
+        s += align_up(b > fp32_parts ? b : fp32_parts, 256) + 256;
+    }
     s += align_up((size_t)d.N * d.Kt * 8, 256);                             // G
     s += align_up((size_t)d.N * d.M * d.Ci * 8, 256);                       // gxh
     if (need_contrib) s += align_up((size_t)d.N * d.K * 8, 256);            // recomputed contrib
@@ -283,15 +288,17 @@ static int backward_common(const Dims& d, const float* x, const float* W, const 
                            GatherT&& gather_transpose, float* gx, float* gW, Arena& ar, int flags, cudaStream_t st) {
     float* Bt = ar.take<float>((size_t)(4 * d.K * d.Co));
     float* P = ar.take<float>((size_t)(4 * d.K * d.Co));
-    float* parts = ar.take<float>((size_t)(4 * d.K * d.Co) * choose_split(2 * d.K, d.N));
+    const int gw_split = choose_split(2 * d.K, d.N);
+    size_t parts_bytes = gemm_ws_bytes(2 * d.K, 2 * d.Co, d.N, 1, 1, gw_split, flags);
+    if (parts_bytes < (size_t)(4 * d.K * d.Co) * gw_split * 4) parts_bytes = (size_t)(4 * d.K * d.Co) * gw_split * 4;
+    float* parts = reinterpret_cast<float*>(ar.take<char>(parts_bytes));
     float* G = ar.take<float>((size_t)d.N * d.Kt * 2);
     float* gxh = ar.take<float>((size_t)d.N * d.M * d.Ci * 2);
     const int64_t tot = d.K * d.Co;
     if (gW) {
         // K4: P[2K x 2Co] = contrib_real^T @ gy_real, split over vertices, fixed-order reduction
-        const int split = choose_split(2 * d.K, d.N);
-        int rc = launch_gemm(contrib, gy, P, 2 * d.K, 2 * d.Co, d.N, 2 * d.K, 2 * d.Co, 2 * d.Co, 1, 1, 0, 0, 0, split, parts,
-                             (size_t)(4 * d.K * d.Co) * split * 4, flags, st);
+        int rc = launch_gemm(contrib, gy, P, 2 * d.K, 2 * d.Co, d.N, 2 * d.K, 2 * d.Co, 2 * d.Co, 1, 1, 0, 0, 0, gw_split, parts,
+                             parts_bytes, flags, st);
         if (rc) return rc;
         FCB_LAUNCH("combine_gw", st, k_combine_gw<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, reinterpret_cast<float2*>(gW), d.Ci, d.Co, d.R, d.M));
     }

@@ -87,8 +87,10 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
 size_t gemm_tc_ws_bytes(int N, int64_t K, int batch);
 // column-chunk width + number of hi*hi accumulators for `ksteps` accumulating MMA steps (0: tensor cores not usable)
 int gemm_tc_plan(int N, int64_t ksteps, int mode, int* n_main);
+size_t gemm_tc_tn_ws_bytes(int N, int64_t Kv);
 int launch_gemm_tc_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
-                      int64_t ldc, int split, int64_t k_per_split, float* parts, int mode, int n_main, cudaStream_t st);
+                      int64_t ldc, int split, int64_t k_per_split, float* parts, int mode, int n_main, void* bp_ws,
+                      size_t bp_bytes, cudaStream_t st);
 int launch_reduce_splits(const float* partials, float* C, int64_t M, int N, int64_t ldc, int64_t sc, int batch, int split_k,
                          cudaStream_t st);
 int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,

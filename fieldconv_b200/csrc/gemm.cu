@@ -201,7 +201,9 @@ static bool use_tc(int N, int64_t K, int trans_a, int batch, int split_k, int fl
 
 size_t gemm_ws_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags) {
     if (use_tc(N, K, trans_a, batch, split_k, flags) && !trans_a) return gemm_tc_ws_bytes(N, K, batch);
-    return split_k > 1 ? align_up((size_t)split_k * batch * M * N * 4, 256) : 0;
+    const size_t parts = split_k > 1 ? align_up((size_t)split_k * batch * M * N * 4, 256) : 0;
+    if (use_tc(N, K, trans_a, batch, split_k, flags) && trans_a) return parts + gemm_tc_tn_ws_bytes(N, K);   // + packed B
+    return parts;
 }
 
 int launch_reduce_splits(const float* partials, float* C, int64_t M, int N, int64_t ldc, int64_t sc, int batch, int split_k,
@@ -248,17 +250,20 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
         return FCB_OK;
     }
     float* partials = static_cast<float*>(ws);
-    if (use_tc(N, K, trans_a, batch, split_k, flags) && trans_a && (lda % 4) == 0 && (ldb % 4) == 0 && aligned16(A) &&
-        aligned16(Bm)) {
-        FCB_REQUIRE(split_k == 1 || (partials && ws_bytes >= (size_t)split_k * M * N * 4), FCB_E_WORKSPACE,
-                    "gemm: split_k > 1 needs a workspace of split_k*M*N floats");
+    if (use_tc(N, K, trans_a, batch, split_k, flags) && trans_a && (lda % 4) == 0 && aligned16(A)) {
+        const size_t parts_bytes = split_k > 1 ? align_up((size_t)split_k * M * N * 4, 256) : 0;
+        FCB_REQUIRE(ws && ws_bytes >= parts_bytes + gemm_tc_tn_ws_bytes(N, K), FCB_E_WORKSPACE,
+                    "gemm: workspace too small (fcb_gemm_workspace_bytes)");
+        void* bp_ws = static_cast<char*>(ws) + parts_bytes;
+        const size_t bp_bytes = ws_bytes - parts_bytes;
         int64_t kps_tc = (K + split_k - 1) / split_k;
         kps_tc = (kps_tc + 31) / 32 * 32;
         int n_main = 1;
         const int chunk = gemm_tc_plan(N, kps_tc / 8, mode, &n_main);
         for (int n0 = 0; n0 < N; n0 += chunk) {
             const int nc = N - n0 < chunk ? N - n0 : chunk;
-            int rc = launch_gemm_tc_tn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, split_k, kps_tc, partials, mode, n_main, st);
+            int rc = launch_gemm_tc_tn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, split_k, kps_tc, partials, mode, n_main,
+                                       bp_ws, bp_bytes, st);
             if (rc) return rc;
             if (split_k > 1) {
                 rc = launch_reduce_splits(partials, C + n0, M, nc, ldc, 0, 1, split_k, st);

@@ -381,9 +381,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_nn(const Params p) {
 // own partial tile, summed later in split order (k_reduce_splits) so the result is deterministic.
 struct ParamsTN {
     const float* A;    // [Kv x Mr], lda
-    const float* B;    // [Kv x N], ldb
+    const float* Bp;   // packed B: [chunk of 32 vertices][plane(hi,lo)] shared-memory images (k_pack_b_tn)
     float* C;          // partials [split][Mr][N] or C itself when split == 1 (ldc)
-    int64_t Mr, Kv, lda, ldb, ldc, k_per_split, part_stride;
+    int64_t Mr, Kv, lda, ldc, k_per_split, part_stride;
     int N, Npad, nb_atoms, stages, mode, n_main;
     uint32_t tmem_cols;
 };
@@ -399,10 +399,19 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
 }
 
 constexpr int KV = 32;   // vertices per stage (4 MMA K-steps of 8)
-// producer prefetch depth of the TN kernel (chunks of both operands in flight in registers), bounded by registers
-__host__ __device__ constexpr int pft_for(int nb4) { return nb4 <= 3 ? 4 : (nb4 == 4 ? 3 : 2); }
+constexpr int PFT = 6;   // producer prefetch depth (chunks of A in flight in registers)
 
-template <int NB4>   // float4 of the B operand per producer thread and stage == number of 32-feature atoms
+// byte offset of the 16-byte piece holding elements (vertex v of the chunk, features 4*f4 .. 4*f4+3) inside an
+// MN-major SWIZZLE_128B_BASE32B operand tile with `atoms` 32-feature atoms per vertex row
+__host__ __device__ __forceinline__ uint32_t tn_tile_off(int v, int f4, int atoms) {
+    const int kq = v >> 2, row = v & 3, at = f4 >> 3, unit = f4 & 7;
+    return (uint32_t)((kq * atoms + at) * 512 + row * 128 + (((unit >> 1) ^ row) << 5) + ((unit & 1) << 4));
+}
+
+// The weight gradient's B operand (gy) is the same for every 128-column tile of contrib, so it is split into hi/lo
+// and laid out as the exact shared-memory image of every 32-vertex chunk ONCE (k_pack_b_tn); the GEMM CTAs fetch it
+// with one cp.async.bulk per stage.  Only the A operand (contrib, read exactly once overall) goes through the
+// producer warps' registers.
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -410,25 +419,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
     uint8_t* sm = smem_raw + (base - raw);
     const int S = p.stages;
     const uint32_t b_plane = (uint32_t)KV * (uint32_t)p.nb_atoms * 128u;   // 32 vertices x nb_atoms x 128 B
-    const uint32_t a_hi0 = base, a_lo0 = base + S * A_PLANE, b_hi0 = base + 2 * S * A_PLANE, b_lo0 = b_hi0 + S * b_plane;
-    const uint32_t bars = b_lo0 + S * b_plane;
-    auto full = [&](int s) { return bars + 8u * s; };
-    auto empty = [&](int s) { return bars + 8u * (S + s); };
-    const uint32_t tmem_full = bars + 8u * (2 * S);
-    const uint32_t tmem_slot = bars + 8u * (2 * S + 1);
+    // layout: A_hi[S] | A_lo[S] | B[S] (hi,lo) | barriers
+    const uint32_t a_hi0 = base, a_lo0 = base + S * A_PLANE, b0 = base + 2 * S * A_PLANE;
+    const uint32_t bars = b0 + S * 2 * b_plane;
+    auto full_a = [&](int s) { return bars + 8u * s; };
+    auto full_b = [&](int s) { return bars + 8u * (S + s); };
+    auto empty = [&](int s) { return bars + 8u * (2 * S + s); };
+    const uint32_t tmem_full = bars + 8u * (3 * S);
+    const uint32_t tmem_slot = bars + 8u * (3 * S + 1);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(sm + (tmem_slot - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long* const trace = (blockIdx.x == 0 && blockIdx.z == 0) ? g_trace : nullptr;
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int split = blockIdx.z;
-    const int64_t kb = (int64_t)split * p.k_per_split;
+    const int64_t kb = (int64_t)split * p.k_per_split;       // multiple of KV
     const int64_t ke = min(p.Kv, kb + p.k_per_split);
     const int nchunks = kb < ke ? (int)((ke - kb + KV - 1) / KV) : 0;
     float* C = p.C + (int64_t)split * p.part_stride;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full(s), N_PROD_WARPS);
+            mbar_init(full_a(s), N_PROD_WARPS);
+            mbar_init(full_b(s), 1);
             mbar_init(empty(s), 1);
         }
         mbar_init(tmem_full, 1);
@@ -447,10 +460,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
 
     if (warp < N_PROD_WARPS) {
         const int t = threadIdx.x;
-        constexpr int nf4_b = NB4 * 8;                    // float4 slots per vertex row of the B operand (padded)
-        constexpr int B_ITEMS = KV * nf4_b;               // 256 * NB4
-        constexpr int B_F4 = (B_ITEMS + N_PROD - 1) / N_PROD;
-        // hoisted addressing: element pointers at the split's first vertex, advanced by kc*KV rows per stage
+        // hoisted addressing: element pointers at the split's first vertex, advanced by KV rows per stage
         const float* a_src[A_F4];
         uint32_t a_off[A_F4];
         int a_v[A_F4], a_cnt[A_F4];                       // vertex within the stage, valid floats (0..4)
@@ -462,57 +472,45 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
             a_v[i] = v;
             a_cnt[i] = (int)max((int64_t)0, min((int64_t)4, p.Mr - m));
             a_src[i] = p.A + (kb + v) * p.lda + m;
-            const int kq = v >> 2, row = v & 3, ma = f4 >> 3, unit = f4 & 7;
-            a_off[i] = (uint32_t)((kq * 4 + ma) * 512 + row * 128 + (((unit >> 1) ^ row) << 5) + ((unit & 1) << 4));
+            a_off[i] = tn_tile_off(v, f4, 4);
         }
-        const float* b_src[B_F4];
-        uint32_t b_off[B_F4];
-        int b_v[B_F4], b_cnt[B_F4];
-#pragma unroll
-        for (int i = 0; i < B_F4; ++i) {
-            const int idx = t + N_PROD * i;
-            const int v = idx / nf4_b, f4 = idx - v * nf4_b;
-            const int n = 4 * f4;
-            b_v[i] = v;
-            b_cnt[i] = idx < B_ITEMS ? max(0, min(4, p.N - n)) : -1;      // -1: this thread has no such item
-            b_src[i] = p.B + (kb + v) * p.ldb + n;
-            const int kq = v >> 2, row = v & 3, na = f4 >> 3, unit = f4 & 7;
-            b_off[i] = (uint32_t)((kq * NB4 + na) * 512 + row * 128 + (((unit >> 1) ^ row) << 5) + ((unit & 1) << 4));
-        }
-        auto load4 = [&](const float* q, int cnt) {
-            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (cnt == 4) r = __ldg(reinterpret_cast<const float4*>(q));
-            else {
-                if (cnt > 0) r.x = q[0];
-                if (cnt > 1) r.y = q[1];
-                if (cnt > 2) r.z = q[2];
-            }
-            return r;
-        };
-        constexpr int PFT = pft_for(NB4);
-        float4 va[PFT][A_F4], vb[PFT][B_F4];
-        auto issue = [&](int kc, float4(&da)[A_F4], float4(&db)[B_F4]) {
+        const bool cols_full = (m0 + BM <= p.Mr);        // CTA-uniform: every column piece of this tile is complete
+        const int64_t a_step = (int64_t)KV * p.lda;
+        float4 va[PFT][A_F4];
+        auto issue = [&](int kc, float4(&da)[A_F4]) {
             const int64_t v0 = kb + (int64_t)kc * KV;
-            const bool full_chunk = (v0 + KV <= ke);
+            if (cols_full && v0 + KV <= ke) {            // fast path: no guards
 #pragma unroll
-            for (int i = 0; i < A_F4; ++i) {
-                const bool ok = full_chunk || (v0 + a_v[i] < ke);
-                da[i] = ok ? load4(a_src[i] + (int64_t)kc * KV * p.lda, a_cnt[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+                for (int i = 0; i < A_F4; ++i) {
+                    da[i] = __ldg(reinterpret_cast<const float4*>(a_src[i]));
+                    a_src[i] += a_step;
+                }
+            } else {
 #pragma unroll
-            for (int i = 0; i < B_F4; ++i) {
-                const bool ok = b_cnt[i] > 0 && (full_chunk || (v0 + b_v[i] < ke));
-                db[i] = ok ? load4(b_src[i] + (int64_t)kc * KV * p.ldb, b_cnt[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < A_F4; ++i) {
+                    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (v0 + a_v[i] < ke) {
+                        const float* q = a_src[i];
+                        if (a_cnt[i] == 4) r = __ldg(reinterpret_cast<const float4*>(q));
+                        else {
+                            if (a_cnt[i] > 0) r.x = q[0];
+                            if (a_cnt[i] > 1) r.y = q[1];
+                            if (a_cnt[i] > 2) r.z = q[2];
+                        }
+                    }
+                    da[i] = r;
+                    a_src[i] += a_step;
+                }
             }
         };
         uint8_t* const ahi = sm + (a_hi0 - base);
         uint8_t* const alo = sm + (a_lo0 - base);
-        uint8_t* const bhi = sm + (b_hi0 - base);
-        uint8_t* const blo = sm + (b_lo0 - base);
         uint32_t ps = 0, pph = 1;
-        auto commit = [&](int kc, const float4(&sa)[A_F4], const float4(&sb)[B_F4]) {
+        auto commit = [&](int kc, const float4(&sa)[A_F4]) {
             const uint32_t s = ps;
+            FCB_TRACE(0, kc, t == 0);
             mbar_wait(empty(s), pph);
+            FCB_TRACE(1, kc, t == 0);
 #pragma unroll
             for (int i = 0; i < A_F4; ++i) {
                 const float4 hi = make_float4(tf32_hi(sa[i].x), tf32_hi(sa[i].y), tf32_hi(sa[i].z), tf32_hi(sa[i].w));
@@ -521,31 +519,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
                     *reinterpret_cast<float4*>(alo + s * A_PLANE + a_off[i]) =
                         make_float4(sa[i].x - hi.x, sa[i].y - hi.y, sa[i].z - hi.z, sa[i].w - hi.w);
             }
-#pragma unroll
-            for (int i = 0; i < B_F4; ++i) {
-                if (b_cnt[i] >= 0) {
-                    const float4 hi = make_float4(tf32_hi(sb[i].x), tf32_hi(sb[i].y), tf32_hi(sb[i].z), tf32_hi(sb[i].w));
-                    *reinterpret_cast<float4*>(bhi + s * b_plane + b_off[i]) = hi;
-                    if (split3)
-                        *reinterpret_cast<float4*>(blo + s * b_plane + b_off[i]) =
-                            make_float4(sb[i].x - hi.x, sb[i].y - hi.y, sb[i].z - hi.z, sb[i].w - hi.w);
-                }
-            }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(full(s));
+            if (lane == 0) mbar_arrive(full_a(s));
+            FCB_TRACE(2, kc, t == 0);
             if (++ps == (uint32_t)S) { ps = 0; pph ^= 1u; }
         };
 #pragma unroll
         for (int u = 0; u < PFT - 1; ++u)
-            if (u < nchunks) issue(u, va[u], vb[u]);
+            if (u < nchunks) issue(u, va[u]);
         for (int kc = 0; kc < nchunks; kc += PFT) {
 #pragma unroll
             for (int u = 0; u < PFT; ++u) {
                 const int k = kc + u;
                 if (k < nchunks) {
-                    if (k + PFT - 1 < nchunks) issue(k + PFT - 1, va[(u + PFT - 1) % PFT], vb[(u + PFT - 1) % PFT]);
-                    commit(k, va[u], vb[u]);
+                    if (k + PFT - 1 < nchunks) issue(k + PFT - 1, va[(u + PFT - 1) % PFT]);
+                    commit(k, va[u]);
                 }
             }
         }
@@ -585,14 +574,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
             const uint32_t idesc = make_idesc_tf32(p.Npad) | (1u << 15) | (1u << 16);
             const uint32_t sbo_a = 4 * 512, sbo_b = (uint32_t)p.nb_atoms * 512;   // between 4-vertex K groups
             const uint64_t a_hi_d = make_desc_mn_sw128(a_hi0, 512, sbo_a), a_lo_d = make_desc_mn_sw128(a_lo0, 512, sbo_a);
-            const uint64_t b_hi_d = make_desc_mn_sw128(b_hi0, 512, sbo_b), b_lo_d = make_desc_mn_sw128(b_lo0, 512, sbo_b);
-            const uint64_t a_stage = (uint64_t)(A_PLANE >> 4), b_stage = (uint64_t)(b_plane >> 4);
+            const uint64_t b_hi_d = make_desc_mn_sw128(b0, 512, sbo_b), b_lo_d = make_desc_mn_sw128(b0 + b_plane, 512, sbo_b);
+            const uint64_t a_stage = (uint64_t)(A_PLANE >> 4), b_stage = (uint64_t)((2 * b_plane) >> 4);
             const uint64_t a_kg = (uint64_t)((2 * sbo_a) >> 4), b_kg = (uint64_t)((2 * sbo_b) >> 4);   // 8 vertices
             const uint32_t d_x = tmem_d + (uint32_t)(p.n_main * p.Npad);
             const uint32_t n_main = (uint32_t)p.n_main, npad = (uint32_t)p.Npad;
             uint32_t s = 0, ph = 0, acc = 0, d_main = tmem_d, first = n_main, x_acc = 0;
             for (int kc = 0; kc < nchunks; ++kc) {
-                mbar_wait(full(s), ph);
+                FCB_TRACE(3, kc, true);
+                mbar_wait(full_a(s), ph);
+                FCB_TRACE(4, kc, true);
+                mbar_wait(full_b(s), ph);
+                FCB_TRACE(5, kc, true);
                 tc_fence_after();
                 uint64_t a_hi = a_hi_d + s * a_stage, a_lo = a_lo_d + s * a_stage;
                 uint64_t b_hi = b_hi_d + s * b_stage, b_lo = b_lo_d + s * b_stage;
@@ -609,9 +602,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
                     a_hi += a_kg; a_lo += a_kg; b_hi += b_kg; b_lo += b_kg;
                 }
                 tc_commit(empty(s));
+                FCB_TRACE(6, kc, true);
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
             }
             tc_commit(tmem_full);
+        }
+        __syncwarp();
+    } else {
+        // B loader (one thread, TMA bulk copies of the pre-packed chunk images)
+        if (lane == 0) {
+            const uint32_t bytes = (split3 ? 2u : 1u) * b_plane;
+            const int64_t img = (int64_t)2 * (b_plane / 4);                 // floats per chunk image (hi + lo)
+            const float* src = p.Bp + (kb / KV) * img;
+            uint32_t s = 0, ph = 1;
+            for (int kc = 0; kc < nchunks; ++kc) {
+                mbar_wait(empty(s), ph);
+                FCB_TRACE(7, kc, true);
+                mbar_expect_tx(full_b(s), bytes);
+                bulk_copy_g2s(b0 + s * 2 * b_plane, src, bytes, full_b(s));
+                src += img;
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+            }
         }
         __syncwarp();
     }
@@ -620,6 +631,33 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_tn(const ParamsTN p) {
     if (warp == N_PROD_WARPS) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(p.tmem_cols) : "memory");
     }
+}
+
+// B[Kv x N] row-major (ldb) -> per 32-vertex chunk the MN-major swizzled shared-memory image, hi plane then lo plane
+// (hi = tf32(b), lo = b - hi); vertices >= Kv and features >= N are zero.  One thread per 16-byte piece.
+__global__ void k_pack_b_tn(const float* __restrict__ B, float* __restrict__ Bp, int64_t Kv, int N, int atoms, int64_t ldb,
+                            int64_t nchunks) {
+    const int f4_per_row = atoms * 8;
+    const int64_t per_chunk = (int64_t)KV * f4_per_row;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nchunks * per_chunk) return;
+    const int64_t c = i / per_chunk;
+    const int r = (int)(i - c * per_chunk);
+    const int v = r / f4_per_row, f4 = r - v * f4_per_row;
+    const int64_t vg = c * KV + v;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vg < Kv) {
+        const float* q = B + vg * ldb + 4 * f4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (4 * f4 + e < N) x[e] = q[e];
+    }
+    float4 hi = make_float4(tf32_hi(x[0]), tf32_hi(x[1]), tf32_hi(x[2]), tf32_hi(x[3]));
+    float4 lo = make_float4(x[0] - hi.x, x[1] - hi.y, x[2] - hi.z, x[3] - hi.w);
+    const int64_t plane = (int64_t)KV * atoms * 32;                       // floats per plane
+    float* dst = Bp + c * 2 * plane + tn_tile_off(v, f4, atoms) / 4;
+    *reinterpret_cast<float4*>(dst) = hi;
+    *reinterpret_cast<float4*>(dst + plane) = lo;
 }
 
 // B[K x N] row-major (ldb) -> [chunk][plane][Npad][32] with the 128B swizzle applied (16-byte unit j of row n
@@ -751,19 +789,38 @@ int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N
     return FCB_OK;
 }
 
-// P[Mr x N] = A^T B on the tensor cores; split >= 1 vertex ranges; `parts` (split*Mr*N floats) is used when split > 1.
+// workspace of the packed B operand of the TN GEMM (hi + lo images of every 32-vertex chunk)
+size_t gemm_tc_tn_ws_bytes(int N, int64_t Kv) {
+    const int npad = (N + 15) / 16 * 16;
+    const int atoms = (npad + 31) / 32;
+    const int64_t nchunks = (Kv + tc::KV - 1) / tc::KV;
+    return align_up((size_t)nchunks * 2 * tc::KV * atoms * 128, 256) + 256;
+}
+
+// P[Mr x N] = A^T B on the tensor cores; split >= 1 vertex ranges; `parts` (split*Mr*N floats) is used when split > 1;
+// `bp_ws` (gemm_tc_tn_ws_bytes) receives the packed B operand.
 int launch_gemm_tc_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
-                      int64_t ldc, int split, int64_t k_per_split, float* parts, int mode, int n_main, cudaStream_t st) {
-    FCB_REQUIRE(A && B && C, FCB_E_ARG, "gemm_tc_tn: null pointer");
+                      int64_t ldc, int split, int64_t k_per_split, float* parts, int mode, int n_main, void* bp_ws,
+                      size_t bp_bytes, cudaStream_t st) {
+    FCB_REQUIRE(A && B && C && bp_ws, FCB_E_ARG, "gemm_tc_tn: null pointer");
     FCB_REQUIRE(N > 0 && N <= 256 && split >= 1 && split <= 65535, FCB_E_UNSUPPORTED, "gemm_tc_tn: unsupported shape");
-    FCB_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && aligned16(A) && aligned16(B), FCB_E_ALIGN, "gemm_tc_tn: alignment");
+    FCB_REQUIRE((lda % 4) == 0 && aligned16(A) && aligned16(bp_ws), FCB_E_ALIGN, "gemm_tc_tn: alignment");
+    FCB_REQUIRE(k_per_split % tc::KV == 0 || split == 1, FCB_E_ARG, "gemm_tc_tn: vertex ranges must be multiples of 32");
+    FCB_REQUIRE(bp_bytes >= gemm_tc_tn_ws_bytes(N, Kv), FCB_E_WORKSPACE, "gemm_tc_tn: packed-operand workspace too small");
     if (Mr == 0) return FCB_OK;
     const int npad = (N + 15) / 16 * 16;
     const int nb_atoms = (npad + 31) / 32;
+    const int64_t nchunks = (Kv + tc::KV - 1) / tc::KV;
+    float* Bp = static_cast<float*>(bp_ws);
+    {
+        const int64_t items = nchunks * tc::KV * nb_atoms * 8;
+        if (items > 0)
+            FCB_LAUNCH("pack_b_tn", st, tc::k_pack_b_tn<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(B, Bp, Kv, N, nb_atoms, ldb, nchunks));
+    }
     tc::ParamsTN p;
-    p.A = A; p.B = B;
+    p.A = A; p.Bp = Bp;
     p.C = split > 1 ? parts : C;
-    p.Mr = Mr; p.Kv = Kv; p.lda = lda; p.ldb = ldb;
+    p.Mr = Mr; p.Kv = Kv; p.lda = lda;
     p.ldc = split > 1 ? N : ldc;
     p.k_per_split = k_per_split;
     p.part_stride = split > 1 ? Mr * (int64_t)N : 0;
@@ -779,29 +836,18 @@ int launch_gemm_tc_tn(const float* A, const float* B, float* C, int64_t Mr, int 
     if (stages > 8) stages = 8;
     FCB_REQUIRE(stages >= 1, FCB_E_UNSUPPORTED, "gemm_tc_tn: tile does not fit shared memory");
     p.stages = stages;
-    const size_t smem = stages * stage_bytes + 1024 + 8 * (2 * stages + 2) + 64;
+    const size_t smem = stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
     dim3 grid((unsigned)((Mr + tc::BM - 1) / tc::BM), 1, (unsigned)split);
-    static bool attr_set[9] = {false};
-#define FCB_TN_CASE(NB)                                                                                                  \
-    case NB: {                                                                                                           \
-        if (!attr_set[NB]) {                                                                                             \
-            cudaError_t e = cudaFuncSetAttribute(tc::k_gemm_tc_tn<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
-            if (e != cudaSuccess) {                                                                                      \
-                set_error("gemm_tc_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                                \
-                return FCB_E_CUDA;                                                                                       \
-            }                                                                                                            \
-            attr_set[NB] = true;                                                                                         \
-        }                                                                                                                \
-        tc::k_gemm_tc_tn<NB><<<grid, tc::THREADS, smem, st>>>(p);                                                        \
-    } break;
-    prof_begin("gemm_tc_tn", st);
-    switch (nb_atoms) {
-        FCB_TN_CASE(1) FCB_TN_CASE(2) FCB_TN_CASE(3) FCB_TN_CASE(4) FCB_TN_CASE(5) FCB_TN_CASE(6) FCB_TN_CASE(7) FCB_TN_CASE(8)
-        default: set_error("gemm_tc_tn: bad atom count"); return FCB_E_ARG;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc::k_gemm_tc_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+            set_error("gemm_tc_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return FCB_E_CUDA;
+        }
+        attr_set = true;
     }
-#undef FCB_TN_CASE
-    prof_end(st);
-    FCB_CUDA_LAUNCH_CHECK("gemm_tc_tn");
+    FCB_LAUNCH("gemm_tc_tn", st, tc::k_gemm_tc_tn<<<grid, tc::THREADS, smem, st>>>(p));
     return FCB_OK;
 }
 

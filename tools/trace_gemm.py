@@ -7,11 +7,15 @@ lib.fcb_debug_trace.argtypes = [ctypes.c_void_p]
 dev = 'cuda:0'
 M, N, K = int(sys.argv[1]) if len(sys.argv) > 1 else 80656, 96, 2880
 mode = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-a = torch.randn(M, K, device=dev); b = torch.randn(K, N, device=dev)
-for _ in range(3): ops.gemm(a, b, False, mode)
+trans = len(sys.argv) > 3 and sys.argv[3] == 'tn'
+if trans:
+    a = torch.randn(M, K, device=dev); b = torch.randn(M, N, device=dev)      # P[K x N] = a^T b, reduction over M rows
+else:
+    a = torch.randn(M, K, device=dev); b = torch.randn(K, N, device=dev)
+for _ in range(3): ops.gemm(a, b, trans, mode)
 buf = torch.zeros(8 * 64, dtype=torch.int64, device=dev)
 lib.fcb_debug_trace(buf.data_ptr())
-ops.gemm(a, b, False, mode); torch.cuda.synchronize()
+ops.gemm(a, b, trans, mode); torch.cuda.synchronize()
 lib.fcb_debug_trace(None)
 t = buf.cpu().view(8, 64)
 t0 = int(t[0, 0])
