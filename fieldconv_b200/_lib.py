@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libfieldconv_b200.so")
 GEMM_SIMT_FP32 = 0
 GEMM_TC_3XTF32 = 1
 GEMM_TC_TF32 = 2
+GEMM_TC_2XF16 = 3
 
 _P = ctypes.c_void_p
 _I64 = ctypes.c_int64
@@ -26,11 +27,11 @@ SIGNATURES = {
     "fcb_plan_dense_workspace_bytes": [_I64, _I64, _PSZ],
     "fcb_plan_build_dense": [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P],
     "fcb_fwd_workspace_bytes": [_I64, _I, _I, _I, _I, _I, _PSZ],
-    "fcb_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_bwd_workspace_bytes": [_I64, _I, _I, _I, _I, _I, _PSZ],
-    "fcb_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
-    "fcb_fwd_dense_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
-    "fcb_bwd_dense_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_fwd_dense_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_bwd_dense_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_aggregate_f32": [_P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _P],
     "fcb_gemm_workspace_bytes": [_I64, _I, _I64, _I, _I, _I, _I, _PSZ],
     "fcb_gemm_tc_feasible": [_I, _I64, _I, _I, _I],

@@ -66,10 +66,23 @@ __device__ __forceinline__ void gauge_align(float2 z, float2* xh) {
 // store the 2 x M complex values a lane holds for one ring: one float4 (channels 2cp, 2cp+1) per m, `m_stride`
 // float4 apart.  Forward layout out[row][ring][m][c] (m_stride = C/2), transposed layout out[row][m][ring][o]
 // (m_stride = R*C/2): in both, consecutive lanes write consecutive 16-byte pieces -> full-line coalesced stores.
+// `mx` follows max|value stored| (the operand scale of the 2xFP16 contraction, gemm_h.cu): FMNMX runs on the ALU pipe,
+// off the FMA pipe that bounds these kernels.
 template <int M>
-__device__ __forceinline__ void store_ring(float4* __restrict__ dst, const float2 (&acc)[2][M], int64_t m_stride) {
+__device__ __forceinline__ void store_ring(float4* __restrict__ dst, const float2 (&acc)[2][M], int64_t m_stride, float& mx) {
 #pragma unroll
-    for (int m = 0; m < M; ++m) dst[m * m_stride] = make_float4(acc[0][m].x, acc[0][m].y, acc[1][m].x, acc[1][m].y);
+    for (int m = 0; m < M; ++m) {
+        dst[m * m_stride] = make_float4(acc[0][m].x, acc[0][m].y, acc[1][m].x, acc[1][m].y);
+        mx = fmaxf(fmaxf(mx, fabsf(acc[0][m].x)), fmaxf(fabsf(acc[0][m].y), fmaxf(fabsf(acc[1][m].x), fabsf(acc[1][m].y))));
+    }
+}
+
+// fold a warp's max|value| into *amax (bit pattern of a non-negative float; max is order-independent, so the result is
+// deterministic).  Every lane of the warp must call this.  The plain read first keeps the atomics to the handful of
+// warps that actually raise the running maximum.
+__device__ __forceinline__ void fold_amax(uint32_t* amax, float mx) {
+    const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+    if (amax && (threadIdx.x & 31) == 0 && w > *reinterpret_cast<volatile uint32_t*>(amax)) atomicMax(amax, w);
 }
 
 // The two live rings sit in two fixed accumulator sets selected by ring
@@ -77,12 +90,14 @@ __device__ __forceinline__ void store_ring(float4* __restrict__ dst, const float
 template <int B, bool TRANSPOSE>
 __global__ void __launch_bounds__(256, 2) k_aggregate(const float4* __restrict__ feat, const int32_t* __restrict__ rowptr,
                                                       const int4* __restrict__ rec, const float2* __restrict__ rot,
-                                                      float4* __restrict__ out, int64_t N, int C, int R) {
+                                                      float4* __restrict__ out, int64_t N, int C, int R,
+                                                      uint32_t* __restrict__ amax) {
     constexpr int M = 2 * B + 1;
     const int P = C >> 1;
     const int64_t lane_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t row = lane_id / P;
-    if (row >= N) return;
+    float mx = 0.f;
+    if (row < N) {
     const int cp = (int)(lane_id - row * P);
 
     float2 acc0[2][M], acc1[2][M];   // even rings / odd rings
@@ -100,11 +115,11 @@ __global__ void __launch_bounds__(256, 2) k_aggregate(const float4* __restrict__
     // ring fcur is complete: write it once and clear its accumulator set (it becomes ring fcur + 2)
     auto retire = [&](int ring) {
         if (ring & 1) {
-            store_ring<M>(dst, acc1, m_stride);
+            store_ring<M>(dst, acc1, m_stride, mx);
 #pragma unroll
             for (int m = 0; m < M; ++m) acc1[0][m] = acc1[1][m] = make_float2(0.f, 0.f);
         } else {
-            store_ring<M>(dst, acc0, m_stride);
+            store_ring<M>(dst, acc0, m_stride, mx);
 #pragma unroll
             for (int m = 0; m < M; ++m) acc0[0][m] = acc0[1][m] = make_float2(0.f, 0.f);
         }
@@ -163,6 +178,8 @@ __global__ void __launch_bounds__(256, 2) k_aggregate(const float4* __restrict__
         }
     }
     while (fcur < R) retire(fcur++);
+    }
+    fold_amax(amax, mx);
 }
 
 // Dense-stencil variant: arbitrary supp_sten (E,R,M), one lane per (row, ring, channel pair).
@@ -170,13 +187,14 @@ template <int B, bool TRANSPOSE>
 __global__ void __launch_bounds__(256) k_aggregate_dense(const float4* __restrict__ feat, const float2* __restrict__ sten,
                                                          const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
                                                          const int32_t* __restrict__ perm, float4* __restrict__ out,
-                                                         int64_t N, int C, int R) {
+                                                         int64_t N, int C, int R, uint32_t* __restrict__ amax) {
     constexpr int M = 2 * B + 1;
     const int P = C >> 1;
     const int64_t lane_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t unit = lane_id / P;  // (row, ring)
     const int64_t row = unit / R;
-    if (row >= N) return;
+    float mx = 0.f;
+    if (row < N) {
     const int ring = (int)(unit - row * R);
     const int cp = (int)(lane_id - unit * P);
     float2 acc[2][M];
@@ -207,12 +225,15 @@ __global__ void __launch_bounds__(256) k_aggregate_dense(const float4* __restric
         }
     }
     float4* orow = out + row * ((int64_t)R * C * M / 2);
-    store_ring<M>(orow + (TRANSPOSE ? (int64_t)ring * P : (int64_t)ring * M * P) + cp, acc, TRANSPOSE ? (int64_t)R * P : (int64_t)P);
+    store_ring<M>(orow + (TRANSPOSE ? (int64_t)ring * P : (int64_t)ring * M * P) + cp, acc, TRANSPOSE ? (int64_t)R * P : (int64_t)P, mx);
+    }
+    fold_amax(amax, mx);
 }
 
 template <bool TRANSPOSE>
 static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const void* rec, const float* rot, float* out,
-                              int64_t N, int C, int B, int R, cudaStream_t st) {
+                              int64_t N, int C, int B, int R, float* amax, cudaStream_t st) {
+    uint32_t* am = reinterpret_cast<uint32_t*>(amax);
     const int64_t lanes = N * (C / 2);
     if (lanes == 0) return FCB_OK;
     const unsigned blocks = (unsigned)((lanes + 255) / 256);
@@ -222,11 +243,11 @@ static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const vo
     float4* o4 = reinterpret_cast<float4*>(out);
     prof_begin(TRANSPOSE ? "aggregate_T" : "aggregate", st);
     switch (B) {
-        case 0: k_aggregate<0, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R); break;
-        case 1: k_aggregate<1, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R); break;
-        case 2: k_aggregate<2, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R); break;
-        case 3: k_aggregate<3, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R); break;
-        case 4: k_aggregate<4, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R); break;
+        case 0: k_aggregate<0, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am); break;
+        case 1: k_aggregate<1, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am); break;
+        case 2: k_aggregate<2, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am); break;
+        case 3: k_aggregate<3, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am); break;
+        case 4: k_aggregate<4, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am); break;
         default: set_error("aggregate: band_limit %d unsupported", B); return FCB_E_UNSUPPORTED;
     }
     prof_end(st);
@@ -235,19 +256,21 @@ static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const vo
 }
 
 int launch_aggregate(const float* feat, const int32_t* rowptr, const void* rec, const float* rot, float* out, int64_t N,
-                     int C, int B, int R, int transpose, cudaStream_t st) {
+                     int C, int B, int R, int transpose, float* amax, cudaStream_t st) {
     FCB_REQUIRE(N >= 0 && C > 0 && R >= 2 && R <= FCB_MAX_RINGS, FCB_E_ARG, "aggregate: bad sizes");
     FCB_REQUIRE(B >= 0 && B <= FCB_MAX_BAND_LIMIT, FCB_E_UNSUPPORTED, "aggregate: band_limit %d unsupported", B);
     FCB_REQUIRE((C & 1) == 0, FCB_E_ALIGN, "aggregate: channel count must be even (16-byte feature rows)");
     FCB_REQUIRE(aligned16(feat) && aligned16(out) && aligned16(rec), FCB_E_ALIGN, "aggregate: pointers must be 16-byte aligned");
     FCB_REQUIRE(N * (int64_t)(C / 2) < 0xffffffffLL, FCB_E_UNSUPPORTED, "aggregate: N*C/2 must fit 32 bits");
-    return transpose ? dispatch_aggregate<true>(feat, rowptr, rec, rot, out, N, C, B, R, st)
-                     : dispatch_aggregate<false>(feat, rowptr, rec, rot, out, N, C, B, R, st);
+    return transpose ? dispatch_aggregate<true>(feat, rowptr, rec, rot, out, N, C, B, R, amax, st)
+                     : dispatch_aggregate<false>(feat, rowptr, rec, rot, out, N, C, B, R, amax, st);
 }
 
 template <bool TRANSPOSE>
 static int dispatch_aggregate_dense(const float* feat, const float* sten, const int32_t* rowptr, const int32_t* nbr,
-                                    const int32_t* perm, float* out, int64_t N, int C, int B, int R, cudaStream_t st) {
+                                    const int32_t* perm, float* out, int64_t N, int C, int B, int R, float* amax,
+                                    cudaStream_t st) {
+    uint32_t* am = reinterpret_cast<uint32_t*>(amax);
     const int64_t lanes = N * R * (C / 2);
     if (lanes == 0) return FCB_OK;
     const unsigned blocks = (unsigned)((lanes + 255) / 256);
@@ -256,11 +279,11 @@ static int dispatch_aggregate_dense(const float* feat, const float* sten, const 
     float4* o4 = reinterpret_cast<float4*>(out);
     prof_begin(TRANSPOSE ? "aggregate_dense_T" : "aggregate_dense", st);
     switch (B) {
-        case 0: k_aggregate_dense<0, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, s2, rowptr, nbr, perm, o4, N, C, R); break;
-        case 1: k_aggregate_dense<1, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, s2, rowptr, nbr, perm, o4, N, C, R); break;
-        case 2: k_aggregate_dense<2, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, s2, rowptr, nbr, perm, o4, N, C, R); break;
-        case 3: k_aggregate_dense<3, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, s2, rowptr, nbr, perm, o4, N, C, R); break;
-        case 4: k_aggregate_dense<4, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, s2, rowptr, nbr, perm, o4, N, C, R); break;
+        case 0: k_aggregate_dense<0, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, s2, rowptr, nbr, perm, o4, N, C, R, am); break;
+        case 1: k_aggregate_dense<1, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, s2, rowptr, nbr, perm, o4, N, C, R, am); break;
+        case 2: k_aggregate_dense<2, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, s2, rowptr, nbr, perm, o4, N, C, R, am); break;
+        case 3: k_aggregate_dense<3, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, s2, rowptr, nbr, perm, o4, N, C, R, am); break;
+        case 4: k_aggregate_dense<4, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, s2, rowptr, nbr, perm, o4, N, C, R, am); break;
         default: set_error("aggregate_dense: band_limit %d unsupported", B); return FCB_E_UNSUPPORTED;
     }
     prof_end(st);
@@ -270,14 +293,14 @@ static int dispatch_aggregate_dense(const float* feat, const float* sten, const 
 
 int launch_aggregate_dense(const float* feat, const float* sten, const int32_t* rowptr, const int32_t* nbr,
                            const int32_t* perm, float* out, int64_t N, int C, int B, int R, int transpose,
-                           cudaStream_t st) {
+                           float* amax, cudaStream_t st) {
     FCB_REQUIRE(N >= 0 && C > 0 && R >= 1 && R <= FCB_MAX_RINGS, FCB_E_ARG, "aggregate_dense: bad sizes");
     FCB_REQUIRE(B >= 0 && B <= FCB_MAX_BAND_LIMIT, FCB_E_UNSUPPORTED, "aggregate_dense: band_limit %d unsupported", B);
     FCB_REQUIRE((C & 1) == 0, FCB_E_ALIGN, "aggregate_dense: channel count must be even");
     FCB_REQUIRE(aligned16(feat) && aligned16(out), FCB_E_ALIGN, "aggregate_dense: pointers must be 16-byte aligned");
     FCB_REQUIRE(N * (int64_t)R * (C / 2) / 256 < 0x7fffffffLL, FCB_E_UNSUPPORTED, "aggregate_dense: grid too large");
-    return transpose ? dispatch_aggregate_dense<true>(feat, sten, rowptr, nbr, perm, out, N, C, B, R, st)
-                     : dispatch_aggregate_dense<false>(feat, sten, rowptr, nbr, perm, out, N, C, B, R, st);
+    return transpose ? dispatch_aggregate_dense<true>(feat, sten, rowptr, nbr, perm, out, N, C, B, R, amax, st)
+                     : dispatch_aggregate_dense<false>(feat, sten, rowptr, nbr, perm, out, N, C, B, R, amax, st);
 }
 
 }  // namespace fcb
@@ -285,6 +308,6 @@ int launch_aggregate_dense(const float* feat, const float* sten, const int32_t* 
 extern "C" int fcb_aggregate_f32(const float* feat, const int32_t* rowptr, const void* rec, const float* rot,
                                  float* out, int64_t N, int C, int band_limit, int R, int transpose, void* stream) {
     FCB_REQUIRE(feat && rowptr && rec && rot && out, FCB_E_ARG, "aggregate: null pointer");
-    return fcb::launch_aggregate(feat, rowptr, rec, rot, out, N, C, band_limit, R, transpose,
+    return fcb::launch_aggregate(feat, rowptr, rec, rot, out, N, C, band_limit, R, transpose, nullptr,
                                  static_cast<cudaStream_t>(stream));
 }

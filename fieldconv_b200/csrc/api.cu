@@ -238,10 +238,11 @@ static int check_dims(const char* who, int64_t N, int Ci, int Co, int B, int R, 
 // Vertex ranges of the weight-gradient reduction: enough CTAs for (at most) four full waves on 148 SMs, and short
 // enough that each range's accumulating MMA steps fit three TMEM accumulators of the tensor-core plan (400 steps of
 // 8 vertices each: gemm_tc_plan) so the 3xTF32 kernel keeps its full 128-column tiles.
-static int choose_split(int64_t rows_m, int64_t kdim) {
+static int choose_split(int64_t rows_m, int64_t kdim, int flags) {
     const int64_t tiles = (rows_m + 127) / 128;
     int64_t s = (4 * 148) / tiles;
-    const int64_t s_acc = (kdim + 3 * 400 * 8 - 1) / (3 * 400 * 8);
+    const int64_t per_mma = (flags & FCB_GEMM_MASK) == FCB_GEMM_TC_2XF16 ? 16 : 8;     // vertices per accumulating MMA
+    const int64_t s_acc = (kdim + 3 * 400 * per_mma - 1) / (3 * 400 * per_mma);
     if (s < s_acc) s = s_acc;
     const int64_t cap = kdim / 512;
     if (s > cap) s = cap;
@@ -250,47 +251,63 @@ static int choose_split(int64_t rows_m, int64_t kdim) {
     return (int)s;
 }
 
+static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
+
 static size_t fwd_ws(const Dims& d) {
-    return align_up((size_t)(4 * d.K * d.Co) * 4, 256) + gemm_tc_ws_bytes(2 * d.Co, 2 * d.K, 1) + 512;
+    return 256 /* max|contrib| slot */ + align_up((size_t)(4 * d.K * d.Co) * 4, 256) +
+           max_sz(gemm_tc_ws_bytes(2 * d.Co, 2 * d.K, 1), gemm_h_ws_bytes(2 * d.Co, 2 * d.K, 1)) + 512;
 }
 
-static size_t bwd_ws(const Dims& d, bool need_contrib) {
-    size_t s = 0;
+static size_t gw_parts_bytes(const Dims& d, int flags) {
+    const int sp = choose_split(2 * d.K, d.N, flags);
+    const size_t b = gemm_ws_bytes(2 * d.K, 2 * d.Co, d.N, 1, 1, sp, flags);
+    const size_t fp32_parts = (size_t)(4 * d.K * d.Co) * 4 * sp;
+    return align_up(b > fp32_parts ? b : fp32_parts, 256) + 256;
+}
+
+static size_t bwd_ws(const Dims& d, bool need_contrib, int flags) {
+    size_t s = 512;                                                         // max|contrib|, max|G| slots
     s += align_up((size_t)(4 * d.K * d.Co) * 4, 256);                       // Bt
     s += align_up((size_t)(4 * d.K * d.Co) * 4, 256);                       // P
-    {   // split-K partials (+ the packed gy operand of the tensor-core weight-gradient GEMM)
-        const int sp = choose_split(2 * d.K, d.N);
-        size_t b = gemm_ws_bytes(2 * d.K, 2 * d.Co, d.N, 1, 1, sp, FCB_GEMM_TC_3XTF32);
-        const size_t fp32_parts = (size_t)(4 * d.K * d.Co) * 4 * sp;
-        s += align_up(b > fp32_parts ? b : fp32_parts, 256) + 256;
-    }
+    s += gw_parts_bytes(d, flags);                                          // split-K partials (+ the packed gy operand)
     s += align_up((size_t)d.N * d.Kt * 8, 256);                             // G
     s += align_up((size_t)d.N * d.M * d.Ci * 8, 256);                       // gxh
     if (need_contrib) s += align_up((size_t)d.N * d.K * 8, 256);            // recomputed contrib
-    s += gemm_tc_ws_bytes(2 * d.Ci, 2 * (int64_t)d.R * d.Co, d.M);           // packed operand of the tensor-core grad-x GEMM
+    // packed operand of the tensor-core grad-x GEMM
+    s += max_sz(gemm_tc_ws_bytes(2 * d.Ci, 2 * (int64_t)d.R * d.Co, d.M), gemm_h_ws_bytes(2 * d.Ci, 2 * (int64_t)d.R * d.Co, d.M));
     return s + 2048;
 }
 
-static int contract_fwd(const Dims& d, const float* contrib, const float* W, float* y, void* ws, size_t ws_bytes, int flags,
-                        cudaStream_t st) {
+// The forward drivers aggregate into `contrib` first; *amax (max|contrib|, folded by the aggregation kernel) is the
+// operand scale of the 2xFP16 contraction.
+static float* fwd_amax_slot(void* ws, float* user_slot, cudaStream_t st) {
+    if (user_slot) return user_slot;
+    float* slot = static_cast<float*>(ws);
+    cudaMemsetAsync(slot, 0, 4, st);
+    return slot;
+}
+
+static int contract_fwd(const Dims& d, const float* contrib, const float* amax, const float* W, float* y, void* ws,
+                        size_t ws_bytes, int flags, cudaStream_t st) {
     FCB_REQUIRE(ws_bytes >= fwd_ws(d), FCB_E_WORKSPACE, "fwd: workspace too small");
     Arena ar(ws, ws_bytes);
+    ar.take<char>(256);      // the max|contrib| slot (fwd_amax_slot)
     float* Bw = ar.take<float>((size_t)(4 * d.K * d.Co));
     const int64_t tot = d.K * d.Co;
     FCB_LAUNCH("pack_w_fwd", st, k_pack_w_fwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bw, d.Ci, d.Co, d.R, d.M));
-    const size_t tcb = gemm_tc_ws_bytes(2 * d.Co, 2 * d.K, 1);
+    const size_t tcb = max_sz(gemm_tc_ws_bytes(2 * d.Co, 2 * d.K, 1), gemm_h_ws_bytes(2 * d.Co, 2 * d.K, 1));
     void* tcw = ar.take<char>(tcb);
-    return launch_gemm(contrib, Bw, y, d.N, 2 * d.Co, 2 * d.K, 2 * d.K, 2 * d.Co, 2 * d.Co, 0, 1, 0, 0, 0, 1, tcw, tcb, flags, st);
+    return launch_gemm(contrib, Bw, y, d.N, 2 * d.Co, 2 * d.K, 2 * d.K, 2 * d.Co, 2 * d.Co, 0, 1, 0, 0, 0, 1, tcw, tcb, flags, amax, st);
 }
 
 template <typename GatherT>
 static int backward_common(const Dims& d, const float* x, const float* W, const float* gy, const float* contrib,
-                           GatherT&& gather_transpose, float* gx, float* gW, Arena& ar, int flags, cudaStream_t st) {
+                           const float* contrib_amax, float* g_amax, GatherT&& gather_transpose, float* gx, float* gW,
+                           Arena& ar, int flags, cudaStream_t st) {
     float* Bt = ar.take<float>((size_t)(4 * d.K * d.Co));
     float* P = ar.take<float>((size_t)(4 * d.K * d.Co));
-    const int gw_split = choose_split(2 * d.K, d.N);
-    size_t parts_bytes = gemm_ws_bytes(2 * d.K, 2 * d.Co, d.N, 1, 1, gw_split, flags);
-    if (parts_bytes < (size_t)(4 * d.K * d.Co) * gw_split * 4) parts_bytes = (size_t)(4 * d.K * d.Co) * gw_split * 4;
+    const int gw_split = choose_split(2 * d.K, d.N, flags);
+    const size_t parts_bytes = gw_parts_bytes(d, flags);
     float* parts = reinterpret_cast<float*>(ar.take<char>(parts_bytes));
     float* G = ar.take<float>((size_t)d.N * d.Kt * 2);
     float* gxh = ar.take<float>((size_t)d.N * d.M * d.Ci * 2);
@@ -298,25 +315,26 @@ static int backward_common(const Dims& d, const float* x, const float* W, const 
     if (gW) {
         // K4: P[2K x 2Co] = contrib_real^T @ gy_real, split over vertices, fixed-order reduction
         int rc = launch_gemm(contrib, gy, P, 2 * d.K, 2 * d.Co, d.N, 2 * d.K, 2 * d.Co, 2 * d.Co, 1, 1, 0, 0, 0, gw_split, parts,
-                             parts_bytes, flags, st);
+                             parts_bytes, flags, contrib_amax, st);
         if (rc) return rc;
         FCB_LAUNCH("combine_gw", st, k_combine_gw<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, reinterpret_cast<float2*>(gW), d.Ci, d.Co, d.R, d.M));
     }
     if (gx) {
         // K5a: G[j][m][r][o] = sum_{e: src=j} conj(sten) gy[tgt]
-        int rc = gather_transpose(G);
+        cudaMemsetAsync(g_amax, 0, 4, st);
+        int rc = gather_transpose(G, g_amax);
         if (rc) return rc;
         // K5b: gxh[:, m, :] = G[:, m, :] @ conj(W)[m]  (one real GEMM per m, batched)
         FCB_LAUNCH("pack_w_bwd", st, k_pack_w_bwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bt, d.Ci, d.Co, d.R, d.M));
         const int64_t Q2 = 2 * (int64_t)d.R * d.Co;
-        const size_t tcb = gemm_tc_ws_bytes(2 * d.Ci, Q2, d.M);
+        const size_t tcb = max_sz(gemm_tc_ws_bytes(2 * d.Ci, Q2, d.M), gemm_h_ws_bytes(2 * d.Ci, Q2, d.M));
         void* tcw = ar.take<char>(tcb);
         int grouped = 0;     // all m in one pass over G (one long-K tensor-core pipeline) when the plan allows
-        rc = launch_gemm_grouped(G, Bt, gxh, d.N, 2 * d.Ci, Q2, d.M, flags, tcw, tcb, &grouped, st);
+        rc = launch_gemm_grouped(G, Bt, gxh, d.N, 2 * d.Ci, Q2, d.M, flags, g_amax, tcw, tcb, &grouped, st);
         if (rc) return rc;
         if (!grouped) {
             rc = launch_gemm(G, Bt, gxh, d.N, 2 * d.Ci, Q2, (int64_t)d.M * Q2, 2 * d.Ci, (int64_t)d.M * 2 * d.Ci, 0, d.M, Q2,
-                             Q2 * 2 * d.Ci, 2 * d.Ci, 1, tcw, tcb, flags, st);
+                             Q2 * 2 * d.Ci, 2 * d.Ci, 1, tcw, tcb, flags, g_amax, st);
             if (rc) return rc;
         }
         const int64_t el = d.N * d.Ci;
@@ -415,13 +433,13 @@ extern "C" int fcb_bwd_workspace_bytes(int64_t N, int Ci, int Co, int band_limit
     FCB_REQUIRE(bytes, FCB_E_ARG, "bwd_workspace: null");
     int rc = check_dims("bwd_workspace", N, Ci, Co, band_limit, R, &d);
     if (rc) return rc;
-    *bytes = bwd_ws(d, !(flags & FCB_FLAG_HAVE_CONTRIB));
+    *bytes = bwd_ws(d, !(flags & FCB_FLAG_HAVE_CONTRIB), flags);
     return FCB_OK;
 }
 
 extern "C" int fcb_fwd_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
-                           const float* rot_tgt, float* y, float* contrib, int64_t N, int Ci, int Co, int band_limit,
-                           int R, int flags, void* ws, size_t ws_bytes, void* stream) {
+                           const float* rot_tgt, float* y, float* contrib, float* contrib_absmax, int64_t N, int Ci, int Co,
+                           int band_limit, int R, int flags, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Dims d;
     int rc = check_dims("fwd", N, Ci, Co, band_limit, R, &d);
@@ -430,14 +448,16 @@ extern "C" int fcb_fwd_f32(const float* x, const float* W, const int32_t* rowptr
     FCB_REQUIRE(x && W && rowptr_tgt && rec_tgt && rot_tgt && y && ws, FCB_E_ARG, "fwd: null pointer");
     FCB_REQUIRE(contrib, FCB_E_UNSUPPORTED, "fwd: this path needs a contrib buffer (N*R*Ci*M complex)");
     FCB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(W) && aligned16(contrib), FCB_E_ALIGN, "fwd: pointers must be 16-byte aligned");
+    FCB_REQUIRE(ws_bytes >= fwd_ws(d), FCB_E_WORKSPACE, "fwd: workspace too small");
     if (N == 0) return FCB_OK;
-    rc = launch_aggregate(x, rowptr_tgt, rec_tgt, rot_tgt, contrib, N, Ci, band_limit, R, 0, st);
+    float* amax = fwd_amax_slot(ws, contrib_absmax, st);
+    rc = launch_aggregate(x, rowptr_tgt, rec_tgt, rot_tgt, contrib, N, Ci, band_limit, R, 0, amax, st);
     if (rc) return rc;
-    return contract_fwd(d, contrib, W, y, ws, ws_bytes, flags, st);
+    return contract_fwd(d, contrib, amax, W, y, ws, ws_bytes, flags, st);
 }
 
 extern "C" int fcb_bwd_f32(const float* x, const float* W, const float* gy, const float* contrib,
-                           const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
+                           const float* contrib_absmax, const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
                            const int32_t* rowptr_src, const void* rec_src, const float* rot_src, float* gx, float* gW,
                            int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws, size_t ws_bytes,
                            void* stream) {
@@ -451,40 +471,47 @@ extern "C" int fcb_bwd_f32(const float* x, const float* W, const float* gy, cons
     FCB_REQUIRE(!gW || contrib || (rowptr_tgt && rec_tgt && rot_tgt), FCB_E_ARG, "bwd: grad W needs contrib or the by-target plan");
     FCB_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(W), FCB_E_ALIGN, "bwd: pointers must be 16-byte aligned");
     const bool recompute = gW && !contrib;
-    FCB_REQUIRE(ws_bytes >= bwd_ws(d, recompute), FCB_E_WORKSPACE, "bwd: workspace too small");
+    FCB_REQUIRE(ws_bytes >= bwd_ws(d, recompute, flags), FCB_E_WORKSPACE, "bwd: workspace too small");
     if (N == 0) {
         if (gW) cudaMemsetAsync(gW, 0, (size_t)d.K * d.Co * 8, st);
         return FCB_OK;
     }
     Arena ar(ws, ws_bytes);
+    float* slots = ar.take<float>(128);          // [0] max|contrib| when recomputed here, [64] max|G|
     if (recompute) {
         float* c2 = ar.take<float>((size_t)d.N * d.K * 2);
-        rc = launch_aggregate(x, rowptr_tgt, rec_tgt, rot_tgt, c2, N, Ci, band_limit, R, 0, st);
+        cudaMemsetAsync(slots, 0, 4, st);
+        rc = launch_aggregate(x, rowptr_tgt, rec_tgt, rot_tgt, c2, N, Ci, band_limit, R, 0, slots, st);
         if (rc) return rc;
         contrib = c2;
+        contrib_absmax = slots;
     }
-    auto gather = [&](float* G) { return launch_aggregate(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, st); };
-    return backward_common(d, x, W, gy, contrib, gather, gx, gW, ar, flags, st);
+    auto gather = [&](float* G, float* g_amax) {
+        return launch_aggregate(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, g_amax, st);
+    };
+    return backward_common(d, x, W, gy, contrib, contrib_absmax, slots + 64, gather, gx, gW, ar, flags, st);
 }
 
 extern "C" int fcb_fwd_dense_f32(const float* x, const float* W, const float* sten, const int32_t* rowptr_tgt,
-                                 const int32_t* nbr_tgt, const int32_t* perm_tgt, float* y, float* contrib, int64_t N,
-                                 int Ci, int Co, int band_limit, int R, int flags, void* ws, size_t ws_bytes,
-                                 void* stream) {
+                                 const int32_t* nbr_tgt, const int32_t* perm_tgt, float* y, float* contrib,
+                                 float* contrib_absmax, int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws,
+                                 size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Dims d;
     int rc = check_dims("fwd_dense", N, Ci, Co, band_limit, R, &d);
     if (rc) return rc;
     FCB_REQUIRE(x && W && rowptr_tgt && nbr_tgt && perm_tgt && y && contrib && ws, FCB_E_ARG, "fwd_dense: null pointer");
     FCB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(W) && aligned16(contrib), FCB_E_ALIGN, "fwd_dense: pointers must be 16-byte aligned");
+    FCB_REQUIRE(ws_bytes >= fwd_ws(d), FCB_E_WORKSPACE, "fwd_dense: workspace too small");
     if (N == 0) return FCB_OK;
-    rc = launch_aggregate_dense(x, sten, rowptr_tgt, nbr_tgt, perm_tgt, contrib, N, Ci, band_limit, R, 0, st);
+    float* amax = fwd_amax_slot(ws, contrib_absmax, st);
+    rc = launch_aggregate_dense(x, sten, rowptr_tgt, nbr_tgt, perm_tgt, contrib, N, Ci, band_limit, R, 0, amax, st);
     if (rc) return rc;
-    return contract_fwd(d, contrib, W, y, ws, ws_bytes, flags, st);
+    return contract_fwd(d, contrib, amax, W, y, ws, ws_bytes, flags, st);
 }
 
 extern "C" int fcb_bwd_dense_f32(const float* x, const float* W, const float* gy, const float* contrib,
-                                 const float* sten, const int32_t* rowptr_src, const int32_t* nbr_src,
+                                 const float* contrib_absmax, const float* sten, const int32_t* rowptr_src, const int32_t* nbr_src,
                                  const int32_t* perm_src, float* gx, float* gW, int64_t N, int Ci, int Co,
                                  int band_limit, int R, int flags, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -494,16 +521,17 @@ extern "C" int fcb_bwd_dense_f32(const float* x, const float* W, const float* gy
     FCB_REQUIRE(x && W && gy && ws, FCB_E_ARG, "bwd_dense: null pointer");
     FCB_REQUIRE(!gW || contrib, FCB_E_ARG, "bwd_dense: grad W needs the contrib saved by the forward");
     FCB_REQUIRE(!gx || (sten && rowptr_src && nbr_src && perm_src), FCB_E_ARG, "bwd_dense: grad x needs the by-source plan");
-    FCB_REQUIRE(ws_bytes >= bwd_ws(d, false), FCB_E_WORKSPACE, "bwd_dense: workspace too small");
+    FCB_REQUIRE(ws_bytes >= bwd_ws(d, false, flags), FCB_E_WORKSPACE, "bwd_dense: workspace too small");
     if (N == 0) {
         if (gW) cudaMemsetAsync(gW, 0, (size_t)d.K * d.Co * 8, st);
         return FCB_OK;
     }
     Arena ar(ws, ws_bytes);
-    auto gather = [&](float* G) {
-        return launch_aggregate_dense(gy, sten, rowptr_src, nbr_src, perm_src, G, N, Co, band_limit, R, 1, st);
+    float* slots = ar.take<float>(128);
+    auto gather = [&](float* G, float* g_amax) {
+        return launch_aggregate_dense(gy, sten, rowptr_src, nbr_src, perm_src, G, N, Co, band_limit, R, 1, g_amax, st);
     };
-    return backward_common(d, x, W, gy, contrib, gather, gx, gW, ar, flags, st);
+    return backward_common(d, x, W, gy, contrib, contrib_absmax, slots + 64, gather, gx, gW, ar, flags, st);
 }
 
 extern "C" int fcb_modrelu_fwd_f32(const float* x, const float* bias, float* y, int64_t N, int C, void* stream) {

@@ -73,18 +73,31 @@ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {  // a * conj(b
 int sort_pairs(uint32_t* k_in, uint32_t* v_in, uint32_t* k_out, uint32_t* v_out, int64_t n, int bits,
                void* ws, size_t ws_bytes, cudaStream_t st);
 size_t sort_workspace(int64_t n);
+// amax (nullable): device float, bit-pattern max of |out| is atomically folded into it (caller zeroes it first)
 int launch_aggregate(const float* feat, const int32_t* rowptr, const void* rec, const float* rot, float* out,
-                     int64_t N, int C, int B, int R, int transpose, cudaStream_t st);
+                     int64_t N, int C, int B, int R, int transpose, float* amax, cudaStream_t st);
 int launch_aggregate_dense(const float* feat, const float* sten, const int32_t* rowptr, const int32_t* nbr,
                            const int32_t* perm, float* out, int64_t N, int C, int B, int R, int transpose,
-                           cudaStream_t st);
+                           float* amax, cudaStream_t st);
 // Real GEMM dispatcher.  flags & FCB_GEMM_MASK selects FP32 FMA or the tcgen05 path (trans_a == 0, N <= 256 only;
 // anything else runs on the FMA path).  ws must hold gemm_ws_bytes(...) bytes.
 size_t gemm_ws_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags);
 int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                 int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k,
-                void* ws, size_t ws_bytes, int flags, cudaStream_t st);
+                void* ws, size_t ws_bytes, int flags, const float* a_amax, cudaStream_t st);
 size_t gemm_tc_ws_bytes(int N, int64_t K, int batch);
+// 2xFP16 tensor-core kernels (gemm_h.cu).  a_amax: device float holding max|A| (from the kernel that produced A).
+int gemm_h_plan_nn(int N, int64_t ksteps, int* n_pairs);
+size_t gemm_h_ws_bytes(int N, int64_t K, int batch);
+size_t gemm_h_tn_ws_bytes(int N, int64_t Kv);
+float* gemm_h_amax_slot(void* ws);      // scratch float inside a gemm_h workspace for max|A| computed by the dispatcher
+int launch_absmax_f32(const float* p, int64_t rows, int cols, int64_t ld, int batch, int64_t stride, float* out, cudaStream_t st);
+int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
+                     int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int n_pairs, int kgroups,
+                     const float* amax_a, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
+                     int64_t ldc, int split, int64_t k_per_split, float* parts, int n_main, const float* amax_a, void* bp_ws,
+                     size_t bp_bytes, cudaStream_t st);
 // column-chunk width + number of hi*hi accumulators for `ksteps` accumulating MMA steps (0: tensor cores not usable)
 int gemm_tc_plan(int N, int64_t ksteps, int mode, int* n_main);
 size_t gemm_tc_tn_ws_bytes(int N, int64_t Kv);
@@ -99,6 +112,6 @@ int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N
 // grad-x contraction gxh[:, m, :] = G[:, m, :] @ Bt[m] for all m in one pass over G when the tensor-core plan allows
 // (returns FCB_OK and sets *done = 1), otherwise leaves *done = 0 for the caller to use the batched path
 int launch_gemm_grouped(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t Kg, int groups, int flags,
-                        void* ws, size_t ws_bytes, int* done, cudaStream_t st);
+                        const float* a_amax, void* ws, size_t ws_bytes, int* done, cudaStream_t st);
 
 }  // namespace fcb

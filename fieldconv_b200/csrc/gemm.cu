@@ -183,26 +183,41 @@ static int dispatch_gemm(const float* A, const float* Bm, float* C, int64_t M, i
     return FCB_OK;
 }
 
-static int64_t tc_ksteps(int64_t K, int trans_a, int split_k) {
-    if (!trans_a) return (K + 31) / 32 * 4;
+static bool mode_is_tc(int mode) { return mode == FCB_GEMM_TC_3XTF32 || mode == FCB_GEMM_TC_TF32 || mode == FCB_GEMM_TC_2XF16; }
+
+// vertices (TN) / reals (NN) per stage and per MMA K-step of the tensor-core kernels
+static int tc_stage(int mode) { return mode == FCB_GEMM_TC_2XF16 ? 64 : 32; }
+static int tc_kstep(int mode) { return mode == FCB_GEMM_TC_2XF16 ? 16 : 8; }
+
+static int64_t tc_ksteps(int64_t K, int trans_a, int split_k, int mode) {
+    const int st = tc_stage(mode), ks = tc_kstep(mode);
+    if (!trans_a) return (K + st - 1) / st * (st / ks);
     int64_t kps = (K + split_k - 1) / split_k;
-    kps = (kps + 31) / 32 * 32;
-    return kps / 8;
+    kps = (kps + st - 1) / st * st;
+    return kps / ks;
+}
+
+// accumulation plan of the selected tensor-core kernel: column-chunk width (0: not feasible) and accumulator count
+static int tc_plan(int N, int64_t ksteps, int mode, int trans_a, int* n_acc) {
+    if (mode == FCB_GEMM_TC_2XF16) return trans_a ? gemm_tc_plan(N, ksteps, FCB_GEMM_TC_3XTF32, n_acc) : gemm_h_plan_nn(N, ksteps, n_acc);
+    return gemm_tc_plan(N, ksteps, mode, n_acc);
 }
 
 // tensor cores are used when the mode asks for them and the accumulation plan fits TMEM (gemm_tc_plan)
 static bool use_tc(int N, int64_t K, int trans_a, int batch, int split_k, int flags) {
     const int mode = flags & FCB_GEMM_MASK;
-    if (!(mode == FCB_GEMM_TC_3XTF32 || mode == FCB_GEMM_TC_TF32) || N <= 0 || K <= 0) return false;
+    if (!mode_is_tc(mode) || N <= 0 || K <= 0) return false;
     if (trans_a && batch != 1) return false;
     int n_main;
-    return gemm_tc_plan(N, tc_ksteps(K, trans_a, split_k), mode, &n_main) > 0;
+    return tc_plan(N, tc_ksteps(K, trans_a, split_k, mode), mode, trans_a, &n_main) > 0;
 }
 
 size_t gemm_ws_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags) {
-    if (use_tc(N, K, trans_a, batch, split_k, flags) && !trans_a) return gemm_tc_ws_bytes(N, K, batch);
+    const bool h = (flags & FCB_GEMM_MASK) == FCB_GEMM_TC_2XF16;
+    if (use_tc(N, K, trans_a, batch, split_k, flags) && !trans_a) return h ? gemm_h_ws_bytes(N, K, batch) : gemm_tc_ws_bytes(N, K, batch);
     const size_t parts = split_k > 1 ? align_up((size_t)split_k * batch * M * N * 4, 256) : 0;
-    if (use_tc(N, K, trans_a, batch, split_k, flags) && trans_a) return parts + gemm_tc_tn_ws_bytes(N, K);   // + packed B
+    if (use_tc(N, K, trans_a, batch, split_k, flags) && trans_a)
+        return parts + (h ? gemm_h_tn_ws_bytes(N, K) : gemm_tc_tn_ws_bytes(N, K));   // + packed B
     return parts;
 }
 
@@ -216,11 +231,27 @@ int launch_reduce_splits(const float* partials, float* C, int64_t M, int N, int6
 
 // A = [M x groups*Kg] row-major (lda = groups*Kg), Bm = groups matrices [Kg x N] back to back, C = [M x groups*N].
 int launch_gemm_grouped(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t Kg, int groups, int flags,
-                        void* ws, size_t ws_bytes, int* done, cudaStream_t st) {
+                        const float* a_amax, void* ws, size_t ws_bytes, int* done, cudaStream_t st) {
     *done = 0;
     const int mode = flags & FCB_GEMM_MASK;
-    if (!(mode == FCB_GEMM_TC_3XTF32 || mode == FCB_GEMM_TC_TF32) || groups < 2) return FCB_OK;
+    if (!mode_is_tc(mode) || groups < 2) return FCB_OK;
     const int npad = (N + 15) / 16 * 16;
+    if (mode == FCB_GEMM_TC_2XF16) {
+        const int64_t mmas_h = Kg / 64 * 4 * 3;                                  // accumulating MMAs per accumulator
+        if (Kg % 64 != 0 || N > 128 || npad * groups > 512 || mmas_h > TC_MAX_ACC_MMAS_GROUPED || ((groups * (int64_t)N) % 4) != 0 ||
+            ((groups * Kg) % 4) != 0 || !aligned16(A) || !aligned16(C) || ws_bytes < gemm_h_ws_bytes(N, Kg, groups))
+            return FCB_OK;
+        if (!a_amax) {
+            float* slot = gemm_h_amax_slot(ws);
+            int rc = launch_absmax_f32(A, M, (int)(groups * Kg), groups * Kg, 1, 0, slot, st);
+            if (rc) return rc;
+            a_amax = slot;
+        }
+        int rc = launch_gemm_h_nn(A, Bm, C, M, N, Kg, groups * Kg, N, groups * (int64_t)N, 1, 0, Kg * N, 0, 1, groups, a_amax, ws,
+                                  ws_bytes, st);
+        if (rc == FCB_OK) *done = 1;
+        return rc;
+    }
     const int64_t chunks = Kg / 32;
     const int64_t mmas = chunks * 4 * (mode == FCB_GEMM_TC_3XTF32 ? 3 : 1);     // accumulating MMAs per accumulator
     if (Kg % 32 != 0 || npad * groups > 512 || mmas > TC_MAX_ACC_MMAS_GROUPED || ((groups * (int64_t)N) % 4) != 0 ||
@@ -234,17 +265,32 @@ int launch_gemm_grouped(const float* A, const float* Bm, float* C, int64_t M, in
 
 int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                 int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k, void* ws,
-                size_t ws_bytes, int flags, cudaStream_t st) {
+                size_t ws_bytes, int flags, const float* a_amax, cudaStream_t st) {
     FCB_REQUIRE(A && Bm && C, FCB_E_ARG, "gemm: null pointer");
     FCB_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 1 && split_k >= 1, FCB_E_ARG, "gemm: bad sizes");
     const int mode = flags & FCB_GEMM_MASK;
-    if (use_tc(N, K, trans_a, batch, split_k, flags) && !trans_a && (ldc % 4) == 0 && (sc % 4) == 0 && aligned16(C)) {
+    const bool h = mode == FCB_GEMM_TC_2XF16;
+    if (use_tc(N, K, trans_a, batch, split_k, flags) && !trans_a && (ldc % 4) == 0 && (sc % 4) == 0 && aligned16(C) &&
+        (!h || ((lda % 4) == 0 && (sa % 4) == 0 && aligned16(A)))) {
         int n_main = 1;
-        const int chunk = gemm_tc_plan(N, tc_ksteps(K, 0, 1), mode, &n_main);
+        const int chunk = tc_plan(N, tc_ksteps(K, 0, 1, mode), mode, 0, &n_main);
+        if (h) {
+            FCB_REQUIRE(ws && ws_bytes >= gemm_h_ws_bytes(N, K, batch), FCB_E_WORKSPACE, "gemm: workspace too small (fcb_gemm_workspace_bytes)");
+            if (M == 0) return FCB_OK;
+            if (!a_amax) {       // operand maximum not supplied by the producer of A: one extra pass over A
+                float* slot = gemm_h_amax_slot(ws);
+                const bool contiguous = (lda == K) && (batch == 1 || sa == M * K);
+                int rc = contiguous ? launch_absmax_f32(A, (int64_t)batch * M, (int)K, K, 1, 0, slot, st)
+                                    : launch_absmax_f32(A, M, (int)K, lda, batch, sa, slot, st);
+                if (rc) return rc;
+                a_amax = slot;
+            }
+        }
         for (int n0 = 0; n0 < N; n0 += chunk) {      // column chunks (one unless N is wide): same A, offset B and C
             const int nc = N - n0 < chunk ? N - n0 : chunk;
-            int rc = launch_gemm_tc_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, mode, n_main, 1, ws,
-                                       ws_bytes, st);
+            int rc = h ? launch_gemm_h_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, n_main, 1, a_amax, ws, ws_bytes, st)
+                       : launch_gemm_tc_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, mode, n_main, 1, ws,
+                                           ws_bytes, st);
             if (rc) return rc;
         }
         return FCB_OK;
@@ -252,18 +298,27 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
     float* partials = static_cast<float*>(ws);
     if (use_tc(N, K, trans_a, batch, split_k, flags) && trans_a && (lda % 4) == 0 && aligned16(A)) {
         const size_t parts_bytes = split_k > 1 ? align_up((size_t)split_k * M * N * 4, 256) : 0;
-        FCB_REQUIRE(ws && ws_bytes >= parts_bytes + gemm_tc_tn_ws_bytes(N, K), FCB_E_WORKSPACE,
+        FCB_REQUIRE(ws && ws_bytes >= parts_bytes + (h ? gemm_h_tn_ws_bytes(N, K) : gemm_tc_tn_ws_bytes(N, K)), FCB_E_WORKSPACE,
                     "gemm: workspace too small (fcb_gemm_workspace_bytes)");
         void* bp_ws = static_cast<char*>(ws) + parts_bytes;
         const size_t bp_bytes = ws_bytes - parts_bytes;
+        const int stg = tc_stage(mode);
         int64_t kps_tc = (K + split_k - 1) / split_k;
-        kps_tc = (kps_tc + 31) / 32 * 32;
+        kps_tc = (kps_tc + stg - 1) / stg * stg;
         int n_main = 1;
-        const int chunk = gemm_tc_plan(N, kps_tc / 8, mode, &n_main);
+        const int chunk = tc_plan(N, kps_tc / tc_kstep(mode), mode, 1, &n_main);
+        if (h && !a_amax && M > 0 && K > 0) {
+            float* slot = gemm_h_amax_slot(bp_ws);
+            int rc = launch_absmax_f32(A, K, (int)M, lda, 1, 0, slot, st);
+            if (rc) return rc;
+            a_amax = slot;
+        }
         for (int n0 = 0; n0 < N; n0 += chunk) {
             const int nc = N - n0 < chunk ? N - n0 : chunk;
-            int rc = launch_gemm_tc_tn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, split_k, kps_tc, partials, mode, n_main,
-                                       bp_ws, bp_bytes, st);
+            int rc = h ? launch_gemm_h_tn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, split_k, kps_tc, partials, n_main, a_amax, bp_ws,
+                                          bp_bytes, st)
+                       : launch_gemm_tc_tn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, split_k, kps_tc, partials, mode, n_main,
+                                           bp_ws, bp_bytes, st);
             if (rc) return rc;
             if (split_k > 1) {
                 rc = launch_reduce_splits(partials, C + n0, M, nc, ldc, 0, 1, split_k, st);
@@ -314,5 +369,5 @@ extern "C" int fcb_gemm_f32(const float* A, const float* B, float* C, int64_t M,
                             int64_t stride_c, int split_k, void* workspace, size_t workspace_bytes, int flags,
                             void* stream) {
     return fcb::launch_gemm(A, B, C, M, N, K, lda, ldb, ldc, trans_a, batch, stride_a, stride_b, stride_c, split_k,
-                            workspace, workspace_bytes, flags, static_cast<cudaStream_t>(stream));
+                            workspace, workspace_bytes, flags, nullptr, static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,860 @@
+// K2 / K4 / K5b on the 5th-generation tensor cores, "2xFP16" mode: C = A * B with fp32 inputs and fp32 output, computed
+// with tcgen05.mma kind::f16 on operands that are split into TWO fp16 planes each.
+//
+// Why fp16 pairs instead of 3xTF32 (gemm_tc.cu): a tf32 operand occupies 4 bytes of shared memory for 11 bits of
+// significand, so the SS-mode MMAs of the 3xTF32 kernel are bound by shared-memory bandwidth (ncu r01c: tensor pipe 36 %).
+// An fp16 carries the same 11 bits in 2 bytes and the f16 MMA runs at twice the tf32 rate, so the identical
+// three-product scheme  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  moves half the bytes and takes half the tensor time.
+//   hi = fp16(s*x), lo = fp16(s*x - hi):  hi + lo carries 22 bits of s*x (relative error 2^-23 while lo is a normal
+//   fp16, absolute error <= 2^-25 below that).  fp16 has a 5-bit exponent, so each operand is first scaled by a power
+//   of two s = 2^(14 - floor(log2 max|x|)) that puts its largest entry in [2^14, 2^15): entries down to 2^-17 of the
+//   largest keep full precision, smaller ones lose bits only in ABSOLUTE terms (<= 2^-40 of the largest entry) — far
+//   inside the normwise fp32 parity budget.  The epilogue multiplies by 1/(s_A s_B), exact.  max|x| comes from the
+//   kernel that produced the operand (the aggregation kernels track it for free) or from k_absmax.
+//   The accumulator behaviour is the one described in gemm_tc.cu: no accumulator receives more than 400 accumulating
+//   MMAs of hi*hi products (one f16 MMA covers 16 reals of K, twice a tf32 MMA).
+//
+// NN kernel (y = contrib W, gxh = G conj(W)): one CTA = one 128-row tile of A and all N <= 128 columns.
+//   warps 0-15 producers: 256-bit coalesced loads of the fp32 A tile (64 reals = 256 B per row and stage), scale + hi/lo
+//              split in registers, 128-bit stores into the canonical SWIZZLE_128B K-major layout (one 128-byte row =
+//              64 fp16 of one A row), fence.proxy.async, mbarrier arrive; afterwards the epilogue.
+//   warp 16    single-thread MMA issue.  The two B planes are adjacent in shared memory, so  A_hi * [B_hi | B_lo]  is ONE
+//              MMA of width 2*Npad whose accumulator holds the main product in columns [0, Npad) and the hi*lo cross
+//              term in [Npad, 2 Npad);  A_lo * B_hi  is a second MMA of width Npad accumulating into the cross block:
+//              A_hi is read from shared memory once for two products (-19 % operand bytes).
+//   warp 17    B operand: pre-packed images (k_pack_b_h) fetched with one cp.async.bulk per stage.
+// TN kernel (P = contrib^T gy, the weight gradient): both operands MN-major (the hardware transposes), SWIZZLE_128B
+//   atoms of 8 vertices x 64 fp16; gy is packed once (k_pack_b_h_tn), contrib goes through the producer warps.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace fcb {
+namespace th {
+
+using tc::BM;
+using namespace tc;
+
+constexpr int KC = 64;         // reals per stage (NN): one 128-byte swizzle row of fp16
+constexpr int KV = 64;         // vertices per stage (TN): four MMA K-steps of 16
+constexpr int N_PROD_WARPS = 16;
+constexpr int N_PROD = N_PROD_WARPS * 32;
+constexpr int THREADS = (N_PROD_WARPS + 2) * 32;
+constexpr uint32_t A_PLANE = BM * 128;   // 16 KB: 128 rows x 64 fp16 (NN) or 64 vertices x 128 columns (TN)
+constexpr int UN = 2;          // 16-byte output units (8 reals) per producer thread and stage
+constexpr int PF = 3;          // chunks of A in flight in registers per producer thread (96 KB per SM)
+
+// power-of-two operand scale from max|x| (bit pattern of a non-negative float): largest entry -> [2^14, 2^15)
+__host__ __device__ __forceinline__ uint32_t scale_field(uint32_t amax_bits) {
+    const int e = (int)((amax_bits >> 23) & 0xffu);
+    if (e == 255) return 127u;                 // inf / NaN operand: scale 1, the result is non-finite as in fp32
+    int f = 268 - e;                           // (127 + 14) + (127 - e)
+    if (f > 253) f = 253;                      // max|x| < 2^-112 (or 0): everything underflows anyway
+    if (f < 1) f = 1;
+    return (uint32_t)f;
+}
+__device__ __forceinline__ float scale_of(const float* amax) { return __uint_as_float(scale_field(__float_as_uint(__ldg(amax))) << 23); }
+__device__ __forceinline__ float inv_scale_of(const float* amax) {
+    return __uint_as_float((254u - scale_field(__float_as_uint(__ldg(amax)))) << 23);
+}
+
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Instruction descriptor: D = f32 (bit 4), A = B = f16 (format 0), M = 128, N = n; K-major unless the major bits are or-ed in.
+__host__ __device__ inline uint32_t make_idesc_f16(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+// MN-major SWIZZLE_128B descriptor (16-bit operands): atoms of 64 MN-elements (128 B) x 8 K-rows; LBO = distance between
+// atoms along MN, SBO = distance between 8-row K groups.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128_h(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
+
+struct F8 {
+    float v[8];
+};
+__device__ __forceinline__ void ld256(const float* p, F8& r) {   // one 256-bit read-only load (32-byte aligned)
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void ld2x128(const float* p, F8& r) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+}
+__device__ __forceinline__ void zero8(F8& r) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r.v[e] = 0.f;
+}
+// 8 reals -> 8 fp16 hi + 8 fp16 lo of s*x (element e at the lower address)
+__device__ __forceinline__ void split8(const F8& x, float s, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a0 = x.v[2 * i] * s, a1 = x.v[2 * i + 1] * s;
+        const __half2 hh = __floats2half2_rn(a0, a1);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ------------------------------------------------------------------------------------------------------------ max|x|
+// out (uint32 bit pattern of a non-negative float, or NaN bits) = max(out, max |p[b][r][c]|); out is pre-zeroed.
+__global__ void __launch_bounds__(256) k_absmax(const float* __restrict__ p, int64_t rows, int cols, int64_t ld, int batch,
+                                                int64_t stride, int flat4, uint32_t* __restrict__ out) {
+    uint32_t mx = 0;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+    if (flat4) {       // contiguous and 16-byte aligned: float4 sweep
+        const int64_t n4 = (int64_t)batch * rows * cols / 4;
+        const float4* q = reinterpret_cast<const float4*>(p);
+        for (int64_t i = t0; i < n4; i += nt) {
+            const float4 v = __ldg(q + i);
+            mx = max(mx, __float_as_uint(fabsf(v.x)));
+            mx = max(mx, __float_as_uint(fabsf(v.y)));
+            mx = max(mx, __float_as_uint(fabsf(v.z)));
+            mx = max(mx, __float_as_uint(fabsf(v.w)));
+        }
+    } else {
+        const int64_t per = rows * cols, tot = per * batch;
+        for (int64_t i = t0; i < tot; i += nt) {
+            const int64_t b = i / per, r = (i - b * per) / cols;
+            const int c = (int)(i - b * per - r * cols);
+            mx = max(mx, __float_as_uint(fabsf(p[b * stride + r * ld + c])));
+        }
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx > *reinterpret_cast<volatile uint32_t*>(out)) atomicMax(out, mx);
+}
+
+static int launch_absmax(const float* p, int64_t rows, int cols, int64_t ld, int batch, int64_t stride, float* out,
+                         cudaStream_t st) {
+    if (cudaMemsetAsync(out, 0, 4, st) != cudaSuccess) {
+        set_error("absmax: cudaMemsetAsync failed");
+        return FCB_E_CUDA;
+    }
+    const int64_t tot = (int64_t)batch * rows * cols;
+    if (tot == 0) return FCB_OK;
+    const bool contiguous = (ld == cols) && (batch == 1 || stride == rows * (int64_t)cols);
+    const int flat4 = (contiguous && (tot % 4) == 0 && aligned16(p)) ? 1 : 0;
+    int64_t blocks = (tot / (flat4 ? 4 : 1) + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    FCB_LAUNCH("absmax", st, k_absmax<<<(unsigned)blocks, 256, 0, st>>>(p, rows, cols, ld, batch, stride, flat4,
+                                                                        reinterpret_cast<uint32_t*>(out)));
+    return FCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------ NN
+struct Params {
+    const float* A;
+    const __half* Bp;   // packed B: [batch][chunk of 64 k][plane(hi,lo)][Npad][64 fp16] swizzled (k_pack_b_h)
+    float* C;
+    const float *amax_a, *amax_b;
+    int64_t M, K, lda, ldc, sa, sc;
+    int64_t bp_batch_stride;   // fp16 elements
+    int N, Npad, nchunks, stages;
+    int n_pairs;               // (main, cross) accumulator pairs the k-steps are dealt over, round-robin
+    int kgroups, cpg;          // grouped-K mode (kgroups > 1): K = kgroups * cpg chunks; group g accumulates all three
+                               // products into its own accumulator and lands in C columns [g*N, (g+1)*N)
+    int wide;                  // rows are 32-byte aligned: 256-bit loads
+    uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw);
+    const int S = p.stages;
+    const uint32_t b_plane = (uint32_t)p.Npad * 128u;
+    // layout: A_hi[S] | A_lo[S] | B[S] (hi plane, lo plane adjacent) | barriers
+    const uint32_t a_hi0 = base, a_lo0 = base + S * A_PLANE, b0 = base + 2 * S * A_PLANE;
+    const uint32_t bars = b0 + S * 2 * b_plane;
+    auto full_a = [&](int s) { return bars + 8u * s; };
+    auto full_b = [&](int s) { return bars + 8u * (S + s); };
+    auto empty = [&](int s) { return bars + 8u * (2 * S + s); };
+    const uint32_t tmem_full = bars + 8u * (3 * S);
+    const uint32_t tmem_slot = bars + 8u * (3 * S + 1);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(sm + (tmem_slot - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int batch = blockIdx.y;
+    const float* A = p.A + batch * p.sa;
+    const __half* Bp = p.Bp + batch * p.bp_batch_stride;
+    float* C = p.C + batch * p.sc;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_a(s), N_PROD_WARPS);
+            mbar_init(full_b(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == N_PROD_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot_ptr;
+
+    if (warp < N_PROD_WARPS) {
+        // ------------------------------------------------------------------ producers
+        const int t = threadIdx.x;
+        const float* src[UN];
+        uint32_t off[UN];
+        int kcol[UN];
+#pragma unroll
+        for (int i = 0; i < UN; ++i) {
+            const int idx = t + N_PROD * i;
+            const int row = idx >> 3, j = idx & 7;          // 8 units of 8 reals per row and stage
+            const int64_t m = m0 + row;
+            src[i] = (m < p.M) ? (A + m * p.lda + 8 * j) : nullptr;
+            kcol[i] = 8 * j;
+            off[i] = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
+        }
+        uint8_t* const hi_base = sm + (a_hi0 - base);
+        uint8_t* const lo_base = sm + (a_lo0 - base);
+        const float s_a = scale_of(p.amax_a);
+        const bool wide = p.wide != 0;
+        F8 v[PF][UN];
+        auto issue = [&](int kc, F8(&dst)[UN]) {
+            const int64_t k0 = (int64_t)kc * KC;
+            if (k0 + KC <= p.K) {                        // full chunk (CTA-uniform)
+#pragma unroll
+                for (int i = 0; i < UN; ++i) {
+                    if (!src[i]) zero8(dst[i]);
+                    else if (wide) ld256(src[i] + k0, dst[i]);
+                    else ld2x128(src[i] + k0, dst[i]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < UN; ++i) {
+                    zero8(dst[i]);
+                    if (src[i]) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (k0 + kcol[i] + e < p.K) dst[i].v[e] = src[i][k0 + e];
+                    }
+                }
+            }
+        };
+        uint32_t ps = 0, pph = 1;     // producer stage / parity of the `empty` barrier it waits for
+        auto commit = [&](const F8(&sv)[UN]) {
+            const uint32_t s = ps;
+            mbar_wait(empty(s), pph);
+#pragma unroll
+            for (int i = 0; i < UN; ++i) {
+                uint4 hi, lo;
+                split8(sv[i], s_a, hi, lo);
+                *reinterpret_cast<uint4*>(hi_base + s * A_PLANE + off[i]) = hi;
+                *reinterpret_cast<uint4*>(lo_base + s * A_PLANE + off[i]) = lo;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_a(s));
+            if (++ps == (uint32_t)S) { ps = 0; pph ^= 1u; }
+        };
+#pragma unroll
+        for (int u = 0; u < PF - 1; ++u)
+            if (u < p.nchunks) issue(u, v[u]);
+        for (int kc = 0; kc < p.nchunks; kc += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int k = kc + u;
+                if (k < p.nchunks) {
+                    if (k + PF - 1 < p.nchunks) issue(k + PF - 1, v[(u + PF - 1) % PF]);
+                    commit(v[u]);
+                }
+            }
+        }
+        // ------------------------------------------------------------------ epilogue
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const float inv_a = inv_scale_of(p.amax_a), inv_b = inv_scale_of(p.amax_b);
+        const int q = warp & 3, part = warp >> 2;
+        const int64_t m = m0 + 32 * q + lane;
+        const int groups = p.Npad / 16;
+        const bool grouped = p.kgroups > 1;
+        const int items = groups * (grouped ? p.kgroups : 1);       // (k-group, 16-column group) pairs
+        const uint32_t lane_base = tmem_d + ((uint32_t)(32 * q) << 16);
+        for (int it = part; it < items; it += N_PROD_WARPS / 4) {
+            const int kg = it / groups, g = it - kg * groups;
+            uint32_t r[16];
+            float acc[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+            if (grouped) {
+                tc_ld16(lane_base + (uint32_t)(kg * p.Npad + 16 * g), r);
+                tc_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[e] = __uint_as_float(r[e]);
+            } else {
+                for (int pass = 1; pass >= 0; --pass)            // cross-term blocks first (small), then the main products
+                    for (int pr = 0; pr < p.n_pairs; ++pr) {
+                        tc_ld16(lane_base + (uint32_t)((2 * pr + pass) * p.Npad + 16 * g), r);
+                        tc_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(r[e]);
+                    }
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] = acc[e] * inv_a * inv_b;
+            if (m < p.M) {
+                float* dst = C + m * p.ldc + (int64_t)kg * p.N + 16 * g;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int n = 16 * g + 4 * c4;
+                    if (n + 3 < p.N) {
+                        *reinterpret_cast<float4*>(dst + 4 * c4) = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (n + e < p.N) dst[4 * c4 + e] = acc[4 * c4 + e];
+                    }
+                }
+            }
+        }
+    } else if (warp == N_PROD_WARPS) {
+        // ------------------------------------------------------------------ MMA issuer (one thread; counters and pre-built
+        // descriptors only — see gemm_tc.cu)
+        if (lane == 0) {
+            const uint32_t npad = (uint32_t)p.Npad;
+            const uint32_t idesc1 = make_idesc_f16(p.Npad), idesc2 = make_idesc_f16(2 * p.Npad);
+            const uint64_t a_hi_d = make_desc_k_sw128(a_hi0), a_lo_d = make_desc_k_sw128(a_lo0);
+            const uint64_t b_hi_d = make_desc_k_sw128(b0), b_lo_d = make_desc_k_sw128(b0 + b_plane);
+            const uint64_t a_step = (uint64_t)(A_PLANE >> 4), b_step = (uint64_t)((2 * b_plane) >> 4);
+            const uint32_t n_pairs = (uint32_t)p.n_pairs;
+            uint32_t s = 0, ph = 0;
+            uint32_t pr = 0, d_pair = tmem_d, first = n_pairs;       // the first n_pairs k-steps overwrite their pair
+            const bool grouped = p.kgroups > 1;
+            uint32_t g_left = (uint32_t)p.cpg, d_grp = tmem_d;
+            for (int kc = 0; kc < p.nchunks; ++kc) {
+                mbar_wait(full_a(s), ph);
+                mbar_wait(full_b(s), ph);
+                tc_fence_after();
+                const uint64_t a_hi = a_hi_d + s * a_step, a_lo = a_lo_d + s * a_step;
+                const uint64_t b_hi = b_hi_d + s * b_step, b_lo = b_lo_d + s * b_step;
+#pragma unroll
+                for (int ks = 0; ks < KC / 16; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 2);   // 16 fp16 = 32 B = 2 x 16 B along K inside the swizzle row
+                    if (grouped) {
+                        tc_mma_f16(d_grp, a_hi + adv, b_hi + adv, idesc1, (ks == 0 && g_left == (uint32_t)p.cpg) ? 0u : 1u);
+                        tc_mma_f16(d_grp, a_lo + adv, b_hi + adv, idesc1, 1u);
+                        tc_mma_f16(d_grp, a_hi + adv, b_lo + adv, idesc1, 1u);
+                        continue;
+                    }
+                    tc_mma_f16(d_pair, a_hi + adv, b_hi + adv, idesc2, first ? 0u : 1u);    // [main | cross] (+)= A_hi [B_hi | B_lo]
+                    tc_mma_f16(d_pair + npad, a_lo + adv, b_hi + adv, idesc1, 1u);          // cross += A_lo B_hi
+                    if (first) --first;
+                    if (++pr == n_pairs) { pr = 0; d_pair = tmem_d; } else d_pair += 2 * npad;
+                }
+                if (grouped && --g_left == 0) { g_left = (uint32_t)p.cpg; d_grp += npad; }
+                tc_commit(empty(s));      // frees the stage once these MMAs have read it
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+            }
+            tc_commit(tmem_full);
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ B loader (one thread, TMA bulk copies)
+        if (lane == 0) {
+            const uint32_t bytes = 2u * b_plane;
+            const __half* src = Bp;
+            const int64_t src_step = (int64_t)2 * p.Npad * KC;
+            uint32_t s = 0, ph = 1;
+            for (int kc = 0; kc < p.nchunks; ++kc) {
+                mbar_wait(empty(s), ph);
+                mbar_expect_tx(full_b(s), bytes);
+                bulk_copy_g2s(b0 + s * 2 * b_plane, src, bytes, full_b(s));
+                src += src_step;
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+            }
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == N_PROD_WARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// B[K x N] row-major (ldb) -> [batch][chunk][plane][Npad][64 fp16] with the 128B swizzle applied (16-byte unit u of row
+// n stored at unit u ^ (n & 7)); hi = fp16(s b), lo = fp16(s b - hi); rows n >= N and k >= K are zero.  One thread per
+// 16-byte piece (8 consecutive k of one column n); consecutive threads take consecutive n (coalesced reads of B rows).
+__global__ void k_pack_b_h(const float* __restrict__ B, __half* __restrict__ Bp, int64_t K, int N, int Npad, int64_t ldb,
+                           int nchunks, int64_t sb, int64_t bp_batch_stride, const float* __restrict__ amax_b) {
+    const int64_t per = (int64_t)nchunks * Npad * 8;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per) return;
+    const int batch = blockIdx.y;
+    const int n = (int)(i % Npad);
+    const int u = (int)((i / Npad) & 7);
+    const int64_t c = i / ((int64_t)Npad * 8);
+    const float s = scale_of(amax_b);
+    F8 x;
+    zero8(x);
+    if (n < N) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int64_t k = c * KC + 8 * u + e;
+            if (k < K) x.v[e] = B[batch * sb + k * ldb + n];
+        }
+    }
+    uint4 hi, lo;
+    split8(x, s, hi, lo);
+    __half* dst = Bp + batch * bp_batch_stride + (c * 2) * (int64_t)Npad * KC + (int64_t)n * KC + ((u ^ (n & 7)) << 3);
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + (int64_t)Npad * KC) = lo;
+}
+
+// ------------------------------------------------------------------------------------------------------------ TN
+// P[Mr x N] = A^T B with A = [Kv x Mr] and B = [Kv x N] row-major: both operands MN-major.  A stage holds 64 vertices:
+// A planes = 8 K-groups x 2 atoms (64 columns each) x 1 KB, B planes = 8 K-groups x nb_atoms x 1 KB.
+struct ParamsTN {
+    const float* A;     // [Kv x Mr], lda
+    const __half* Bp;   // packed B: per 64-vertex chunk the hi image then the lo image (k_pack_b_h_tn)
+    float* C;           // partials [split][Mr][N] or C itself when split == 1 (ldc)
+    const float *amax_a, *amax_b;
+    int64_t Mr, Kv, lda, ldc, k_per_split, part_stride;
+    int N, Npad, nb_atoms, stages, n_main, wide;
+    uint32_t tmem_cols;
+};
+
+// byte offset of the 16-byte piece (vertex v of the chunk, columns 8*f8 .. 8*f8+7) in an MN-major SWIZZLE_128B plane
+__host__ __device__ __forceinline__ uint32_t tn_off_h(int v, int f8, int atoms) {
+    return (uint32_t)((((v >> 3) * atoms + (f8 >> 3)) << 10) + ((v & 7) << 7) + ((((f8 & 7) ^ (v & 7))) << 4));
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_h_tn(const ParamsTN p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw);
+    const int S = p.stages;
+    const uint32_t b_plane = (uint32_t)KV * (uint32_t)p.nb_atoms * 128u;
+    const uint32_t a_hi0 = base, a_lo0 = base + S * A_PLANE, b0 = base + 2 * S * A_PLANE;
+    const uint32_t bars = b0 + S * 2 * b_plane;
+    auto full_a = [&](int s) { return bars + 8u * s; };
+    auto full_b = [&](int s) { return bars + 8u * (S + s); };
+    auto empty = [&](int s) { return bars + 8u * (2 * S + s); };
+    const uint32_t tmem_full = bars + 8u * (3 * S);
+    const uint32_t tmem_slot = bars + 8u * (3 * S + 1);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(sm + (tmem_slot - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int split = blockIdx.z;
+    const int64_t kb = (int64_t)split * p.k_per_split;       // multiple of KV
+    const int64_t ke = min(p.Kv, kb + p.k_per_split);
+    const int nchunks = kb < ke ? (int)((ke - kb + KV - 1) / KV) : 0;
+    float* C = p.C + (int64_t)split * p.part_stride;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_a(s), N_PROD_WARPS);
+            mbar_init(full_b(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == N_PROD_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot_ptr;
+
+    if (warp < N_PROD_WARPS) {
+        const int t = threadIdx.x;
+        const float* a_src[UN];
+        uint32_t a_off[UN];
+        int a_v[UN], a_cnt[UN];                            // vertex within the stage, valid columns (0..8)
+#pragma unroll
+        for (int i = 0; i < UN; ++i) {
+            const int idx = t + N_PROD * i;
+            const int v = idx >> 4, f8 = idx & 15;          // 16 units of 8 columns per vertex
+            const int64_t m = m0 + 8 * f8;
+            a_v[i] = v;
+            a_cnt[i] = (int)max((int64_t)0, min((int64_t)8, p.Mr - m));
+            a_src[i] = p.A + (kb + v) * p.lda + m;
+            a_off[i] = tn_off_h(v, f8, 2);
+        }
+        const bool cols_full = (m0 + BM <= p.Mr);
+        const bool wide = p.wide != 0;
+        const int64_t a_step = (int64_t)KV * p.lda;
+        const float s_a = scale_of(p.amax_a);
+        F8 va[PF][UN];
+        auto issue = [&](int kc, F8(&da)[UN]) {
+            const int64_t v0 = kb + (int64_t)kc * KV;
+            if (cols_full && v0 + KV <= ke) {            // fast path: no guards (CTA-uniform)
+#pragma unroll
+                for (int i = 0; i < UN; ++i) {
+                    if (wide) ld256(a_src[i], da[i]);
+                    else ld2x128(a_src[i], da[i]);
+                    a_src[i] += a_step;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < UN; ++i) {
+                    zero8(da[i]);
+                    if (v0 + a_v[i] < ke) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (e < a_cnt[i]) da[i].v[e] = a_src[i][e];
+                    }
+                    a_src[i] += a_step;
+                }
+            }
+        };
+        uint8_t* const ahi = sm + (a_hi0 - base);
+        uint8_t* const alo = sm + (a_lo0 - base);
+        uint32_t ps = 0, pph = 1;
+        auto commit = [&](const F8(&sa)[UN]) {
+            const uint32_t s = ps;
+            mbar_wait(empty(s), pph);
+#pragma unroll
+            for (int i = 0; i < UN; ++i) {
+                uint4 hi, lo;
+                split8(sa[i], s_a, hi, lo);
+                *reinterpret_cast<uint4*>(ahi + s * A_PLANE + a_off[i]) = hi;
+                *reinterpret_cast<uint4*>(alo + s * A_PLANE + a_off[i]) = lo;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_a(s));
+            if (++ps == (uint32_t)S) { ps = 0; pph ^= 1u; }
+        };
+#pragma unroll
+        for (int u = 0; u < PF - 1; ++u)
+            if (u < nchunks) issue(u, va[u]);
+        for (int kc = 0; kc < nchunks; kc += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int k = kc + u;
+                if (k < nchunks) {
+                    if (k + PF - 1 < nchunks) issue(k + PF - 1, va[(u + PF - 1) % PF]);
+                    commit(va[u]);
+                }
+            }
+        }
+        // epilogue
+        const int q = warp & 3, part = warp >> 2;
+        const int64_t m = m0 + 32 * q + lane;
+        const int groups = p.Npad / 16;
+        const int n_acc = p.n_main + 1;
+        const float inv_a = inv_scale_of(p.amax_a), inv_b = inv_scale_of(p.amax_b);
+        if (nchunks > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        for (int g = part; g < groups; g += N_PROD_WARPS / 4) {
+            uint32_t r[16];
+            float acc[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+            if (nchunks > 0) {
+                for (int a = n_acc - 1; a >= 0; --a) {       // cross-term accumulator (last) first
+                    tc_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(a * p.Npad + 16 * g), r);
+                    tc_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(r[e]);
+                }
+            }
+            if (m < p.Mr) {
+                float* dst = C + m * p.ldc + 16 * g;
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (16 * g + e < p.N) dst[e] = acc[e] * inv_a * inv_b;
+            }
+        }
+    } else if (warp == N_PROD_WARPS) {
+        if (lane == 0 && nchunks > 0) {
+            // D = f32, A = B = f16, both MN-major (bits 15, 16), M = 128, N = Npad
+            const uint32_t idesc = make_idesc_f16(p.Npad) | (1u << 15) | (1u << 16);
+            const uint32_t sbo_a = 2 * 1024, sbo_b = (uint32_t)p.nb_atoms * 1024;   // between 8-vertex K groups
+            const uint64_t a_hi_d = make_desc_mn_sw128_h(a_hi0, 1024, sbo_a), a_lo_d = make_desc_mn_sw128_h(a_lo0, 1024, sbo_a);
+            const uint64_t b_hi_d = make_desc_mn_sw128_h(b0, 1024, sbo_b), b_lo_d = make_desc_mn_sw128_h(b0 + b_plane, 1024, sbo_b);
+            const uint64_t a_stage = (uint64_t)(A_PLANE >> 4), b_stage = (uint64_t)((2 * b_plane) >> 4);
+            const uint64_t a_kg = (uint64_t)((2 * sbo_a) >> 4), b_kg = (uint64_t)((2 * sbo_b) >> 4);   // 16 vertices
+            const uint32_t d_x = tmem_d + (uint32_t)(p.n_main * p.Npad);
+            const uint32_t n_main = (uint32_t)p.n_main, npad = (uint32_t)p.Npad;
+            uint32_t s = 0, ph = 0, acc = 0, d_main = tmem_d, first = n_main, x_acc = 0;
+            for (int kc = 0; kc < nchunks; ++kc) {
+                mbar_wait(full_a(s), ph);
+                mbar_wait(full_b(s), ph);
+                tc_fence_after();
+                uint64_t a_hi = a_hi_d + s * a_stage, a_lo = a_lo_d + s * a_stage;
+                uint64_t b_hi = b_hi_d + s * b_stage, b_lo = b_lo_d + s * b_stage;
+#pragma unroll
+                for (int kg = 0; kg < KV / 16; ++kg) {
+                    tc_mma_f16(d_main, a_hi, b_hi, idesc, first ? 0u : 1u);
+                    if (first) --first;
+                    if (++acc == n_main) { acc = 0; d_main = tmem_d; } else d_main += npad;
+                    tc_mma_f16(d_x, a_lo, b_hi, idesc, x_acc);
+                    tc_mma_f16(d_x, a_hi, b_lo, idesc, 1u);
+                    x_acc = 1u;
+                    a_hi += a_kg; a_lo += a_kg; b_hi += b_kg; b_lo += b_kg;
+                }
+                tc_commit(empty(s));
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+            }
+            tc_commit(tmem_full);
+        }
+        __syncwarp();
+    } else {
+        if (lane == 0) {
+            const uint32_t bytes = 2u * b_plane;
+            const int64_t img = (int64_t)b_plane;                          // fp16 elements per chunk image (hi + lo planes)
+            const __half* src = p.Bp + (kb / KV) * img;
+            uint32_t s = 0, ph = 1;
+            for (int kc = 0; kc < nchunks; ++kc) {
+                mbar_wait(empty(s), ph);
+                mbar_expect_tx(full_b(s), bytes);
+                bulk_copy_g2s(b0 + s * 2 * b_plane, src, bytes, full_b(s));
+                src += img;
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+            }
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == N_PROD_WARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// B[Kv x N] row-major (ldb) -> per 64-vertex chunk the MN-major swizzled image, hi plane then lo plane; vertices >= Kv
+// and columns >= N are zero.  One thread per 16-byte piece.
+__global__ void k_pack_b_h_tn(const float* __restrict__ B, __half* __restrict__ Bp, int64_t Kv, int N, int atoms, int64_t ldb,
+                              int64_t nchunks, const float* __restrict__ amax_b) {
+    const int u_per_row = atoms * 8;
+    const int64_t per_chunk = (int64_t)KV * u_per_row;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nchunks * per_chunk) return;
+    const int64_t c = i / per_chunk;
+    const int r = (int)(i - c * per_chunk);
+    const int v = r / u_per_row, f8 = r - v * u_per_row;
+    const int64_t vg = c * KV + v;
+    const float s = scale_of(amax_b);
+    F8 x;
+    zero8(x);
+    if (vg < Kv) {
+        const float* q = B + vg * ldb + 8 * f8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (8 * f8 + e < N) x.v[e] = q[e];
+    }
+    uint4 hi, lo;
+    split8(x, s, hi, lo);
+    const int64_t plane = (int64_t)KV * atoms * 64;                       // fp16 elements per plane
+    __half* dst = Bp + c * 2 * plane + tn_off_h(v, f8, atoms) / 2;
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + plane) = lo;
+}
+
+}  // namespace th
+
+// ------------------------------------------------------------------------------------------------------------ host side
+constexpr int64_t H_MAX_ACC_MMAS = 400;
+
+// NN: column-chunk width + number of (main, cross) accumulator pairs for `ksteps` k-steps of 16 reals (0: not feasible)
+int gemm_h_plan_nn(int N, int64_t ksteps, int* n_pairs_out) {
+    if (N <= 0) return 0;
+    const int64_t need = (ksteps + H_MAX_ACC_MMAS - 1) / H_MAX_ACC_MMAS;
+    const int widths[3] = {128, 64, 32};
+    for (int w : widths) {
+        const int nc = N < w ? N : w;
+        const int npad = (nc + 15) / 16 * 16;
+        const int avail = 512 / (2 * npad);
+        if (avail >= 1 && need <= avail) {
+            int n_pairs = avail < 2 ? avail : 2;
+            if (n_pairs < need) n_pairs = (int)need;
+            if (n_pairs > ksteps) n_pairs = (int)(ksteps < 1 ? 1 : ksteps);
+            *n_pairs_out = n_pairs;
+            return nc;
+        }
+    }
+    return 0;
+}
+
+static size_t packed_b_bytes(int N, int64_t K, int batch) {
+    const int npad = (N + 15) / 16 * 16;
+    const int64_t nchunks = (K + th::KC - 1) / th::KC;
+    return (size_t)batch * nchunks * 2 * npad * th::KC * 2;
+}
+
+// workspace: [256 B of scalars: max|B|, max|A| when computed here][packed B]
+size_t gemm_h_ws_bytes(int N, int64_t K, int batch) { return 256 + align_up(packed_b_bytes(N, K, batch), 256) + 256; }
+
+float* gemm_h_amax_slot(void* ws) { return static_cast<float*>(ws) + 1; }
+
+int launch_absmax_f32(const float* p, int64_t rows, int cols, int64_t ld, int batch, int64_t stride, float* out, cudaStream_t st) {
+    return th::launch_absmax(p, rows, cols, ld, batch, stride, out, st);
+}
+
+int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
+                     int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int n_pairs, int kgroups,
+                     const float* amax_a, void* ws, size_t ws_bytes, cudaStream_t st) {
+    FCB_REQUIRE(A && B && C && ws && amax_a, FCB_E_ARG, "gemm_h: null pointer");
+    FCB_REQUIRE(M >= 0 && N > 0 && K > 0 && batch >= 1 && batch <= 65535, FCB_E_ARG, "gemm_h: bad sizes");
+    FCB_REQUIRE(N <= 128, FCB_E_UNSUPPORTED, "gemm_h: N=%d > 128 not supported by one accumulator pair", N);
+    FCB_REQUIRE((lda % 4) == 0 && (ldc % 4) == 0 && (sa % 4) == 0 && (sc % 4) == 0 && aligned16(A) && aligned16(C),
+                FCB_E_ALIGN, "gemm_h: A/C leading dimensions and strides must be multiples of 4 floats, 16-byte aligned");
+    FCB_REQUIRE(kgroups >= 1 && (kgroups == 1 || (batch == 1 && K % th::KC == 0)), FCB_E_ARG, "gemm_h: bad k-group shape");
+    FCB_REQUIRE(ws_bytes >= gemm_h_ws_bytes(N, K, batch * kgroups), FCB_E_WORKSPACE, "gemm_h: workspace too small");
+    if (M == 0) return FCB_OK;
+    const int npad = (N + 15) / 16 * 16;
+    const int nchunks = (int)((K + th::KC - 1) / th::KC);
+    float* amax_b = static_cast<float*>(ws);
+    __half* Bp = reinterpret_cast<__half*>(static_cast<char*>(ws) + 256);
+    const int64_t bp_stride = (int64_t)nchunks * 2 * npad * th::KC;
+    {
+        // one common scale for all batches / k-groups of B
+        const bool contiguous = (ldb == N) && (batch * kgroups == 1 || sb == K * (int64_t)N);
+        int rc = contiguous ? th::launch_absmax(B, (int64_t)batch * kgroups * K, N, N, 1, 0, amax_b, st)
+                            : th::launch_absmax(B, K, N, ldb, batch * kgroups, sb, amax_b, st);
+        if (rc) return rc;
+        const int64_t per = (int64_t)nchunks * npad * 8;
+        dim3 grid((unsigned)((per + 255) / 256), (unsigned)(batch * kgroups));
+        FCB_LAUNCH("pack_b_h", st, th::k_pack_b_h<<<grid, 256, 0, st>>>(B, Bp, K, N, npad, ldb, nchunks, sb, bp_stride, amax_b));
+    }
+    th::Params p;
+    p.A = A; p.Bp = Bp; p.C = C;
+    p.amax_a = amax_a; p.amax_b = amax_b;
+    p.M = M; p.K = K; p.lda = lda; p.ldc = ldc; p.sa = sa; p.sc = sc;
+    p.bp_batch_stride = bp_stride;
+    p.N = N; p.Npad = npad; p.nchunks = nchunks * kgroups;
+    p.kgroups = kgroups; p.cpg = nchunks;
+    p.wide = ((lda % 8) == 0 && (sa % 8) == 0 && (reinterpret_cast<uintptr_t>(A) & 31u) == 0) ? 1 : 0;
+    int cols_needed;
+    if (kgroups > 1) {
+        p.K = K * kgroups;
+        n_pairs = 1;
+        cols_needed = npad * kgroups;
+    } else {
+        cols_needed = 2 * npad * n_pairs;
+    }
+    FCB_REQUIRE(n_pairs >= 1 && cols_needed <= 512, FCB_E_ARG, "gemm_h: accumulators do not fit TMEM");
+    p.n_pairs = n_pairs;
+    uint32_t cols = 32;
+    while ((int)cols < cols_needed) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t stage_bytes = 2 * th::A_PLANE + 2 * (size_t)npad * 128;
+    int stages = (int)((220 * 1024 - 2048) / stage_bytes);
+    if (stages > 6) stages = 6;
+    if (stages > p.nchunks) stages = p.nchunks < 1 ? 1 : p.nchunks;
+    FCB_REQUIRE(stages >= 1, FCB_E_UNSUPPORTED, "gemm_h: tile does not fit shared memory");
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + 1024 /*align slack*/ + 8 * (3 * stages + 2) + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(th::k_gemm_h_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+            set_error("gemm_h: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return FCB_E_CUDA;
+        }
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((M + th::BM - 1) / th::BM), (unsigned)batch);
+    FCB_LAUNCH("gemm_h_nn", st, th::k_gemm_h_nn<<<grid, th::THREADS, smem, st>>>(p));
+    return FCB_OK;
+}
+
+// packed gy operand of the TN GEMM: [256 B scalars][hi + lo images of every 64-vertex chunk]
+size_t gemm_h_tn_ws_bytes(int N, int64_t Kv) {
+    const int npad = (N + 15) / 16 * 16;
+    const int atoms = (npad + 63) / 64;
+    const int64_t nchunks = (Kv + th::KV - 1) / th::KV;
+    return 256 + align_up((size_t)nchunks * 2 * th::KV * atoms * 128, 256) + 256;
+}
+
+int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
+                     int64_t ldc, int split, int64_t k_per_split, float* parts, int n_main, const float* amax_a, void* bp_ws,
+                     size_t bp_bytes, cudaStream_t st) {
+    FCB_REQUIRE(A && B && C && bp_ws && amax_a, FCB_E_ARG, "gemm_h_tn: null pointer");
+    FCB_REQUIRE(N > 0 && N <= 256 && split >= 1 && split <= 65535, FCB_E_UNSUPPORTED, "gemm_h_tn: unsupported shape");
+    FCB_REQUIRE((lda % 4) == 0 && aligned16(A) && aligned16(bp_ws), FCB_E_ALIGN, "gemm_h_tn: alignment");
+    FCB_REQUIRE(k_per_split % th::KV == 0 || split == 1, FCB_E_ARG, "gemm_h_tn: vertex ranges must be multiples of 64");
+    FCB_REQUIRE(bp_bytes >= gemm_h_tn_ws_bytes(N, Kv), FCB_E_WORKSPACE, "gemm_h_tn: packed-operand workspace too small");
+    if (Mr == 0) return FCB_OK;
+    const int npad = (N + 15) / 16 * 16;
+    const int nb_atoms = (npad + 63) / 64;
+    const int64_t nchunks = (Kv + th::KV - 1) / th::KV;
+    float* amax_b = static_cast<float*>(bp_ws);
+    __half* Bp = reinterpret_cast<__half*>(static_cast<char*>(bp_ws) + 256);
+    {
+        int rc = th::launch_absmax(B, Kv, N, ldb, 1, 0, amax_b, st);
+        if (rc) return rc;
+        const int64_t items = nchunks * th::KV * nb_atoms * 8;
+        if (items > 0)
+            FCB_LAUNCH("pack_b_h_tn", st, th::k_pack_b_h_tn<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(B, Bp, Kv, N, nb_atoms, ldb, nchunks, amax_b));
+    }
+    th::ParamsTN p;
+    p.A = A; p.Bp = Bp;
+    p.C = split > 1 ? parts : C;
+    p.amax_a = amax_a; p.amax_b = amax_b;
+    p.Mr = Mr; p.Kv = Kv; p.lda = lda;
+    p.ldc = split > 1 ? N : ldc;
+    p.k_per_split = k_per_split;
+    p.part_stride = split > 1 ? Mr * (int64_t)N : 0;
+    p.N = N; p.Npad = npad; p.nb_atoms = nb_atoms;
+    p.wide = ((lda % 8) == 0 && (reinterpret_cast<uintptr_t>(A) & 31u) == 0) ? 1 : 0;
+    FCB_REQUIRE(n_main >= 1 && npad * (n_main + 1) <= 512, FCB_E_ARG, "gemm_h_tn: accumulators do not fit TMEM");
+    p.n_main = n_main;
+    uint32_t cols = 32;
+    while ((int)cols < npad * (n_main + 1)) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t stage_bytes = 2 * th::A_PLANE + 2 * (size_t)th::KV * nb_atoms * 128;
+    int stages = (int)((220 * 1024 - 2048) / stage_bytes);
+    if (stages > 6) stages = 6;
+    FCB_REQUIRE(stages >= 1, FCB_E_UNSUPPORTED, "gemm_h_tn: tile does not fit shared memory");
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
+    dim3 grid((unsigned)((Mr + th::BM - 1) / th::BM), 1, (unsigned)split);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(th::k_gemm_h_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+            set_error("gemm_h_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return FCB_E_CUDA;
+        }
+        attr_set = true;
+    }
+    FCB_LAUNCH("gemm_h_tn", st, th::k_gemm_h_tn<<<grid, th::THREADS, smem, st>>>(p));
+    return FCB_OK;
+}
+
+}  // namespace fcb

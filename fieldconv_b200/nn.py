@@ -17,19 +17,24 @@ from . import _lib, ops
 from .partition import MeshPartition, partitioned_field_conv
 from .plan import DensePlan, Plan, build_dense_plan
 
-_PRECISIONS = {"fp32": _lib.GEMM_SIMT_FP32, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32": _lib.GEMM_TC_TF32, "auto": -1}
+_PRECISIONS = {"fp32": _lib.GEMM_SIMT_FP32, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32": _lib.GEMM_TC_TF32,
+               "2xf16": _lib.GEMM_TC_2XF16, "auto": -1}
 
 
 def _resolve_precision(precision, ci, co, n_rings, band_limit):
-    """"auto": error-compensated tensor cores (3xTF32) when the library's accumulation plan (column chunks x TMEM
-    accumulators, at most 400 accumulating MMAs each — DESIGN.md §4) keeps the forward and the grad-x contractions
-    inside the fp32 path's 1e-5 parity budget, else the FP32-FMA kernels."""
+    """"auto": error-compensated tensor cores — operands as scaled fp16 (hi, lo) pairs ("2xf16", fastest), else
+    3xTF32 — when the library's accumulation plan (column chunks x TMEM accumulators, at most 400 accumulating MMAs
+    each — DESIGN.md §4) keeps the forward and the grad-x contractions inside the fp32 path's 1e-5 parity budget,
+    else the FP32-FMA kernels."""
     if precision != "auto":
         return _PRECISIONS[precision]
     m = 2 * band_limit + 1
-    fwd = _lib.tc_feasible(2 * co, 2 * n_rings * ci * m)
-    bwd = _lib.tc_feasible(2 * ci, 2 * n_rings * co)
-    return _lib.GEMM_TC_3XTF32 if (fwd and bwd) else _lib.GEMM_SIMT_FP32
+    for mode in (_lib.GEMM_TC_2XF16, _lib.GEMM_TC_3XTF32):
+        fwd = _lib.tc_feasible(2 * co, 2 * n_rings * ci * m, flags=mode)
+        bwd = _lib.tc_feasible(2 * ci, 2 * n_rings * co, flags=mode)
+        if fwd and bwd:
+            return mode
+    return _lib.GEMM_SIMT_FP32
 
 
 def fold_weights(zonal, spherical, phase, ftype, band_limit):

@@ -56,7 +56,7 @@ def _check(x, name, dtype=torch.complex64):
 @torch.library.custom_op("fieldconv_b200::fc_fwd", mutates_args=())
 def fc_fwd(x: Tensor, W: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: Tensor, rowptr_src: Tensor,
            rec_src: Tensor, rot_src: Tensor, band_limit: int, n_rings: int, flags: int,
-           keep_contrib: bool) -> Tuple[Tensor, Tensor]:
+           keep_contrib: bool) -> Tuple[Tensor, Tensor, Tensor]:
     # the by-source plan tensors are unused here; they are inputs so autograd can hand them to fc_bwd
     _check(x, "x")
     _check(W, "W")
@@ -66,26 +66,28 @@ def fc_fwd(x: Tensor, W: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: T
     k = n_rings * ci * (2 * band_limit + 1)
     y = torch.empty(n, co, dtype=torch.complex64, device=x.device)
     contrib = torch.empty(n, k, dtype=torch.complex64, device=x.device)
+    cmax = torch.zeros(1, dtype=torch.float32, device=x.device)     # max|contrib|: operand scale of the 2xFP16 contraction
     nbytes = _lib.query_bytes("fcb_fwd_workspace_bytes", n, ci, co, band_limit, n_rings, flags)
     ws = _ws(nbytes, x.device)
     with torch.cuda.device(x.device):
         _lib.call("fcb_fwd_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
-                  rot_tgt.data_ptr(), _real(y).data_ptr(), _real(contrib).data_ptr(), n, ci, co, band_limit, n_rings,
-                  flags, ws.data_ptr(), nbytes, _lib.stream_ptr())
+                  rot_tgt.data_ptr(), _real(y).data_ptr(), _real(contrib).data_ptr(), cmax.data_ptr(), n, ci, co,
+                  band_limit, n_rings, flags, ws.data_ptr(), nbytes, _lib.stream_ptr())
     if not keep_contrib:
         contrib = torch.empty(0, dtype=torch.complex64, device=x.device)
-    return y, contrib
+    return y, contrib, cmax
 
 
 @fc_fwd.register_fake
 def _(x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings, flags, keep_contrib):
     n, ci = x.shape
     k = n_rings * ci * (2 * band_limit + 1)
-    return x.new_empty(n, W.shape[0]), x.new_empty((n, k) if keep_contrib else (0,))
+    return (x.new_empty(n, W.shape[0]), x.new_empty((n, k) if keep_contrib else (0,)),
+            x.new_empty(1, dtype=torch.float32))
 
 
 @torch.library.custom_op("fieldconv_b200::fc_bwd", mutates_args=())
-def fc_bwd(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: Tensor,
+def fc_bwd(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, cmax: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: Tensor,
            rowptr_src: Tensor, rec_src: Tensor, rot_src: Tensor, band_limit: int, n_rings: int, flags: int,
            need_gx: bool, need_gw: bool) -> Tuple[Tensor, Tensor]:
     _check(gy, "grad_output")
@@ -100,7 +102,7 @@ def fc_bwd(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, rowptr_tgt: Tensor
     ws = _ws(nbytes, x.device)
     with torch.cuda.device(x.device):
         _lib.call("fcb_bwd_f32", _real(x).data_ptr(), _real(W).data_ptr(), _real(gy).data_ptr(),
-                  _real(contrib).data_ptr() if have_contrib else 0,
+                  _real(contrib).data_ptr() if have_contrib else 0, cmax.data_ptr() if have_contrib else 0,
                   rowptr_tgt.data_ptr(), rec_tgt.data_ptr(), rot_tgt.data_ptr(),
                   rowptr_src.data_ptr(), rec_src.data_ptr(), rot_src.data_ptr(),
                   _real(gx).data_ptr() if need_gx else 0, _real(gw).data_ptr() if need_gw else 0,
@@ -109,25 +111,25 @@ def fc_bwd(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, rowptr_tgt: Tensor
 
 
 @fc_bwd.register_fake
-def _(x, W, gy, contrib, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings, flags,
+def _(x, W, gy, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings, flags,
       need_gx, need_gw):
     return (torch.empty_like(x) if need_gx else x.new_empty(0)), (torch.empty_like(W) if need_gw else W.new_empty(0))
 
 
 def _fc_setup(ctx, inputs, output):
     x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings, flags, keep = inputs
-    _, contrib = output
-    ctx.save_for_backward(x, W, contrib, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src)
+    _, contrib, cmax = output
+    ctx.save_for_backward(x, W, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src)
     ctx.cfg = (band_limit, n_rings, flags)
     ctx.set_materialize_grads(False)      # no N*K zero tensor for the unused contrib output
 
 
-def _fc_backward(ctx, gy, _gcontrib):
+def _fc_backward(ctx, gy, _gcontrib, _gcmax):
     if gy is None:
         return (None,) * 12
-    x, W, contrib, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src = ctx.saved_tensors
+    x, W, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src = ctx.saved_tensors
     band_limit, n_rings, flags = ctx.cfg
-    gx, gw = fc_bwd(x, W, gy, contrib, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings,
+    gx, gw = fc_bwd(x, W, gy, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings,
                     flags, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
     return (gx if ctx.needs_input_grad[0] else None, gw if ctx.needs_input_grad[1] else None) + (None,) * 10
 
@@ -140,15 +142,15 @@ def field_conv(x, W, plan, band_limit, flags=0, keep_contrib=None):
     n, ci = x.shape
     if keep_contrib is None:
         keep_contrib = keep_contrib_default(n * plan.n_rings * ci * (2 * band_limit + 1) * 8, x.device)
-    y, _ = fc_fwd(x, W, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src, plan.rot_src,
-                  band_limit, plan.n_rings, flags, bool(keep_contrib))
+    y, _, _ = fc_fwd(x, W, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src, plan.rot_src,
+                     band_limit, plan.n_rings, flags, bool(keep_contrib))
     return y
 
 
 # --------------------------------------------------------------------------- dense-stencil ops
 @torch.library.custom_op("fieldconv_b200::fc_fwd_dense", mutates_args=())
 def fc_fwd_dense(x: Tensor, W: Tensor, sten: Tensor, rowptr_tgt: Tensor, nbr_tgt: Tensor, perm_tgt: Tensor,
-                 rowptr_src: Tensor, nbr_src: Tensor, perm_src: Tensor, flags: int) -> Tuple[Tensor, Tensor]:
+                 rowptr_src: Tensor, nbr_src: Tensor, perm_src: Tensor, flags: int) -> Tuple[Tensor, Tensor, Tensor]:
     _check(x, "x")
     _check(W, "W")
     _check(sten, "supp_sten")
@@ -158,24 +160,26 @@ def fc_fwd_dense(x: Tensor, W: Tensor, sten: Tensor, rowptr_tgt: Tensor, nbr_tgt
     b = (m - 1) // 2
     y = torch.empty(n, co, dtype=torch.complex64, device=x.device)
     contrib = torch.empty(n, r * ci * m, dtype=torch.complex64, device=x.device)
+    cmax = torch.zeros(1, dtype=torch.float32, device=x.device)
     nbytes = _lib.query_bytes("fcb_fwd_workspace_bytes", n, ci, co, b, r, flags)
     ws = _ws(nbytes, x.device)
     with torch.cuda.device(x.device):
         _lib.call("fcb_fwd_dense_f32", _real(x).data_ptr(), _real(W).data_ptr(), _real(sten).data_ptr(),
                   rowptr_tgt.data_ptr(), nbr_tgt.data_ptr(), perm_tgt.data_ptr(), _real(y).data_ptr(),
-                  _real(contrib).data_ptr(), n, ci, co, b, r, flags, ws.data_ptr(), nbytes, _lib.stream_ptr())
-    return y, contrib
+                  _real(contrib).data_ptr(), cmax.data_ptr(), n, ci, co, b, r, flags, ws.data_ptr(), nbytes,
+                  _lib.stream_ptr())
+    return y, contrib, cmax
 
 
 @fc_fwd_dense.register_fake
 def _(x, W, sten, rowptr_tgt, nbr_tgt, perm_tgt, rowptr_src, nbr_src, perm_src, flags):
     n, ci = x.shape
     co, _, r, m = W.shape
-    return x.new_empty(n, co), x.new_empty(n, r * ci * m)
+    return x.new_empty(n, co), x.new_empty(n, r * ci * m), x.new_empty(1, dtype=torch.float32)
 
 
 @torch.library.custom_op("fieldconv_b200::fc_bwd_dense", mutates_args=())
-def fc_bwd_dense(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, sten: Tensor, rowptr_src: Tensor, nbr_src: Tensor,
+def fc_bwd_dense(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, cmax: Tensor, sten: Tensor, rowptr_src: Tensor, nbr_src: Tensor,
                  perm_src: Tensor, flags: int, need_gx: bool, need_gw: bool) -> Tuple[Tensor, Tensor]:
     x, W, gy, sten = x.contiguous(), W.contiguous(), gy.contiguous(), sten.contiguous()
     n, ci = x.shape
@@ -187,29 +191,29 @@ def fc_bwd_dense(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, sten: Tensor
     ws = _ws(nbytes, x.device)
     with torch.cuda.device(x.device):
         _lib.call("fcb_bwd_dense_f32", _real(x).data_ptr(), _real(W).data_ptr(), _real(gy).data_ptr(),
-                  _real(contrib).data_ptr(), _real(sten).data_ptr(), rowptr_src.data_ptr(), nbr_src.data_ptr(),
+                  _real(contrib).data_ptr(), cmax.data_ptr(), _real(sten).data_ptr(), rowptr_src.data_ptr(), nbr_src.data_ptr(),
                   perm_src.data_ptr(), _real(gx).data_ptr() if need_gx else 0, _real(gw).data_ptr() if need_gw else 0,
                   n, ci, co, b, r, flags, ws.data_ptr(), nbytes, _lib.stream_ptr())
     return gx, gw
 
 
 @fc_bwd_dense.register_fake
-def _(x, W, gy, contrib, sten, rowptr_src, nbr_src, perm_src, flags, need_gx, need_gw):
+def _(x, W, gy, contrib, cmax, sten, rowptr_src, nbr_src, perm_src, flags, need_gx, need_gw):
     return (torch.empty_like(x) if need_gx else x.new_empty(0)), (torch.empty_like(W) if need_gw else W.new_empty(0))
 
 
 def _fcd_setup(ctx, inputs, output):
     x, W, sten, rowptr_tgt, nbr_tgt, perm_tgt, rowptr_src, nbr_src, perm_src, flags = inputs
-    ctx.save_for_backward(x, W, output[1], sten, rowptr_src, nbr_src, perm_src)
+    ctx.save_for_backward(x, W, output[1], output[2], sten, rowptr_src, nbr_src, perm_src)
     ctx.flags = flags
     ctx.set_materialize_grads(False)
 
 
-def _fcd_backward(ctx, gy, _gc):
+def _fcd_backward(ctx, gy, _gc, _gm):
     if gy is None:
         return (None,) * 10
-    x, W, contrib, sten, rowptr_src, nbr_src, perm_src = ctx.saved_tensors
-    gx, gw = fc_bwd_dense(x, W, gy, contrib, sten, rowptr_src, nbr_src, perm_src, ctx.flags,
+    x, W, contrib, cmax, sten, rowptr_src, nbr_src, perm_src = ctx.saved_tensors
+    gx, gw = fc_bwd_dense(x, W, gy, contrib, cmax, sten, rowptr_src, nbr_src, perm_src, ctx.flags,
                           ctx.needs_input_grad[0], ctx.needs_input_grad[1])
     return (gx if ctx.needs_input_grad[0] else None, gw if ctx.needs_input_grad[1] else None) + (None,) * 8
 
@@ -218,7 +222,7 @@ fc_fwd_dense.register_autograd(_fcd_backward, setup_context=_fcd_setup)
 
 
 def field_conv_dense(x, W, supp_sten, plan, flags=0):
-    y, _ = fc_fwd_dense(x, W, supp_sten, plan.rowptr_tgt, plan.nbr_tgt, plan.perm_tgt, plan.rowptr_src, plan.nbr_src,
+    y, _, _ = fc_fwd_dense(x, W, supp_sten, plan.rowptr_tgt, plan.nbr_tgt, plan.perm_tgt, plan.rowptr_src, plan.nbr_src,
                         plan.perm_src, flags)
     return y
 

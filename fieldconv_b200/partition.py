@@ -217,6 +217,7 @@ class _PartitionedFieldConv(torch.autograd.Function):
         y = torch.empty(n_own, co, dtype=torch.complex64, device=dev)
         keep = ops.keep_contrib_default(n_own * k * 8, dev)
         contrib = torch.empty(n_own, k, dtype=torch.complex64, device=dev)
+        cmax = torch.zeros(1, dtype=torch.float32, device=dev)      # max|contrib| over both row ranges (atomic max)
 
         def rows(a, b):
             if b <= a:
@@ -225,8 +226,8 @@ class _PartitionedFieldConv(torch.autograd.Function):
             ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
             _lib.call("fcb_fwd_f32", torch.view_as_real(x_ext).data_ptr(), torch.view_as_real(W).data_ptr(),
                       plan.rowptr_tgt[a:].data_ptr(), plan.rec_tgt.data_ptr(), plan.rot_tgt.data_ptr(),
-                      torch.view_as_real(y)[a:].data_ptr(), torch.view_as_real(contrib)[a:].data_ptr(), b - a, ci, co,
-                      band_limit, plan.n_rings, flags, ws.data_ptr(), nbytes, _lib.stream_ptr())
+                      torch.view_as_real(y)[a:].data_ptr(), torch.view_as_real(contrib)[a:].data_ptr(), cmax.data_ptr(),
+                      b - a, ci, co, band_limit, plan.n_rings, flags, ws.data_ptr(), nbytes, _lib.stream_ptr())
 
         with torch.cuda.device(dev):
             rows(0, n_int)                       # interior: every source is local
@@ -234,7 +235,7 @@ class _PartitionedFieldConv(torch.autograd.Function):
             rows(n_int, n_own)                   # boundary: needs the halo rows
         halo.record_stream(main)
         ctx.part, ctx.cfg = part, (band_limit, flags)
-        ctx.save_for_backward(x_ext, W, contrib if keep else torch.empty(0, dtype=torch.complex64, device=dev))
+        ctx.save_for_backward(x_ext, W, contrib if keep else torch.empty(0, dtype=torch.complex64, device=dev), cmax)
         return y
 
     @staticmethod
@@ -242,7 +243,7 @@ class _PartitionedFieldConv(torch.autograd.Function):
         part = ctx.part
         plan = part.plan
         band_limit, flags = ctx.cfg
-        x_ext, W, contrib = ctx.saved_tensors
+        x_ext, W, contrib, cmax = ctx.saved_tensors
         dev = gy.device
         n_own, n_ext = part.n_own, part.n_ext
         ci, co = x_ext.shape[1], W.shape[0]
@@ -261,6 +262,7 @@ class _PartitionedFieldConv(torch.autograd.Function):
             _lib.call("fcb_bwd_f32", torch.view_as_real(x_ext)[a:].data_ptr(), torch.view_as_real(W).data_ptr(),
                       torch.view_as_real(gy).data_ptr(),
                       torch.view_as_real(contrib)[a:].data_ptr() if (have and with_gw) else 0,
+                      cmax.data_ptr() if (have and with_gw) else 0,
                       plan.rowptr_tgt[a:].data_ptr(), plan.rec_tgt.data_ptr(), plan.rot_tgt.data_ptr(),
                       plan.rowptr_src[a:].data_ptr(), plan.rec_src.data_ptr(), plan.rot_src.data_ptr(),
                       torch.view_as_real(gx_ext)[a:].data_ptr() if need_gx else 0,

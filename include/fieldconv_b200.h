@@ -47,6 +47,7 @@ extern "C" {
 #define FCB_GEMM_SIMT_FP32 0  /* contraction on FP32 FMA (bit-for-bit fp32 semantics) */
 #define FCB_GEMM_TC_3XTF32 1  /* tcgen05 tensor cores, error-compensated 3xTF32 (fp32-grade) */
 #define FCB_GEMM_TC_TF32 2    /* tcgen05 tensor cores, plain TF32 (looser tolerance) */
+#define FCB_GEMM_TC_2XF16 3   /* tcgen05 tensor cores, operands as scaled fp16 (hi, lo) pairs (fp32-grade, fastest) */
 #define FCB_GEMM_MASK 0xff
 #define FCB_FLAG_HAVE_CONTRIB 0x100 /* fcb_bwd_workspace_bytes: contrib will be supplied, no recompute buffer */
 
@@ -98,13 +99,16 @@ int fcb_plan_build_dense(const int64_t* edges_ji, int64_t E, int64_t N,
  *   contrib[i, r, m, c] = sum_{e: tgt(e)=i} x[src(e),c] conj(u)^m * sten[e,r,m]   (deterministic
  *                         segmented reduction over the CSR row, fixed order)
  *   y[i, o]             = sum_{c,r,m} contrib[i,r,m,c] * W[o,c,r,m]
- * contrib (N x R*M*Ci complex, k = (r*M + m)*Ci + c) is an OUTPUT the caller may keep for backward, or
- * NULL on the fused tensor-core path that never materialises it.
+ * contrib (N x R*M*Ci complex, k = (r*M + m)*Ci + c) is an OUTPUT the caller may keep for backward.
+ * contrib_absmax (one device float, may be NULL): max|contrib| is folded into it with an atomic max
+ * (the caller zero-initialises it; several calls on row sub-ranges may share one slot).  It is the
+ * operand scale of the FCB_GEMM_TC_2XF16 contraction; hand it back to fcb_bwd_f32 with contrib.
  * W is complex (Co,Ci,R,M) contiguous.  M = 2*band_limit+1. */
 int fcb_fwd_workspace_bytes(int64_t N, int Ci, int Co, int band_limit, int R, int flags, size_t* bytes);
 int fcb_fwd_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
-                const float* rot_tgt, float* y, float* contrib, int64_t N, int Ci, int Co,
-                int band_limit, int R, int flags, void* workspace, size_t workspace_bytes, void* stream);
+                const float* rot_tgt, float* y, float* contrib, float* contrib_absmax, int64_t N, int Ci,
+                int Co, int band_limit, int R, int flags, void* workspace, size_t workspace_bytes,
+                void* stream);
 
 /* ------------------------------------------------------------------ backward (K4 + K5)
  * Replaces torch autograd through nn/field_conv.py:128-137 (PyTorch complex convention
@@ -113,10 +117,12 @@ int fcb_fwd_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const
  *   gx          = softAngle chain rule applied to the transposed gather over the by-source
  *                 CSR of gy Wh conj(sten)                   
  * contrib may be NULL: it is then recomputed from x with the by-target plan (which must be
- * given).  gW is complex (Co,Ci,R,M); either of gx / gW may be NULL to skip it. */
+ * given).  contrib_absmax: the slot filled by the forward (any upper bound of max|contrib| within
+ * a factor 2^10 works), or NULL — the 2xFP16 mode then spends one extra pass over contrib on it.
+ * gW is complex (Co,Ci,R,M); either of gx / gW may be NULL to skip it. */
 int fcb_bwd_workspace_bytes(int64_t N, int Ci, int Co, int band_limit, int R, int flags, size_t* bytes);
 int fcb_bwd_f32(const float* x, const float* W, const float* gy, const float* contrib,
-                const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
+                const float* contrib_absmax, const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
                 const int32_t* rowptr_src, const void* rec_src, const float* rot_src,
                 float* gx, float* gW, int64_t N, int Ci, int Co, int band_limit, int R, int flags,
                 void* workspace, size_t workspace_bytes, void* stream);
@@ -126,10 +132,10 @@ int fcb_bwd_f32(const float* x, const float* W, const float* gy, const float* co
  * of non-zero rings per edge.  Same outputs as above. */
 int fcb_fwd_dense_f32(const float* x, const float* W, const float* sten, const int32_t* rowptr_tgt,
                       const int32_t* nbr_tgt, const int32_t* perm_tgt, float* y, float* contrib,
-                      int64_t N, int Ci, int Co, int band_limit, int R, int flags,
+                      float* contrib_absmax, int64_t N, int Ci, int Co, int band_limit, int R, int flags,
                       void* workspace, size_t workspace_bytes, void* stream);
 int fcb_bwd_dense_f32(const float* x, const float* W, const float* gy, const float* contrib,
-                      const float* sten, const int32_t* rowptr_src, const int32_t* nbr_src,
+                      const float* contrib_absmax, const float* sten, const int32_t* rowptr_src, const int32_t* nbr_src,
                       const int32_t* perm_src, float* gx, float* gW, int64_t N, int Ci, int Co,
                       int band_limit, int R, int flags, void* workspace, size_t workspace_bytes,
                       void* stream);
@@ -141,7 +147,7 @@ int fcb_aggregate_f32(const float* feat, const int32_t* rowptr, const void* rec,
 /* Real fp32 GEMM C[MxN] = A*B (trans_a=0: A is MxK row-major; trans_a=1: A is KxM row-major),
  * B is KxN row-major; batch >= 1 with element strides; split_k >= 1 writes per-split partials into
  * the workspace and reduces them in a fixed order (deterministic).  flags & FCB_GEMM_MASK selects
- * the FP32-FMA kernel or the tcgen05 tensor-core kernel (trans_a=0 and N<=256; otherwise FMA).
+ * the FP32-FMA kernel or a tcgen05 tensor-core kernel (3xTF32 / TF32 / 2xFP16) when its accumulation plan fits.
  * The workspace size comes from fcb_gemm_workspace_bytes with the same arguments. */
 int fcb_gemm_workspace_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags,
                              size_t* bytes);

@@ -54,7 +54,7 @@ def test_workspace_queries_and_errors():
 
 def test_null_pointer_calls_are_rejected_without_touching_the_gpu():
     lib = _lib.load()
-    rc = lib.fcb_fwd_f32(None, None, None, None, None, None, None, 10, 4, 4, 1, 6, 0, None, 0, None)
+    rc = lib.fcb_fwd_f32(None, None, None, None, None, None, None, None, 10, 4, 4, 1, 6, 0, None, 0, None)
     assert rc == -1
     rc = lib.fcb_plan_build(None, None, None, None, None, None, 1.0, 10, 10, 1, None, None, None, None,
                             None, None, None, None, None, 0, None)
@@ -71,3 +71,8 @@ def test_tensor_core_accumulation_plan():
     assert not _lib.tc_feasible(96, 2880, flags=0)    # FP32-FMA mode never uses tensor cores
     assert _lib.tc_feasible(96, 80000, trans_a=1, split_k=26)
     assert not _lib.tc_feasible(64, 10 ** 6)          # too many accumulating steps for any plan
+    # 2xFP16 mode (flags=3): 16 reals per MMA, (main, cross) accumulator pairs
+    assert _lib.tc_feasible(96, 2880, flags=3)
+    assert _lib.tc_feasible(256, 7680, flags=3)       # two 128-column chunks, two pairs each
+    assert _lib.tc_feasible(96, 80000, trans_a=1, split_k=26, flags=3)
+    assert not _lib.tc_feasible(64, 10 ** 6, flags=3)

@@ -178,11 +178,12 @@ def test_tangent_lin_matches_oracle():
         assert_close_normwise(lin_d.Im.grad, g_im, 2e-6, "TangentLin gIm")
 
 
-@pytest.mark.parametrize("mode,tol", [(1, 5e-6), (2, 3e-3)])
+@pytest.mark.parametrize("mode,tol", [(1, 5e-6), (2, 3e-3), (3, 5e-6)])
 @pytest.mark.parametrize("m,n,k", [(128, 96, 32), (128, 96, 2880), (1000, 96, 576), (80656, 96, 2880), (300, 64, 1152),
-                                   (257, 256, 520), (130, 20, 36), (5, 12, 8), (4096, 16, 64)])
+                                   (257, 256, 520), (130, 20, 36), (5, 12, 8), (4096, 16, 64), (640, 128, 7680),
+                                   (200, 96, 100)])
 def test_tensor_core_gemm(m, n, k, mode, tol):
-    """tcgen05 kind::tf32 GEMM: 3xTF32 (mode 1) must sit at fp32-grade accuracy, plain TF32 (mode 2) at ~1e-3."""
+    """tcgen05 GEMM: 3xTF32 (mode 1) and 2xFP16 (mode 3) must sit at fp32-grade accuracy, plain TF32 (mode 2) at ~1e-3."""
     g = torch.Generator(device="cpu").manual_seed(m + n + k)
     k_pad = (k + 3) // 4 * 4
     a = torch.randn(m, k_pad, generator=g).to(DEV)
@@ -198,9 +199,9 @@ def test_tensor_core_gemm(m, n, k, mode, tol):
         assert err > 1e-6 or k <= 8
 
 
-@pytest.mark.parametrize("mode,tol", [(1, 5e-6), (2, 3e-3)])
+@pytest.mark.parametrize("mode,tol", [(1, 5e-6), (2, 3e-3), (3, 5e-6)])
 @pytest.mark.parametrize("m,n,k", [(128, 96, 32), (2880, 96, 80656), (1152, 64, 5041), (300, 256, 1000), (36, 20, 77),
-                                   (7680, 256, 6889), (128, 16, 8)])
+                                   (7680, 256, 6889), (128, 16, 8), (256, 96, 64), (100, 72, 200)])
 def test_tensor_core_gemm_transposed(m, n, k, mode, tol):
     """gW-shaped product P[m x n] = A^T B, A = (k x m), B = (k x n): MN-major UMMA operands + split reduction."""
     g = torch.Generator(device="cpu").manual_seed(m + n + k + 1)
@@ -213,3 +214,33 @@ def test_tensor_core_gemm_transposed(m, n, k, mode, tol):
     ref = (a.double().t() @ b.double())[:m]
     assert_close_normwise(c, ref.float(), tol, "tensor-core gemm^T mode %d" % mode)
     assert torch.equal(c, ops.gemm(a, b, True, mode)[:m]), "deterministic"
+
+
+@pytest.mark.parametrize("sa,sb", [(1.0, 1.0), (3e-21, 7e14), (2e18, 5e-9), (1e-30, 1e-30)])
+@pytest.mark.parametrize("trans", [False, True])
+def test_fp16_pair_gemm_operand_scaling(sa, sb, trans):
+    """2xFP16 mode: the power-of-two operand scales (from max|A|, max|B|) make the fp16 exponent range a non-issue —
+    the result is fp32-grade whatever the magnitudes, and rows 2^12 below the largest keep ~fp32 relative accuracy."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    m, n, k = 384, 96, 1152
+    a = torch.randn(m, k, generator=g)
+    a[64:128] *= 2.0 ** -12          # a block of small rows
+    b = torch.randn(k, n, generator=g)
+    a, b = (a * sa).to(DEV), (b * sb).to(DEV)
+    if trans:
+        c = ops.gemm(a.t().contiguous(), b, True, 3)
+    else:
+        c = ops.gemm(a, b, False, 3)
+    ref = (a.double() @ b.double())
+    assert torch.isfinite(c).all()
+    assert_close_normwise(c, ref.float(), 5e-6, "2xFP16 gemm scaled")
+    small = slice(64, 128)
+    err = float((c[small].double() - ref[small]).norm() / ref[small].norm())
+    assert err < 2e-4, err           # absolute error <= 2^-25 of the scaled range: still ~1e-5 relative 2^12 down
+
+
+def test_fp16_pair_gemm_zero_operand():
+    a = torch.zeros(256, 128, device=DEV)
+    b = torch.randn(128, 64, device=DEV)
+    assert torch.count_nonzero(ops.gemm(a, b, False, 3)) == 0
+    assert torch.count_nonzero(ops.gemm(b, torch.zeros(128, 32, device=DEV), True, 3)) == 0
