@@ -1,9 +1,10 @@
 """fieldconv_b200 — B200-native (sm_100a) FieldConv hot path behind the reference's module API.
 
-    from fieldconv_b200 import FieldConv, FCResNetBlock, build_plan
+    from fieldconv_b200 import FieldConv, FCResNetBlock, FCPrecomp, build_plan
 """
 from .plan import DensePlan, Plan, build_dense_plan, build_plan  # noqa: F401
 from .partition import MeshPartition, allreduce_gradients, partition_mesh  # noqa: F401
+from .transforms import FCPrecomp  # noqa: F401
 from .nn import FCResNetBlock, FieldConv, TangentLin, TangentNonLin, fold_weights  # noqa: F401
 
 __version__ = "0.1.0"

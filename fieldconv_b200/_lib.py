@@ -26,6 +26,8 @@ SIGNATURES = {
     "fcb_plan_build": [_P, _P, _P, _P, _P, _P, _F, _I64, _I64, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P],
     "fcb_plan_dense_workspace_bytes": [_I64, _I64, _PSZ],
     "fcb_plan_build_dense": [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _SZ, _P],
+    "fcb_precomp_workspace_bytes": [_I64, _PSZ],
+    "fcb_precomp_expand_f32": [_P, _P, _P, _F, _I64, _I64, _I, _I, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P],
     "fcb_fwd_workspace_bytes": [_I64, _I, _I, _I, _I, _I, _PSZ],
     "fcb_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_bwd_workspace_bytes": [_I64, _I, _I, _I, _I, _I, _PSZ],

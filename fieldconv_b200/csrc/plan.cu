@@ -424,3 +424,94 @@ extern "C" int fcb_plan_build_dense(const int64_t* edges, int64_t E, int64_t N, 
     }
     return FCB_OK;
 }
+
+// ----------------------------------------------------------------------------- FCPrecomp outputs in the reference's dense form
+// transforms/fc_precomp.py:53-97 returns (supp_edges', supp_sten (E',R,M), ln (E'), wxp (E')) with the kept edges in
+// INPUT order.  The compact plan already holds (f, t, wxp) per kept edge; this expands it.
+namespace fcb {
+
+__global__ void k_keep_flags(const int64_t* __restrict__ edges, const float* __restrict__ log_mag, float eps, int64_t E,
+                             int64_t N, uint32_t* __restrict__ flag) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const int64_t j = edges[2 * e], i = edges[2 * e + 1];
+    const bool ok = j >= 0 && j < N && i >= 0 && i < N && __fdiv_rn(log_mag[e], eps) <= 1.0f;   // fc_precomp.py:67-69
+    flag[e] = ok ? 1u : 0u;
+}
+
+// one thread per kept edge (by-target sorted position p); slot[e] = rank of input edge e among the kept edges
+__global__ void k_expand_stencil(const int32_t* __restrict__ rowptr, const int4* __restrict__ rec,
+                                 const int32_t* __restrict__ perm, const uint32_t* __restrict__ slot,
+                                 const int64_t* __restrict__ edges, const float* __restrict__ log_mag,
+                                 const float* __restrict__ log_ang, float eps, int64_t E, int64_t N, int R, int B,
+                                 int64_t E_out, int64_t* __restrict__ edges_out, float2* __restrict__ sten,
+                                 float2* __restrict__ ln, float2* __restrict__ wxp_out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= E || p >= rowptr[N]) return;
+    const int64_t e = perm[p];
+    const int64_t q = slot[e];
+    if (q >= E_out) return;
+    const int4 rc = rec[p];
+    const int f = (int)((uint32_t)rc.x >> NBR_BITS);
+    const float t = __int_as_float(rc.y);
+    const float2 wxp = make_float2(__int_as_float(rc.z), __int_as_float(rc.w));
+    const float theta = log_ang[e];
+    const float rn = __fdiv_rn(log_mag[e], eps);
+    edges_out[2 * q] = edges[2 * e];
+    edges_out[2 * q + 1] = edges[2 * e + 1];
+    float s1, c1;
+    sincosf(theta, &s1, &c1);
+    ln[q] = make_float2(rn * c1, rn * s1);                 // fc_precomp.py:77
+    wxp_out[q] = wxp;                                      // fc_precomp.py:92
+    const int M = 2 * B + 1;
+    float2* dst = sten + q * (int64_t)R * M;
+    for (int r = 0; r < R; ++r) {
+        const float w = (r == f + 1) ? t : (r == f ? __fsub_rn(1.0f, t) : 0.f);   // fc_precomp.py:24-25
+        for (int m = -B; m <= B; ++m) {
+            float sm, cm;
+            sincosf(__fmul_rn((float)m, theta), &sm, &cm);                         // fc_precomp.py:83-84
+            const float ax = __fmul_rn(w, cm), ay = __fmul_rn(w, sm);
+            dst[r * M + m + B] = make_float2(__fsub_rn(__fmul_rn(ax, wxp.x), __fmul_rn(ay, wxp.y)),
+                                             __fadd_rn(__fmul_rn(ax, wxp.y), __fmul_rn(ay, wxp.x)));   // :95
+        }
+    }
+}
+
+}  // namespace fcb
+
+extern "C" int fcb_precomp_workspace_bytes(int64_t E, size_t* bytes) {
+    FCB_REQUIRE(E >= 0 && bytes, FCB_E_ARG, "precomp_workspace: bad arguments");
+    *bytes = fcb::align_up((size_t)(E > 0 ? E : 1) * 4, 256) + fcb::align_up(fcb::scan_scratch_elems(E) * 4, 256) + 512;
+    return FCB_OK;
+}
+
+extern "C" int fcb_precomp_expand_f32(const int64_t* edges, const float* log_mag, const float* log_ang, float epsilon,
+                                      int64_t E, int64_t N, int R, int band_limit, const int32_t* rowptr_tgt,
+                                      const void* rec_tgt, const int32_t* perm_tgt, int64_t E_kept, int64_t* edges_out,
+                                      float* supp_sten, float* ln, float* wxp, void* ws, size_t ws_bytes, void* stream) {
+    using namespace fcb;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FCB_REQUIRE(E >= 0 && N >= 0 && E_kept >= 0 && E_kept <= E, FCB_E_ARG, "precomp_expand: bad sizes");
+    FCB_REQUIRE(R >= 2 && R <= FCB_MAX_RINGS && band_limit >= 0 && band_limit <= FCB_MAX_BAND_LIMIT, FCB_E_UNSUPPORTED,
+                "precomp_expand: unsupported n_rings / band_limit");
+    FCB_REQUIRE(epsilon > 0.f, FCB_E_ARG, "precomp_expand: epsilon must be positive");
+    if (E == 0 || E_kept == 0) return FCB_OK;
+    FCB_REQUIRE(edges && log_mag && log_ang && rowptr_tgt && rec_tgt && perm_tgt && edges_out && supp_sten && ln && wxp && ws,
+                FCB_E_ARG, "precomp_expand: null pointer");
+    size_t need = 0;
+    fcb_precomp_workspace_bytes(E, &need);
+    FCB_REQUIRE(ws_bytes >= need, FCB_E_WORKSPACE, "precomp_expand: workspace too small");
+    Arena ar(ws, ws_bytes);
+    uint32_t* slot = ar.take<uint32_t>((size_t)E);
+    uint32_t* scratch = ar.take<uint32_t>(scan_scratch_elems(E));
+    const unsigned eb = (unsigned)((E + 255) / 256);
+    FCB_LAUNCH("keep_flags", st, k_keep_flags<<<eb, 256, 0, st>>>(edges, log_mag, epsilon, E, N, slot));
+    int rc = exclusive_scan(slot, E, scratch, st);
+    if (rc) return rc;
+    FCB_LAUNCH("expand_stencil", st, k_expand_stencil<<<eb, 256, 0, st>>>(rowptr_tgt, static_cast<const int4*>(rec_tgt), perm_tgt, slot,
+                                     edges, log_mag, log_ang, epsilon, E, N, R, band_limit, E_kept, edges_out,
+                                     reinterpret_cast<float2*>(supp_sten), reinterpret_cast<float2*>(ln),
+                                     reinterpret_cast<float2*>(wxp)));
+    return FCB_OK;
+}
+

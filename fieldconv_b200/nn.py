@@ -16,6 +16,7 @@ from torch.nn import Parameter
 from . import _lib, ops
 from .partition import MeshPartition, partitioned_field_conv
 from .plan import DensePlan, Plan, build_dense_plan
+from .transforms import attached_plan
 
 _PRECISIONS = {"fp32": _lib.GEMM_SIMT_FP32, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32": _lib.GEMM_TC_TF32,
                "2xf16": _lib.GEMM_TC_2XF16, "auto": -1}
@@ -105,6 +106,9 @@ class FieldConv(nn.Module):
             w = torch.cat((w, torch.zeros_like(w[:, :1])), dim=1)
         if co % 2:
             w = torch.cat((w, torch.zeros_like(w[:1])), dim=0)
+        if plan is None and supp_sten is not None:
+            # (supp_edges, supp_sten) straight from fieldconv_b200.FCPrecomp: use the compact plan it was expanded from
+            plan = attached_plan(supp_edges, supp_sten, self.R, x.shape[0])
         if plan is not None and not plan.dense:
             if plan.n_rings != self.R:
                 raise ValueError("plan was built for n_rings=%d, layer has %d" % (plan.n_rings, self.R))
@@ -122,9 +126,13 @@ class FieldConv(nn.Module):
 class TangentLin(nn.Module):
     """nn/tangent_lin.py:12-29 — y = x @ (Re + i Im)^T, carried as one real GEMM on the interleaved storage."""
 
-    def __init__(self, in_channels, out_channels):
+    def __init__(self, in_channels, out_channels, *, precision="auto"):
         super().__init__()
+        if precision not in _PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
         self.in_channels, self.out_channels = in_channels, out_channels
+        # "auto": scaled fp16-pair tensor cores (fp32-grade, 5e-6); the library falls back to FP32 FMA where no plan fits
+        self.gemm_flags = _lib.GEMM_TC_2XF16 if precision == "auto" else _PRECISIONS[precision]
         self.Re = Parameter(torch.empty(out_channels, in_channels))
         self.Im = Parameter(torch.empty(out_channels, in_channels))
         nn.init.xavier_uniform_(self.Re)
@@ -140,7 +148,7 @@ class TangentLin(nn.Module):
             pad_i, pad_o = (2 * ci) % 4, (2 * co) % 4
             xr = torch.nn.functional.pad(xr, (0, pad_i))
             emb = torch.nn.functional.pad(emb, (0, pad_o, 0, pad_i))
-        y = ops.gemm(xr, emb.contiguous(), False)[:, :2 * co]
+        y = ops.gemm(xr, emb.contiguous(), False, self.gemm_flags)[:, :2 * co]
         return torch.view_as_complex(y.reshape(x.shape[0], co, 2).contiguous())
 
 
@@ -166,7 +174,7 @@ class FCResNetBlock(nn.Module):
         self.conv2 = FieldConv(mid, out_channels, band_limit=band_limit, n_rings=n_rings, ftype=ftype, precision=precision)
         self.nonlin1 = TangentNonLin(mid)
         self.nonlin2 = TangentNonLin(out_channels)
-        self.res = TangentLin(in_channels, out_channels)
+        self.res = TangentLin(in_channels, out_channels, precision=precision)
 
     def forward(self, x, supp_edges=None, supp_sten=None, *, plan=None):
         if isinstance(supp_edges, (Plan, DensePlan, MeshPartition)):

@@ -93,6 +93,18 @@ int fcb_plan_build_dense(const int64_t* edges_ji, int64_t E, int64_t N,
                          int32_t* rowptr_src, int32_t* nbr_src, int32_t* perm_src,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* FCPrecomp.__call__ outputs in the reference's own dense form (transforms/fc_precomp.py:53-97):
+ * expands a plan built by fcb_plan_build from the same inputs into
+ *   edges_out (E_kept,2) int64, supp_sten (E_kept,R,2B+1) complex, ln (E_kept) complex = polar(r/eps, theta),
+ *   wxp (E_kept) complex, the kept edges in INPUT order (what boolean-mask indexing produces, :69-74).
+ * E_kept = rowptr_tgt[N], read back by the caller (the reference synchronises at torch.nonzero, :69). */
+int fcb_precomp_workspace_bytes(int64_t E, size_t* bytes);
+int fcb_precomp_expand_f32(const int64_t* edges_ji, const float* log_mag, const float* log_ang, float epsilon,
+                           int64_t E, int64_t N, int R, int band_limit, const int32_t* rowptr_tgt,
+                           const void* rec_tgt, const int32_t* perm_tgt, int64_t E_kept, int64_t* edges_out,
+                           float* supp_sten, float* ln, float* wxp, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
 /* ------------------------------------------------------------------ forward (K1 + K2)
  * Replaces nn/field_conv.py:128-137 (+ utils/field.py:40-48, + the weightContrib* reduction
  * :10-33 given the folded weight W[o,c,r,m] = coeff/(2B+1)):

@@ -149,6 +149,56 @@ def test_bitwise_determinism():
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "auto"])
+def test_cuda_graph_capture_replay(precision):
+    """The ops enqueue on the current stream, allocate only through torch's allocator and never synchronise, so a
+    whole FCResNetBlock fwd+bwd captures into one CUDA graph; replays on new inputs match eager runs bit for bit."""
+    mesh = torus_mesh(30, deg=40.0, seed=6, device=DEV)
+    torch.manual_seed(2)
+    blk = fcb.FCResNetBlock(16, 16, 1, 6, 1, precision=precision).to(DEV)
+    plan = fcb.build_plan(mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp, mesh.w, 6, mesh.epsilon)
+    n = mesh.num_nodes
+    x_static = random_features(n, 16, seed=1, device=DEV).requires_grad_(True)
+    gy = random_features(n, 16, seed=2, zero_frac=0, device=DEV)
+
+    def fwd_bwd():
+        for p in blk.parameters():
+            p.grad = None
+        x_static.grad = None
+        y = blk(x_static, plan)
+        y.backward(gy)
+        return y
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            fwd_bwd()                      # warm-up outside the capture (one-time cudaFuncSetAttribute calls)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        y_static = fwd_bwd()
+    grads_static = [x_static.grad] + [p.grad for p in blk.parameters()]
+    for seed in (11, 12):
+        x_new = random_features(n, 16, seed=seed, device=DEV)
+        with torch.no_grad():
+            x_static.copy_(x_new)
+        g.replay()
+        torch.cuda.synchronize()
+        got = [y_static.detach().clone()] + [t.clone() for t in grads_static]
+        xe = x_new.clone().requires_grad_(True)
+        for p in blk.parameters():
+            p.grad = None
+        ye = blk(xe, plan)
+        ye.backward(gy)
+        want = [ye.detach(), xe.grad] + [p.grad for p in blk.parameters()]
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+        for p, gs in zip(blk.parameters(), grads_static[1:]):
+            p.grad = gs                     # hand the static buffers back before the next replay
+
+
 def test_full_size_properties_config2_layer():
     """At BASELINE config-2 layer size (16 x 5k-vertex meshes merged, C=48, B=2, R=6) the oracle is too slow, so
     check size-independent properties: (a) block-diagonal batching == per-mesh results, (b) linearity in W,
@@ -243,3 +293,33 @@ def test_tensor_core_precision_vs_fp64_oracle(n_side, ci, co, B, R, precision, t
     assert_close_normwise(m.zonal.grad, gp_ref[0].float(), tol, precision + " grad zonal")
     assert_close_normwise(m.spherical.grad, gp_ref[1].float(), tol, precision + " grad spherical")
     assert_close_normwise(m.phase.grad, gp_ref[2].float(), tol, precision + " grad phase")
+
+
+@pytest.mark.parametrize("name", golden_names("fc_"))
+def test_fcprecomp_dropin_matches_reference_outputs(name):
+    """fieldconv_b200.FCPrecomp(band_limit, n_rings, epsilon)(data) returns the reference transform's four outputs
+    (transforms/fc_precomp.py:53-97): kept edges bit-exact and in input order, supp_sten / ln / wxp to fp32 rounding;
+    and the reference call forward(x, supp_edges, supp_sten) on those outputs rides the attached compact plan."""
+    from types import SimpleNamespace
+    g = load_golden(name)
+    data = SimpleNamespace(supp_edges=g["raw_edges"].to(DEV), logMag=g["logMag"].to(DEV), logAng=g["logAng"].to(DEV),
+                           xp=g["xp"].to(DEV), w=g["w"].to(DEV))
+    pre = fcb.FCPrecomp(g["B"], g["R"], g["epsilon"])
+    e, sten, ln, wxp = pre(data)
+    assert e.dtype == torch.int64 and torch.equal(e.cpu(), g["supp_edges"])
+    assert sten.shape == g["supp_sten"].shape and sten.dtype == torch.complex64
+    assert_close_normwise(sten, g["supp_sten"], 1e-6, "supp_sten")
+    assert_close_normwise(ln, g["ln"], 1e-6, "ln")
+    assert_close_normwise(wxp, g["wxp"], 1e-6, "wxp")
+    # zero pattern of the radial two-tap stencil is exact (ring floor f bit-identical)
+    assert torch.equal(sten.cpu().abs() > 0, g["supp_sten"].abs() > 0)
+    from fieldconv_b200.transforms import attached_plan
+    assert attached_plan(e, sten, g["R"], g["n"]) is not None
+    m = _layer_from_golden(g)
+    x = g["x"].to(DEV).requires_grad_(True)
+    y = m(x, e, sten)                           # compact fast path through the attached plan
+    _check_against_golden(g, m, y, x)
+    m2 = _layer_from_golden(g)
+    x2 = g["x"].to(DEV).requires_grad_(True)
+    y2 = m2(x2, e.clone(), sten.clone())        # clones carry no plan: dense-stencil path on our own FCPrecomp output
+    _check_against_golden(g, m2, y2, x2)

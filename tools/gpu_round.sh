@@ -11,7 +11,7 @@ nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_rea
     --format=csv -lms 500 > $OUT/${TAG}_clocks.csv &
 SMI=$!
 if [ -z "$SKIP_TESTS" ]; then
-  timeout 600 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
+  timeout 600 python -m pytest tests -m gpu -q -rf --tb=short -p no:cacheprovider > $OUT/${TAG}_pytest.log 2>&1
   echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
   tail -3 $OUT/${TAG}_pytest.log
 fi
@@ -31,10 +31,10 @@ if [ -z "$SKIP_NCU" ]; then
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv \
       --log-file $OUT/${TAG}_ncu_launch_list.csv python bench.py --steps 2 --warmup 1 > $OUT/${TAG}_ncu_bench.log 2>&1
   FIELDCONV_B200_NCU=1 timeout 500 ncu --set full --clock-control none --import-source on --profile-from-start off \
-      -k regex:'k_aggregate|k_gemm_tc' -o $OUT/${TAG}_full_cfg2 -f \
+      -k regex:'k_aggregate|k_gemm_tc|k_gemm_h' -o $OUT/${TAG}_full_cfg2 -f \
       python tools/layer_bench.py --side 284 --channels 48 --band 2 --rings 6 > $OUT/${TAG}_ncu_full_cfg2.log 2>&1
   FIELDCONV_B200_NCU=1 timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off \
-      -k regex:'k_aggregate|k_gemm_tc' -o $OUT/${TAG}_full_c128 -f \
+      -k regex:'k_aggregate|k_gemm_tc|k_gemm_h' -o $OUT/${TAG}_full_c128 -f \
       python tools/layer_bench.py --side 284 --channels 128 --band 1 --rings 6 > $OUT/${TAG}_ncu_full_c128.log 2>&1
   ls -la $OUT | tail -12
 fi

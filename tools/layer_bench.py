@@ -37,7 +37,7 @@ def algorithmic_bytes(n, e, ci, co, b, r):
     return fwd, fwd + bwd
 
 
-def run_one(mesh, plan, c, b, r, precision, steps, warmup, dev, ftype=1, tag=""):
+def run_one(mesh, plan, c, b, r, precision, steps, warmup, dev, ftype=1, tag="", graph=False):
     import fieldconv_b200 as fcb
     from fieldconv_b200 import _lib
     from fieldconv_b200.synthetic import random_features
@@ -57,6 +57,16 @@ def run_one(mesh, plan, c, b, r, precision, steps, warmup, dev, ftype=1, tag="")
 
     for _ in range(warmup):
         step()
+    eager_step = step
+    if graph:
+        # the whole fwd+bwd (fold_weights, every library launch, autograd glue) as ONE CUDA graph: small meshes are
+        # launch-bound in eager mode (cfg 1: 0.24 ms of kernels inside 1.0 ms of wall time)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            eager_step()
+        step = g.replay
+        step()
     if os.environ.get("FIELDCONV_B200_NCU"):
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -73,7 +83,7 @@ def run_one(mesh, plan, c, b, r, precision, steps, warmup, dev, ftype=1, tag="")
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / steps
     _lib.profile_enable(4096)
-    step()
+    eager_step()
     torch.cuda.synchronize()
     recs = _lib.profile_collect(4096)
     kern = {}
@@ -84,7 +94,7 @@ def run_one(mesh, plan, c, b, r, precision, steps, warmup, dev, ftype=1, tag="")
     m = 2 * b + 1
     flops = 3 * 8.0 * r * c * m * c * n + 3 * 14.0 * c * m * e
     return {"tag": tag, "vertices": n, "edges": e, "channels": c, "band_limit": b, "n_rings": r, "precision": precision,
-            "flags": layer_flags(layer), "ms_fwd_bwd": round(ms, 4), "edges_per_s": e / (ms * 1e-3),
+            "cuda_graph": bool(graph), "flags": layer_flags(layer), "ms_fwd_bwd": round(ms, 4), "edges_per_s": e / (ms * 1e-3),
             "algorithmic_GBps": all_b / (ms * 1e-3) / 1e9, "hbm_frac": all_b / (ms * 1e-3) / 1e9 / hbm, "hbm_peak": hbm,
             "peak_source": which, "algorithmic_TFLOPs": flops / (ms * 1e-3) / 1e12, "kernels_ms": kern,
             "library_ms": round(sum(kern.values()), 4)}
@@ -106,6 +116,7 @@ def main():
     ap.add_argument("--precision", default="auto")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays of the captured fwd+bwd")
     ap.add_argument("--permute", action="store_true", help="random vertex numbering (cache-hostile case)")
     ap.add_argument("--sweep", action="store_true", help="cfg 5: C x band_limit x n_rings grid on a 1000x1000 mesh")
     ap.add_argument("--sweep-side", type=int, default=1000)
@@ -119,7 +130,7 @@ def main():
         mesh = torus_mesh(args.side, deg=args.deg, seed=0, device=dev, permute=args.permute)
         plan = fcb.build_plan(mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp, mesh.w, args.rings, mesh.epsilon)
         out = run_one(mesh, plan, args.channels, args.band, args.rings, args.precision, args.steps, args.warmup, dev,
-                      tag="permuted" if args.permute else "tiled")
+                      tag="permuted" if args.permute else "tiled", graph=args.graph)
         if out:
             print(json.dumps(out), flush=True)
         return
