@@ -12,6 +12,8 @@
 // Thread mapping: one lane owns (row, channel pair): a 128-bit load fetches two complex
 // channels of the neighbour's feature row; consecutive lanes read consecutive 16-byte pieces
 // of the same row, so a row of C channels is fetched as C/2 coalesced float4 loads.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace fcb {
@@ -85,18 +87,69 @@ __device__ __forceinline__ void fold_amax(uint32_t* amax, float mx) {
     if (amax && (threadIdx.x & 31) == 0 && w > *reinterpret_cast<volatile uint32_t*>(amax)) atomicMax(amax, w);
 }
 
+// Packed-operand store (PK format, common.cuh): the 2 x M complex values a lane holds for one ring go out as scaled fp16
+// (hi, lo) pairs straight into the swizzled tile image the 2xFP16 GEMMs bulk-copy, so the contraction kernels need no
+// producer warps at all.  `row_base` = block of (row tile, chunk 0, hi) + r*128; kk = real column of the m = -B entry,
+// kk_m = columns between consecutive m.  A lane's 4 reals (two complex channels) are one 8-byte half of a 16-byte unit:
+// two adjacent lanes fill a unit, the lanes of a row cover consecutive 8-byte pieces -> full-sector stores.
+template <int M>
+__device__ __forceinline__ void store_ring_packed(uint8_t* __restrict__ row_base, uint32_t rsw, const float2 (&acc)[2][M],
+                                                  uint32_t kk, uint32_t kk_m, float s) {
+#pragma unroll
+    for (int m = 0; m < M; ++m, kk += kk_m) {
+        const float a0 = acc[0][m].x * s, a1 = acc[0][m].y * s, a2 = acc[1][m].x * s, a3 = acc[1][m].y * s;
+        const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
+        uint8_t* p = row_base + (size_t)(kk >> 6) * PK_BLOCK_BYTES + ((((kk >> 3) & 7u) ^ rsw) << 4) + (((kk >> 2) & 1u) << 3);
+        *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        *reinterpret_cast<uint2*>(p + PK_PLANE_BYTES) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
+}
+
 // The two live rings sit in two fixed accumulator sets selected by ring
 // parity (ring r lives in acc[r & 1]), so sliding the two-ring window costs one store + one clear, no moves.
-template <int B, bool TRANSPOSE>
+// PACK: `out` is a PK buffer (common.cuh) of pk_rows_padded(N) rows x 2*R*M*C columns instead of the fp32 matrix;
+// the operand scale comes from the a-priori bound  max|out| <= max|feat| * max_row sum_e |wxp_e|  (pk_feat_amax,
+// pk_norm: device floats; block 0 publishes the product in *pk_bound for the GEMM's epilogue), and the lanes of the
+// rows N .. pk_rows_padded(N)-1 zero-fill the tail of the last row tile (the weight-gradient GEMM reduces over rows).
+template <int B, bool TRANSPOSE, bool PACK>
 __global__ void __launch_bounds__(256, 2) k_aggregate(const float4* __restrict__ feat, const int32_t* __restrict__ rowptr,
                                                       const int4* __restrict__ rec, const float2* __restrict__ rot,
                                                       float4* __restrict__ out, int64_t N, int C, int R,
-                                                      uint32_t* __restrict__ amax) {
+                                                      uint32_t* __restrict__ amax, const float* __restrict__ pk_feat_amax,
+                                                      const float* __restrict__ pk_norm, float* __restrict__ pk_bound) {
     constexpr int M = 2 * B + 1;
     const int P = C >> 1;
     const int64_t lane_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t row = lane_id / P;
     float mx = 0.f;
+    // PK addressing of this lane: first byte of its row inside (row tile, chunk 0, hi plane); real column of (ring 0, m = -B)
+    uint8_t* pk_row = nullptr;
+    uint32_t pk_rsw = 0, pk_kk = 0, pk_kk_ring = 0, pk_kk_m = 0;
+    float pk_s = 0.f;
+    if (PACK) {
+        const float bound = __ldg(pk_feat_amax) * __ldg(pk_norm);
+        pk_s = __uint_as_float(scale_field(__float_as_uint(fabsf(bound))) << 23);
+        if (lane_id == 0) *pk_bound = fabsf(bound);
+        const int cp = (int)(lane_id - row * P);
+        const uint32_t nchunks = (uint32_t)(2 * R * M * C) >> 6;
+        pk_row = reinterpret_cast<uint8_t*>(out) + (size_t)(row >> 7) * nchunks * PK_BLOCK_BYTES + (size_t)(row & 127) * 128u;
+        pk_rsw = (uint32_t)(row & 7);
+        pk_kk = 4u * (uint32_t)cp;
+        pk_kk_ring = TRANSPOSE ? 2u * (uint32_t)C : 2u * (uint32_t)(M * C);
+        pk_kk_m = TRANSPOSE ? 2u * (uint32_t)(R * C) : 2u * (uint32_t)C;
+        if (row >= N) {
+            if (row < ((N + 127) & ~(int64_t)127)) {      // tail of the last row tile: zeros
+                float2 z[2][M];
+#pragma unroll
+                for (int m = 0; m < M; ++m) z[0][m] = z[1][m] = make_float2(0.f, 0.f);
+                for (int ring = 0; ring < R; ++ring) store_ring_packed<M>(pk_row, pk_rsw, z, pk_kk + ring * pk_kk_ring, pk_kk_m, 0.f);
+            }
+            return;
+        }
+    }
     if (row < N) {
     const int cp = (int)(lane_id - row * P);
 
@@ -115,15 +168,18 @@ __global__ void __launch_bounds__(256, 2) k_aggregate(const float4* __restrict__
     // ring fcur is complete: write it once and clear its accumulator set (it becomes ring fcur + 2)
     auto retire = [&](int ring) {
         if (ring & 1) {
-            store_ring<M>(dst, acc1, m_stride, mx);
+            if (PACK) store_ring_packed<M>(pk_row, pk_rsw, acc1, pk_kk, pk_kk_m, pk_s);
+            else store_ring<M>(dst, acc1, m_stride, mx);
 #pragma unroll
             for (int m = 0; m < M; ++m) acc1[0][m] = acc1[1][m] = make_float2(0.f, 0.f);
         } else {
-            store_ring<M>(dst, acc0, m_stride, mx);
+            if (PACK) store_ring_packed<M>(pk_row, pk_rsw, acc0, pk_kk, pk_kk_m, pk_s);
+            else store_ring<M>(dst, acc0, m_stride, mx);
 #pragma unroll
             for (int m = 0; m < M; ++m) acc0[0][m] = acc0[1][m] = make_float2(0.f, 0.f);
         }
         dst += ring_stride;
+        pk_kk += pk_kk_ring;
     };
 
     int fcur = 0;
@@ -179,7 +235,7 @@ __global__ void __launch_bounds__(256, 2) k_aggregate(const float4* __restrict__
     }
     while (fcur < R) retire(fcur++);
     }
-    fold_amax(amax, mx);
+    if (!PACK) fold_amax(amax, mx);
 }
 
 // Dense-stencil variant: arbitrary supp_sten (E,R,M), one lane per (row, ring, channel pair).
@@ -230,40 +286,94 @@ __global__ void __launch_bounds__(256) k_aggregate_dense(const float4* __restric
     fold_amax(amax, mx);
 }
 
-template <bool TRANSPOSE>
+template <bool TRANSPOSE, bool PACK>
 static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const void* rec, const float* rot, float* out,
-                              int64_t N, int C, int B, int R, float* amax, cudaStream_t st) {
+                              int64_t N, int C, int B, int R, float* amax, const float* pk_feat_amax, const float* pk_norm,
+                              float* pk_bound, cudaStream_t st) {
     uint32_t* am = reinterpret_cast<uint32_t*>(amax);
-    const int64_t lanes = N * (C / 2);
+    const int64_t lanes = (PACK ? pk_rows_padded(N) : N) * (C / 2);
     if (lanes == 0) return FCB_OK;
     const unsigned blocks = (unsigned)((lanes + 255) / 256);
     const float4* f4 = reinterpret_cast<const float4*>(feat);
     const int4* r4 = static_cast<const int4*>(rec);
     const float2* rt = reinterpret_cast<const float2*>(rot);
     float4* o4 = reinterpret_cast<float4*>(out);
-    prof_begin(TRANSPOSE ? "aggregate_T" : "aggregate", st);
+    prof_begin(PACK ? (TRANSPOSE ? "aggregate_T_pk" : "aggregate_pk") : (TRANSPOSE ? "aggregate_T" : "aggregate"), st);
+#define FCB_AGG_CASE(b) \
+    case b: k_aggregate<b, TRANSPOSE, PACK><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am, pk_feat_amax, pk_norm, pk_bound); break;
     switch (B) {
-        case 0: k_aggregate<0, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am); break;
-        case 1: k_aggregate<1, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am); break;
-        case 2: k_aggregate<2, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am); break;
-        case 3: k_aggregate<3, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am); break;
-        case 4: k_aggregate<4, TRANSPOSE><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am); break;
+        FCB_AGG_CASE(0)
+        FCB_AGG_CASE(1)
+        FCB_AGG_CASE(2)
+        FCB_AGG_CASE(3)
+        FCB_AGG_CASE(4)
         default: set_error("aggregate: band_limit %d unsupported", B); return FCB_E_UNSUPPORTED;
     }
+#undef FCB_AGG_CASE
     prof_end(st);
     FCB_CUDA_LAUNCH_CHECK("aggregate");
     return FCB_OK;
 }
 
-int launch_aggregate(const float* feat, const int32_t* rowptr, const void* rec, const float* rot, float* out, int64_t N,
-                     int C, int B, int R, int transpose, float* amax, cudaStream_t st) {
+static int check_aggregate(const float* feat, const void* rec, const float* out, int64_t N, int C, int B, int R) {
     FCB_REQUIRE(N >= 0 && C > 0 && R >= 2 && R <= FCB_MAX_RINGS, FCB_E_ARG, "aggregate: bad sizes");
     FCB_REQUIRE(B >= 0 && B <= FCB_MAX_BAND_LIMIT, FCB_E_UNSUPPORTED, "aggregate: band_limit %d unsupported", B);
     FCB_REQUIRE((C & 1) == 0, FCB_E_ALIGN, "aggregate: channel count must be even (16-byte feature rows)");
     FCB_REQUIRE(aligned16(feat) && aligned16(out) && aligned16(rec), FCB_E_ALIGN, "aggregate: pointers must be 16-byte aligned");
-    FCB_REQUIRE(N * (int64_t)(C / 2) < 0xffffffffLL, FCB_E_UNSUPPORTED, "aggregate: N*C/2 must fit 32 bits");
-    return transpose ? dispatch_aggregate<true>(feat, rowptr, rec, rot, out, N, C, B, R, amax, st)
-                     : dispatch_aggregate<false>(feat, rowptr, rec, rot, out, N, C, B, R, amax, st);
+    FCB_REQUIRE((N + 128) * (int64_t)(C / 2) < 0xffffffffLL, FCB_E_UNSUPPORTED, "aggregate: N*C/2 must fit 32 bits");
+    return FCB_OK;
+}
+
+int launch_aggregate(const float* feat, const int32_t* rowptr, const void* rec, const float* rot, float* out, int64_t N,
+                     int C, int B, int R, int transpose, float* amax, cudaStream_t st) {
+    const int rc = check_aggregate(feat, rec, out, N, C, B, R);
+    if (rc) return rc;
+    return transpose ? dispatch_aggregate<true, false>(feat, rowptr, rec, rot, out, N, C, B, R, amax, nullptr, nullptr, nullptr, st)
+                     : dispatch_aggregate<false, false>(feat, rowptr, rec, rot, out, N, C, B, R, amax, nullptr, nullptr, nullptr, st);
+}
+
+// PK output (see k_aggregate): out_pk holds pk_bytes(N, 2*R*M*C) bytes; *bound receives feat_amax * norm.
+int launch_aggregate_packed(const float* feat, const int32_t* rowptr, const void* rec, const float* rot, void* out_pk,
+                            int64_t N, int C, int B, int R, int transpose, const float* feat_amax, const float* norm,
+                            float* bound, cudaStream_t st) {
+    const int rc = check_aggregate(feat, rec, static_cast<const float*>(out_pk), N, C, B, R);
+    if (rc) return rc;
+    FCB_REQUIRE(feat_amax && norm && bound, FCB_E_ARG, "aggregate_packed: null scale pointers");
+    FCB_REQUIRE(((2 * (int64_t)R * (2 * B + 1) * C) % PK_COLS) == 0, FCB_E_UNSUPPORTED, "aggregate_packed: 2*R*M*C must be a multiple of 64");
+    FCB_REQUIRE((reinterpret_cast<uintptr_t>(out_pk) & 127u) == 0, FCB_E_ALIGN, "aggregate_packed: output must be 128-byte aligned");
+    float* o = static_cast<float*>(out_pk);
+    return transpose ? dispatch_aggregate<true, true>(feat, rowptr, rec, rot, o, N, C, B, R, nullptr, feat_amax, norm, bound, st)
+                     : dispatch_aggregate<false, true>(feat, rowptr, rec, rot, o, N, C, B, R, nullptr, feat_amax, norm, bound, st);
+}
+
+// max over the CSR rows of sum_e |wxp_e| (the l-infinity operator norm of the aggregation, all rings and frequencies
+// included: ring weights are in [0,1], |e^{i m theta}| = 1): with positive vertex weights it is <= 1 for the by-target
+// order (fc_precomp.py:87 normalises the row mass) and the column mass for the by-source order.
+__global__ void __launch_bounds__(256) k_plan_norm(const int32_t* __restrict__ rowptr, const int4* __restrict__ rec, int64_t N,
+                                                   uint32_t* __restrict__ out) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float s = 0.f;
+    if (row < N) {
+        const int p1 = rowptr[row + 1];
+        for (int p = rowptr[row]; p < p1; ++p) {
+            const int4 rc = __ldg(rec + p);
+            const float a = __int_as_float(rc.z), b = __int_as_float(rc.w);
+            s += sqrtf(a * a + b * b);
+        }
+        s *= 1.0001f;      // the bound only feeds a power-of-two scale with a factor-2 headroom; keep it on the safe side
+    }
+    fold_amax(out, s);
+}
+
+int launch_plan_norm(const int32_t* rowptr, const void* rec, int64_t N, float* out, cudaStream_t st) {
+    if (cudaMemsetAsync(out, 0, 4, st) != cudaSuccess) {
+        set_error("plan_norm: cudaMemsetAsync failed");
+        return FCB_E_CUDA;
+    }
+    if (N == 0) return FCB_OK;
+    FCB_LAUNCH("plan_norm", st, k_plan_norm<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(rowptr, static_cast<const int4*>(rec), N,
+                                                                                      reinterpret_cast<uint32_t*>(out)));
+    return FCB_OK;
 }
 
 template <bool TRANSPOSE>
@@ -304,6 +414,11 @@ int launch_aggregate_dense(const float* feat, const float* sten, const int32_t* 
 }
 
 }  // namespace fcb
+
+extern "C" int fcb_plan_norm(const int32_t* rowptr, const void* rec, int64_t N, float* out, void* stream) {
+    FCB_REQUIRE(rowptr && rec && out && N >= 0, FCB_E_ARG, "plan_norm: bad arguments");
+    return fcb::launch_plan_norm(rowptr, rec, N, out, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int fcb_aggregate_f32(const float* feat, const int32_t* rowptr, const void* rec, const float* rot,
                                  float* out, int64_t N, int C, int band_limit, int R, int transpose, void* stream) {

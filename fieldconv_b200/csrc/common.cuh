@@ -59,6 +59,8 @@ struct Arena {
     bool ok() const { return off <= cap; }
 };
 
+constexpr int FCB_FLAG_A_PACKED = 0x10000;    // internal (launch_gemm / launch_gemm_grouped): A operand is a PK buffer
+
 constexpr int NBR_BITS = 27;
 constexpr uint32_t NBR_MASK = (1u << NBR_BITS) - 1u;
 
@@ -69,6 +71,32 @@ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {  // a * conj(b
     return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
 
+// ---- operand scale of the 2xFP16 contraction (gemm_h.cu; also used by the packing aggregation kernels)
+// power-of-two scale from max|x| (bit pattern of a non-negative float): largest entry -> [2^14, 2^15)
+__host__ __device__ __forceinline__ uint32_t scale_field(uint32_t amax_bits) {
+    const int e = (int)((amax_bits >> 23) & 0xffu);
+    if (e == 255) return 127u;                 // inf / NaN operand: scale 1, the result is non-finite as in fp32
+    int f = 268 - e;                           // (127 + 14) + (127 - e)
+    if (f > 253) f = 253;                      // max|x| < 2^-112 (or 0): everything underflows anyway
+    if (f < 1) f = 1;
+    return (uint32_t)f;
+}
+__device__ __forceinline__ float scale_of(const float* amax) { return __uint_as_float(scale_field(__float_as_uint(__ldg(amax))) << 23); }
+__device__ __forceinline__ float inv_scale_of(const float* amax) {
+    return __uint_as_float((254u - scale_field(__float_as_uint(__ldg(amax)))) << 23);
+}
+
+// ---- packed operand format ("PK") written by the packing aggregation kernels and bulk-copied by the 2xFP16 GEMMs:
+// a real matrix [rows x cols] (cols % 64 == 0) is stored as [row tile of 128][chunk of 64 columns][plane hi, lo] blocks of
+// 16 KB, each block the shared-memory image of a SWIZZLE_128B K-major tile: row r at r*128 B, its 16-byte unit u (8 fp16)
+// at unit u ^ (r & 7).  hi = fp16(s*v), lo = fp16(s*v - hi).  Rows past the matrix end inside the last tile are zero.
+constexpr int PK_ROWS = 128;
+constexpr int PK_COLS = 64;
+constexpr uint32_t PK_PLANE_BYTES = PK_ROWS * PK_COLS * 2;      // 16 KB
+constexpr uint32_t PK_BLOCK_BYTES = 2 * PK_PLANE_BYTES;         // hi + lo
+static inline int64_t pk_rows_padded(int64_t rows) { return (rows + PK_ROWS - 1) / PK_ROWS * PK_ROWS; }
+static inline size_t pk_bytes(int64_t rows, int64_t cols) { return (size_t)(pk_rows_padded(rows) / PK_ROWS) * (size_t)(cols / PK_COLS) * PK_BLOCK_BYTES; }
+
 // internal entry points shared between translation units
 int sort_pairs(uint32_t* k_in, uint32_t* v_in, uint32_t* k_out, uint32_t* v_out, int64_t n, int bits,
                void* ws, size_t ws_bytes, cudaStream_t st);
@@ -76,12 +104,18 @@ size_t sort_workspace(int64_t n);
 // amax (nullable): device float, bit-pattern max of |out| is atomically folded into it (caller zeroes it first)
 int launch_aggregate(const float* feat, const int32_t* rowptr, const void* rec, const float* rot, float* out,
                      int64_t N, int C, int B, int R, int transpose, float* amax, cudaStream_t st);
+// PK-format output (packing aggregation): out_pk = pk_bytes(N, 2*R*M*C) bytes, *bound = *feat_amax * *norm (operand scale)
+int launch_aggregate_packed(const float* feat, const int32_t* rowptr, const void* rec, const float* rot, void* out_pk,
+                            int64_t N, int C, int B, int R, int transpose, const float* feat_amax, const float* norm,
+                            float* bound, cudaStream_t st);
+int launch_plan_norm(const int32_t* rowptr, const void* rec, int64_t N, float* out, cudaStream_t st);
 int launch_aggregate_dense(const float* feat, const float* sten, const int32_t* rowptr, const int32_t* nbr,
                            const int32_t* perm, float* out, int64_t N, int C, int B, int R, int transpose,
                            float* amax, cudaStream_t st);
 // Real GEMM dispatcher.  flags & FCB_GEMM_MASK selects FP32 FMA or the tcgen05 path (trans_a == 0, N <= 256 only;
 // anything else runs on the FMA path).  ws must hold gemm_ws_bytes(...) bytes.
 size_t gemm_ws_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags);
+// flags & FCB_FLAG_A_PACKED: A is a PK buffer (only with FCB_GEMM_TC_2XF16, batch == 1 and gemm_pk_*_ok shapes)
 int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                 int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k,
                 void* ws, size_t ws_bytes, int flags, const float* a_amax, cudaStream_t st);
@@ -92,12 +126,17 @@ size_t gemm_h_ws_bytes(int N, int64_t K, int batch);
 size_t gemm_h_tn_ws_bytes(int N, int64_t Kv);
 float* gemm_h_amax_slot(void* ws);      // scratch float inside a gemm_h workspace for max|A| computed by the dispatcher
 int launch_absmax_f32(const float* p, int64_t rows, int cols, int64_t ld, int batch, int64_t stride, float* out, cudaStream_t st);
+// a_packed != 0: A is a PK buffer (lda / sa ignored; NN: M x kgroups*K, TN: Kv x Mr) and amax_a the scale it was packed with
 int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int n_pairs, int kgroups,
-                     const float* amax_a, void* ws, size_t ws_bytes, cudaStream_t st);
+                     const float* amax_a, void* ws, size_t ws_bytes, int a_packed, cudaStream_t st);
 int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
                      int64_t ldc, int split, int64_t k_per_split, float* parts, int n_main, const float* amax_a, void* bp_ws,
-                     size_t bp_bytes, cudaStream_t st);
+                     size_t bp_bytes, int a_packed, cudaStream_t st);
+// whether the 2xFP16 kernels can consume PK operands for these shapes (same tests the dispatchers apply)
+bool gemm_pk_nn_ok(int N, int64_t K);
+bool gemm_pk_tn_ok(int64_t Mr, int N, int64_t Kv, int split);
+bool gemm_pk_grouped_ok(int N, int64_t Kg, int groups);
 // column-chunk width + number of hi*hi accumulators for `ksteps` accumulating MMA steps (0: tensor cores not usable)
 int gemm_tc_plan(int N, int64_t ksteps, int mode, int* n_main);
 size_t gemm_tc_tn_ws_bytes(int N, int64_t Kv);

@@ -238,9 +238,13 @@ int launch_gemm_grouped(const float* A, const float* Bm, float* C, int64_t M, in
     const int npad = (N + 15) / 16 * 16;
     if (mode == FCB_GEMM_TC_2XF16) {
         const int64_t mmas_h = Kg / 64 * 4 * 3;                                  // accumulating MMAs per accumulator
+        const bool packed = (flags & FCB_FLAG_A_PACKED) != 0;
         if (Kg % 64 != 0 || N > 128 || npad * groups > 512 || mmas_h > TC_MAX_ACC_MMAS_GROUPED || ((groups * (int64_t)N) % 4) != 0 ||
-            ((groups * Kg) % 4) != 0 || !aligned16(A) || !aligned16(C) || ws_bytes < gemm_h_ws_bytes(N, Kg, groups))
+            ((groups * Kg) % 4) != 0 || !aligned16(A) || !aligned16(C) || ws_bytes < gemm_h_ws_bytes(N, Kg, groups)) {
+            FCB_REQUIRE(!packed, FCB_E_ARG, "gemm_grouped: packed A operand with an infeasible grouped shape");
             return FCB_OK;
+        }
+        FCB_REQUIRE(!packed || a_amax, FCB_E_ARG, "gemm_grouped: a packed A operand needs its scale");
         if (!a_amax) {
             float* slot = gemm_h_amax_slot(ws);
             int rc = launch_absmax_f32(A, M, (int)(groups * Kg), groups * Kg, 1, 0, slot, st);
@@ -248,7 +252,7 @@ int launch_gemm_grouped(const float* A, const float* Bm, float* C, int64_t M, in
             a_amax = slot;
         }
         int rc = launch_gemm_h_nn(A, Bm, C, M, N, Kg, groups * Kg, N, groups * (int64_t)N, 1, 0, Kg * N, 0, 1, groups, a_amax, ws,
-                                  ws_bytes, st);
+                                  ws_bytes, packed ? 1 : 0, st);
         if (rc == FCB_OK) *done = 1;
         return rc;
     }
@@ -270,6 +274,12 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
     FCB_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 1 && split_k >= 1, FCB_E_ARG, "gemm: bad sizes");
     const int mode = flags & FCB_GEMM_MASK;
     const bool h = mode == FCB_GEMM_TC_2XF16;
+    const bool packed = (flags & FCB_FLAG_A_PACKED) != 0;
+    if (packed) {
+        FCB_REQUIRE(h && batch == 1 && a_amax && (trans_a ? gemm_pk_tn_ok(M, N, K, split_k) : gemm_pk_nn_ok(N, K)), FCB_E_ARG,
+                    "gemm: packed A operand not supported for this shape / mode");
+        lda = 4; sa = 0;      // unused by the packed kernels; keep the alignment tests below neutral
+    }
     if (use_tc(N, K, trans_a, batch, split_k, flags) && !trans_a && (ldc % 4) == 0 && (sc % 4) == 0 && aligned16(C) &&
         (!h || ((lda % 4) == 0 && (sa % 4) == 0 && aligned16(A)))) {
         int n_main = 1;
@@ -288,7 +298,8 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
         }
         for (int n0 = 0; n0 < N; n0 += chunk) {      // column chunks (one unless N is wide): same A, offset B and C
             const int nc = N - n0 < chunk ? N - n0 : chunk;
-            int rc = h ? launch_gemm_h_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, n_main, 1, a_amax, ws, ws_bytes, st)
+            int rc = h ? launch_gemm_h_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, n_main, 1, a_amax, ws, ws_bytes,
+                                          packed ? 1 : 0, st)
                        : launch_gemm_tc_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, mode, n_main, 1, ws,
                                            ws_bytes, st);
             if (rc) return rc;
@@ -316,7 +327,7 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
         for (int n0 = 0; n0 < N; n0 += chunk) {
             const int nc = N - n0 < chunk ? N - n0 : chunk;
             int rc = h ? launch_gemm_h_tn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, split_k, kps_tc, partials, n_main, a_amax, bp_ws,
-                                          bp_bytes, st)
+                                          bp_bytes, packed ? 1 : 0, st)
                        : launch_gemm_tc_tn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, split_k, kps_tc, partials, mode, n_main,
                                            bp_ws, bp_bytes, st);
             if (rc) return rc;
@@ -327,6 +338,7 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
         }
         return FCB_OK;
     }
+    FCB_REQUIRE(!packed, FCB_E_ARG, "gemm: packed A operand reached the FP32 path");
     FCB_REQUIRE(split_k == 1 || (partials && ws_bytes >= (size_t)split_k * batch * M * N * 4), FCB_E_WORKSPACE,
                 "gemm: split_k > 1 needs a workspace of split_k*batch*M*N floats");
     FCB_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (sa % 4) == 0 && (sb % 4) == 0 && aligned16(A) && aligned16(Bm),
@@ -349,6 +361,20 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
     rc = trans_a ? dispatch_gemm<true>(A, Bm, out, M, N, K, lda, ldb, ldc, batch, sa, sb, sc, 1, kps, 0, st)
                  : dispatch_gemm<false>(A, Bm, out, M, N, K, lda, ldb, ldc, batch, sa, sb, sc, 1, kps, 0, st);
     return rc;
+}
+
+// PK operands: the same feasibility tests the dispatchers above apply (shape only; the buffers are the library's own)
+bool gemm_pk_nn_ok(int N, int64_t K) {
+    return (K % 64) == 0 && (N % 4) == 0 && use_tc(N, K, 0, 1, 1, FCB_GEMM_TC_2XF16);
+}
+bool gemm_pk_tn_ok(int64_t Mr, int N, int64_t Kv, int split) {
+    return (Mr % 64) == 0 && use_tc(N, Kv, 1, 1, split < 1 ? 1 : split, FCB_GEMM_TC_2XF16);
+}
+bool gemm_pk_grouped_ok(int N, int64_t Kg, int groups) {
+    const int npad = (N + 15) / 16 * 16;
+    const int64_t mmas_h = Kg / 64 * 4 * 3;
+    return groups >= 2 && Kg % 64 == 0 && N <= 128 && npad * groups <= 512 && mmas_h <= TC_MAX_ACC_MMAS_GROUPED &&
+           ((groups * (int64_t)N) % 4) == 0;
 }
 
 }  // namespace fcb

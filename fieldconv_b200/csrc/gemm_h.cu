@@ -45,20 +45,6 @@ constexpr uint32_t A_PLANE = BM * 128;   // 16 KB: 128 rows x 64 fp16 (NN) or 64
 constexpr int UN = 2;          // 16-byte output units (8 reals) per producer thread and stage
 constexpr int PF = 3;          // chunks of A in flight in registers per producer thread (96 KB per SM)
 
-// power-of-two operand scale from max|x| (bit pattern of a non-negative float): largest entry -> [2^14, 2^15)
-__host__ __device__ __forceinline__ uint32_t scale_field(uint32_t amax_bits) {
-    const int e = (int)((amax_bits >> 23) & 0xffu);
-    if (e == 255) return 127u;                 // inf / NaN operand: scale 1, the result is non-finite as in fp32
-    int f = 268 - e;                           // (127 + 14) + (127 - e)
-    if (f > 253) f = 253;                      // max|x| < 2^-112 (or 0): everything underflows anyway
-    if (f < 1) f = 1;
-    return (uint32_t)f;
-}
-__device__ __forceinline__ float scale_of(const float* amax) { return __uint_as_float(scale_field(__float_as_uint(__ldg(amax))) << 23); }
-__device__ __forceinline__ float inv_scale_of(const float* amax) {
-    return __uint_as_float((254u - scale_field(__float_as_uint(__ldg(amax)))) << 23);
-}
-
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -178,9 +164,14 @@ struct Params {
     int kgroups, cpg;          // grouped-K mode (kgroups > 1): K = kgroups * cpg chunks; group g accumulates all three
                                // products into its own accumulator and lands in C columns [g*N, (g+1)*N)
     int wide;                  // rows are 32-byte aligned: 256-bit loads
+    int64_t a_tile_stride;     // PACKED: bytes between consecutive 128-row tiles of the PK buffer
     uint32_t tmem_cols;
 };
 
+// PACKED: A is a PK buffer (common.cuh) — the (hi, lo) planes of every 64-column chunk are already the swizzled tile
+// images, so the loader thread brings them in with two 16 KB bulk copies per stage on the stage's `full_b` barrier and
+// the 16 producer warps only run the epilogue.
+template <bool PACKED>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -225,6 +216,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
     const uint32_t tmem_d = *tmem_slot_ptr;
 
     if (warp < N_PROD_WARPS) {
+        if (!PACKED) {
         // ------------------------------------------------------------------ producers
         const int t = threadIdx.x;
         const float* src[UN];
@@ -294,6 +286,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
                 }
             }
         }
+        }
         // ------------------------------------------------------------------ epilogue
         mbar_wait(tmem_full, 0);
         tc_fence_after();
@@ -356,7 +349,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
             const bool grouped = p.kgroups > 1;
             uint32_t g_left = (uint32_t)p.cpg, d_grp = tmem_d;
             for (int kc = 0; kc < p.nchunks; ++kc) {
-                mbar_wait(full_a(s), ph);
+                if (!PACKED) mbar_wait(full_a(s), ph);
                 mbar_wait(full_b(s), ph);
                 tc_fence_after();
                 const uint64_t a_hi = a_hi_d + s * a_step, a_lo = a_lo_d + s * a_step;
@@ -388,11 +381,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
             const uint32_t bytes = 2u * b_plane;
             const __half* src = Bp;
             const int64_t src_step = (int64_t)2 * p.Npad * KC;
+            const uint8_t* a_src = reinterpret_cast<const uint8_t*>(p.A) + (int64_t)blockIdx.x * p.a_tile_stride;
             uint32_t s = 0, ph = 1;
             for (int kc = 0; kc < p.nchunks; ++kc) {
                 mbar_wait(empty(s), ph);
-                mbar_expect_tx(full_b(s), bytes);
+                mbar_expect_tx(full_b(s), PACKED ? bytes + PK_BLOCK_BYTES : bytes);
                 bulk_copy_g2s(b0 + s * 2 * b_plane, src, bytes, full_b(s));
+                if (PACKED) {
+                    bulk_copy_g2s(a_hi0 + s * A_PLANE, a_src, PK_PLANE_BYTES, full_b(s));
+                    bulk_copy_g2s(a_lo0 + s * A_PLANE, a_src + PK_PLANE_BYTES, PK_PLANE_BYTES, full_b(s));
+                    a_src += PK_BLOCK_BYTES;
+                }
                 src += src_step;
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
             }
@@ -445,6 +444,8 @@ struct ParamsTN {
     const float *amax_a, *amax_b;
     int64_t Mr, Kv, lda, ldc, k_per_split, part_stride;
     int N, Npad, nb_atoms, stages, n_main, wide;
+    int64_t a_tile_stride;     // PACKED: bytes between consecutive 128-vertex tiles of the PK buffer
+    int a_chunks;              // PACKED: 64-column chunks in the PK buffer (= Mr / 64)
     uint32_t tmem_cols;
 };
 
@@ -453,6 +454,11 @@ __host__ __device__ __forceinline__ uint32_t tn_off_h(int v, int f8, int atoms) 
     return (uint32_t)((((v >> 3) * atoms + (f8 >> 3)) << 10) + ((v & 7) << 7) + ((((f8 & 7) ^ (v & 7))) << 4));
 }
 
+// PACKED: A is the PK buffer of [Kv x Mr] (rows = vertices).  A stage = 64 vertices x 128 columns = for each of the two
+// 64-column chunks and each plane the 8 KB half (vertex rows 0-63 or 64-127) of that chunk's tile image: as an MN-major
+// operand the image is 8 K-groups (8 vertices, 1 KB atoms) per chunk, so LBO (between the two column atoms) = 8 KB and
+// SBO (between K-groups) = 1 KB.  The loader thread issues the 4 bulk copies; the producer warps only run the epilogue.
+template <bool PACKED>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_tn(const ParamsTN p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -497,6 +503,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_tn(const ParamsTN p) {
     const uint32_t tmem_d = *tmem_slot_ptr;
 
     if (warp < N_PROD_WARPS) {
+        if (!PACKED) {
         const int t = threadIdx.x;
         const float* a_src[UN];
         uint32_t a_off[UN];
@@ -569,6 +576,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_tn(const ParamsTN p) {
                 }
             }
         }
+        }
         // epilogue
         const int q = warp & 3, part = warp >> 2;
         const int64_t m = m0 + 32 * q + lane;
@@ -603,8 +611,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_tn(const ParamsTN p) {
         if (lane == 0 && nchunks > 0) {
             // D = f32, A = B = f16, both MN-major (bits 15, 16), M = 128, N = Npad
             const uint32_t idesc = make_idesc_f16(p.Npad) | (1u << 15) | (1u << 16);
-            const uint32_t sbo_a = 2 * 1024, sbo_b = (uint32_t)p.nb_atoms * 1024;   // between 8-vertex K groups
-            const uint64_t a_hi_d = make_desc_mn_sw128_h(a_hi0, 1024, sbo_a), a_lo_d = make_desc_mn_sw128_h(a_lo0, 1024, sbo_a);
+            const uint32_t sbo_a = PACKED ? 1024 : 2 * 1024, sbo_b = (uint32_t)p.nb_atoms * 1024;   // between 8-vertex K groups
+            const uint32_t lbo_a = PACKED ? 8 * 1024 : 1024;                                       // between the two column atoms
+            const uint64_t a_hi_d = make_desc_mn_sw128_h(a_hi0, lbo_a, sbo_a), a_lo_d = make_desc_mn_sw128_h(a_lo0, lbo_a, sbo_a);
             const uint64_t b_hi_d = make_desc_mn_sw128_h(b0, 1024, sbo_b), b_lo_d = make_desc_mn_sw128_h(b0 + b_plane, 1024, sbo_b);
             const uint64_t a_stage = (uint64_t)(A_PLANE >> 4), b_stage = (uint64_t)((2 * b_plane) >> 4);
             const uint64_t a_kg = (uint64_t)((2 * sbo_a) >> 4), b_kg = (uint64_t)((2 * sbo_b) >> 4);   // 16 vertices
@@ -612,7 +621,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_tn(const ParamsTN p) {
             const uint32_t n_main = (uint32_t)p.n_main, npad = (uint32_t)p.Npad;
             uint32_t s = 0, ph = 0, acc = 0, d_main = tmem_d, first = n_main, x_acc = 0;
             for (int kc = 0; kc < nchunks; ++kc) {
-                mbar_wait(full_a(s), ph);
+                if (!PACKED) mbar_wait(full_a(s), ph);
                 mbar_wait(full_b(s), ph);
                 tc_fence_after();
                 uint64_t a_hi = a_hi_d + s * a_stage, a_lo = a_lo_d + s * a_stage;
@@ -638,11 +647,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_tn(const ParamsTN p) {
             const uint32_t bytes = 2u * b_plane;
             const int64_t img = (int64_t)b_plane;                          // fp16 elements per chunk image (hi + lo planes)
             const __half* src = p.Bp + (kb / KV) * img;
+            // PACKED: column chunks c0, c0+1 of this CTA's 128 columns (the second may lie past the matrix end: its D
+            // rows are never stored, so it is simply not loaded)
+            const int c0 = (int)(m0 / PK_COLS);
+            const int n_ca = (c0 + 1 < p.a_chunks) ? 2 : 1;
+            const uint8_t* a_base = reinterpret_cast<const uint8_t*>(p.A) + (int64_t)c0 * PK_BLOCK_BYTES;
             uint32_t s = 0, ph = 1;
             for (int kc = 0; kc < nchunks; ++kc) {
                 mbar_wait(empty(s), ph);
-                mbar_expect_tx(full_b(s), bytes);
+                mbar_expect_tx(full_b(s), PACKED ? bytes + (uint32_t)n_ca * 2u * 8192u : bytes);
                 bulk_copy_g2s(b0 + s * 2 * b_plane, src, bytes, full_b(s));
+                if (PACKED) {
+                    const int64_t v0 = kb + (int64_t)kc * KV;                       // first vertex of the stage (multiple of 64)
+                    const uint8_t* a_src = a_base + (v0 >> 7) * p.a_tile_stride + ((v0 >> 6) & 1) * 8192;
+                    for (int j = 0; j < n_ca; ++j) {
+                        bulk_copy_g2s(a_hi0 + s * A_PLANE + j * 8192u, a_src + (int64_t)j * PK_BLOCK_BYTES, 8192u, full_b(s));
+                        bulk_copy_g2s(a_lo0 + s * A_PLANE + j * 8192u, a_src + (int64_t)j * PK_BLOCK_BYTES + PK_PLANE_BYTES, 8192u,
+                                      full_b(s));
+                    }
+                }
                 src += img;
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
             }
@@ -727,10 +750,15 @@ int launch_absmax_f32(const float* p, int64_t rows, int cols, int64_t ld, int ba
 
 int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int n_pairs, int kgroups,
-                     const float* amax_a, void* ws, size_t ws_bytes, cudaStream_t st) {
+                     const float* amax_a, void* ws, size_t ws_bytes, int a_packed, cudaStream_t st) {
     FCB_REQUIRE(A && B && C && ws && amax_a, FCB_E_ARG, "gemm_h: null pointer");
     FCB_REQUIRE(M >= 0 && N > 0 && K > 0 && batch >= 1 && batch <= 65535, FCB_E_ARG, "gemm_h: bad sizes");
     FCB_REQUIRE(N <= 128, FCB_E_UNSUPPORTED, "gemm_h: N=%d > 128 not supported by one accumulator pair", N);
+    if (a_packed) {
+        FCB_REQUIRE(batch == 1 && (K % th::KC) == 0 && (reinterpret_cast<uintptr_t>(A) & 127u) == 0, FCB_E_ARG,
+                    "gemm_h: a packed A operand needs batch == 1, K %% 64 == 0 and a 128-byte aligned buffer");
+        lda = 4; sa = 0;
+    }
     FCB_REQUIRE((lda % 4) == 0 && (ldc % 4) == 0 && (sa % 4) == 0 && (sc % 4) == 0 && aligned16(A) && aligned16(C),
                 FCB_E_ALIGN, "gemm_h: A/C leading dimensions and strides must be multiples of 4 floats, 16-byte aligned");
     FCB_REQUIRE(kgroups >= 1 && (kgroups == 1 || (batch == 1 && K % th::KC == 0)), FCB_E_ARG, "gemm_h: bad k-group shape");
@@ -759,6 +787,7 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
     p.N = N; p.Npad = npad; p.nchunks = nchunks * kgroups;
     p.kgroups = kgroups; p.cpg = nchunks;
     p.wide = ((lda % 8) == 0 && (sa % 8) == 0 && (reinterpret_cast<uintptr_t>(A) & 31u) == 0) ? 1 : 0;
+    p.a_tile_stride = (int64_t)nchunks * kgroups * PK_BLOCK_BYTES;
     int cols_needed;
     if (kgroups > 1) {
         p.K = K * kgroups;
@@ -781,7 +810,8 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
     const size_t smem = stages * stage_bytes + 1024 /*align slack*/ + 8 * (3 * stages + 2) + 64;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(th::k_gemm_h_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(th::k_gemm_h_nn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(th::k_gemm_h_nn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_error("gemm_h: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return FCB_E_CUDA;
@@ -789,7 +819,8 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
         attr_set = true;
     }
     dim3 grid((unsigned)((M + th::BM - 1) / th::BM), (unsigned)batch);
-    FCB_LAUNCH("gemm_h_nn", st, th::k_gemm_h_nn<<<grid, th::THREADS, smem, st>>>(p));
+    if (a_packed) FCB_LAUNCH("gemm_p_nn", st, th::k_gemm_h_nn<true><<<grid, th::THREADS, smem, st>>>(p));
+    else FCB_LAUNCH("gemm_h_nn", st, th::k_gemm_h_nn<false><<<grid, th::THREADS, smem, st>>>(p));
     return FCB_OK;
 }
 
@@ -803,9 +834,14 @@ size_t gemm_h_tn_ws_bytes(int N, int64_t Kv) {
 
 int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
                      int64_t ldc, int split, int64_t k_per_split, float* parts, int n_main, const float* amax_a, void* bp_ws,
-                     size_t bp_bytes, cudaStream_t st) {
+                     size_t bp_bytes, int a_packed, cudaStream_t st) {
     FCB_REQUIRE(A && B && C && bp_ws && amax_a, FCB_E_ARG, "gemm_h_tn: null pointer");
     FCB_REQUIRE(N > 0 && N <= 256 && split >= 1 && split <= 65535, FCB_E_UNSUPPORTED, "gemm_h_tn: unsupported shape");
+    if (a_packed) {
+        FCB_REQUIRE((Mr % PK_COLS) == 0 && (reinterpret_cast<uintptr_t>(A) & 127u) == 0, FCB_E_ARG,
+                    "gemm_h_tn: a packed A operand needs Mr %% 64 == 0 and a 128-byte aligned buffer");
+        lda = 4;
+    }
     FCB_REQUIRE((lda % 4) == 0 && aligned16(A) && aligned16(bp_ws), FCB_E_ALIGN, "gemm_h_tn: alignment");
     FCB_REQUIRE(k_per_split % th::KV == 0 || split == 1, FCB_E_ARG, "gemm_h_tn: vertex ranges must be multiples of 64");
     FCB_REQUIRE(bp_bytes >= gemm_h_tn_ws_bytes(N, Kv), FCB_E_WORKSPACE, "gemm_h_tn: packed-operand workspace too small");
@@ -832,6 +868,8 @@ int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N
     p.part_stride = split > 1 ? Mr * (int64_t)N : 0;
     p.N = N; p.Npad = npad; p.nb_atoms = nb_atoms;
     p.wide = ((lda % 8) == 0 && (reinterpret_cast<uintptr_t>(A) & 31u) == 0) ? 1 : 0;
+    p.a_chunks = (int)(Mr / PK_COLS);
+    p.a_tile_stride = (int64_t)p.a_chunks * PK_BLOCK_BYTES;
     FCB_REQUIRE(n_main >= 1 && npad * (n_main + 1) <= 512, FCB_E_ARG, "gemm_h_tn: accumulators do not fit TMEM");
     p.n_main = n_main;
     uint32_t cols = 32;
@@ -846,14 +884,16 @@ int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N
     dim3 grid((unsigned)((Mr + th::BM - 1) / th::BM), 1, (unsigned)split);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(th::k_gemm_h_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(th::k_gemm_h_tn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(th::k_gemm_h_tn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_error("gemm_h_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return FCB_E_CUDA;
         }
         attr_set = true;
     }
-    FCB_LAUNCH("gemm_h_tn", st, th::k_gemm_h_tn<<<grid, th::THREADS, smem, st>>>(p));
+    if (a_packed) FCB_LAUNCH("gemm_p_tn", st, th::k_gemm_h_tn<true><<<grid, th::THREADS, smem, st>>>(p));
+    else FCB_LAUNCH("gemm_h_tn", st, th::k_gemm_h_tn<false><<<grid, th::THREADS, smem, st>>>(p));
     return FCB_OK;
 }
 
