@@ -325,32 +325,47 @@ def run_ours(args):
     lib_ms = sum(v[1] for v in tot.values())
     shares = {k: {"launches": v[0], "ms": round(v[1], 4), "share_of_step": round(v[1] / ms_step, 4)} for k, v in
               sorted(tot.items(), key=lambda kv: -kv[1][1])}
-    dominant = max(tot.items(), key=lambda kv: kv[1][1])[0]
+    # dominant kernel among the FieldConv path's own kernels (the "lin_*" records are TangentLin's small GEMMs)
+    dominant = max(((k, v) for k, v in tot.items() if not k.startswith("lin_")), key=lambda kv: kv[1][1])[0]
     m = 2 * B + 1
     k_complex = R * C * m
-    if dominant in ("aggregate", "aggregate_T"):
+    avg_ms = tot[dominant][1] / tot[dominant][0]
+    if dominant.startswith("aggregate"):
         per_launch = algorithmic_bytes_aggregate(n, e_kept, C)
-        avg_ms = tot[dominant][1] / tot[dominant][0]
-        roof = {"kernel": "k_aggregate" + ("<transpose>" if dominant.endswith("_T") else ""), "bound": "hbm",
-                "achieved": per_launch / (avg_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                "algorithmic_bytes_per_launch": per_launch}
+        roof = {"kernel": "k_aggregate" + ("<transpose>" if "_T" in dominant else "") + (" (packed fp16 output)" if dominant.endswith("_pk") else ""),
+                "bound": "hbm", "achieved": per_launch / (avg_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                "algorithmic_bytes_per_launch": per_launch,
+                "algorithmic_tflops": 14.0 * C * m * e_kept / (avg_ms * 1e-3) / 1e12,
+                "note": "gather + segmented reduction: E*24 B of plan records, the feature rows once, the N x R*M*C complex "
+                        "result written once; ncu (profiles/) shows the kernel issue/FMA-pipe bound (65 % issue-active), "
+                        "the HBM fraction is the contract's figure"}
     else:
-        # GEMM launches differ in shape; report the forward-shaped contraction (N x 2K) @ (2K x 2Co):
-        # its algorithmic bytes are the A operand read once + B + C written once
+        # contraction launches of one name share one shape family: the forward-shaped (N x 2K) @ (2K x 2Co) product;
+        # algorithmic bytes = the A operand read once + B + C written once
         per_launch = n * 2 * k_complex * 4 + 2 * k_complex * 2 * C * 4 + n * 2 * C * 4
-        avg_ms = tot[dominant][1] / tot[dominant][0]
         flops = 8.0 * n * k_complex * C
         roof = {"kernel": "k_gemm (" + dominant + ")", "bound": "hbm", "achieved": per_launch / (avg_ms * 1e-3) / 1e9,
                 "peak": hbm, "unit": "GB/s", "algorithmic_bytes_per_launch": per_launch,
                 "fp32_tflops_achieved": flops / (avg_ms * 1e-3) / 1e12,
-                "note": ("tcgen05 contraction: reads the fp32 contrib tile once (HBM floor), splits it into fp16/tf32 "
-                         "(hi, lo) planes in shared memory; %.0f flop/B" if dominant.startswith(("gemm_h", "gemm_tc")) else
+                "note": ("tcgen05 contraction: reads the contrib operand once (HBM floor) — fp32 split into fp16 (hi, lo) planes "
+                         "by producer warps (gemm_h_*) or packed fp16 planes bulk-copied (gemm_p_*); %.0f flop/B"
+                         if dominant.startswith(("gemm_h", "gemm_p", "gemm_tc")) else
                          "FP32-FMA contraction (arithmetic intensity %.0f flop/B): the binding resource is the FMA pipe, "
                          "the HBM fraction is reported because the contract asks for it") % (flops / per_launch)}
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["peak_source"] = which
     roof["avg_launch_ms"] = avg_ms
+    roof["launches_averaged"] = tot[dominant][0]
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
+    # layer shape (profiles/ncu_traffic.json, written from profiles/*_ncu_full_summary.md), or null for kernels without one
     roof["traffic"] = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if dominant in tr.get("cfg2_layer", {}):
+            roof["traffic"] = tr["cfg2_layer"][dominant]
+            roof["traffic_source"] = tr.get("source")
+    except (OSError, ValueError):
+        pass
 
     # ---- CPU baseline on the box's host cores (bounded sample)
     edges_c, times_c, n_c = cpu_sample(steps=2, warmup=1)

@@ -11,6 +11,11 @@ GEMM_SIMT_FP32 = 0
 GEMM_TC_3XTF32 = 1
 GEMM_TC_TF32 = 2
 GEMM_TC_2XF16 = 3
+GEMM_MASK = 0xff
+FLAG_HAVE_CONTRIB = 0x100
+# Python-level only (ops.py): run the layer through fcb_fwd_pk_f32 / fcb_bwd_pk_f32 (packed fp16 operand planes written by
+# the aggregation kernels, bulk-copied by the contraction kernels); never passed to the library
+FLAG_PACKED = 0x200
 
 _P = ctypes.c_void_p
 _I64 = ctypes.c_int64
@@ -34,6 +39,10 @@ SIGNATURES = {
     "fcb_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_fwd_dense_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_bwd_dense_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_plan_norm": [_P, _P, _I64, _P, _P],
+    "fcb_pk_contrib_bytes": [_I64, _I, _I, _I, _PSZ],
+    "fcb_fwd_pk_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_bwd_pk_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_aggregate_f32": [_P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _P],
     "fcb_gemm_workspace_bytes": [_I64, _I, _I64, _I, _I, _I, _I, _PSZ],
     "fcb_gemm_tc_feasible": [_I, _I64, _I, _I, _I],
@@ -68,6 +77,8 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = ctypes.c_int
+        lib.fcb_pk_supported.argtypes = [_I64, _I, _I, _I, _I]
+        lib.fcb_pk_supported.restype = ctypes.c_int
         lib.fcb_last_error.argtypes = []
         lib.fcb_last_error.restype = ctypes.c_char_p
         lib.fcb_launch_count.argtypes = []
@@ -93,6 +104,11 @@ def query_bytes(name, *args):
 
 def tc_feasible(n, k, trans_a=0, split_k=1, flags=GEMM_TC_3XTF32):
     return bool(load().fcb_gemm_tc_feasible(int(n), int(k), int(trans_a), int(split_k), int(flags)))
+
+
+def pk_supported(n, ci, co, band_limit, n_rings):
+    """Whether the packed-operand path (fcb_fwd_pk_f32 / fcb_bwd_pk_f32) takes this layer shape."""
+    return bool(load().fcb_pk_supported(int(n), int(ci), int(co), int(band_limit), int(n_rings)))
 
 
 def ptr(t):

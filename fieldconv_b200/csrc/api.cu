@@ -20,9 +20,24 @@ static ProfRec* g_prof = nullptr;
 static int g_prof_cap = 0, g_prof_n = 0;
 static bool g_prof_on = false;
 
+// launches made on behalf of fcb_gemm_f32 (TangentLin, not the FieldConv contraction) are recorded as "lin_<name>" so
+// per-kernel averages of the contraction kernels are not diluted by the small TangentLin GEMMs
+static thread_local bool g_prof_lin = false;
+static const char* prof_alias(const char* name) {
+    static const char* const tab[][2] = {
+        {"gemm_h_nn", "lin_gemm_h_nn"}, {"gemm_h_tn", "lin_gemm_h_tn"}, {"gemm_nn", "lin_gemm_nn"}, {"gemm_tn", "lin_gemm_tn"},
+        {"gemm_tc_nn", "lin_gemm_tc_nn"}, {"gemm_tc_tn", "lin_gemm_tc_tn"}, {"absmax", "lin_absmax"}, {"pack_b_h", "lin_pack_b_h"},
+        {"pack_b_h_tn", "lin_pack_b_h_tn"}, {"pack_b_tc", "lin_pack_b_tc"}, {"pack_b_tn", "lin_pack_b_tn"},
+        {"reduce_splits", "lin_reduce_splits"}};
+    for (const auto& t : tab)
+        if (strcmp(name, t[0]) == 0) return t[1];
+    return name;
+}
+void prof_scope_lin(bool on) { g_prof_lin = on; }
+
 void prof_begin(const char* name, cudaStream_t st) {
     if (!g_prof_on || g_prof_n >= g_prof_cap) return;
-    g_prof[g_prof_n].name = name;
+    g_prof[g_prof_n].name = g_prof_lin ? prof_alias(name) : name;
     cudaEventRecord(g_prof[g_prof_n].a, st);
 }
 void prof_end(cudaStream_t st) {
@@ -270,13 +285,24 @@ static size_t bwd_ws(const Dims& d, bool need_contrib, int flags) {
     s += align_up((size_t)(4 * d.K * d.Co) * 4, 256);                       // Bt
     s += align_up((size_t)(4 * d.K * d.Co) * 4, 256);                       // P
     s += gw_parts_bytes(d, flags);                                          // split-K partials (+ the packed gy operand)
-    s += align_up((size_t)d.N * d.Kt * 8, 256);                             // G
+    const size_t n_pad = (size_t)pk_rows_padded(d.N);                       // PK buffers hold whole 128-row tiles
+    s += align_up(n_pad * d.Kt * 8, 256);                                   // G
     s += align_up((size_t)d.N * d.M * d.Ci * 8, 256);                       // gxh
-    if (need_contrib) s += align_up((size_t)d.N * d.K * 8, 256);            // recomputed contrib
+    if (need_contrib) s += align_up(n_pad * d.K * 8, 256);                  // recomputed contrib
     // packed operand of the tensor-core grad-x GEMM
     s += max_sz(gemm_tc_ws_bytes(2 * d.Ci, 2 * (int64_t)d.R * d.Co, d.M), gemm_h_ws_bytes(2 * d.Ci, 2 * (int64_t)d.R * d.Co, d.M));
     return s + 2048;
 }
+
+// Packed-operand (PK) mode, fcb_*_pk_f32: the aggregation kernels write scaled fp16 (hi, lo) tile images and the 2xFP16
+// GEMMs bulk-copy them.  contrib is packed when both its consumers (forward contraction, weight gradient) can take it;
+// G when the grouped grad-x contraction can.  Pure functions of the layer dimensions: forward and backward agree.
+static bool pk_contrib_ok(const Dims& d) {
+    const int64_t K2 = 2 * d.K;
+    if ((K2 % PK_COLS) != 0 || d.R < 2) return false;
+    return gemm_pk_nn_ok(2 * d.Co, K2) && gemm_pk_tn_ok(K2, 2 * d.Co, d.N, choose_split(K2, d.N, FCB_GEMM_TC_2XF16));
+}
+static bool pk_g_ok(const Dims& d) { return gemm_pk_grouped_ok(2 * d.Ci, 2 * (int64_t)d.R * d.Co, d.M); }
 
 // The forward drivers aggregate into `contrib` first; *amax (max|contrib|, folded by the aggregation kernel) is the
 // operand scale of the 2xFP16 contraction.
@@ -300,29 +326,30 @@ static int contract_fwd(const Dims& d, const float* contrib, const float* amax, 
     return launch_gemm(contrib, Bw, y, d.N, 2 * d.Co, 2 * d.K, 2 * d.K, 2 * d.Co, 2 * d.Co, 0, 1, 0, 0, 0, 1, tcw, tcb, flags, amax, st);
 }
 
+// contrib_packed / g_packed: contrib is (G will be) a PK buffer; gather_transpose(G, g_amax, g_packed) fills G either way.
 template <typename GatherT>
 static int backward_common(const Dims& d, const float* x, const float* W, const float* gy, const float* contrib,
                            const float* contrib_amax, float* g_amax, GatherT&& gather_transpose, float* gx, float* gW,
-                           Arena& ar, int flags, cudaStream_t st) {
+                           Arena& ar, int flags, cudaStream_t st, bool contrib_packed = false, bool g_packed = false) {
     float* Bt = ar.take<float>((size_t)(4 * d.K * d.Co));
     float* P = ar.take<float>((size_t)(4 * d.K * d.Co));
     const int gw_split = choose_split(2 * d.K, d.N, flags);
     const size_t parts_bytes = gw_parts_bytes(d, flags);
     float* parts = reinterpret_cast<float*>(ar.take<char>(parts_bytes));
-    float* G = ar.take<float>((size_t)d.N * d.Kt * 2);
+    float* G = ar.take<float>((size_t)pk_rows_padded(d.N) * d.Kt * 2);
     float* gxh = ar.take<float>((size_t)d.N * d.M * d.Ci * 2);
     const int64_t tot = d.K * d.Co;
     if (gW) {
         // K4: P[2K x 2Co] = contrib_real^T @ gy_real, split over vertices, fixed-order reduction
         int rc = launch_gemm(contrib, gy, P, 2 * d.K, 2 * d.Co, d.N, 2 * d.K, 2 * d.Co, 2 * d.Co, 1, 1, 0, 0, 0, gw_split, parts,
-                             parts_bytes, flags, contrib_amax, st);
+                             parts_bytes, flags | (contrib_packed ? FCB_FLAG_A_PACKED : 0), contrib_amax, st);
         if (rc) return rc;
         FCB_LAUNCH("combine_gw", st, k_combine_gw<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, reinterpret_cast<float2*>(gW), d.Ci, d.Co, d.R, d.M));
     }
     if (gx) {
         // K5a: G[j][m][r][o] = sum_{e: src=j} conj(sten) gy[tgt]
         cudaMemsetAsync(g_amax, 0, 4, st);
-        int rc = gather_transpose(G, g_amax);
+        int rc = gather_transpose(G, g_amax, g_packed);
         if (rc) return rc;
         // K5b: gxh[:, m, :] = G[:, m, :] @ conj(W)[m]  (one real GEMM per m, batched)
         FCB_LAUNCH("pack_w_bwd", st, k_pack_w_bwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bt, d.Ci, d.Co, d.R, d.M));
@@ -330,8 +357,10 @@ static int backward_common(const Dims& d, const float* x, const float* W, const 
         const size_t tcb = max_sz(gemm_tc_ws_bytes(2 * d.Ci, Q2, d.M), gemm_h_ws_bytes(2 * d.Ci, Q2, d.M));
         void* tcw = ar.take<char>(tcb);
         int grouped = 0;     // all m in one pass over G (one long-K tensor-core pipeline) when the plan allows
-        rc = launch_gemm_grouped(G, Bt, gxh, d.N, 2 * d.Ci, Q2, d.M, flags, g_amax, tcw, tcb, &grouped, st);
+        rc = launch_gemm_grouped(G, Bt, gxh, d.N, 2 * d.Ci, Q2, d.M, flags | (g_packed ? FCB_FLAG_A_PACKED : 0), g_amax, tcw, tcb,
+                                 &grouped, st);
         if (rc) return rc;
+        FCB_REQUIRE(grouped || !g_packed, FCB_E_ARG, "bwd: packed G but the grouped contraction did not run");
         if (!grouped) {
             rc = launch_gemm(G, Bt, gxh, d.N, 2 * d.Ci, Q2, (int64_t)d.M * Q2, 2 * d.Ci, (int64_t)d.M * 2 * d.Ci, 0, d.M, Q2,
                              Q2 * 2 * d.Ci, 2 * d.Ci, 1, tcw, tcb, flags, g_amax, st);
@@ -486,10 +515,91 @@ extern "C" int fcb_bwd_f32(const float* x, const float* W, const float* gy, cons
         contrib = c2;
         contrib_absmax = slots;
     }
-    auto gather = [&](float* G, float* g_amax) {
+    auto gather = [&](float* G, float* g_amax, bool) {
         return launch_aggregate(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, g_amax, st);
     };
     return backward_common(d, x, W, gy, contrib, contrib_absmax, slots + 64, gather, gx, gW, ar, flags, st);
+}
+
+// ------------------------------------------------------------------ packed-operand (PK) variants
+extern "C" int fcb_pk_supported(int64_t N, int Ci, int Co, int band_limit, int R) {
+    Dims d;
+    if (check_dims("pk_supported", N, Ci, Co, band_limit, R, &d)) return 0;
+    return pk_contrib_ok(d) ? 1 : 0;
+}
+
+extern "C" int fcb_pk_contrib_bytes(int64_t N, int Ci, int band_limit, int R, size_t* bytes) {
+    FCB_REQUIRE(bytes && N >= 0 && Ci > 0 && band_limit >= 0 && R >= 1, FCB_E_ARG, "pk_contrib_bytes: bad arguments");
+    const int64_t K2 = 2 * (int64_t)R * Ci * (2 * band_limit + 1);
+    FCB_REQUIRE((K2 % PK_COLS) == 0, FCB_E_UNSUPPORTED, "pk_contrib_bytes: 2*R*M*Ci must be a multiple of 64");
+    *bytes = pk_bytes(N, K2);
+    return FCB_OK;
+}
+
+extern "C" int fcb_fwd_pk_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
+                              const float* rot_tgt, const float* norm_tgt, float* y, void* contrib_pk, float* contrib_scale,
+                              int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws, size_t ws_bytes,
+                              void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Dims d;
+    int rc = check_dims("fwd_pk", N, Ci, Co, band_limit, R, &d);
+    if (rc) return rc;
+    FCB_REQUIRE((flags & FCB_GEMM_MASK) == FCB_GEMM_TC_2XF16, FCB_E_ARG, "fwd_pk: needs FCB_GEMM_TC_2XF16");
+    FCB_REQUIRE(x && W && rowptr_tgt && rec_tgt && rot_tgt && norm_tgt && y && contrib_pk && contrib_scale && ws, FCB_E_ARG, "fwd_pk: null pointer");
+    FCB_REQUIRE(pk_contrib_ok(d), FCB_E_UNSUPPORTED, "fwd_pk: shape not supported by the packed path (fcb_pk_supported)");
+    FCB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(W), FCB_E_ALIGN, "fwd_pk: pointers must be 16-byte aligned");
+    FCB_REQUIRE(ws_bytes >= fwd_ws(d), FCB_E_WORKSPACE, "fwd_pk: workspace too small");
+    if (N == 0) return FCB_OK;
+    float* x_amax = static_cast<float*>(ws) + 16;          // inside the 256-byte scalar area at the head of the workspace
+    rc = launch_absmax_f32(x, N, 2 * Ci, 2 * (int64_t)Ci, 1, 0, x_amax, st);
+    if (rc) return rc;
+    rc = launch_aggregate_packed(x, rowptr_tgt, rec_tgt, rot_tgt, contrib_pk, N, Ci, band_limit, R, 0, x_amax, norm_tgt, contrib_scale, st);
+    if (rc) return rc;
+    return contract_fwd(d, static_cast<const float*>(contrib_pk), contrib_scale, W, y, ws, ws_bytes, flags | FCB_FLAG_A_PACKED, st);
+}
+
+extern "C" int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, const void* contrib_pk,
+                              const float* contrib_scale, const int32_t* rowptr_tgt, const void* rec_tgt,
+                              const float* rot_tgt, const float* norm_tgt, const int32_t* rowptr_src, const void* rec_src,
+                              const float* rot_src, const float* norm_src, float* gx, float* gW, int64_t N, int Ci, int Co,
+                              int band_limit, int R, int flags, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Dims d;
+    int rc = check_dims("bwd_pk", N, Ci, Co, band_limit, R, &d);
+    if (rc) return rc;
+    FCB_REQUIRE((flags & FCB_GEMM_MASK) == FCB_GEMM_TC_2XF16, FCB_E_ARG, "bwd_pk: needs FCB_GEMM_TC_2XF16");
+    FCB_REQUIRE(x && W && gy && ws, FCB_E_ARG, "bwd_pk: null pointer");
+    FCB_REQUIRE(!gx || (rowptr_src && rec_src && rot_src && norm_src), FCB_E_ARG, "bwd_pk: grad x needs the by-source plan and its norm");
+    FCB_REQUIRE(!gW || (contrib_pk && contrib_scale) || (rowptr_tgt && rec_tgt && rot_tgt && norm_tgt), FCB_E_ARG,
+                "bwd_pk: grad W needs the packed contrib + its scale, or the by-target plan and its norm");
+    FCB_REQUIRE(pk_contrib_ok(d), FCB_E_UNSUPPORTED, "bwd_pk: shape not supported by the packed path (fcb_pk_supported)");
+    FCB_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(W), FCB_E_ALIGN, "bwd_pk: pointers must be 16-byte aligned");
+    const bool recompute = gW && !(contrib_pk && contrib_scale);
+    FCB_REQUIRE(ws_bytes >= bwd_ws(d, recompute, flags), FCB_E_WORKSPACE, "bwd_pk: workspace too small");
+    if (N == 0) {
+        if (gW) cudaMemsetAsync(gW, 0, (size_t)d.K * d.Co * 8, st);
+        return FCB_OK;
+    }
+    Arena ar(ws, ws_bytes);
+    float* slots = ar.take<float>(128);   // [0] contrib scale when recomputed here, [16] max|x|, [64] G scale / max|G|, [80] max|gy|
+    const float* contrib = static_cast<const float*>(contrib_pk);
+    if (recompute) {
+        float* c2 = ar.take<float>((size_t)pk_rows_padded(d.N) * d.K * 2);
+        rc = launch_absmax_f32(x, N, 2 * Ci, 2 * (int64_t)Ci, 1, 0, slots + 16, st);
+        if (rc) return rc;
+        rc = launch_aggregate_packed(x, rowptr_tgt, rec_tgt, rot_tgt, c2, N, Ci, band_limit, R, 0, slots + 16, norm_tgt, slots, st);
+        if (rc) return rc;
+        contrib = c2;
+        contrib_scale = slots;
+    }
+    const bool g_pk = pk_g_ok(d);
+    auto gather = [&](float* G, float* g_amax, bool packed) {
+        if (!packed) return launch_aggregate(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, g_amax, st);
+        int r2 = launch_absmax_f32(gy, N, 2 * Co, 2 * (int64_t)Co, 1, 0, slots + 80, st);
+        if (r2) return r2;
+        return launch_aggregate_packed(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, slots + 80, norm_src, g_amax, st);
+    };
+    return backward_common(d, x, W, gy, contrib, contrib_scale, slots + 64, gather, gx, gW, ar, flags, st, true, g_pk);
 }
 
 extern "C" int fcb_fwd_dense_f32(const float* x, const float* W, const float* sten, const int32_t* rowptr_tgt,
@@ -528,7 +638,7 @@ extern "C" int fcb_bwd_dense_f32(const float* x, const float* W, const float* gy
     }
     Arena ar(ws, ws_bytes);
     float* slots = ar.take<float>(128);
-    auto gather = [&](float* G, float* g_amax) {
+    auto gather = [&](float* G, float* g_amax, bool) {
         return launch_aggregate_dense(gy, sten, rowptr_src, nbr_src, perm_src, G, N, Co, band_limit, R, 1, g_amax, st);
     };
     return backward_common(d, x, W, gy, contrib, contrib_absmax, slots + 64, gather, gx, gW, ar, flags, st);

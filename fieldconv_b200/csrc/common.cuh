@@ -13,6 +13,7 @@ void count_launch();   // bumps the process-wide kernel-launch counter read by f
 // optional per-launch CUDA-event timing (fcb_profile_*): no-ops unless enabled
 void prof_begin(const char* name, cudaStream_t st);
 void prof_end(cudaStream_t st);
+void prof_scope_lin(bool on);   // records of this thread's following launches are named "lin_<kernel>" (fcb_gemm_f32)
 
 // FCB_LAUNCH("name", stream, kernel<<<grid, block, smem, stream>>>(args...));
 #define FCB_LAUNCH(name, st, ...)            \

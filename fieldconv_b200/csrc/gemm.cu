@@ -394,6 +394,10 @@ extern "C" int fcb_gemm_f32(const float* A, const float* B, float* C, int64_t M,
                             int64_t ldb, int64_t ldc, int trans_a, int batch, int64_t stride_a, int64_t stride_b,
                             int64_t stride_c, int split_k, void* workspace, size_t workspace_bytes, int flags,
                             void* stream) {
-    return fcb::launch_gemm(A, B, C, M, N, K, lda, ldb, ldc, trans_a, batch, stride_a, stride_b, stride_c, split_k,
-                            workspace, workspace_bytes, flags, nullptr, static_cast<cudaStream_t>(stream));
+    fcb::prof_scope_lin(true);
+    const int rc = fcb::launch_gemm(A, B, C, M, N, K, lda, ldb, ldc, trans_a, batch, stride_a, stride_b, stride_c, split_k,
+                                    workspace, workspace_bytes, flags & ~fcb::FCB_FLAG_A_PACKED, nullptr,
+                                    static_cast<cudaStream_t>(stream));
+    fcb::prof_scope_lin(false);
+    return rc;
 }

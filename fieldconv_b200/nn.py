@@ -9,6 +9,8 @@ Parameter / buffer names, shapes and initialisation are the reference's (state_d
 Extra, keyword-only: ``precision=`` selects the contraction arithmetic, and ``forward(x, plan)`` accepts
 a compact ``fieldconv_b200.Plan`` instead of (supp_edges, supp_sten) — the fast path.
 """
+import os
+
 import torch
 import torch.nn as nn
 from torch.nn import Parameter
@@ -19,7 +21,27 @@ from .plan import DensePlan, Plan, build_dense_plan
 from .transforms import attached_plan
 
 _PRECISIONS = {"fp32": _lib.GEMM_SIMT_FP32, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32": _lib.GEMM_TC_TF32,
-               "2xf16": _lib.GEMM_TC_2XF16, "auto": -1}
+               "2xf16": _lib.GEMM_TC_2XF16, "2xf16p": _lib.GEMM_TC_2XF16 | _lib.FLAG_PACKED, "auto": -1}
+
+# "auto" uses the packed-operand variant of the 2xFP16 path ("2xf16p": same arithmetic, the aggregation kernels write the
+# fp16 operand planes themselves) where the library supports the layer shape, unless FIELDCONV_B200_PACKED=0.
+PACKED_DEFAULT = os.environ.get("FIELDCONV_B200_PACKED", "0") != "0"
+
+
+def packed_flags(flags, plan, n, ci, co, band_limit, n_rings, explicit):
+    """Resolve FLAG_PACKED for one call: keep it only for a compact plan with norms and a supported shape.  An
+    explicit precision="2xf16p" raises when the shape is not supported instead of silently changing kernels."""
+    want = bool(flags & _lib.FLAG_PACKED) or (PACKED_DEFAULT and not explicit and (flags & _lib.GEMM_MASK) == _lib.GEMM_TC_2XF16)
+    flags &= ~_lib.FLAG_PACKED
+    if not want:
+        return flags
+    ok = getattr(plan, "norms", None) is not None and _lib.pk_supported(n, ci, co, band_limit, n_rings)
+    if ok:
+        return flags | _lib.FLAG_PACKED
+    if explicit:
+        raise RuntimeError("fieldconv_b200: precision='2xf16p' does not support this layer shape / plan "
+                           "(N=%d, Ci=%d, Co=%d, B=%d, R=%d)" % (n, ci, co, band_limit, n_rings))
+    return flags
 
 
 def _resolve_precision(precision, ci, co, n_rings, band_limit):
@@ -112,8 +134,10 @@ class FieldConv(nn.Module):
         if plan is not None and not plan.dense:
             if plan.n_rings != self.R:
                 raise ValueError("plan was built for n_rings=%d, layer has %d" % (plan.n_rings, self.R))
+            flags = packed_flags(flags, plan, x.shape[0], x.shape[1], w.shape[0], self.B, self.R, self.precision == "2xf16p")
             y = ops.field_conv(x, w, plan, self.B, flags)
         else:
+            flags &= ~_lib.FLAG_PACKED
             if supp_sten is None:
                 raise ValueError("forward needs (supp_edges, supp_sten) or a compact plan")
             if tuple(supp_sten.shape[1:]) != (self.R, 2 * self.B + 1):
@@ -132,7 +156,7 @@ class TangentLin(nn.Module):
             raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
         self.in_channels, self.out_channels = in_channels, out_channels
         # "auto": scaled fp16-pair tensor cores (fp32-grade, 5e-6); the library falls back to FP32 FMA where no plan fits
-        self.gemm_flags = _lib.GEMM_TC_2XF16 if precision == "auto" else _PRECISIONS[precision]
+        self.gemm_flags = _lib.GEMM_TC_2XF16 if precision == "auto" else (_PRECISIONS[precision] & _lib.GEMM_MASK)
         self.Re = Parameter(torch.empty(out_channels, in_channels))
         self.Im = Parameter(torch.empty(out_channels, in_channels))
         nn.init.xavier_uniform_(self.Re)

@@ -53,9 +53,13 @@ def _check(x, name, dtype=torch.complex64):
 
 
 # --------------------------------------------------------------------------- compact plan ops
+def _padded_rows(n):
+    return (n + 127) // 128 * 128
+
+
 @torch.library.custom_op("fieldconv_b200::fc_fwd", mutates_args=())
 def fc_fwd(x: Tensor, W: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: Tensor, rowptr_src: Tensor,
-           rec_src: Tensor, rot_src: Tensor, band_limit: int, n_rings: int, flags: int,
+           rec_src: Tensor, rot_src: Tensor, norms: Tensor, band_limit: int, n_rings: int, flags: int,
            keep_contrib: bool) -> Tuple[Tensor, Tensor, Tensor]:
     # the by-source plan tensors are unused here; they are inputs so autograd can hand them to fc_bwd
     _check(x, "x")
@@ -64,85 +68,108 @@ def fc_fwd(x: Tensor, W: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: T
     n, ci = x.shape
     co = W.shape[0]
     k = n_rings * ci * (2 * band_limit + 1)
+    packed = bool(flags & _lib.FLAG_PACKED)
+    cflags = flags & ~_lib.FLAG_PACKED
     y = torch.empty(n, co, dtype=torch.complex64, device=x.device)
-    contrib = torch.empty(n, k, dtype=torch.complex64, device=x.device)
-    cmax = torch.zeros(1, dtype=torch.float32, device=x.device)     # max|contrib|: operand scale of the 2xFP16 contraction
-    nbytes = _lib.query_bytes("fcb_fwd_workspace_bytes", n, ci, co, band_limit, n_rings, flags)
+    # rows padded to whole 128-row tiles: the packed (PK) layout needs them, the fp32 layout ignores the tail
+    contrib = torch.empty(_padded_rows(n), k, dtype=torch.complex64, device=x.device)
+    cmax = torch.zeros(1, dtype=torch.float32, device=x.device)     # max|contrib| (or its bound): operand scale of the 2xFP16 contraction
+    nbytes = _lib.query_bytes("fcb_fwd_workspace_bytes", n, ci, co, band_limit, n_rings, cflags)
     ws = _ws(nbytes, x.device)
     with torch.cuda.device(x.device):
-        _lib.call("fcb_fwd_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
-                  rot_tgt.data_ptr(), _real(y).data_ptr(), _real(contrib).data_ptr(), cmax.data_ptr(), n, ci, co,
-                  band_limit, n_rings, flags, ws.data_ptr(), nbytes, _lib.stream_ptr())
+        if packed:
+            _lib.call("fcb_fwd_pk_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
+                      rot_tgt.data_ptr(), norms.data_ptr(), _real(y).data_ptr(), _real(contrib).data_ptr(), cmax.data_ptr(),
+                      n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes, _lib.stream_ptr())
+        else:
+            _lib.call("fcb_fwd_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
+                      rot_tgt.data_ptr(), _real(y).data_ptr(), _real(contrib).data_ptr(), cmax.data_ptr(), n, ci, co,
+                      band_limit, n_rings, cflags, ws.data_ptr(), nbytes, _lib.stream_ptr())
     if not keep_contrib:
         contrib = torch.empty(0, dtype=torch.complex64, device=x.device)
     return y, contrib, cmax
 
 
 @fc_fwd.register_fake
-def _(x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings, flags, keep_contrib):
+def _(x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, keep_contrib):
     n, ci = x.shape
     k = n_rings * ci * (2 * band_limit + 1)
-    return (x.new_empty(n, W.shape[0]), x.new_empty((n, k) if keep_contrib else (0,)),
+    return (x.new_empty(n, W.shape[0]), x.new_empty((_padded_rows(n), k) if keep_contrib else (0,)),
             x.new_empty(1, dtype=torch.float32))
 
 
 @torch.library.custom_op("fieldconv_b200::fc_bwd", mutates_args=())
 def fc_bwd(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, cmax: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: Tensor,
-           rowptr_src: Tensor, rec_src: Tensor, rot_src: Tensor, band_limit: int, n_rings: int, flags: int,
+           rowptr_src: Tensor, rec_src: Tensor, rot_src: Tensor, norms: Tensor, band_limit: int, n_rings: int, flags: int,
            need_gx: bool, need_gw: bool) -> Tuple[Tensor, Tensor]:
     _check(gy, "grad_output")
     x, W, gy = x.contiguous(), W.contiguous(), gy.contiguous()
     n, ci = x.shape
     co = W.shape[0]
+    packed = bool(flags & _lib.FLAG_PACKED)
+    cflags = flags & ~_lib.FLAG_PACKED
     gx = torch.empty_like(x) if need_gx else torch.empty(0, dtype=x.dtype, device=x.device)
     gw = torch.empty_like(W) if need_gw else torch.empty(0, dtype=W.dtype, device=x.device)
     have_contrib = contrib.numel() > 0
     nbytes = _lib.query_bytes("fcb_bwd_workspace_bytes", n, ci, co, band_limit, n_rings,
-                              flags | (0x100 if have_contrib else 0))
+                              cflags | (_lib.FLAG_HAVE_CONTRIB if have_contrib else 0))
     ws = _ws(nbytes, x.device)
     with torch.cuda.device(x.device):
-        _lib.call("fcb_bwd_f32", _real(x).data_ptr(), _real(W).data_ptr(), _real(gy).data_ptr(),
-                  _real(contrib).data_ptr() if have_contrib else 0, cmax.data_ptr() if have_contrib else 0,
-                  rowptr_tgt.data_ptr(), rec_tgt.data_ptr(), rot_tgt.data_ptr(),
-                  rowptr_src.data_ptr(), rec_src.data_ptr(), rot_src.data_ptr(),
-                  _real(gx).data_ptr() if need_gx else 0, _real(gw).data_ptr() if need_gw else 0,
-                  n, ci, co, band_limit, n_rings, flags, ws.data_ptr(), nbytes, _lib.stream_ptr())
+        if packed:
+            _lib.call("fcb_bwd_pk_f32", _real(x).data_ptr(), _real(W).data_ptr(), _real(gy).data_ptr(),
+                      _real(contrib).data_ptr() if have_contrib else 0, cmax.data_ptr() if have_contrib else 0,
+                      rowptr_tgt.data_ptr(), rec_tgt.data_ptr(), rot_tgt.data_ptr(), norms[0:].data_ptr(),
+                      rowptr_src.data_ptr(), rec_src.data_ptr(), rot_src.data_ptr(), norms[1:].data_ptr(),
+                      _real(gx).data_ptr() if need_gx else 0, _real(gw).data_ptr() if need_gw else 0,
+                      n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes, _lib.stream_ptr())
+        else:
+            _lib.call("fcb_bwd_f32", _real(x).data_ptr(), _real(W).data_ptr(), _real(gy).data_ptr(),
+                      _real(contrib).data_ptr() if have_contrib else 0, cmax.data_ptr() if have_contrib else 0,
+                      rowptr_tgt.data_ptr(), rec_tgt.data_ptr(), rot_tgt.data_ptr(),
+                      rowptr_src.data_ptr(), rec_src.data_ptr(), rot_src.data_ptr(),
+                      _real(gx).data_ptr() if need_gx else 0, _real(gw).data_ptr() if need_gw else 0,
+                      n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes, _lib.stream_ptr())
     return gx, gw
 
 
 @fc_bwd.register_fake
-def _(x, W, gy, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings, flags,
+def _(x, W, gy, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags,
       need_gx, need_gw):
     return (torch.empty_like(x) if need_gx else x.new_empty(0)), (torch.empty_like(W) if need_gw else W.new_empty(0))
 
 
 def _fc_setup(ctx, inputs, output):
-    x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings, flags, keep = inputs
+    x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, keep = inputs
     _, contrib, cmax = output
-    ctx.save_for_backward(x, W, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src)
+    ctx.save_for_backward(x, W, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms)
     ctx.cfg = (band_limit, n_rings, flags)
     ctx.set_materialize_grads(False)      # no N*K zero tensor for the unused contrib output
 
 
 def _fc_backward(ctx, gy, _gcontrib, _gcmax):
     if gy is None:
-        return (None,) * 12
-    x, W, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src = ctx.saved_tensors
+        return (None,) * 13
+    x, W, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms = ctx.saved_tensors
     band_limit, n_rings, flags = ctx.cfg
-    gx, gw = fc_bwd(x, W, gy, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, band_limit, n_rings,
-                    flags, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
-    return (gx if ctx.needs_input_grad[0] else None, gw if ctx.needs_input_grad[1] else None) + (None,) * 10
+    gx, gw = fc_bwd(x, W, gy, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit,
+                    n_rings, flags, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+    return (gx if ctx.needs_input_grad[0] else None, gw if ctx.needs_input_grad[1] else None) + (None,) * 11
 
 
 fc_fwd.register_autograd(_fc_backward, setup_context=_fc_setup)
 
 
 def field_conv(x, W, plan, band_limit, flags=0, keep_contrib=None):
-    """y = FieldConv(x) for the compact plan; differentiable w.r.t. x and W."""
+    """y = FieldConv(x) for the compact plan; differentiable w.r.t. x and W.  flags may carry _lib.FLAG_PACKED."""
     n, ci = x.shape
     if keep_contrib is None:
         keep_contrib = keep_contrib_default(n * plan.n_rings * ci * (2 * band_limit + 1) * 8, x.device)
-    y, _, _ = fc_fwd(x, W, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src, plan.rot_src,
+    norms = getattr(plan, "norms", None)
+    if norms is None:
+        if flags & _lib.FLAG_PACKED:
+            raise RuntimeError("fieldconv_b200: the packed path needs a plan built by build_plan (plan.norms)")
+        norms = torch.zeros(2, dtype=torch.float32, device=x.device)
+    y, _, _ = fc_fwd(x, W, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src, plan.rot_src, norms,
                      band_limit, plan.n_rings, flags, bool(keep_contrib))
     return y
 

@@ -310,7 +310,7 @@ def partitioned_field_conv(layer, x_own, part):
     ci, co = layer.in_channels, layer.out_channels
     if ci % 2 or co % 2:
         raise ValueError("partitioned FieldConv needs even channel counts")
-    flags = _resolve_precision(layer.precision, ci, co, layer.R, layer.B)
+    flags = _resolve_precision(layer.precision, ci, co, layer.R, layer.B) & _lib.GEMM_MASK   # row sub-ranges: fp32 operand layout
     return _PartitionedFieldConv.apply(x_own, layer.weight(), part, layer.B, flags)
 
 

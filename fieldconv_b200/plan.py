@@ -97,6 +97,11 @@ def build_plan(supp_edges, logMag, logAng, xp, w, n_rings, epsilon, num_nodes=No
                   p.rowptr_tgt.data_ptr(), p.rec_tgt.data_ptr(), p.rot_tgt.data_ptr(), p.perm_tgt.data_ptr(),
                   p.rowptr_src.data_ptr(), p.rec_src.data_ptr(), p.rot_src.data_ptr(), p.perm_src.data_ptr(),
                   ws.data_ptr(), nbytes, _lib.stream_ptr())
+        # [0]: max over targets of sum_e |wxp_e| (by-target order), [1]: the same over sources — the a-priori bounds
+        # max|contrib| <= norms[0] max|x| and max|G| <= norms[1] max|gy| that scale the packed fp16 operand planes
+        p.norms = torch.zeros(2, dtype=torch.float32, device=dev)
+        _lib.call("fcb_plan_norm", p.rowptr_tgt.data_ptr(), p.rec_tgt.data_ptr(), n, p.norms[0:].data_ptr(), _lib.stream_ptr())
+        _lib.call("fcb_plan_norm", p.rowptr_src.data_ptr(), p.rec_src.data_ptr(), n, p.norms[1:].data_ptr(), _lib.stream_ptr())
     return p
 
 

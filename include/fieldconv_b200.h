@@ -139,6 +139,32 @@ int fcb_bwd_f32(const float* x, const float* W, const float* gy, const float* co
                 float* gx, float* gW, int64_t N, int Ci, int Co, int band_limit, int R, int flags,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ packed-operand variants (FCB_GEMM_TC_2XF16 only)
+ * Same results as fcb_fwd_f32 / fcb_bwd_f32 (nn/field_conv.py:128-137 and its autograd), different intermediate
+ * format: the aggregation kernels write contrib (and, in the backward, G) directly as the scaled fp16 (hi, lo) tile
+ * images the tensor-core contractions consume ("PK": 128-row x 64-column blocks, SWIZZLE_128B, hi plane then lo
+ * plane), so the contraction kernels fetch their A operand with bulk copies instead of converting fp32 in
+ * producer warps.  The operand scale must be known BEFORE the aggregation runs, so it comes from the a-priori bound
+ *   max|contrib| <= max|x| * max_i sum_{e->i} |wxp_e|        (by-target plan;  <= max|x| for positive vertex weights:
+ *   max|G|       <= max|gy| * max_j sum_{e: src=j} |wxp_e|     fc_precomp.py:87 normalises the row mass)
+ * fcb_plan_norm computes max_row sum_e |wxp_e| of one CSR order of a plan (one device float, once per mesh).
+ * contrib_pk: fcb_pk_contrib_bytes(...) bytes, 128-byte aligned, opaque; contrib_scale (one device float, written
+ * by the forward) travels with it to the backward.  fcb_pk_supported: 1 when the layer shape is taken by this path
+ * (2*R*M*Ci a multiple of 64 and the 2xFP16 accumulation plans of gemm_h.cu feasible), else 0 — use fcb_fwd_f32.
+ * Workspaces: fcb_fwd_workspace_bytes / fcb_bwd_workspace_bytes with the same flags. */
+int fcb_plan_norm(const int32_t* rowptr, const void* rec, int64_t N, float* norm_out, void* stream);
+int fcb_pk_supported(int64_t N, int Ci, int Co, int band_limit, int R);
+int fcb_pk_contrib_bytes(int64_t N, int Ci, int band_limit, int R, size_t* bytes);
+int fcb_fwd_pk_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
+                   const float* rot_tgt, const float* norm_tgt, float* y, void* contrib_pk, float* contrib_scale,
+                   int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, const void* contrib_pk,
+                   const float* contrib_scale, const int32_t* rowptr_tgt, const void* rec_tgt,
+                   const float* rot_tgt, const float* norm_tgt, const int32_t* rowptr_src, const void* rec_src,
+                   const float* rot_src, const float* norm_src, float* gx, float* gW, int64_t N, int Ci, int Co,
+                   int band_limit, int R, int flags, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ dense-stencil forward/backward
  * Exact drop-in for arbitrary supp_sten (E,R,M) complex (nn/field_conv.py:114-116), any number
  * of non-zero rings per edge.  Same outputs as above. */

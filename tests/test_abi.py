@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_binding_covers_header():
-    bound = set(_lib.SIGNATURES) | {"fcb_last_error", "fcb_launch_count"}
+    bound = set(_lib.SIGNATURES) | {"fcb_last_error", "fcb_launch_count", "fcb_pk_supported", "fcb_gemm_tc_feasible"}
     assert set(header_symbols()) <= bound
 
 
@@ -76,3 +76,19 @@ def test_tensor_core_accumulation_plan():
     assert _lib.tc_feasible(256, 7680, flags=3)       # two 128-column chunks, two pairs each
     assert _lib.tc_feasible(96, 80000, trans_a=1, split_k=26, flags=3)
     assert not _lib.tc_feasible(64, 10 ** 6, flags=3)
+
+
+def test_packed_path_shape_support_and_sizes():
+    # 2*R*M*Ci must be a multiple of 64 and the 2xFP16 accumulation plans must fit (host-side predicates only)
+    assert _lib.pk_supported(80656, 48, 48, 2, 6)          # BASELINE cfg 2 layer
+    assert _lib.pk_supported(5041, 32, 32, 1, 6)           # cfg 1
+    assert _lib.pk_supported(6889, 128, 128, 2, 6)         # cfg 3
+    assert not _lib.pk_supported(5041, 6, 6, 1, 3)         # 2*3*3*6 = 108 columns: not a multiple of 64
+    n, ci, b, r = 1000, 32, 1, 6
+    nbytes = _lib.query_bytes("fcb_pk_contrib_bytes", n, ci, b, r)
+    assert nbytes == 1024 * (r * ci * 3) * 8               # same bytes as the fp32 layout, rows padded to 128
+    lib = _lib.load()
+    rc = lib.fcb_fwd_pk_f32(None, None, None, None, None, None, None, None, None, 10, 32, 32, 1, 6, 3, None, 0, None)
+    assert rc == -1
+    rc = lib.fcb_plan_norm(None, None, 10, None, None)
+    assert rc == -1
