@@ -13,6 +13,7 @@
 // channels of the neighbour's feature row; consecutive lanes read consecutive 16-byte pieces
 // of the same row, so a row of C channels is fetched as C/2 coalesced float4 loads.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -114,8 +115,10 @@ __device__ __forceinline__ void store_ring_packed(uint8_t* __restrict__ row_base
 // the operand scale comes from the a-priori bound  max|out| <= max|feat| * max_row sum_e |wxp_e|  (pk_feat_amax,
 // pk_norm: device floats; block 0 publishes the product in *pk_bound for the GEMM's epilogue), and the lanes of the
 // rows N .. pk_rows_padded(N)-1 zero-fill the tail of the last row tile (the weight-gradient GEMM reduces over rows).
-template <int B, bool TRANSPOSE, bool PACK>
-__global__ void __launch_bounds__(256, 2) k_aggregate(const float4* __restrict__ feat, const int32_t* __restrict__ rowptr,
+// MINB: minimum resident CTAs per SM the register allocation is held to (2: up to 128 registers; 3: 85 — more warps to
+// hide the gather latency at the price of a tighter register budget; chosen per band limit by agg_min_blocks()).
+template <int B, bool TRANSPOSE, bool PACK, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restrict__ feat, const int32_t* __restrict__ rowptr,
                                                       const int4* __restrict__ rec, const float2* __restrict__ rot,
                                                       float4* __restrict__ out, int64_t N, int C, int R,
                                                       uint32_t* __restrict__ amax, const float* __restrict__ pk_feat_amax,
@@ -130,7 +133,8 @@ __global__ void __launch_bounds__(256, 2) k_aggregate(const float4* __restrict__
     uint32_t pk_rsw = 0, pk_kk = 0, pk_kk_ring = 0, pk_kk_m = 0;
     float pk_s = 0.f;
     if (PACK) {
-        const float bound = __ldg(pk_feat_amax) * __ldg(pk_norm);
+        // pk_feat_amax is the largest REAL component; a complex modulus can be sqrt(2) larger
+        const float bound = __ldg(pk_feat_amax) * __ldg(pk_norm) * 1.41422f;
         pk_s = __uint_as_float(scale_field(__float_as_uint(fabsf(bound))) << 23);
         if (lane_id == 0) *pk_bound = fabsf(bound);
         const int cp = (int)(lane_id - row * P);
@@ -286,6 +290,17 @@ __global__ void __launch_bounds__(256) k_aggregate_dense(const float4* __restric
     fold_amax(amax, mx);
 }
 
+// Resident CTAs per SM requested for the band_limit <= 1 aggregation kernels (their accumulators are small enough for an
+// 85-register budget).  FIELDCONV_B200_AGG_OCC=3 selects it; default 2 until the B200 measurement says otherwise.
+static int agg_min_blocks() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("FIELDCONV_B200_AGG_OCC");
+        v = (e && atoi(e) >= 3) ? 3 : 2;
+    }
+    return v;
+}
+
 template <bool TRANSPOSE, bool PACK>
 static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const void* rec, const float* rot, float* out,
                               int64_t N, int C, int B, int R, float* amax, const float* pk_feat_amax, const float* pk_norm,
@@ -299,8 +314,13 @@ static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const vo
     const float2* rt = reinterpret_cast<const float2*>(rot);
     float4* o4 = reinterpret_cast<float4*>(out);
     prof_begin(PACK ? (TRANSPOSE ? "aggregate_T_pk" : "aggregate_pk") : (TRANSPOSE ? "aggregate_T" : "aggregate"), st);
-#define FCB_AGG_CASE(b) \
-    case b: k_aggregate<b, TRANSPOSE, PACK><<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am, pk_feat_amax, pk_norm, pk_bound); break;
+#define FCB_AGG_ARGS <<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am, pk_feat_amax, pk_norm, pk_bound)
+#define FCB_AGG_CASE(b)                                                           \
+    case b:                                                                       \
+        if (b <= 1 && occ3) k_aggregate<b, TRANSPOSE, PACK, (b <= 1 ? 3 : 2)> FCB_AGG_ARGS; \
+        else k_aggregate<b, TRANSPOSE, PACK, 2> FCB_AGG_ARGS;                     \
+        break;
+    const bool occ3 = agg_min_blocks() >= 3;
     switch (B) {
         FCB_AGG_CASE(0)
         FCB_AGG_CASE(1)
@@ -310,6 +330,7 @@ static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const vo
         default: set_error("aggregate: band_limit %d unsupported", B); return FCB_E_UNSUPPORTED;
     }
 #undef FCB_AGG_CASE
+#undef FCB_AGG_ARGS
     prof_end(st);
     FCB_CUDA_LAUNCH_CHECK("aggregate");
     return FCB_OK;

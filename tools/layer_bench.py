@@ -103,7 +103,7 @@ def run_one(mesh, plan, c, b, r, precision, steps, warmup, dev, ftype=1, tag="",
 def layer_flags(layer):
     from fieldconv_b200 import nn as fnn
     ci, co = layer.in_channels, layer.out_channels
-    return int(fnn._resolve_precision(layer.precision, ci + ci % 2, co + co % 2, layer.R, layer.B))
+    return int(fnn._resolve_precision(layer.precision, ci + ci % 2, co + co % 2, layer.R, layer.B))   # may carry FLAG_PACKED
 
 
 def main():
@@ -120,6 +120,7 @@ def main():
     ap.add_argument("--permute", action="store_true", help="random vertex numbering (cache-hostile case)")
     ap.add_argument("--sweep", action="store_true", help="cfg 5: C x band_limit x n_rings grid on a 1000x1000 mesh")
     ap.add_argument("--sweep-side", type=int, default=1000)
+    ap.add_argument("--tag", default=None, help="label copied into the output line (e.g. an environment setting under test)")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("layer_bench: needs a CUDA device (no CPU path)")
@@ -130,7 +131,7 @@ def main():
         mesh = torus_mesh(args.side, deg=args.deg, seed=0, device=dev, permute=args.permute)
         plan = fcb.build_plan(mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp, mesh.w, args.rings, mesh.epsilon)
         out = run_one(mesh, plan, args.channels, args.band, args.rings, args.precision, args.steps, args.warmup, dev,
-                      tag="permuted" if args.permute else "tiled", graph=args.graph)
+                      tag=args.tag or ("permuted" if args.permute else "tiled"), graph=args.graph)
         if out:
             print(json.dumps(out), flush=True)
         return
