@@ -262,7 +262,6 @@ def run_ours(args):
     #      A loader stream stages step k+1 (H2D copies + plan build) while step k computes — every step's copies and
     #      plan build are still inside the timed region, the first step's included.
     loader = torch.cuda.Stream(device=dev)
-    plan_attrs = ("rowptr_tgt", "rowptr_src", "rec_tgt", "rec_src", "rot_tgt", "rot_src", "perm_tgt", "perm_src")
 
     def stage():
         with torch.cuda.stream(loader):
@@ -276,7 +275,7 @@ def run_ours(args):
         d, pl, ready = staged
         main = torch.cuda.current_stream()
         main.wait_event(ready)
-        for t in (d["x"], d["labels"]) + tuple(getattr(pl, a) for a in plan_attrs):
+        for t in (d["x"], d["labels"]) + pl.tensors():
             t.record_stream(main)           # allocated on the loader stream, used on the compute stream
         return d["x"], pl, d["labels"]
 
@@ -368,11 +367,14 @@ def run_ours(args):
         pass
 
     # ---- CPU baseline on the box's host cores (bounded sample)
-    edges_c, times_c, n_c = cpu_sample(steps=2, warmup=1)
-    cpu_val = edges_c / (sum(times_c) / len(times_c))
-    cpu = {"value": cpu_val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-           "sample": "1 FCResNetBlock(48,48,B=2,R=6) fwd+bwd on one %d-vertex mesh, reference formulation "
-                     "(oracle/restate.py field_conv_refstyle), mean of 2 runs after 1 warm-up" % n_c}
+    if args.skip_cpu_baseline:             # A/B runs of tools/*.sh only; the driver's command never passes this
+        cpu = None
+    else:
+        edges_c, times_c, n_c = cpu_sample(steps=2, warmup=1)
+        cpu_val = edges_c / (sum(times_c) / len(times_c))
+        cpu = {"value": cpu_val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "1 FCResNetBlock(48,48,B=2,R=6) fwd+bwd on one %d-vertex mesh, reference formulation "
+                         "(oracle/restate.py field_conv_refstyle), mean of 2 runs after 1 warm-up" % n_c}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -535,6 +537,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("FIELDCONV_B200_PRECISION", "auto"))
+    ap.add_argument("--skip-cpu-baseline", action="store_true", help="kernel A/B runs only: omit the cpu_baseline leg")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"],
                     help="cfg2 (default, the driver's line): FC-ResNet on a batch of 16 meshes per GPU, data parallel; "
                          "cfg4: one large mesh vertex-partitioned across the GPUs with NVLink halo exchange (strong scaling)")

@@ -290,13 +290,17 @@ __global__ void __launch_bounds__(256) k_aggregate_dense(const float4* __restric
     fold_amax(amax, mx);
 }
 
-// Resident CTAs per SM requested for the band_limit <= 1 aggregation kernels (their accumulators are small enough for an
-// 85-register budget).  FIELDCONV_B200_AGG_OCC=3 selects it; default 2 until the B200 measurement says otherwise.
-static int agg_min_blocks() {
-    static int v = 0;
-    if (v == 0) {
-        const char* e = getenv("FIELDCONV_B200_AGG_OCC");
-        v = (e && atoi(e) >= 3) ? 3 : 2;
+// Largest band limit whose aggregation kernels are compiled for 3 resident CTAs per SM (85 registers) instead of 2 (128).
+// Measured on B200 (profiles/r01f): band_limit <= 1 gains 10-25 % from the extra warps (1M vertices, C=32: 3.80 -> 3.10 ms
+// forward, 3.57 -> 2.68 ms transposed).  FIELDCONV_B200_AGG_OCC3_MAX_B overrides (-1: never, 2: also band_limit 2, whose
+// 40 accumulator registers leave the tighter budget little room).
+static int agg_occ3_max_band() {
+    static int v = -2;
+    if (v == -2) {
+        const char* e = getenv("FIELDCONV_B200_AGG_OCC3_MAX_B");
+        v = e ? atoi(e) : 1;
+        if (v > 2) v = 2;
+        if (v < -1) v = -1;
     }
     return v;
 }
@@ -317,10 +321,10 @@ static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const vo
 #define FCB_AGG_ARGS <<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am, pk_feat_amax, pk_norm, pk_bound)
 #define FCB_AGG_CASE(b)                                                           \
     case b:                                                                       \
-        if (b <= 1 && occ3) k_aggregate<b, TRANSPOSE, PACK, (b <= 1 ? 3 : 2)> FCB_AGG_ARGS; \
+        if (b <= occ3_max_b) k_aggregate<b, TRANSPOSE, PACK, (b <= 2 ? 3 : 2)> FCB_AGG_ARGS; \
         else k_aggregate<b, TRANSPOSE, PACK, 2> FCB_AGG_ARGS;                     \
         break;
-    const bool occ3 = agg_min_blocks() >= 3;
+    const int occ3_max_b = agg_occ3_max_band();
     switch (B) {
         FCB_AGG_CASE(0)
         FCB_AGG_CASE(1)

@@ -23,15 +23,25 @@ from .transforms import attached_plan
 _PRECISIONS = {"fp32": _lib.GEMM_SIMT_FP32, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32": _lib.GEMM_TC_TF32,
                "2xf16": _lib.GEMM_TC_2XF16, "2xf16p": _lib.GEMM_TC_2XF16 | _lib.FLAG_PACKED, "auto": -1}
 
-# "auto" uses the packed-operand variant of the 2xFP16 path ("2xf16p": same arithmetic, the aggregation kernels write the
-# fp16 operand planes themselves) where the library supports the layer shape, unless FIELDCONV_B200_PACKED=0.
-PACKED_DEFAULT = os.environ.get("FIELDCONV_B200_PACKED", "0") != "0"
+# precision="auto" takes the packed-operand variant of the 2xFP16 path ("2xf16p": same arithmetic, the aggregation kernels
+# write the fp16 operand planes themselves) where the library supports the layer shape and the B200 measurements favour it
+# (profiles/r01f: band_limit <= 1 gains 7-8 % per layer — 1M vertices C=32 11.2 -> 10.3 ms, C=128 57.0 -> 52.8 ms; at
+# band_limit 2 the extra conversion work in the aggregation cancels the contraction's gain).
+# FIELDCONV_B200_PACKED=1: wherever supported; =0: never; unset/"auto": band_limit <= 1.
+PACKED_POLICY = os.environ.get("FIELDCONV_B200_PACKED", "auto")
 
 
-def packed_flags(flags, plan, n, ci, co, band_limit, n_rings, explicit):
+def _packed_by_default(band_limit):
+    if PACKED_POLICY == "0":
+        return False
+    return True if PACKED_POLICY == "1" else band_limit <= 1
+
+
+def packed_flags(flags, plan, n, ci, co, band_limit, n_rings, explicit, auto=False):
     """Resolve FLAG_PACKED for one call: keep it only for a compact plan with norms and a supported shape.  An
-    explicit precision="2xf16p" raises when the shape is not supported instead of silently changing kernels."""
-    want = bool(flags & _lib.FLAG_PACKED) or (PACKED_DEFAULT and not explicit and (flags & _lib.GEMM_MASK) == _lib.GEMM_TC_2XF16)
+    explicit precision="2xf16p" raises when the shape is not supported instead of silently changing kernels;
+    precision="auto" follows the measured policy above."""
+    want = bool(flags & _lib.FLAG_PACKED) or (auto and _packed_by_default(band_limit) and (flags & _lib.GEMM_MASK) == _lib.GEMM_TC_2XF16)
     flags &= ~_lib.FLAG_PACKED
     if not want:
         return flags
@@ -134,7 +144,8 @@ class FieldConv(nn.Module):
         if plan is not None and not plan.dense:
             if plan.n_rings != self.R:
                 raise ValueError("plan was built for n_rings=%d, layer has %d" % (plan.n_rings, self.R))
-            flags = packed_flags(flags, plan, x.shape[0], x.shape[1], w.shape[0], self.B, self.R, self.precision == "2xf16p")
+            flags = packed_flags(flags, plan, x.shape[0], x.shape[1], w.shape[0], self.B, self.R, self.precision == "2xf16p",
+                                 auto=self.precision == "auto")
             y = ops.field_conv(x, w, plan, self.B, flags)
         else:
             flags &= ~_lib.FLAG_PACKED

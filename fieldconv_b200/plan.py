@@ -27,6 +27,11 @@ class Plan:
     def num_edges(self):  # host sync
         return int(self.rowptr_tgt[-1].item())
 
+    def tensors(self):
+        """Every device tensor of the plan (e.g. to record_stream() them when the plan is built on a side stream)."""
+        names = ("rowptr_tgt", "rowptr_src", "rec_tgt", "rec_src", "rot_tgt", "rot_src", "perm_tgt", "perm_src", "norms")
+        return tuple(getattr(self, a) for a in names if getattr(self, a, None) is not None)
+
     def edges_by_target(self):
         """(j, i) of the kept edges in by-(target, ring) order — for index parity checks."""
         e = self.num_edges

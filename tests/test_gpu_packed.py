@@ -3,8 +3,7 @@ aggregation kernels write the scaled fp16 (hi, lo) tile images, the contraction 
 arithmetic as "2xf16", so it is held to the fp32 path's 1e-5 normwise tolerance against the fp64 oracle and the
 reference's golden outputs, and to 3e-6 against the unpacked 2xFP16 path.
 
-Run with FIELDCONV_B200_TEST_PACKED=1 (the path is opt-in until it has a green GPU run on record:
-FIELDCONV_B200_PACKED=1 or precision="2xf16p")."""
+First green B200 run: profiles/r01f_pytest_packed.log.  FIELDCONV_B200_TEST_PACKED=0 skips this file."""
 import os
 
 import pytest
@@ -18,7 +17,7 @@ from oracle import restate
 from test_gpu_parity import _oracle_layer
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FIELDCONV_B200_TEST_PACKED", "0") == "0", reason="packed-path tests disabled")]
+              pytest.mark.skipif(os.environ.get("FIELDCONV_B200_TEST_PACKED", "1") == "0", reason="packed-path tests disabled")]
 DEV = "cuda:0"
 TOL = 1e-5
 
