@@ -117,7 +117,9 @@ __device__ __forceinline__ void store_ring_packed(uint8_t* __restrict__ row_base
 // rows N .. pk_rows_padded(N)-1 zero-fill the tail of the last row tile (the weight-gradient GEMM reduces over rows).
 // MINB: minimum resident CTAs per SM the register allocation is held to (2: up to 128 registers; 3: 85 — more warps to
 // hide the gather latency at the price of a tighter register budget; chosen per band limit by agg_min_blocks()).
-template <int B, bool TRANSPOSE, bool PACK, int MINB>
+// DEPTH: software-pipeline depth of the edge loop (2: the record of edge p+2 and the feature row of edge p+1 are in flight;
+// 1: both of edge p+1 only — 6 registers fewer, for the register-capped high-occupancy variants).
+template <int B, bool TRANSPOSE, bool PACK, int MINB, int DEPTH>
 __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restrict__ feat, const int32_t* __restrict__ rowptr,
                                                       const int4* __restrict__ rec, const float2* __restrict__ rot,
                                                       float4* __restrict__ out, int64_t N, int C, int R,
@@ -200,20 +202,31 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
         int4 rcA = __ldg(rec + p0);
         float2 rtA = __ldg(rot + p0);
         const int pb = min(p0 + 1, last);
-        int4 rcB = __ldg(rec + pb);
-        float2 rtB = __ldg(rot + pb);
+        int4 rcB = rcA;
+        float2 rtB = rtA;
+        if (DEPTH == 2) {
+            rcB = __ldg(rec + pb);
+            rtB = __ldg(rot + pb);
+        }
         float4 vA = __ldg(fbase + ((uint32_t)rcA.x & NBR_MASK) * (uint32_t)P);
 #pragma unroll 2
         for (int p = p0; p < p1; ++p) {
             const int4 rc = rcA;
             const float2 rt = rtA;
             const float4 v = vA;
-            rcA = rcB;
-            rtA = rtB;
-            vA = __ldg(fbase + ((uint32_t)rcA.x & NBR_MASK) * (uint32_t)P);
-            const int pn = min(p + 2, last);
-            rcB = __ldg(rec + pn);
-            rtB = __ldg(rot + pn);
+            if (DEPTH == 2) {
+                rcA = rcB;
+                rtA = rtB;
+                vA = __ldg(fbase + ((uint32_t)rcA.x & NBR_MASK) * (uint32_t)P);
+                const int pn = min(p + 2, last);
+                rcB = __ldg(rec + pn);
+                rtB = __ldg(rot + pn);
+            } else {
+                const int pn = min(p + 1, last);
+                rcA = __ldg(rec + pn);
+                rtA = __ldg(rot + pn);
+                vA = __ldg(fbase + ((uint32_t)rcA.x & NBR_MASK) * (uint32_t)P);
+            }
 
             const int f = (int)((uint32_t)rc.x >> NBR_BITS);
             while (fcur < f) retire(fcur++);
@@ -290,19 +303,26 @@ __global__ void __launch_bounds__(256) k_aggregate_dense(const float4* __restric
     fold_amax(amax, mx);
 }
 
-// Largest band limit whose aggregation kernels are compiled for 3 resident CTAs per SM (85 registers) instead of 2 (128).
-// Measured on B200 (profiles/r01f): band_limit <= 1 gains 10-25 % from the extra warps (1M vertices, C=32: 3.80 -> 3.10 ms
-// forward, 3.57 -> 2.68 ms transposed).  FIELDCONV_B200_AGG_OCC3_MAX_B overrides (-1: never, 2: also band_limit 2, whose
-// 40 accumulator registers leave the tighter budget little room).
-static int agg_occ3_max_band() {
-    static int v = -2;
-    if (v == -2) {
-        const char* e = getenv("FIELDCONV_B200_AGG_OCC3_MAX_B");
-        v = e ? atoi(e) : 1;
-        if (v > 2) v = 2;
-        if (v < -1) v = -1;
+// Register-allocation variant of the aggregation kernel, 10 * (resident CTAs per SM) + (pipeline depth), per band limit and
+// output format.  Measured on B200 (profiles/r01f_layers_occ3.jsonl, r01g_ab_*, r01h_aggregate_variants.jsonl): resident
+// warps hide the gather latency better than a deeper software pipeline, until the register cap starts to spill —
+//   fp32 output,  band_limit <= 1: 41 (64 registers)   1M vertices C=32: fwd 3.80 -> 2.78 ms, transposed 3.57 -> 2.43 ms
+//   fp32 output,  band_limit 2   : 31 (80 registers)   cfg-2 layer: 0.520 -> 0.466 ms, 0.438 -> 0.408 ms  (41: 0.715, spills)
+//   packed output, band_limit <= 1: 32                  1M vertices C=32: 3.69 -> 3.03 ms, 3.52 -> 2.64 ms  (41: 3.22 / 3.26)
+//   packed output, band_limit 2   : 22 (128 registers)  (32: 0.567 -> 0.695 ms — the fp16 split needs the registers)
+// FIELDCONV_B200_AGG_VARIANT=<b0>,<b1>,<b2> (e.g. "32,41,31") overrides the variants of band limits 0, 1, 2 for experiments.
+static int agg_variant(int band_limit, bool pack) {
+    static int tab[3] = {0, 0, 0};
+    static bool init = false;
+    if (!init) {
+        const char* e = getenv("FIELDCONV_B200_AGG_VARIANT");
+        if (e) sscanf(e, "%d,%d,%d", &tab[0], &tab[1], &tab[2]);
+        init = true;
     }
-    return v;
+    if (band_limit > 2) return 22;
+    if (tab[band_limit]) return tab[band_limit];
+    if (band_limit <= 1) return pack ? 32 : 41;
+    return pack ? 22 : 31;
 }
 
 template <bool TRANSPOSE, bool PACK>
@@ -319,12 +339,16 @@ static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const vo
     float4* o4 = reinterpret_cast<float4*>(out);
     prof_begin(PACK ? (TRANSPOSE ? "aggregate_T_pk" : "aggregate_pk") : (TRANSPOSE ? "aggregate_T" : "aggregate"), st);
 #define FCB_AGG_ARGS <<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am, pk_feat_amax, pk_norm, pk_bound)
-#define FCB_AGG_CASE(b)                                                           \
-    case b:                                                                       \
-        if (b <= occ3_max_b) k_aggregate<b, TRANSPOSE, PACK, (b <= 2 ? 3 : 2)> FCB_AGG_ARGS; \
-        else k_aggregate<b, TRANSPOSE, PACK, 2> FCB_AGG_ARGS;                     \
-        break;
-    const int occ3_max_b = agg_occ3_max_band();
+    // variant = (resident CTAs per SM, pipeline depth) for this band limit: see agg_variant()
+#define FCB_AGG_CASE(b)                                                                               \
+    case b: {                                                                                         \
+        const int var = agg_variant(b, PACK);                                                         \
+        if (b <= 2 && var == 42) k_aggregate<b, TRANSPOSE, PACK, (b <= 2 ? 4 : 2), 2> FCB_AGG_ARGS;   \
+        else if (b <= 2 && var == 41) k_aggregate<b, TRANSPOSE, PACK, (b <= 2 ? 4 : 2), 1> FCB_AGG_ARGS; \
+        else if (b <= 2 && var == 32) k_aggregate<b, TRANSPOSE, PACK, (b <= 2 ? 3 : 2), 2> FCB_AGG_ARGS; \
+        else if (b <= 2 && var == 31) k_aggregate<b, TRANSPOSE, PACK, (b <= 2 ? 3 : 2), 1> FCB_AGG_ARGS; \
+        else k_aggregate<b, TRANSPOSE, PACK, 2, 2> FCB_AGG_ARGS;                                      \
+    } break;
     switch (B) {
         FCB_AGG_CASE(0)
         FCB_AGG_CASE(1)

@@ -59,3 +59,32 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_packed_path_selection_policy(monkeypatch):
+    """precision="auto" takes the packed-operand path for band_limit <= 1 where the library supports the shape;
+    an explicit "2xf16p" raises on an unsupported shape instead of silently switching kernels."""
+    from fieldconv_b200 import _lib
+    from fieldconv_b200 import nn as fnn
+
+    class FakePlan:
+        norms = object()
+
+    class NoNorms:
+        pass
+
+    f16 = _lib.GEMM_TC_2XF16
+    monkeypatch.setattr(fnn, "PACKED_POLICY", "auto")
+    assert fnn.packed_flags(f16, FakePlan(), 5041, 32, 32, 1, 6, False, auto=True) == f16 | _lib.FLAG_PACKED
+    assert fnn.packed_flags(f16, FakePlan(), 80656, 48, 48, 2, 6, False, auto=True) == f16          # band_limit 2: unpacked
+    assert fnn.packed_flags(f16, NoNorms(), 5041, 32, 32, 1, 6, False, auto=True) == f16            # plan without norms
+    assert fnn.packed_flags(f16, FakePlan(), 144, 6, 6, 1, 3, False, auto=True) == f16              # 108 columns: unsupported
+    assert fnn.packed_flags(f16, FakePlan(), 5041, 32, 32, 1, 6, False, auto=False) == f16          # explicit "2xf16" stays unpacked
+    assert fnn.packed_flags(_lib.GEMM_TC_3XTF32, FakePlan(), 5041, 32, 32, 1, 6, False, auto=True) == _lib.GEMM_TC_3XTF32
+    assert fnn.packed_flags(f16 | _lib.FLAG_PACKED, FakePlan(), 80656, 48, 48, 2, 6, True) == f16 | _lib.FLAG_PACKED
+    with pytest.raises(RuntimeError, match="2xf16p"):
+        fnn.packed_flags(f16 | _lib.FLAG_PACKED, FakePlan(), 144, 6, 6, 1, 3, True)
+    monkeypatch.setattr(fnn, "PACKED_POLICY", "0")
+    assert fnn.packed_flags(f16, FakePlan(), 5041, 32, 32, 1, 6, False, auto=True) == f16
+    monkeypatch.setattr(fnn, "PACKED_POLICY", "1")
+    assert fnn.packed_flags(f16, FakePlan(), 80656, 48, 48, 2, 6, False, auto=True) == f16 | _lib.FLAG_PACKED
