@@ -26,6 +26,7 @@
 // TN kernel (P = contrib^T gy, the weight gradient): both operands MN-major (the hardware transposes), SWIZZLE_128B
 //   atoms of 8 vertices x 64 fp16; gy is packed once (k_pack_b_h_tn), contrib goes through the producer warps.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -171,7 +172,9 @@ struct Params {
 // PACKED: A is a PK buffer (common.cuh) — the (hi, lo) planes of every 64-column chunk are already the swizzled tile
 // images, so the loader thread brings them in with two 16 KB bulk copies per stage on the stage's `full_b` barrier and
 // the 16 producer warps only run the epilogue.
-template <bool PACKED>
+// PAIRED (fp32 A only): the producers issue the loads of TWO consecutive chunks back to back, so the two 256-byte pieces
+// of a row's 512 bytes reach DRAM together (one page activation instead of two) — 4 chunks of registers instead of 3.
+template <bool PACKED, bool PAIRED>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
         uint8_t* const lo_base = sm + (a_lo0 - base);
         const float s_a = scale_of(p.amax_a);
         const bool wide = p.wide != 0;
-        F8 v[PF][UN];
+        F8 v[PAIRED ? 4 : PF][UN];
         auto issue = [&](int kc, F8(&dst)[UN]) {
             const int64_t k0 = (int64_t)kc * KC;
             if (k0 + KC <= p.K) {                        // full chunk (CTA-uniform)
@@ -273,6 +276,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
             if (lane == 0) mbar_arrive(full_a(s));
             if (++ps == (uint32_t)S) { ps = 0; pph ^= 1u; }
         };
+        if (PAIRED) {
+            const int n = p.nchunks;
+            if (0 < n) issue(0, v[0]);
+            if (1 < n) issue(1, v[1]);
+            for (int kc = 0; kc < n; kc += 4) {          // slots 0,1 hold chunks kc, kc+1; slots 2,3 take kc+2, kc+3
+                if (kc + 2 < n) issue(kc + 2, v[2]);
+                if (kc + 3 < n) issue(kc + 3, v[3]);
+                commit(v[0]);
+                if (kc + 1 < n) commit(v[1]);
+                if (kc + 4 < n) issue(kc + 4, v[0]);
+                if (kc + 5 < n) issue(kc + 5, v[1]);
+                if (kc + 2 < n) commit(v[2]);
+                if (kc + 3 < n) commit(v[3]);
+            }
+        } else {
 #pragma unroll
         for (int u = 0; u < PF - 1; ++u)
             if (u < p.nchunks) issue(u, v[u]);
@@ -285,6 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
                     commit(v[u]);
                 }
             }
+        }
         }
         }
         // ------------------------------------------------------------------ epilogue
@@ -810,8 +829,9 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
     const size_t smem = stages * stage_bytes + 1024 /*align slack*/ + 8 * (3 * stages + 2) + 64;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(th::k_gemm_h_nn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(th::k_gemm_h_nn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(th::k_gemm_h_nn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(th::k_gemm_h_nn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(th::k_gemm_h_nn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_error("gemm_h: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return FCB_E_CUDA;
@@ -819,8 +839,11 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
         attr_set = true;
     }
     dim3 grid((unsigned)((M + th::BM - 1) / th::BM), (unsigned)batch);
-    if (a_packed) FCB_LAUNCH("gemm_p_nn", st, th::k_gemm_h_nn<true><<<grid, th::THREADS, smem, st>>>(p));
-    else FCB_LAUNCH("gemm_h_nn", st, th::k_gemm_h_nn<false><<<grid, th::THREADS, smem, st>>>(p));
+    // FIELDCONV_B200_GEMM_PAIRED=1: paired chunk loads in the fp32-operand producers (experiment switch, read once)
+    static const bool paired = [] { const char* e = getenv("FIELDCONV_B200_GEMM_PAIRED"); return e && atoi(e) != 0; }();
+    if (a_packed) FCB_LAUNCH("gemm_p_nn", st, (th::k_gemm_h_nn<true, false><<<grid, th::THREADS, smem, st>>>(p)));
+    else if (paired) FCB_LAUNCH("gemm_h_nn", st, (th::k_gemm_h_nn<false, true><<<grid, th::THREADS, smem, st>>>(p)));
+    else FCB_LAUNCH("gemm_h_nn", st, (th::k_gemm_h_nn<false, false><<<grid, th::THREADS, smem, st>>>(p)));
     return FCB_OK;
 }
 
