@@ -93,3 +93,47 @@ def test_single_rank_partition_is_identity():
     part = partition_mesh(mesh, 1, 0)
     assert part.n_halo == 0 and part.n_interior == part.n_own == mesh.num_nodes
     assert torch.equal(part.supp_edges, mesh.supp_edges)
+
+
+def _dp_worker(rank, world, port, out_dir):
+    """Data-parallel mode (batches of small meshes): every rank holds its own mesh; the only collective
+    is the all-reduce of the parameter gradients (fieldconv_b200.allreduce_gradients)."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import fieldconv_b200 as fcb
+        from fieldconv_b200.synthetic import random_features, torus_mesh
+        from oracle import restate
+        torch.set_num_threads(1)
+        B, R, C = 1, 3, 4
+
+        def local_grads(seed, params):
+            mesh = torus_mesh(10, deg=12.0, seed=seed)
+            e, sten, _, _, _ = restate.fc_precomp(mesh.logMag, mesh.logAng, mesh.w, mesh.supp_edges, mesh.xp, B, R, mesh.epsilon)
+            x = random_features(mesh.num_nodes, C, seed=10 + seed)
+            gy = random_features(mesh.num_nodes, C, seed=20 + seed, zero_frac=0)
+            W = fcb.fold_weights(params[0], params[1], params[2], 1, B)
+            y = restate.field_conv_lean(x, e, sten, W, B)
+            return torch.autograd.grad((y.real * gy.real + y.imag * gy.imag).sum(), params)
+
+        torch.manual_seed(0)                      # identical parameters on every rank
+        layer = fcb.FieldConv(C, C, B, R, 1)
+        params = [layer.zonal, layer.spherical, layer.phase]
+        for p, g in zip(params, local_grads(rank, params)):
+            p.grad = g.clone()
+        fcb.allreduce_gradients(params)
+        total = [sum(gs) for gs in zip(*[local_grads(r, params) for r in range(world)])]
+        for p, t in zip(params, total):
+            assert float((p.grad - t).abs().max()) <= 1e-6 * float(t.abs().max()) + 1e-12
+        open(os.path.join(out_dir, "dp%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_allreduce_gloo(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_dp_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert os.path.exists(os.path.join(str(tmp_path), "dp%d" % r))
