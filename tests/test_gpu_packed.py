@@ -181,3 +181,30 @@ def test_packed_rejects_unsupported_shape():
     x = random_features(mesh.num_nodes, 6, seed=2, device=DEV)
     with pytest.raises(RuntimeError, match="2xf16p"):
         m(x, plan)
+
+
+@pytest.mark.parametrize("n_side,c,B,R", [(24, 48, 2, 6), (37, 32, 1, 6)])
+def test_packed_contrib_decodes_to_fp32_contrib(n_side, c, B, R):
+    """Format-level parity: the PK buffer the packing aggregation writes, decoded on the host side
+    (fieldconv_b200.packed.unpack: un-swizzle, (hi + lo) / scale), equals the fp32 contrib of the unpacked path to the
+    22 bits the (hi, lo) split carries; the tail rows of the last 128-row tile are zero; y agrees."""
+    from fieldconv_b200 import packed
+    mesh = torus_mesh(n_side, deg=40.0, seed=7, device=DEV)
+    plan = fcb.build_plan(mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp, mesh.w, R, mesh.epsilon)
+    n = mesh.num_nodes
+    assert _lib.pk_supported(n, c, c, B, R)
+    torch.manual_seed(0)
+    W = fcb.FieldConv(c, c, B, R, 1).weight().detach().to(DEV)
+    x = random_features(n, c, seed=2, device=DEV)
+    args = (x, W, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src, plan.rot_src, plan.norms, B, R)
+    y32, c32, cmax32 = ops.fc_fwd(*args, _lib.GEMM_TC_2XF16, True)
+    ypk, cpk, bound = ops.fc_fwd(*args, _lib.GEMM_TC_2XF16 | _lib.FLAG_PACKED, True)
+    cols = 2 * R * (2 * B + 1) * c
+    ref = torch.view_as_real(c32)[:n].reshape(n, cols)
+    dec = packed.unpack(cpk, n, cols, float(bound))
+    amax = float(ref.abs().max())
+    assert float(cmax32) == amax                                     # the unpacked path tracks the exact maximum
+    assert amax <= float(bound) <= 64.0 * amax                       # the a-priori bound holds and is not absurdly loose
+    assert float((dec[:n] - ref).abs().max()) <= 2.0 ** -20 * amax
+    assert float(dec[n:].abs().max()) == 0.0
+    assert_close_normwise(ypk, y32, 3e-6, "y packed vs unpacked")

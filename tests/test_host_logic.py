@@ -88,3 +88,33 @@ def test_packed_path_selection_policy(monkeypatch):
     assert fnn.packed_flags(f16, FakePlan(), 5041, 32, 32, 1, 6, False, auto=True) == f16
     monkeypatch.setattr(fnn, "PACKED_POLICY", "1")
     assert fnn.packed_flags(f16, FakePlan(), 80656, 48, 48, 2, 6, False, auto=True) == f16 | _lib.FLAG_PACKED
+
+
+def test_packed_format_mirror_roundtrip():
+    """fieldconv_b200.packed: encode a small matrix on the host exactly as store_ring_packed addresses it (byte_offset),
+    decode with unpack(): values come back to 2^-21 relative, the tail rows of the last tile are zero."""
+    import numpy as np
+    from fieldconv_b200 import packed
+    rows, cols = 130, 128
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((rows, cols)).astype(np.float32) * np.float32(3.0)
+    bound = float(np.abs(a).max()) * 1.5
+    s = np.float32(packed.scale_of(bound))
+    assert 2.0 ** 14 <= bound * float(s) < 2.0 ** 15
+    raw = np.zeros(packed.pk_bytes(rows, cols), dtype=np.uint8)
+    hi = (a * s).astype(np.float16)
+    lo = (a * s - hi.astype(np.float32)).astype(np.float16)
+    for r in range(rows):
+        for c in range(cols):
+            for plane, src in ((0, hi), (1, lo)):
+                o = packed.byte_offset(r, c, cols, plane)
+                raw[o:o + 2] = np.frombuffer(src[r, c].tobytes(), dtype=np.uint8)
+    assert packed.pk_bytes(rows, cols) == 2 * 2 * packed.BLOCK_BYTES and packed.padded_rows(rows) == 256
+    out = packed.unpack(torch.from_numpy(raw), rows, cols, bound)
+    assert out.shape == (256, cols)
+    assert float((out[:rows] - torch.from_numpy(a)).abs().max()) <= 2.0 ** -21 * float(np.abs(a).max())
+    assert float(out[rows:].abs().max()) == 0.0
+    # units of 8 fp16 stay contiguous and 16-byte aligned; the swizzle permutes units inside one 128-byte row only
+    assert packed.byte_offset(5, 8, cols) % 16 == 0 and packed.byte_offset(5, 9, cols) == packed.byte_offset(5, 8, cols) + 2
+    assert packed.byte_offset(5, 0, cols) // 128 == packed.byte_offset(5, 63, cols) // 128
+    assert packed.byte_offset(0, 64, cols) == packed.BLOCK_BYTES and packed.byte_offset(128, 0, cols) == 2 * packed.BLOCK_BYTES
