@@ -101,6 +101,8 @@ class Net(torch.nn.Module):
         self.head = torch.nn.Linear(C, N_CLASSES)
 
     def forward(self, x, plan):
+        import fieldconv_b200 as fcb
+        fcb.prefold(self)                 # the 10 layers' filters folded in one batch of torch ops (same arithmetic)
         for b in self.blocks:
             x = b(x, plan)
         return self.head(x.abs())

@@ -84,8 +84,28 @@ def fold_weights(zonal, spherical, phase, ftype, band_limit):
         w = torch.cat((sph.conj().flip(-1), zc, sph), dim=-1)
         if ftype == 1:
             ph = torch.cat((phase[..., 1:].flip(-1), phase), dim=-1)          # |m| = B..1, 0, 1..B
-            w = w * torch.polar(torch.ones_like(ph), ph).unsqueeze(2)
+            w = w * torch.polar(torch.ones_like(ph), ph).unsqueeze(-2)
     return (w / (2 * B + 1)).resolve_conj().contiguous()
+
+
+def prefold(module):
+    """Fold the filters of every FieldConv inside `module` in a few batched torch ops and hand each layer its W for its
+    next forward.  fold_weights is ~30 tiny kernels per layer per step (forward + autograd); a 10-layer network spends
+    0.7 ms of a 20 ms step on them.  Layers with identical (ftype, shapes) are stacked, folded once, and unbound — the
+    same arithmetic on the same values, so outputs and gradients are unchanged (tests/test_host_logic.py).  Optional:
+    a layer that was not prefolded folds its own filter as before.  Call once per forward pass, before the layers run."""
+    groups = {}
+    for m in module.modules():
+        if isinstance(m, FieldConv):
+            key = (m.ftype, m.B, tuple(m.zonal.shape), tuple(m.spherical.shape), m.zonal.device)
+            groups.setdefault(key, []).append(m)
+    for (ftype, band_limit, _, _, _), layers in groups.items():
+        if len(layers) == 1:
+            continue
+        w = fold_weights(torch.stack([m.zonal for m in layers]), torch.stack([m.spherical for m in layers]),
+                         torch.stack([m.phase for m in layers]), ftype, band_limit)
+        for m, wi in zip(layers, w.unbind(0)):
+            m._prefolded = wi
 
 
 class FieldConv(nn.Module):
@@ -111,8 +131,13 @@ class FieldConv(nn.Module):
         nn.init.xavier_uniform_(self.zonal)
         nn.init.xavier_uniform_(self.spherical)
         self._dense_cache = None
+        self._prefolded = None
 
     def weight(self):
+        w = self._prefolded
+        if w is not None:                 # handed over by prefold() for exactly one forward
+            self._prefolded = None
+            return w
         return fold_weights(self.zonal, self.spherical, self.phase, self.ftype, self.B)
 
     def _dense_plan(self, supp_edges, n):

@@ -118,3 +118,32 @@ def test_packed_format_mirror_roundtrip():
     assert packed.byte_offset(5, 8, cols) % 16 == 0 and packed.byte_offset(5, 9, cols) == packed.byte_offset(5, 8, cols) + 2
     assert packed.byte_offset(5, 0, cols) // 128 == packed.byte_offset(5, 63, cols) // 128
     assert packed.byte_offset(0, 64, cols) == packed.BLOCK_BYTES and packed.byte_offset(128, 0, cols) == 2 * packed.BLOCK_BYTES
+
+
+@pytest.mark.parametrize("ftype", [0, 1, 2])
+def test_prefold_matches_per_layer_fold(ftype):
+    """fcb.prefold: batched folding of all layers' filters gives the same W and the same parameter gradients as each
+    layer folding its own (nn/field_conv.py:10-33 arithmetic, stacked along a leading axis)."""
+    torch.manual_seed(0)
+    net = torch.nn.ModuleList([fcb.FCResNetBlock(6, 6, 2, 4, ftype) for _ in range(3)] + [fcb.FieldConv(6, 4, 2, 4, ftype)])
+    convs = [m for m in net.modules() if isinstance(m, fcb.FieldConv)]
+    assert len(convs) == 7
+    probes = [torch.randn(m.out_channels, m.in_channels, m.R, 2 * m.B + 1, dtype=torch.complex64) for m in convs]
+
+    def loss(ws):
+        return sum((w.real * p.real + w.imag * p.imag).sum() for w, p in zip(ws, probes))
+
+    ref_w = [m.weight() for m in convs]
+    loss(ref_w).backward()
+    ref_g = [[p.grad.clone() for p in m.parameters()] for m in convs]
+    net.zero_grad()
+    fcb.prefold(net)
+    assert convs[0]._prefolded is not None and convs[-1]._prefolded is None      # the odd-shaped layer folds on its own
+    got_w = [m.weight() for m in convs]
+    assert all(m._prefolded is None for m in convs)                               # consumed by exactly one forward
+    loss(got_w).backward()
+    for a, b in zip(got_w, ref_w):
+        assert a.shape == b.shape and torch.equal(a, b)
+    for m, gs in zip(convs, ref_g):
+        for p, g in zip(m.parameters(), gs):
+            assert torch.allclose(p.grad, g, rtol=1e-6, atol=1e-7)
