@@ -89,8 +89,8 @@ def fold_weights(zonal, spherical, phase, ftype, band_limit):
 
 
 def prefold(module):
-    """Fold the filters of every FieldConv inside `module` in a few batched torch ops and hand each layer its W for its
-    next forward.  fold_weights is ~30 tiny kernels per layer per step (forward + autograd); a 10-layer network spends
+    """Fold the filters of every FieldConv inside `module` (and build the real embedding of every TangentLin) in a few
+    batched torch ops and hand each layer its operand for its next forward.  fold_weights is ~30 tiny kernels per layer per step (forward + autograd); a 10-layer network spends
     0.7 ms of a 20 ms step on them.  Layers with identical (ftype, shapes) are stacked, folded once, and unbound — the
     same arithmetic on the same values, so outputs and gradients are unchanged (tests/test_host_logic.py).  Optional:
     a layer that was not prefolded folds its own filter as before.  Call once per forward pass, before the layers run."""
@@ -106,6 +106,23 @@ def prefold(module):
                          torch.stack([m.phase for m in layers]), ftype, band_limit)
         for m, wi in zip(layers, w.unbind(0)):
             m._prefolded = wi
+    lins = {}
+    for m in module.modules():
+        if isinstance(m, TangentLin):
+            lins.setdefault((m.in_channels, m.out_channels, m.Re.device), []).append(m)
+    for layers in lins.values():
+        if len(layers) > 1:
+            emb = _lin_embedding(torch.stack([m.Re for m in layers]), torch.stack([m.Im for m in layers]))
+            for m, e in zip(layers, emb.unbind(0)):
+                m._preemb = e
+
+
+def _lin_embedding(Re, Im):
+    """(…, Co, Ci) real and imaginary parts -> (…, 2Ci, 2Co) real matrix E with  [x_re, x_im] @ E = [y_re, y_im]  for
+    y = x @ (Re + i Im)^T  (nn/tangent_lin.py:27-29 on the interleaved storage)."""
+    re, im = Re.transpose(-1, -2), Im.transpose(-1, -2)              # (…, Ci, Co)
+    emb = torch.stack((torch.stack((re, im), -1), torch.stack((-im, re), -1)), -3)   # (…, Ci, 2, Co, 2)
+    return emb.reshape(*re.shape[:-2], 2 * re.shape[-2], 2 * re.shape[-1])
 
 
 class FieldConv(nn.Module):
@@ -193,6 +210,7 @@ class TangentLin(nn.Module):
         self.in_channels, self.out_channels = in_channels, out_channels
         # "auto": scaled fp16-pair tensor cores (fp32-grade, 5e-6); the library falls back to FP32 FMA where no plan fits
         self.gemm_flags = _lib.GEMM_TC_2XF16 if precision == "auto" else (_PRECISIONS[precision] & _lib.GEMM_MASK)
+        self._preemb = None
         self.Re = Parameter(torch.empty(out_channels, in_channels))
         self.Im = Parameter(torch.empty(out_channels, in_channels))
         nn.init.xavier_uniform_(self.Re)
@@ -200,9 +218,9 @@ class TangentLin(nn.Module):
 
     def forward(self, x):
         ci, co = self.in_channels, self.out_channels
-        re, im = self.Re.t(), self.Im.t()                       # (Ci, Co)
-        emb = torch.stack((torch.stack((re, im), -1), torch.stack((-im, re), -1)), 1)   # (Ci, 2, Co, 2)
-        emb = emb.reshape(2 * ci, 2 * co)
+        emb, self._preemb = self._preemb, None                  # handed over by prefold() for exactly one forward
+        if emb is None:
+            emb = _lin_embedding(self.Re, self.Im)              # (2Ci, 2Co)
         xr = torch.view_as_real(x.contiguous()).reshape(x.shape[0], 2 * ci)
         if (2 * ci) % 4 or (2 * co) % 4:                         # GEMM wants 16-byte rows
             pad_i, pad_o = (2 * ci) % 4, (2 * co) % 4

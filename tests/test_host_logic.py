@@ -147,3 +147,21 @@ def test_prefold_matches_per_layer_fold(ftype):
     for m, gs in zip(convs, ref_g):
         for p, g in zip(m.parameters(), gs):
             assert torch.allclose(p.grad, g, rtol=1e-6, atol=1e-7)
+
+
+def test_prefold_tangent_lin_embedding_matches():
+    torch.manual_seed(1)
+    net = torch.nn.ModuleList([fcb.TangentLin(5, 3) for _ in range(3)])
+    x = torch.randn(7, 5, dtype=torch.complex64)
+    from fieldconv_b200.nn import _lin_embedding
+    for m in net:
+        e = _lin_embedding(m.Re, m.Im)
+        xr = torch.view_as_real(x).reshape(7, 10)
+        y = torch.view_as_complex((xr @ e).reshape(7, 3, 2))
+        y_ref = x @ torch.complex(m.Re, m.Im).t()                      # nn/tangent_lin.py:29
+        assert torch.allclose(y, y_ref, rtol=1e-5, atol=1e-6)
+    fcb.prefold(net)
+    for m in net:
+        assert torch.equal(m._preemb, _lin_embedding(m.Re, m.Im))
+    g = torch.autograd.grad(sum(m._preemb.sum() for m in net), [m.Re for m in net])
+    assert all(torch.allclose(gi, torch.zeros_like(gi) + 2.0) for gi in g)   # every Re entry appears twice in E
