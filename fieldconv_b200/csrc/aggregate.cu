@@ -29,7 +29,11 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
     return r;
 }
 
-template <int B, bool TRANSPOSE>
+// FAST: frequencies beyond +1 by the three-term recurrence of a unit-modulus rotation,  z q^(m+1) = 2 Re(q) z q^m - z q^(m-1)
+// (and z conj(q) = 2 Re(q) z - z q exactly), one packed FFMA2 per new frequency instead of a 4-instruction complex
+// product: 2 + 1 + (2B - 1)/... complex products become 3 products + (2B - 1) FFMA2.  Deviation from the product form:
+// <= 4e-7 normwise at |m| = 2, 8e-7 at |m| = 3 (|q|^2 = 1 +- 5e-7 enters linearly), inside the fp32 reference's own noise.
+template <int B, bool TRANSPOSE, bool FAST = false>
 __device__ __forceinline__ void edge_products(float2 z, float2 wxp, float2 rot, float2* p) {
     float2 q;
     if (!TRANSPOSE) {
@@ -43,6 +47,17 @@ __device__ __forceinline__ void edge_products(float2 z, float2 wxp, float2 rot, 
     } else {
         q = make_float2(rot.x, -rot.y);
         p[B] = cmul_conj(z, wxp);
+    }
+    if (FAST && B >= 1) {
+        const float2 c2 = make_float2(2.f * q.x, 2.f * q.x);
+        p[B + 1] = cmul(p[B], q);
+        p[B - 1] = __ffma2_rn(c2, p[B], make_float2(-p[B + 1].x, -p[B + 1].y));
+#pragma unroll
+        for (int m = 2; m <= B; ++m) {
+            p[B + m] = __ffma2_rn(c2, p[B + m - 1], make_float2(-p[B + m - 2].x, -p[B + m - 2].y));
+            p[B - m] = __ffma2_rn(c2, p[B - m + 1], make_float2(-p[B - m + 2].x, -p[B - m + 2].y));
+        }
+        return;
     }
 #pragma unroll
     for (int m = 1; m <= B; ++m) {
@@ -119,7 +134,9 @@ __device__ __forceinline__ void store_ring_packed(uint8_t* __restrict__ row_base
 // hide the gather latency at the price of a tighter register budget; chosen per band limit by agg_min_blocks()).
 // DEPTH: software-pipeline depth of the edge loop (2: the record of edge p+2 and the feature row of edge p+1 are in flight;
 // 1: both of edge p+1 only — 6 registers fewer, for the register-capped high-occupancy variants).
-template <int B, bool TRANSPOSE, bool PACK, int MINB, int DEPTH>
+// FAST: three-term frequency recurrence (edge_products) and packed FFMA2 ring accumulation — 25 % fewer instructions in
+// the edge loop; experiment variant (FIELDCONV_B200_AGG_VARIANT codes >= 100), not a default until measured on B200.
+template <int B, bool TRANSPOSE, bool PACK, int MINB, int DEPTH, bool FAST>
 __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restrict__ feat, const int32_t* __restrict__ rowptr,
                                                       const int4* __restrict__ rec, const float2* __restrict__ rot,
                                                       float4* __restrict__ out, int64_t N, int C, int R,
@@ -239,13 +256,22 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
             for (int ch = 0; ch < 2; ++ch) {
                 const float2 z = ch ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
                 float2 pr[M];
-                edge_products<B, TRANSPOSE>(z, wxp, rt, pr);
+                edge_products<B, TRANSPOSE, FAST>(z, wxp, rt, pr);
+                if (FAST) {
+                    const float2 w00 = make_float2(w0, w0), w11 = make_float2(w1, w1);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        acc0[ch][m] = __ffma2_rn(w00, pr[m], acc0[ch][m]);
+                        acc1[ch][m] = __ffma2_rn(w11, pr[m], acc1[ch][m]);
+                    }
+                } else {
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
                     acc0[ch][m].x = fmaf(w0, pr[m].x, acc0[ch][m].x);
                     acc0[ch][m].y = fmaf(w0, pr[m].y, acc0[ch][m].y);
                     acc1[ch][m].x = fmaf(w1, pr[m].x, acc1[ch][m].x);
                     acc1[ch][m].y = fmaf(w1, pr[m].y, acc1[ch][m].y);
+                }
                 }
             }
         }
@@ -310,7 +336,8 @@ __global__ void __launch_bounds__(256) k_aggregate_dense(const float4* __restric
 //   fp32 output,  band_limit 2   : 31 (80 registers)   cfg-2 layer: 0.520 -> 0.466 ms, 0.438 -> 0.408 ms  (41: 0.715, spills)
 //   packed output, band_limit <= 1: 32                  1M vertices C=32: 3.69 -> 3.03 ms, 3.52 -> 2.64 ms  (41: 3.22 / 3.26)
 //   packed output, band_limit 2   : 22 (128 registers)  (32: 0.567 -> 0.695 ms — the fp16 split needs the registers)
-// FIELDCONV_B200_AGG_VARIANT=<b0>,<b1>,<b2> (e.g. "32,41,31") overrides the variants of band limits 0, 1, 2 for experiments.
+// FIELDCONV_B200_AGG_VARIANT=<b0>,<b1>,<b2> (e.g. "32,41,31") overrides the variants of band limits 0, 1, 2 for experiments;
+// adding 100 selects the FAST arithmetic (three-term recurrence + FFMA2), e.g. "132,141,131".
 static int agg_variant(int band_limit, bool pack) {
     static int tab[3] = {0, 0, 0};
     static bool init = false;
@@ -340,14 +367,18 @@ static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const vo
     prof_begin(PACK ? (TRANSPOSE ? "aggregate_T_pk" : "aggregate_pk") : (TRANSPOSE ? "aggregate_T" : "aggregate"), st);
 #define FCB_AGG_ARGS <<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am, pk_feat_amax, pk_norm, pk_bound)
     // variant = (resident CTAs per SM, pipeline depth) for this band limit: see agg_variant()
-#define FCB_AGG_CASE(b)                                                                               \
-    case b: {                                                                                         \
-        const int var = agg_variant(b, PACK);                                                         \
-        if (b <= 2 && var == 42) k_aggregate<b, TRANSPOSE, PACK, (b <= 2 ? 4 : 2), 2> FCB_AGG_ARGS;   \
-        else if (b <= 2 && var == 41) k_aggregate<b, TRANSPOSE, PACK, (b <= 2 ? 4 : 2), 1> FCB_AGG_ARGS; \
-        else if (b <= 2 && var == 32) k_aggregate<b, TRANSPOSE, PACK, (b <= 2 ? 3 : 2), 2> FCB_AGG_ARGS; \
-        else if (b <= 2 && var == 31) k_aggregate<b, TRANSPOSE, PACK, (b <= 2 ? 3 : 2), 1> FCB_AGG_ARGS; \
-        else k_aggregate<b, TRANSPOSE, PACK, 2, 2> FCB_AGG_ARGS;                                      \
+#define FCB_AGG_CASE(b)                                                                                       \
+    case b: {                                                                                                 \
+        const int var = agg_variant(b, PACK);                                                                 \
+        constexpr bool lo = (b <= 2);      /* only band limits 0-2 have the alternative variants compiled */  \
+        if (lo && var == 41) k_aggregate<b, TRANSPOSE, PACK, (lo ? 4 : 2), (lo ? 1 : 2), false> FCB_AGG_ARGS; \
+        else if (lo && var == 32) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), 2, false> FCB_AGG_ARGS;       \
+        else if (lo && var == 31) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 1 : 2), false> FCB_AGG_ARGS; \
+        else if (lo && var == 141) k_aggregate<b, TRANSPOSE, PACK, (lo ? 4 : 2), (lo ? 1 : 2), lo> FCB_AGG_ARGS; \
+        else if (lo && var == 132) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), 2, lo> FCB_AGG_ARGS;         \
+        else if (lo && var == 131) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 1 : 2), lo> FCB_AGG_ARGS; \
+        else if (lo && var == 122) k_aggregate<b, TRANSPOSE, PACK, 2, 2, lo> FCB_AGG_ARGS;                    \
+        else k_aggregate<b, TRANSPOSE, PACK, 2, 2, false> FCB_AGG_ARGS;                                       \
     } break;
     switch (B) {
         FCB_AGG_CASE(0)
