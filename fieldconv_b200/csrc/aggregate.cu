@@ -133,7 +133,8 @@ __device__ __forceinline__ void store_ring_packed(uint8_t* __restrict__ row_base
 // MINB: minimum resident CTAs per SM the register allocation is held to (2: up to 128 registers; 3: 85 — more warps to
 // hide the gather latency at the price of a tighter register budget; chosen per band limit by agg_min_blocks()).
 // DEPTH: software-pipeline depth of the edge loop (2: the record of edge p+2 and the feature row of edge p+1 are in flight;
-// 1: both of edge p+1 only — 6 registers fewer, for the register-capped high-occupancy variants).
+// 1: both of edge p+1 only — 6 registers fewer, for the register-capped high-occupancy variants; 3: as 1 plus the
+// neighbour id of edge p+2, see the loop — experiment variant, not measured yet).
 // FAST: three-term frequency recurrence (edge_products) and packed FFMA2 ring accumulation — 25 % fewer instructions in
 // the edge loop; experiment variant (FIELDCONV_B200_AGG_VARIANT codes >= 100), not a default until measured on B200.
 template <int B, bool TRANSPOSE, bool PACK, int MINB, int DEPTH, bool FAST>
@@ -225,13 +226,23 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
             rcB = __ldg(rec + pb);
             rtB = __ldg(rot + pb);
         }
+        // DEPTH 3 ("light two-deep"): only the neighbour id of edge p+1 travels one iteration ahead of its record (one
+        // register and one 4-byte load that hits the line the 16-byte record load touches next), so the feature gather of
+        // edge p+1 no longer waits for that record — DEPTH 2's latency tolerance at DEPTH 1's register cost.
+        int idN = (DEPTH == 3) ? __ldg(reinterpret_cast<const int*>(rec + pb)) : 0;
         float4 vA = __ldg(fbase + ((uint32_t)rcA.x & NBR_MASK) * (uint32_t)P);
 #pragma unroll 2
         for (int p = p0; p < p1; ++p) {
             const int4 rc = rcA;
             const float2 rt = rtA;
             const float4 v = vA;
-            if (DEPTH == 2) {
+            if (DEPTH == 3) {
+                vA = __ldg(fbase + ((uint32_t)idN & NBR_MASK) * (uint32_t)P);          // edge p+1: id loaded last iteration
+                idN = __ldg(reinterpret_cast<const int*>(rec + min(p + 2, last)));
+                const int pn = min(p + 1, last);
+                rcA = __ldg(rec + pn);
+                rtA = __ldg(rot + pn);
+            } else if (DEPTH == 2) {
                 rcA = rcB;
                 rtA = rtB;
                 vA = __ldg(fbase + ((uint32_t)rcA.x & NBR_MASK) * (uint32_t)P);
@@ -374,6 +385,10 @@ static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const vo
         if (lo && var == 41) k_aggregate<b, TRANSPOSE, PACK, (lo ? 4 : 2), (lo ? 1 : 2), false> FCB_AGG_ARGS; \
         else if (lo && var == 32) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), 2, false> FCB_AGG_ARGS;       \
         else if (lo && var == 31) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 1 : 2), false> FCB_AGG_ARGS; \
+        else if (lo && var == 33) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 3 : 2), false> FCB_AGG_ARGS; \
+        else if (lo && var == 43) k_aggregate<b, TRANSPOSE, PACK, (lo ? 4 : 2), (lo ? 3 : 2), false> FCB_AGG_ARGS; \
+        else if (lo && var == 133) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 3 : 2), lo> FCB_AGG_ARGS; \
+        else if (lo && var == 143) k_aggregate<b, TRANSPOSE, PACK, (lo ? 4 : 2), (lo ? 3 : 2), lo> FCB_AGG_ARGS; \
         else if (lo && var == 141) k_aggregate<b, TRANSPOSE, PACK, (lo ? 4 : 2), (lo ? 1 : 2), lo> FCB_AGG_ARGS; \
         else if (lo && var == 132) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), 2, lo> FCB_AGG_ARGS;         \
         else if (lo && var == 131) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 1 : 2), lo> FCB_AGG_ARGS; \
