@@ -202,14 +202,11 @@ def run_ours(args):
     def allreduce_grads():
         if world == 1:
             return
-        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        grads = [p.grad for p in params]
+        flat = torch.cat([g.reshape(-1) for g in grads])
         dist.all_reduce(flat)
         flat /= world
-        off = 0
-        for p in params:
-            k = p.numel()
-            p.grad.copy_(flat[off:off + k].view_as(p.grad))
-            off += k
+        torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(flat.split([g.numel() for g in grads]), grads)])
 
     def step(x, pl, lab):
         opt.zero_grad(set_to_none=True)

@@ -321,8 +321,4 @@ def allreduce_gradients(params, group=None):
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, group=group)
-    off = 0
-    for g in grads:
-        k = g.numel()
-        g.copy_(flat[off:off + k].view_as(g))
-        off += k
+    torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(flat.split([g.numel() for g in grads]), grads)])
