@@ -117,3 +117,27 @@ def random_features(n, channels, seed=0, zero_frac=0.01, device="cpu"):
     if zero_frac > 0:
         x = torch.where(torch.rand(n, channels, generator=g) < zero_frac, torch.zeros_like(x), x)
     return x.to(device)
+
+
+def with_edge_cases(mesh, isolated=(), duplicate=0, shuffle_seed=None, far=0):
+    """The reference's edge cases applied to a synthetic mesh: `isolated` targets lose every
+    incoming edge (y = 0 there, field_conv.py:134 with dim_size = N), the first `duplicate` edges appear twice (summed,
+    no coalescing), `far` extra edges get r > epsilon (dropped before the weight normalisation, fc_precomp.py:69-74,87),
+    and the edge list is shuffled (any edge order is allowed)."""
+    out = types.SimpleNamespace(**vars(mesh))
+    e, r, t, xp = mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp
+    if len(isolated):
+        iso = torch.as_tensor(list(isolated), device=e.device)
+        keep = ~torch.isin(e[:, 1], iso)
+        e, r, t, xp = e[keep], r[keep], t[keep], xp[keep]
+    if duplicate:
+        e, r, t, xp = (torch.cat((a, a[:duplicate])) for a in (e, r, t, xp))
+    if far:
+        e = torch.cat((e, e[:far].flip(1)))
+        r = torch.cat((r, torch.full((far,), 1.5 * mesh.epsilon, device=r.device, dtype=r.dtype)))
+        t, xp = torch.cat((t, t[:far])), torch.cat((xp, xp[:far]))
+    if shuffle_seed is not None:
+        perm = torch.randperm(e.shape[0], generator=torch.Generator().manual_seed(shuffle_seed)).to(e.device)
+        e, r, t, xp = e[perm], r[perm], t[perm], xp[perm]
+    out.supp_edges, out.logMag, out.logAng, out.xp = e.contiguous(), r.contiguous(), t.contiguous(), xp.contiguous()
+    return out

@@ -323,3 +323,31 @@ def test_fcprecomp_dropin_matches_reference_outputs(name):
     x2 = g["x"].to(DEV).requires_grad_(True)
     y2 = m2(x2, e.clone(), sten.clone())        # clones carry no plan: dense-stencil path on our own FCPrecomp output
     _check_against_golden(g, m2, y2, x2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "2xf16", "2xf16p"])
+def test_reference_edge_cases_on_a_synthetic_mesh(precision):
+    """SURVEY.md appendix B at a shape every contraction path (FP32 FMA, 2xFP16, packed 2xFP16) accepts: targets without
+    incoming edges (one of them the last vertex) give y = 0, duplicate edges are summed, edges with r > epsilon are
+    dropped before the weight normalisation, the edge order is arbitrary, 1 % of the features are exact zeros."""
+    from fieldconv_b200.synthetic import with_edge_cases
+    base = torus_mesh(20, deg=30.0, seed=9, device=DEV)
+    iso = (3, 57, base.num_nodes - 1)
+    mesh = with_edge_cases(base, isolated=iso, duplicate=60, shuffle_seed=1, far=45)
+    ci = co = 32
+    B, R = 1, 6
+    torch.manual_seed(0)
+    m = fcb.FieldConv(ci, co, B, R, 1, precision=precision).to(DEV)
+    plan = fcb.build_plan(mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp, mesh.w, R, mesh.epsilon)
+    assert plan.num_edges == mesh.supp_edges.shape[0] - 45
+    x = random_features(mesh.num_nodes, ci, seed=2, device=DEV).requires_grad_(True)
+    gy = random_features(mesh.num_nodes, co, seed=3, zero_frac=0, device=DEV)
+    y = m(x, plan)
+    (y.real * gy.real + y.imag * gy.imag).sum().backward()
+    assert float(y[list(iso)].abs().max()) == 0.0
+    y_ref, gx_ref, gp_ref = _oracle_layer(mesh, x, m, gy)
+    assert_close_normwise(y, y_ref.to(torch.complex64), TOL, precision + " y")
+    assert_close_normwise(x.grad, gx_ref.to(torch.complex64), TOL, precision + " grad x")
+    assert_close_normwise(m.zonal.grad, gp_ref[0].float(), TOL, precision + " grad zonal")
+    assert_close_normwise(m.spherical.grad, gp_ref[1].float(), TOL, precision + " grad spherical")
+    assert_close_normwise(m.phase.grad, gp_ref[2].float(), TOL, precision + " grad phase")
