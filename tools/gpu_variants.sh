@@ -12,11 +12,11 @@ run() {   # variant-string  layer_bench args...
 }
 {
   # band limit 2, fp32 output (the cfg-2 bench path): default 31 vs depth 3 / FAST arithmetic
-  for v in 32,41,31 32,41,33 32,41,131 32,41,133 32,41,43 32,41,143; do run $v --side 284 --channels 48 --band 2 --rings 6; done
+  for v in 32,41,31 32,41,33 32,41,34 32,41,131 32,41,133 32,41,134 32,41,43 32,41,44; do run $v --side 284 --channels 48 --band 2 --rings 6; done
   # band limit 1, packed output (1 M vertices, C=32): default 32 vs depth 3 / FAST
-  for v in 32,32,31 32,33,31 32,43,31 32,132,31 32,133,31; do run $v --side 1000 --channels 32 --band 1 --rings 6 --steps 5; done
+  for v in 32,32,31 32,33,31 32,34,31 32,44,31 32,132,31 32,134,31; do run $v --side 1000 --channels 32 --band 1 --rings 6 --steps 5; done
   # band limit 1, fp32 output: default 41 vs depth 3 / FAST
-  for v in 32,41,31 32,43,31 32,141,31 32,143,31; do run $v --side 1000 --channels 32 --band 1 --rings 6 --steps 5 --precision 2xf16; done
+  for v in 32,41,31 32,43,31 32,44,31 32,34,31 32,141,31 32,134,31; do run $v --side 1000 --channels 32 --band 1 --rings 6 --steps 5 --precision 2xf16; done
 } > $OUT/${TAG}_variants.jsonl 2> $OUT/${TAG}_variants.err
 python - <<PY
 import json
