@@ -107,13 +107,54 @@ def make_block(seed=11):
     print("block_b2r6", "N", d.num_nodes, "E", e.shape[0])
 
 
+LIFT_CASES = [
+    # name, n_side, deg, Ci, Co, B (of the FCPrecomp stencil the lift stencil is cut from), R, ftype
+    ("lift_b1r6_f1", 8, 12.0, 3, 5, 1, 6, 1),
+    ("lift_b2r4_f0", 7, 14.0, 4, 6, 2, 4, 0),
+]
+
+
+def make_lift(name, n_side, deg, ci, co, B, R, ftype, seed):
+    """TransField (nn/trans_field.py:78-113) on the lift stencil supp_sten[..., B:B+2] — SURVEY.md §8(f) F2 groundwork."""
+    ns = ref_loader.load()
+    d = syn.torus_mesh(n_side, deg=deg, seed=seed, tile=4)
+    g = torch.Generator().manual_seed(seed)
+    keep = d.supp_edges[:, 1] != 5                      # an isolated target
+    for k in ("supp_edges", "logMag", "logAng", "xp"):
+        setattr(d, k, getattr(d, k)[keep])
+    e, sten, _, _ = ns.FCPrecomp(B, R, float(d.epsilon))(d)
+    lift = sten[..., B:B + 2].contiguous()
+    x = torch.randn(d.num_nodes, ci, generator=g)
+    x[torch.rand(x.shape, generator=g) < 0.05] = 0.0
+    torch.manual_seed(seed)
+    tf = ns.TransField(ci, co, n_rings=R, ftype=ftype)
+    xr = x.clone().requires_grad_(True)
+    y = tf(xr, e, lift)
+    gy = torch.complex(torch.randn(y.shape, generator=g), torch.randn(y.shape, generator=g))
+    (y.real * gy.real + y.imag * gy.imag).sum().backward()
+    out = dict(n=np.int64(d.num_nodes), ci=np.int64(ci), co=np.int64(co), B=np.int64(B), R=np.int64(R), ftype=np.int64(ftype),
+               epsilon=np.float64(d.epsilon), supp_edges=_np(e), supp_sten=_np(sten), lift_sten=_np(lift), x=_np(x), gy=_np(gy),
+               zonalAng=_np(tf.zonalAng), zonalMag=_np(tf.zonalMag), phase=_np(tf.phase), y=_np(y), gx=_np(xr.grad),
+               g_zonalAng=_np(tf.zonalAng.grad), g_zonalMag=_np(tf.zonalMag.grad))
+    if ftype == 1:
+        out["g_phase"] = _np(tf.phase.grad)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+    print(name, "N", d.num_nodes, "E", e.shape[0], "|y|max", float(y.abs().max()))
+
+
 def main():
+    import sys
     if not ref_loader.available():
         raise SystemExit("reference tree not present; golden vectors can only be generated in the build container")
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
-    for i, c in enumerate(CASES):
-        make_case(*c, seed=100 + i)
-    make_block()
+    only = sys.argv[1] if len(sys.argv) > 1 else "all"      # "all" | "fc" | "lift"
+    if only in ("all", "fc"):
+        for i, c in enumerate(CASES):
+            make_case(*c, seed=100 + i)
+        make_block()
+    if only in ("all", "lift"):
+        for i, c in enumerate(LIFT_CASES):
+            make_lift(*c, seed=200 + i)
 
 
 if __name__ == "__main__":

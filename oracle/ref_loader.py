@@ -83,6 +83,8 @@ def load():
         FCPrecomp=ref_pre.FCPrecomp,
         radialInterpolant=ref_pre.radialInterpolant,
         softAngle=ref_field.softAngle,
+        TransField=ref_nn.TransField,
+        LiftBlock=ref_nn.LiftBlock,
     )
     _cache["ns"] = ns
     return ns

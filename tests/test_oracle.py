@@ -100,3 +100,22 @@ def test_gauge_equivariance_property():
     xp1 = g["xp"] * torch.polar(torch.ones_like(alpha[src]), alpha[src] - alpha[tgt])
     y1 = run(x1.to(torch.complex64), la1, xp1.to(torch.complex64))
     assert_close_normwise(y1, y0 * rot[:, None], 5e-6, "gauge equivariance")
+
+
+# ---- F2 groundwork: TransField restatements against the unmodified reference's outputs
+@pytest.mark.parametrize("name", golden_names("lift_"))
+def test_trans_field_restatements_match_reference(name):
+    g = load_golden(name)
+    assert torch.equal(restate.lift_stencil(g["supp_sten"], g["B"]), g["lift_sten"])
+    for fn, tol in ((restate.trans_field_refstyle, 1e-6), (restate.trans_field_lean, 2e-6)):
+        x = g["x"].clone().requires_grad_(True)
+        ps = [g[k].clone().requires_grad_(True) for k in ("zonalAng", "zonalMag", "phase")]
+        y = fn(x, g["supp_edges"], g["lift_sten"], ps[0], ps[1], ps[2], g["ftype"])
+        (y.real * g["gy"].real + y.imag * g["gy"].imag).sum().backward()
+        assert_close_normwise(y, g["y"], tol, fn.__name__ + " y")
+        assert_close_normwise(x.grad, g["gx"], 10 * tol, fn.__name__ + " gx")
+        assert_close_normwise(ps[0].grad, g["g_zonalAng"], 10 * tol, fn.__name__ + " g_zonalAng")
+        assert_close_normwise(ps[1].grad, g["g_zonalMag"], 10 * tol, fn.__name__ + " g_zonalMag")
+        if g["ftype"] == 1:
+            assert_close_normwise(ps[2].grad, g["g_phase"], 10 * tol, fn.__name__ + " g_phase")
+    assert float(g["y"][5].abs().max()) == 0.0            # the isolated target
