@@ -115,6 +115,18 @@ __device__ __forceinline__ void store_ring_packed(uint8_t* __restrict__ row_base
     }
 }
 
+// Out-of-line form of the packed ring store for the NI kernel variants: the fp16 split needs a dozen temporaries that are
+// live only at a ring transition (6 times per row), but inlined they inflate the register allocation of the whole edge
+// loop and keep the packed band_limit-2 kernel at 2 CTAs/SM.  The accumulators travel by value (registers, not memory).
+template <int M>
+struct RingAcc {
+    float2 v[2][M];
+};
+template <int M>
+__device__ __noinline__ void store_ring_packed_ni(uint8_t* row_base, uint32_t rsw, RingAcc<M> a, uint32_t kk, uint32_t kk_m, float s) {
+    store_ring_packed<M>(row_base, rsw, a.v, kk, kk_m, s);
+}
+
 constexpr int AGG_STAGE_CAP = 768;      // plan records a CTA of the DEPTH-4 variant can stage (18 KB of shared memory)
 
 // The two live rings sit in two fixed accumulator sets selected by ring
@@ -131,7 +143,8 @@ constexpr int AGG_STAGE_CAP = 768;      // plan records a CTA of the DEPTH-4 var
 // not measured yet).
 // FAST: three-term frequency recurrence (edge_products) and packed FFMA2 ring accumulation — 25 % fewer instructions in
 // the edge loop; experiment variant (FIELDCONV_B200_AGG_VARIANT codes >= 100), not a default until measured on B200.
-template <int B, bool TRANSPOSE, bool PACK, int MINB, int DEPTH, bool FAST>
+// NI (packed output only): ring stores through the out-of-line store_ring_packed_ni — experiment variant (codes 2xx).
+template <int B, bool TRANSPOSE, bool PACK, int MINB, int DEPTH, bool FAST, bool NI = false>
 __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restrict__ feat, const int32_t* __restrict__ rowptr,
                                                       const int4* __restrict__ rec, const float2* __restrict__ rot,
                                                       float4* __restrict__ out, int64_t N, int C, int R,
@@ -212,12 +225,22 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
     // ring fcur is complete: write it once and clear its accumulator set (it becomes ring fcur + 2)
     auto retire = [&](int ring) {
         if (ring & 1) {
-            if (PACK) store_ring_packed<M>(pk_row, pk_rsw, acc1, pk_kk, pk_kk_m, pk_s);
+            if (PACK && NI) {
+                RingAcc<M> a;
+#pragma unroll
+                for (int m = 0; m < M; ++m) { a.v[0][m] = acc1[0][m]; a.v[1][m] = acc1[1][m]; }
+                store_ring_packed_ni<M>(pk_row, pk_rsw, a, pk_kk, pk_kk_m, pk_s);
+            } else if (PACK) store_ring_packed<M>(pk_row, pk_rsw, acc1, pk_kk, pk_kk_m, pk_s);
             else store_ring<M>(dst, acc1, m_stride, mx);
 #pragma unroll
             for (int m = 0; m < M; ++m) acc1[0][m] = acc1[1][m] = make_float2(0.f, 0.f);
         } else {
-            if (PACK) store_ring_packed<M>(pk_row, pk_rsw, acc0, pk_kk, pk_kk_m, pk_s);
+            if (PACK && NI) {
+                RingAcc<M> a;
+#pragma unroll
+                for (int m = 0; m < M; ++m) { a.v[0][m] = acc0[0][m]; a.v[1][m] = acc0[1][m]; }
+                store_ring_packed_ni<M>(pk_row, pk_rsw, a, pk_kk, pk_kk_m, pk_s);
+            } else if (PACK) store_ring_packed<M>(pk_row, pk_rsw, acc0, pk_kk, pk_kk_m, pk_s);
             else store_ring<M>(dst, acc0, m_stride, mx);
 #pragma unroll
             for (int m = 0; m < M; ++m) acc0[0][m] = acc0[1][m] = make_float2(0.f, 0.f);
@@ -322,7 +345,8 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
 //   packed output, band_limit <= 1: 32                  1M vertices C=32: 3.69 -> 3.03 ms, 3.52 -> 2.64 ms  (41: 3.22 / 3.26)
 //   packed output, band_limit 2   : 22 (128 registers)  (32: 0.567 -> 0.695 ms — the fp16 split needs the registers)
 // FIELDCONV_B200_AGG_VARIANT=<b0>,<b1>,<b2> (e.g. "32,41,31") overrides the variants of band limits 0, 1, 2 for experiments;
-// adding 100 selects the FAST arithmetic (three-term recurrence + FFMA2), e.g. "132,141,131".
+// adding 100 selects the FAST arithmetic (three-term recurrence + FFMA2), e.g. "132,141,131"; 2xx / 3xx (packed output
+// only) the out-of-line ring store without / with FAST.
 static inline int agg_variant(int band_limit, bool pack) {
     static int tab[3] = {0, 0, 0};
     static bool init = false;
@@ -370,6 +394,9 @@ static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const vo
         else if (lo && var == 132) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), 2, lo> FCB_AGG_ARGS;         \
         else if (lo && var == 131) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 1 : 2), lo> FCB_AGG_ARGS; \
         else if (lo && var == 122) k_aggregate<b, TRANSPOSE, PACK, 2, 2, lo> FCB_AGG_ARGS;                    \
+        else if (lo && PACK && var == 231) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 1 : 2), false, lo && PACK> FCB_AGG_ARGS; \
+        else if (lo && PACK && var == 232) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), 2, false, lo && PACK> FCB_AGG_ARGS; \
+        else if (lo && PACK && var == 331) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 1 : 2), lo, lo && PACK> FCB_AGG_ARGS; \
         else k_aggregate<b, TRANSPOSE, PACK, 2, 2, false> FCB_AGG_ARGS;                                       \
     } break;
     switch (B) {
