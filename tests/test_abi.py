@@ -92,3 +92,27 @@ def test_packed_path_shape_support_and_sizes():
     assert rc == -1
     rc = lib.fcb_plan_norm(None, None, 10, None, None)
     assert rc == -1
+
+
+def test_default_aggregation_variants_are_compiled_without_heavy_spills():
+    """The variants agg_variant() selects by default (aggregate_kernel.cuh) exist in the library for band limits 1 and 2,
+    both directions, fp32 and packed output, and stay within the spill budget they were measured with."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run(["cuobjdump", "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    lines = out.splitlines()
+    usage = {}
+    for i, l in enumerate(lines):
+        m = re.search(r"Function _ZN3fcb11k_aggregateILi(\d)ELb(\d)ELb(\d)ELi(\d)ELi(\d)ELb(\d)ELb(\d)E", l)
+        if m and i + 1 < len(lines):
+            u = re.search(r"REG:(\d+) STACK:(\d+)", lines[i + 1])
+            usage[tuple(int(x) for x in m.groups())] = (int(u.group(1)), int(u.group(2)))
+    # (band limit, transpose, packed, resident CTAs, depth, FAST, NI)
+    defaults = [(b, t, 0, 4, 1, 0, 0) for b in (1,) for t in (0, 1)] + [(2, t, 0, 3, 1, 0, 0) for t in (0, 1)] + \
+               [(1, t, 1, 3, 2, 0, 0) for t in (0, 1)] + [(2, t, 1, 2, 2, 0, 0) for t in (0, 1)]
+    for key in defaults:
+        assert key in usage, "missing kernel variant %s" % (key,)
+        regs, stack = usage[key]
+        assert regs <= {2: 128, 3: 80, 4: 64}[key[3]] and stack <= 48, (key, regs, stack)
