@@ -827,7 +827,12 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
     FCB_REQUIRE(stages >= 1, FCB_E_UNSUPPORTED, "gemm_h: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = stages * stage_bytes + 1024 /*align slack*/ + 8 * (3 * stages + 2) + 64;
-    static bool attr_set = false;
+    // the opt-in shared-memory size is a per-device (per-context) function attribute: remember it per device
+    static bool attr_set_dev[64] = {};
+    bool attr_unknown_dev = false;
+    int attr_dev = 0;
+    if (cudaGetDevice(&attr_dev) != cudaSuccess) attr_dev = -1;
+    bool& attr_set = (attr_dev >= 0 && attr_dev < 64) ? attr_set_dev[attr_dev] : attr_unknown_dev;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(th::k_gemm_h_nn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(th::k_gemm_h_nn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -905,7 +910,12 @@ int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N
     p.stages = stages;
     const size_t smem = stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
     dim3 grid((unsigned)((Mr + th::BM - 1) / th::BM), 1, (unsigned)split);
-    static bool attr_set = false;
+    // the opt-in shared-memory size is a per-device (per-context) function attribute: remember it per device
+    static bool attr_set_dev[64] = {};
+    bool attr_unknown_dev = false;
+    int attr_dev = 0;
+    if (cudaGetDevice(&attr_dev) != cudaSuccess) attr_dev = -1;
+    bool& attr_set = (attr_dev >= 0 && attr_dev < 64) ? attr_set_dev[attr_dev] : attr_unknown_dev;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(th::k_gemm_h_tn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(th::k_gemm_h_tn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -696,7 +696,12 @@ int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N
     FCB_REQUIRE(stages >= 1, FCB_E_UNSUPPORTED, "gemm_tc: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = stages * stage_bytes + 1024 /*align slack*/ + 8 * (3 * stages + 2) + 64;
-    static bool attr_set = false;
+    // the opt-in shared-memory size is a per-device (per-context) function attribute: remember it per device
+    static bool attr_set_dev[64] = {};
+    bool attr_unknown_dev = false;
+    int attr_dev = 0;
+    if (cudaGetDevice(&attr_dev) != cudaSuccess) attr_dev = -1;
+    bool& attr_set = (attr_dev >= 0 && attr_dev < 64) ? attr_set_dev[attr_dev] : attr_unknown_dev;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc::k_gemm_tc_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
@@ -759,7 +764,12 @@ int launch_gemm_tc_tn(const float* A, const float* B, float* C, int64_t Mr, int 
     p.stages = stages;
     const size_t smem = stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
     dim3 grid((unsigned)((Mr + tc::BM - 1) / tc::BM), 1, (unsigned)split);
-    static bool attr_set = false;
+    // the opt-in shared-memory size is a per-device (per-context) function attribute: remember it per device
+    static bool attr_set_dev[64] = {};
+    bool attr_unknown_dev = false;
+    int attr_dev = 0;
+    if (cudaGetDevice(&attr_dev) != cudaSuccess) attr_dev = -1;
+    bool& attr_set = (attr_dev >= 0 && attr_dev < 64) ? attr_set_dev[attr_dev] : attr_unknown_dev;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc::k_gemm_tc_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
