@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(256) k_aggregate_dense(const float4* __restric
         }
     }
     float4* orow = out + row * ((int64_t)R * C * M / 2);
-    store_ring<M>(orow + (TRANSPOSE ? (int64_t)ring * P : (int64_t)ring * M * P) + cp, acc, TRANSPOSE ? (int64_t)R * P : (int64_t)P, mx);
+    store_ring<M>(reinterpret_cast<char*>(orow + (TRANSPOSE ? (int64_t)ring * P : (int64_t)ring * M * P) + cp), acc,
+                  16u * (uint32_t)(TRANSPOSE ? R * P : P), mx);
     }
     fold_amax(amax, mx);
 }

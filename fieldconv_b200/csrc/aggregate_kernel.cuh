@@ -10,50 +10,62 @@
 namespace fcb {
 
 
-// p[B+m] = conj?(wxp) * z * q^m for m = -B..B, by recurrence on the (unit-modulus) per-edge, per-channel
-// rotation q.  Forward: q = e^{i theta} conj(u) with u = z/|z| (1 at origin entries: utils/field.py:14-16,42-46),
-// so p[B+m] = sten-factor a_{e,m} * xhat[src,c,m] (nn/field_conv.py:128-130 folded with fc_precomp.py:83-95);
-// transposed: q = e^{-i theta}, p[B+m] = conj(a_{e,m}) * gy.  2 + 2B complex products per (edge, channel).
+// p[B+m] = a_m * z * q^m for m = -B..B, by recurrence on the (unit-modulus) per-edge, per-channel rotation q.
+// Forward: q = e^{i theta} conj(u) with u = z/|z| (1 at origin entries: utils/field.py:14-16,42-46), so
+// p[B+m] = sten-factor a_{e,m} * xhat[src,c,m] (nn/field_conv.py:128-130 folded with fc_precomp.py:83-95);
+// transposed: q = e^{-i theta}, p[B+m] = conj(a_{e,m}) * gy.
 __device__ __forceinline__ float rsqrt_ftz(float x) {
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 
-// FAST: frequencies beyond +1 by the three-term recurrence of a unit-modulus rotation,  z q^(m+1) = 2 Re(q) z q^m - z q^(m-1)
-// (and z conj(q) = 2 Re(q) z - z q exactly), one packed FFMA2 per new frequency instead of a 4-instruction complex
-// product: 2 + 1 + (2B - 1)/... complex products become 3 products + (2B - 1) FFMA2.  Deviation from the product form:
-// <= 4e-7 normwise at |m| = 2, 8e-7 at |m| = 3 (|q|^2 = 1 +- 5e-7 enters linearly), inside the fp32 reference's own noise.
-template <int B, bool TRANSPOSE, bool FAST = false>
-__device__ __forceinline__ void edge_products(float2 z, float2 wxp, float2 rot, float2* p) {
-    float2 q;
+// One decoded plan record as the edge loop consumes it (k_aggregate stages these in shared memory, once per record):
+// the complex factors come with their 90-degree rotations so that every complex product below is one FMUL2 + one FFMA2
+// with a broadcast scalar (a b = a.x (b.x, b.y) + a.y (-b.y, b.x)) instead of two FMUL + two FFMA.
+struct EdgeOps {
+    float2 wxp, iwxp;      // wxp (conjugated for the transposed operator, operand scale folded in) and i * wxp
+    float2 q0, miq0;       // e^{i theta} (conjugated when transposed) and -i * q0
+};
+
+// Frequencies 0 and +1 by complex products, the others by the three-term recurrence of a unit-modulus rotation,
+// z q^(m+1) = 2 Re(q) z q^m - z q^(m-1)  (and z conj(q) = 2 Re(q) z - z q exactly): one FFMA2 per new frequency.
+// Deviation from the product form: <= 4e-7 normwise at |m| = 2, 8e-7 at |m| = 3 (|q|^2 = 1 +- 5e-7 enters linearly),
+// inside the fp32 reference's own noise.
+// CM2: the three complex products as FMUL2 + FFMA2 pairs (fewer issue slots, 8 more FMA-pipe cycles per edge for the
+// rotated copy of q) instead of scalar FMUL / FFMA (experiment switch FIELDCONV_B200_AGG_CM2).
+template <int B, bool TRANSPOSE, bool CM2>
+__device__ __forceinline__ void edge_products(float2 z, const EdgeOps& e, float2* p) {
+    if (CM2) p[B] = __ffma2_rn(bc2(z.y), e.iwxp, __fmul2_rn(bc2(z.x), e.wxp));        // wxp * z
+    else p[B] = cmul(e.wxp, z);
+    if (B == 0) return;
+    float2 q, iq;
     if (!TRANSPOSE) {
         // branch-free: at origin entries (|re|,|im| < 1e-7) the selects discard the inf/NaN of rsqrt(0)
         const bool origin = (fabsf(z.x) < 1e-7f) && (fabsf(z.y) < 1e-7f);
         const float ri = rsqrt_ftz(fmaf(z.x, z.x, z.y * z.y));
         const float ux = origin ? 1.f : z.x * ri;
         const float uy = origin ? 0.f : z.y * ri;
-        q = cmul_conj(rot, make_float2(ux, uy));
-        p[B] = cmul(wxp, z);
-    } else {
-        q = make_float2(rot.x, -rot.y);
-        p[B] = cmul_conj(z, wxp);
-    }
-    if (FAST && B >= 1) {
-        const float2 c2 = make_float2(2.f * q.x, 2.f * q.x);
-        p[B + 1] = cmul(p[B], q);
-        p[B - 1] = __ffma2_rn(c2, p[B], make_float2(-p[B + 1].x, -p[B + 1].y));
-#pragma unroll
-        for (int m = 2; m <= B; ++m) {
-            p[B + m] = __ffma2_rn(c2, p[B + m - 1], make_float2(-p[B + m - 2].x, -p[B + m - 2].y));
-            p[B - m] = __ffma2_rn(c2, p[B - m + 1], make_float2(-p[B - m + 2].x, -p[B - m + 2].y));
+        if (CM2) {
+            q = __ffma2_rn(bc2(uy), e.miq0, __fmul2_rn(bc2(ux), e.q0));                 // q0 * conj(u)
+            iq = __ffma2_rn(bc2(uy), e.q0, __fmul2_rn(bc2(ux), neg2(e.miq0)));          // i * q
+        } else {
+            q = cmul_conj(e.q0, make_float2(ux, uy));
         }
-        return;
+    } else {
+        q = e.q0;
+        iq = neg2(e.miq0);
     }
+    if (CM2) p[B + 1] = __ffma2_rn(bc2(p[B].y), iq, __fmul2_rn(bc2(p[B].x), q));      // p0 * q
+    else p[B + 1] = cmul(p[B], q);
+    const float2 c2 = bc2(2.f * q.x);
+    p[B - 1] = __ffma2_rn(c2, p[B], neg2(p[B + 1]));
 #pragma unroll
-    for (int m = 1; m <= B; ++m) {
-        p[B + m] = cmul(p[B + m - 1], q);
-        p[B - m] = cmul_conj(p[B - m + 1], q);
+    for (int m = 2; m <= B; ++m) {
+        p[B + m] = __ffma2_rn(c2, p[B + m - 1], neg2(p[B + m - 2]));
+        p[B - m] = __ffma2_rn(c2, p[B - m + 1], neg2(p[B - m + 2]));
     }
 }
 
@@ -78,10 +90,10 @@ __device__ __forceinline__ void gauge_align(float2 z, float2* xh) {
 // `mx` follows max|value stored| (the operand scale of the 2xFP16 contraction, gemm_h.cu): FMNMX runs on the ALU pipe,
 // off the FMA pipe that bounds these kernels.
 template <int M>
-__device__ __forceinline__ void store_ring(float4* __restrict__ dst, const float2 (&acc)[2][M], int64_t m_stride, float& mx) {
+__device__ __forceinline__ void store_ring(char* __restrict__ dst, const float2 (&acc)[2][M], uint32_t m_stride_bytes, float& mx) {
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-        dst[m * m_stride] = make_float4(acc[0][m].x, acc[0][m].y, acc[1][m].x, acc[1][m].y);
+        *reinterpret_cast<float4*>(dst + (size_t)(m * m_stride_bytes)) = make_float4(acc[0][m].x, acc[0][m].y, acc[1][m].x, acc[1][m].y);
         mx = fmaxf(fmaxf(mx, fabsf(acc[0][m].x)), fmaxf(fabsf(acc[0][m].y), fmaxf(fabsf(acc[1][m].x), fabsf(acc[1][m].y))));
     }
 }
@@ -101,10 +113,11 @@ __device__ __forceinline__ void fold_amax(uint32_t* amax, float mx) {
 // two adjacent lanes fill a unit, the lanes of a row cover consecutive 8-byte pieces -> full-sector stores.
 template <int M>
 __device__ __forceinline__ void store_ring_packed(uint8_t* __restrict__ row_base, uint32_t rsw, const float2 (&acc)[2][M],
-                                                  uint32_t kk, uint32_t kk_m, float s) {
+                                                  uint32_t kk, uint32_t kk_m) {
 #pragma unroll
     for (int m = 0; m < M; ++m, kk += kk_m) {
-        const float a0 = acc[0][m].x * s, a1 = acc[0][m].y * s, a2 = acc[1][m].x * s, a3 = acc[1][m].y * s;
+        // the accumulators already carry the operand scale (folded into wxp when the plan records are decoded)
+        const float a0 = acc[0][m].x, a1 = acc[0][m].y, a2 = acc[1][m].x, a3 = acc[1][m].y;
         const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
         const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
@@ -115,19 +128,7 @@ __device__ __forceinline__ void store_ring_packed(uint8_t* __restrict__ row_base
     }
 }
 
-// Out-of-line form of the packed ring store for the NI kernel variants: the fp16 split needs a dozen temporaries that are
-// live only at a ring transition (6 times per row), but inlined they inflate the register allocation of the whole edge
-// loop and keep the packed band_limit-2 kernel at 2 CTAs/SM.  The accumulators travel by value (registers, not memory).
-template <int M>
-struct RingAcc {
-    float2 v[2][M];
-};
-template <int M>
-__device__ __noinline__ void store_ring_packed_ni(uint8_t* row_base, uint32_t rsw, RingAcc<M> a, uint32_t kk, uint32_t kk_m, float s) {
-    store_ring_packed<M>(row_base, rsw, a.v, kk, kk_m, s);
-}
-
-constexpr int AGG_STAGE_CAP = 768;      // plan records a CTA of the DEPTH-4 variant can stage (18 KB of shared memory)
+constexpr int AGG_CAP = 768;           // plan records staged per CTA and chunk (36 KB of shared memory)
 
 // The two live rings sit in two fixed accumulator sets selected by ring
 // parity (ring r lives in acc[r & 1]), so sliding the two-ring window costs one store + one clear, no moves.
@@ -135,16 +136,21 @@ constexpr int AGG_STAGE_CAP = 768;      // plan records a CTA of the DEPTH-4 var
 // the operand scale comes from the a-priori bound  max|out| <= max|feat| * max_row sum_e |wxp_e|  (pk_feat_amax,
 // pk_norm: device floats; block 0 publishes the product in *pk_bound for the GEMM's epilogue), and the lanes of the
 // rows N .. pk_rows_padded(N)-1 zero-fill the tail of the last row tile (the weight-gradient GEMM reduces over rows).
-// MINB: minimum resident CTAs per SM the register allocation is held to (2: up to 128 registers; 3: 85 — more warps to
-// hide the gather latency at the price of a tighter register budget; chosen per band limit by agg_min_blocks()).
-// DEPTH: software-pipeline depth of the edge loop (2: the record of edge p+2 and the feature row of edge p+1 are in flight;
-// 1: both of edge p+1 only — 6 registers fewer, for the register-capped high-occupancy variants; 3: as 1 plus the
-// neighbour id of edge p+2, see the loop; 4: as 1 with the CTA's records staged in shared memory — experiment variants,
-// not measured yet).
-// FAST: three-term frequency recurrence (edge_products) and packed FFMA2 ring accumulation — 25 % fewer instructions in
-// the edge loop; experiment variant (FIELDCONV_B200_AGG_VARIANT codes >= 100), not a default until measured on B200.
-// NI (packed output only): ring stores through the out-of-line store_ring_packed_ni — experiment variant (codes 2xx).
-template <int B, bool TRANSPOSE, bool PACK, int MINB, int DEPTH, bool FAST, bool NI = false>
+// MINB: minimum resident CTAs per SM the register allocation is held to (3 for band limits <= 2: 80 registers).
+//
+// Records: the CTA's plan records (one contiguous CSR range, ~11 rows x 40 edges at C = 48) are copied into shared
+// memory with coalesced loads first and DECODED once per record instead of once per lane and edge (EdgeOps: ring weights
+// of the even / odd accumulator set, conjugation of the transposed operator, the packed path's operand scale folded into
+// wxp, the rotated factors of the FFMA2 complex products); in the edge loop a record is three LDS.128 and the neighbour
+// id of the next edge is known without a global load, so the feature gather never waits on a record.  Ranges longer than
+// AGG_CAP records are staged chunk by chunk (any vertex degree).  The feature row of edge p+1 is in flight in registers
+// while edge p is accumulated.
+// Measured on B200 (profiles/r02a_, r02b_aggregate_variants.jsonl), cfg-2 layer forward / transposed: round-1 kernel
+// (records through registers, product arithmetic) 0.473 / 0.412 ms -> staged + decoded + recurrence arithmetic
+// 0.386 / 0.319 ms; 1M vertices x C=32: 2.74 / 2.53 -> 2.43 / 2.10 ms.  Deeper feature prefetch (two edges ahead in
+// registers, or a four-deep cp.async ring in shared memory) measured 2-4 % slower: after staging the kernel is bound by
+// instruction issue and the FMA pipe (ncu r02b: issue-active 70 %, FMA pipe 59 %), not by gather latency.
+template <int B, bool TRANSPOSE, bool PACK, int MINB, bool CM2>
 __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restrict__ feat, const int32_t* __restrict__ rowptr,
                                                       const int4* __restrict__ rec, const float2* __restrict__ rot,
                                                       float4* __restrict__ out, int64_t N, int C, int R,
@@ -152,63 +158,38 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
                                                       const float* __restrict__ pk_norm, float* __restrict__ pk_bound) {
     constexpr int M = 2 * B + 1;
     const int P = C >> 1;
-    const int64_t lane_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t lane0 = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t lane_id = lane0 + threadIdx.x;
     const int64_t row = lane_id / P;
+    const int cp = (int)(lane_id - row * P);
+    const bool valid = row < N;
     float mx = 0.f;
-    // DEPTH 4: the plan records of all rows this CTA touches (a contiguous CSR range, ~11 rows x 40 edges x 24 B) are
-    // staged in shared memory with coalesced loads before the edge loops start, so inside the loops a record is an LDS
-    // and the feature gather of edge p+1 never waits for a global record load.  CTAs whose range exceeds the buffer
-    // (CTA-uniform test) read the records from global memory as the other depths do.
-    constexpr int STAGE_CAP = DEPTH == 4 ? AGG_STAGE_CAP : 1;
-    __shared__ int4 s_rec[STAGE_CAP];
-    __shared__ float2 s_rot[STAGE_CAP];
-    int stage_e0 = 0;
-    bool staged = false;
-    if (DEPTH == 4) {
-        const int64_t lane0 = (int64_t)blockIdx.x * blockDim.x;
-        const int64_t row_first = lane0 / P;
-        if (row_first < N) {
-            const int64_t row_last = min(N - 1, (lane0 + blockDim.x - 1) / P);
-            const int e0 = rowptr[row_first], e1 = rowptr[row_last + 1];
-            staged = (e1 - e0) <= STAGE_CAP;
-            stage_e0 = e0;
-            if (staged) {
-                for (int i = threadIdx.x; i < e1 - e0; i += blockDim.x) {
-                    s_rec[i] = __ldg(rec + e0 + i);
-                    s_rot[i] = __ldg(rot + e0 + i);
-                }
-            }
-        }
-        __syncthreads();
-    }
+    __shared__ int4 s_a[AGG_CAP];        // {nbr | f << 27, weight of the even ring set, weight of the odd ring set, -}
+    __shared__ float4 s_b[AGG_CAP];      // {wxp, i wxp}
+    __shared__ float4 s_c[AGG_CAP];      // {q0, -i q0}
+
     // PK addressing of this lane: first byte of its row inside (row tile, chunk 0, hi plane); real column of (ring 0, m = -B)
     uint8_t* pk_row = nullptr;
     uint32_t pk_rsw = 0, pk_kk = 0, pk_kk_ring = 0, pk_kk_m = 0;
-    float pk_s = 0.f;
+    float pk_s = 1.f;
     if (PACK) {
         // pk_feat_amax is the largest REAL component; a complex modulus can be sqrt(2) larger
         const float bound = __ldg(pk_feat_amax) * __ldg(pk_norm) * 1.41422f;
         pk_s = __uint_as_float(scale_field(__float_as_uint(fabsf(bound))) << 23);
         if (lane_id == 0) *pk_bound = fabsf(bound);
-        const int cp = (int)(lane_id - row * P);
         const uint32_t nchunks = (uint32_t)(2 * R * M * C) >> 6;
         pk_row = reinterpret_cast<uint8_t*>(out) + (size_t)(row >> 7) * nchunks * PK_BLOCK_BYTES + (size_t)(row & 127) * 128u;
         pk_rsw = (uint32_t)(row & 7);
         pk_kk = 4u * (uint32_t)cp;
         pk_kk_ring = TRANSPOSE ? 2u * (uint32_t)C : 2u * (uint32_t)(M * C);
         pk_kk_m = TRANSPOSE ? 2u * (uint32_t)(R * C) : 2u * (uint32_t)C;
-        if (row >= N) {
-            if (row < ((N + 127) & ~(int64_t)127)) {      // tail of the last row tile: zeros
-                float2 z[2][M];
+        if (!valid && row < ((N + 127) & ~(int64_t)127)) {      // tail of the last row tile: zeros
+            float2 z[2][M];
 #pragma unroll
-                for (int m = 0; m < M; ++m) z[0][m] = z[1][m] = make_float2(0.f, 0.f);
-                for (int ring = 0; ring < R; ++ring) store_ring_packed<M>(pk_row, pk_rsw, z, pk_kk + ring * pk_kk_ring, pk_kk_m, 0.f);
-            }
-            return;
+            for (int m = 0; m < M; ++m) z[0][m] = z[1][m] = make_float2(0.f, 0.f);
+            for (int ring = 0; ring < R; ++ring) store_ring_packed<M>(pk_row, pk_rsw, z, pk_kk + ring * pk_kk_ring, pk_kk_m);
         }
     }
-    if (row < N) {
-    const int cp = (int)(lane_id - row * P);
 
     float2 acc0[2][M], acc1[2][M];   // even rings / odd rings
 #pragma unroll
@@ -216,31 +197,21 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
         acc0[0][m] = acc0[1][m] = make_float2(0.f, 0.f);
         acc1[0][m] = acc1[1][m] = make_float2(0.f, 0.f);
     }
-    // where ring 0 of this lane goes, and how far apart rings are (float4 units)
-    float4* dst = out + row * ((int64_t)R * C * M / 2) + cp;
-    const int ring_stride = TRANSPOSE ? P : P * M;
-    const int64_t m_stride = TRANSPOSE ? (int64_t)R * P : (int64_t)P;
+    // where ring 0 of this lane goes, and how far apart rings / frequencies are (bytes)
+    char* dst = reinterpret_cast<char*>(out + row * ((int64_t)R * C * M / 2) + cp);
+    const uint32_t ring_stride = 16u * (uint32_t)(TRANSPOSE ? P : P * M);
+    const uint32_t m_stride = 16u * (uint32_t)(TRANSPOSE ? R * P : P);
     const float4* fbase = feat + cp;
 
     // ring fcur is complete: write it once and clear its accumulator set (it becomes ring fcur + 2)
     auto retire = [&](int ring) {
         if (ring & 1) {
-            if (PACK && NI) {
-                RingAcc<M> a;
-#pragma unroll
-                for (int m = 0; m < M; ++m) { a.v[0][m] = acc1[0][m]; a.v[1][m] = acc1[1][m]; }
-                store_ring_packed_ni<M>(pk_row, pk_rsw, a, pk_kk, pk_kk_m, pk_s);
-            } else if (PACK) store_ring_packed<M>(pk_row, pk_rsw, acc1, pk_kk, pk_kk_m, pk_s);
+            if (PACK) store_ring_packed<M>(pk_row, pk_rsw, acc1, pk_kk, pk_kk_m);
             else store_ring<M>(dst, acc1, m_stride, mx);
 #pragma unroll
             for (int m = 0; m < M; ++m) acc1[0][m] = acc1[1][m] = make_float2(0.f, 0.f);
         } else {
-            if (PACK && NI) {
-                RingAcc<M> a;
-#pragma unroll
-                for (int m = 0; m < M; ++m) { a.v[0][m] = acc0[0][m]; a.v[1][m] = acc0[1][m]; }
-                store_ring_packed_ni<M>(pk_row, pk_rsw, a, pk_kk, pk_kk_m, pk_s);
-            } else if (PACK) store_ring_packed<M>(pk_row, pk_rsw, acc0, pk_kk, pk_kk_m, pk_s);
+            if (PACK) store_ring_packed<M>(pk_row, pk_rsw, acc0, pk_kk, pk_kk_m);
             else store_ring<M>(dst, acc0, m_stride, mx);
 #pragma unroll
             for (int m = 0; m < M; ++m) acc0[0][m] = acc0[1][m] = make_float2(0.f, 0.f);
@@ -250,115 +221,67 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
     };
 
     int fcur = 0;
-    const int p0 = rowptr[row], p1 = rowptr[row + 1];
-    if (p0 < p1) {
-        // Software pipeline, two deep: while edge p is accumulated the feature row of edge p+1 and the plan record
-        // of edge p+2 are in flight, so the dependent chain record -> neighbour id -> feature row stays off the
-        // FMA pipe's critical path.  All prefetches are unconditional (indices clamped to the row's last edge) so
-        // the register rotation unrolls away.  (Measured alternatives that were not faster: an explicit L1 prefetch
-        // of the record stream 8 edges ahead plus a two-deep feature gather — more registers, same stalls; packed
-        // FFMA2/FMUL2 arithmetic over the lane's two channels — halves the FMA-pipe instructions but nvcc 12.9 spends
-        // more than it saves on MOVs that build the aligned 64-bit register pairs.)
-        const int last = p1 - 1;
-        auto rec_at = [&](int e) { return (DEPTH == 4 && staged) ? s_rec[e - stage_e0] : __ldg(rec + e); };
-        auto rot_at = [&](int e) { return (DEPTH == 4 && staged) ? s_rot[e - stage_e0] : __ldg(rot + e); };
-        int4 rcA = rec_at(p0);
-        float2 rtA = rot_at(p0);
-        const int pb = min(p0 + 1, last);
-        int4 rcB = rcA;
-        float2 rtB = rtA;
-        if (DEPTH == 2) {
-            rcB = __ldg(rec + pb);
-            rtB = __ldg(rot + pb);
-        }
-        // DEPTH 3 ("light two-deep"): only the neighbour id of edge p+1 travels one iteration ahead of its record (one
-        // register and one 4-byte load that hits the line the 16-byte record load touches next), so the feature gather of
-        // edge p+1 no longer waits for that record — DEPTH 2's latency tolerance at DEPTH 1's register cost.
-        int idN = (DEPTH == 3) ? __ldg(reinterpret_cast<const int*>(rec + pb)) : 0;
-        float4 vA = __ldg(fbase + ((uint32_t)rcA.x & NBR_MASK) * (uint32_t)P);
-#pragma unroll 2
-        for (int p = p0; p < p1; ++p) {
-            const int4 rc = rcA;
-            const float2 rt = rtA;
-            const float4 v = vA;
-            if (DEPTH == 3) {
-                vA = __ldg(fbase + ((uint32_t)idN & NBR_MASK) * (uint32_t)P);          // edge p+1: id loaded last iteration
-                idN = __ldg(reinterpret_cast<const int*>(rec + min(p + 2, last)));
-                const int pn = min(p + 1, last);
-                rcA = __ldg(rec + pn);
-                rtA = __ldg(rot + pn);
-            } else if (DEPTH == 2) {
-                rcA = rcB;
-                rtA = rtB;
-                vA = __ldg(fbase + ((uint32_t)rcA.x & NBR_MASK) * (uint32_t)P);
-                const int pn = min(p + 2, last);
-                rcB = __ldg(rec + pn);
-                rtB = __ldg(rot + pn);
-            } else {
-                const int pn = min(p + 1, last);
-                rcA = rec_at(pn);
-                rtA = rot_at(pn);
-                vA = __ldg(fbase + ((uint32_t)rcA.x & NBR_MASK) * (uint32_t)P);
-            }
-
-            const int f = (int)((uint32_t)rc.x >> NBR_BITS);
-            while (fcur < f) retire(fcur++);
+    const int p0 = valid ? rowptr[row] : 0, p1 = valid ? rowptr[row + 1] : 0;
+    // CSR range of all rows this CTA touches (CTA-uniform)
+    const int64_t row_first = lane0 / P;
+    int e0 = 0, e1 = 0;
+    if (row_first < N) {
+        const int64_t row_last = min(N - 1, (lane0 + blockDim.x - 1) / P);
+        e0 = rowptr[row_first];
+        e1 = rowptr[row_last + 1];
+    }
+    for (int lo = e0; lo < e1; lo += AGG_CAP) {
+        const int hi = min(e1, lo + AGG_CAP);
+        if (lo != e0) __syncthreads();              // every lane is done with the previous chunk
+        for (int i = threadIdx.x; i < hi - lo; i += blockDim.x) {
+            const int4 rc = __ldg(rec + lo + i);
+            const float2 rt = __ldg(rot + lo + i);
             const float t = __int_as_float(rc.y);
             const float omt = 1.0f - t;  // fc_precomp.py:25
-            const float w0 = (f & 1) ? t : omt;   // weight of the even-ring set
-            const float w1 = (f & 1) ? omt : t;   // weight of the odd-ring set
-            const float2 wxp = make_float2(__int_as_float(rc.z), __int_as_float(rc.w));
+            const bool odd = ((uint32_t)rc.x >> NBR_BITS) & 1u;
+            const float wx = __int_as_float(rc.z) * pk_s, wy = (TRANSPOSE ? -__int_as_float(rc.w) : __int_as_float(rc.w)) * pk_s;
+            const float qx = rt.x, qy = TRANSPOSE ? -rt.y : rt.y;
+            s_a[i] = make_int4(rc.x, __float_as_int(odd ? t : omt), __float_as_int(odd ? omt : t), 0);
+            s_b[i] = make_float4(wx, wy, -wy, wx);
+            s_c[i] = make_float4(qx, qy, qy, -qx);
+        }
+        __syncthreads();
+        const int a = max(p0, lo) - lo, b = min(p1, hi) - lo;      // this lane's edges inside the chunk
+        if (a < b) {
+            const int last = b - 1;
+            auto row_of = [&](int i) { return fbase + ((uint32_t)s_a[i].x & NBR_MASK) * (uint32_t)P; };
+            float4 vA = __ldg(row_of(a));
+#pragma unroll 2
+            for (int i = a; i <= last; ++i) {
+                const float4 v = vA;
+                vA = __ldg(row_of(min(i + 1, last)));
+                const int4 ra = s_a[i];
+                const float4 rb = s_b[i], rc4 = s_c[i];
+                const int f = (int)((uint32_t)ra.x >> NBR_BITS);
+                while (fcur < f) retire(fcur++);
+                EdgeOps eo;
+                eo.wxp = make_float2(rb.x, rb.y);
+                eo.iwxp = make_float2(rb.z, rb.w);
+                eo.q0 = make_float2(rc4.x, rc4.y);
+                eo.miq0 = make_float2(rc4.z, rc4.w);
+                const float2 w00 = bc2(__int_as_float(ra.y)), w11 = bc2(__int_as_float(ra.z));
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                const float2 z = ch ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
-                float2 pr[M];
-                edge_products<B, TRANSPOSE, FAST>(z, wxp, rt, pr);
-                if (FAST) {
-                    const float2 w00 = make_float2(w0, w0), w11 = make_float2(w1, w1);
+                for (int ch = 0; ch < 2; ++ch) {
+                    const float2 z = ch ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+                    float2 pr[M];
+                    edge_products<B, TRANSPOSE, CM2>(z, eo, pr);
 #pragma unroll
                     for (int m = 0; m < M; ++m) {
                         acc0[ch][m] = __ffma2_rn(w00, pr[m], acc0[ch][m]);
                         acc1[ch][m] = __ffma2_rn(w11, pr[m], acc1[ch][m]);
                     }
-                } else {
-#pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    acc0[ch][m].x = fmaf(w0, pr[m].x, acc0[ch][m].x);
-                    acc0[ch][m].y = fmaf(w0, pr[m].y, acc0[ch][m].y);
-                    acc1[ch][m].x = fmaf(w1, pr[m].x, acc1[ch][m].x);
-                    acc1[ch][m].y = fmaf(w1, pr[m].y, acc1[ch][m].y);
-                }
                 }
             }
         }
     }
-    while (fcur < R) retire(fcur++);
-    }
+    if (valid)
+        while (fcur < R) retire(fcur++);
     if (!PACK) fold_amax(amax, mx);
-}
-
-// Register-allocation variant of the aggregation kernel, 10 * (resident CTAs per SM) + (pipeline depth), per band limit and
-// output format.  Measured on B200 (profiles/r01f_layers_occ3.jsonl, r01g_ab_*, r01h_aggregate_variants.jsonl): resident
-// warps hide the gather latency better than a deeper software pipeline, until the register cap starts to spill —
-//   fp32 output,  band_limit <= 1: 41 (64 registers)   1M vertices C=32: fwd 3.80 -> 2.78 ms, transposed 3.57 -> 2.43 ms
-//   fp32 output,  band_limit 2   : 31 (80 registers)   cfg-2 layer: 0.520 -> 0.466 ms, 0.438 -> 0.408 ms  (41: 0.715, spills)
-//   packed output, band_limit <= 1: 32                  1M vertices C=32: 3.69 -> 3.03 ms, 3.52 -> 2.64 ms  (41: 3.22 / 3.26)
-//   packed output, band_limit 2   : 22 (128 registers)  (32: 0.567 -> 0.695 ms — the fp16 split needs the registers)
-// FIELDCONV_B200_AGG_VARIANT=<b0>,<b1>,<b2> (e.g. "32,41,31") overrides the variants of band limits 0, 1, 2 for experiments;
-// adding 100 selects the FAST arithmetic (three-term recurrence + FFMA2), e.g. "132,141,131"; 2xx / 3xx (packed output
-// only) the out-of-line ring store without / with FAST.
-static inline int agg_variant(int band_limit, bool pack) {
-    static int tab[3] = {0, 0, 0};
-    static bool init = false;
-    if (!init) {
-        const char* e = getenv("FIELDCONV_B200_AGG_VARIANT");
-        if (e) sscanf(e, "%d,%d,%d", &tab[0], &tab[1], &tab[2]);
-        init = true;
-    }
-    if (band_limit < 1 || band_limit > 2) return 22;
-    if (tab[band_limit]) return tab[band_limit];
-    if (band_limit <= 1) return pack ? 32 : 41;
-    return pack ? 22 : 31;
 }
 
 template <bool TRANSPOSE, bool PACK>
@@ -375,39 +298,16 @@ static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const vo
     float4* o4 = reinterpret_cast<float4*>(out);
     prof_begin(PACK ? (TRANSPOSE ? "aggregate_T_pk" : "aggregate_pk") : (TRANSPOSE ? "aggregate_T" : "aggregate"), st);
 #define FCB_AGG_ARGS <<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am, pk_feat_amax, pk_norm, pk_bound)
-    // variant = (resident CTAs per SM, pipeline depth) for this band limit: see agg_variant()
-#define FCB_AGG_CASE(b)                                                                                       \
-    case b: {                                                                                                 \
-        const int var = agg_variant(b, PACK);                                                                 \
-        constexpr bool lo = (b == 1 || b == 2);   /* only band limits 1 and 2 have the alternative variants compiled */ \
-        if (lo && var == 41) k_aggregate<b, TRANSPOSE, PACK, (lo ? 4 : 2), (lo ? 1 : 2), false> FCB_AGG_ARGS; \
-        else if (lo && var == 32) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), 2, false> FCB_AGG_ARGS;       \
-        else if (lo && var == 31) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 1 : 2), false> FCB_AGG_ARGS; \
-        else if (lo && var == 34) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 4 : 2), false> FCB_AGG_ARGS; \
-        else if (lo && var == 44) k_aggregate<b, TRANSPOSE, PACK, (lo ? 4 : 2), (lo ? 4 : 2), false> FCB_AGG_ARGS; \
-        else if (lo && var == 134) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 4 : 2), lo> FCB_AGG_ARGS; \
-        else if (lo && var == 33) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 3 : 2), false> FCB_AGG_ARGS; \
-        else if (lo && var == 43) k_aggregate<b, TRANSPOSE, PACK, (lo ? 4 : 2), (lo ? 3 : 2), false> FCB_AGG_ARGS; \
-        else if (lo && var == 133) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 3 : 2), lo> FCB_AGG_ARGS; \
-        else if (lo && var == 143) k_aggregate<b, TRANSPOSE, PACK, (lo ? 4 : 2), (lo ? 3 : 2), lo> FCB_AGG_ARGS; \
-        else if (lo && var == 141) k_aggregate<b, TRANSPOSE, PACK, (lo ? 4 : 2), (lo ? 1 : 2), lo> FCB_AGG_ARGS; \
-        else if (lo && var == 132) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), 2, lo> FCB_AGG_ARGS;         \
-        else if (lo && var == 131) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 1 : 2), lo> FCB_AGG_ARGS; \
-        else if (lo && var == 122) k_aggregate<b, TRANSPOSE, PACK, 2, 2, lo> FCB_AGG_ARGS;                    \
-        else if (lo && PACK && var == 231) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 1 : 2), false, lo && PACK> FCB_AGG_ARGS; \
-        else if (lo && PACK && var == 232) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), 2, false, lo && PACK> FCB_AGG_ARGS; \
-        else if (lo && PACK && var == 331) k_aggregate<b, TRANSPOSE, PACK, (lo ? 3 : 2), (lo ? 1 : 2), lo, lo && PACK> FCB_AGG_ARGS; \
-        else k_aggregate<b, TRANSPOSE, PACK, 2, 2, false> FCB_AGG_ARGS;                                       \
-    } break;
+    // resident CTAs per SM: 3 (<= 85 registers) up to band limit 2, 2 beyond (the accumulators alone take 56+ registers)
+    static const bool cm2 = [] { const char* e = getenv("FIELDCONV_B200_AGG_CM2"); return e && atoi(e) != 0; }();
     switch (B) {
-        FCB_AGG_CASE(0)
-        FCB_AGG_CASE(1)
-        FCB_AGG_CASE(2)
-        FCB_AGG_CASE(3)
-        FCB_AGG_CASE(4)
+        case 0: k_aggregate<0, TRANSPOSE, PACK, 3, false> FCB_AGG_ARGS; break;
+        case 1: if (cm2) k_aggregate<1, TRANSPOSE, PACK, 3, true> FCB_AGG_ARGS; else k_aggregate<1, TRANSPOSE, PACK, 3, false> FCB_AGG_ARGS; break;
+        case 2: if (cm2) k_aggregate<2, TRANSPOSE, PACK, 3, true> FCB_AGG_ARGS; else k_aggregate<2, TRANSPOSE, PACK, 3, false> FCB_AGG_ARGS; break;
+        case 3: k_aggregate<3, TRANSPOSE, PACK, 2, false> FCB_AGG_ARGS; break;
+        case 4: k_aggregate<4, TRANSPOSE, PACK, 2, false> FCB_AGG_ARGS; break;
         default: set_error("aggregate: band_limit %d unsupported", B); return FCB_E_UNSUPPORTED;
     }
-#undef FCB_AGG_CASE
 #undef FCB_AGG_ARGS
     prof_end(st);
     FCB_CUDA_LAUNCH_CHECK("aggregate");

@@ -104,6 +104,43 @@ __global__ void k_combine_gw(const float* __restrict__ P, float2* __restrict__ g
     gW[(((int64_t)o * Ci + c) * R + r) * M + m] = make_float2(row0[0] + row1[1], row0[1] - row1[0]);
 }
 
+// Weight gradient from G (no contrib in the backward): P[m][(r,o,a)][(c,b)] = sum_j G[j,m,r,o]_a xhat[j,c,m]_b  ->
+//   gW[o,c,r,m] = sum_j conj(xhat[j,c,m]) G[j,m,r,o] = (P_rr + P_ii) + i (P_ir - P_ri)   (first index: part of G)
+__global__ void k_combine_gw_g(const float* __restrict__ P, float2* __restrict__ gW, int Ci, int Co, int R, int M) {
+    const int64_t tot = (int64_t)R * Ci * M * Co;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= tot) return;
+    const int c = (int)(i % Ci);
+    const int o = (int)((i / Ci) % Co);
+    const int r = (int)((i / ((int64_t)Ci * Co)) % R);
+    const int m = (int)(i / ((int64_t)Ci * Co * R));
+    const int64_t q = (int64_t)r * Co + o;
+    const float* row0 = P + ((int64_t)m * 2 * R * Co + 2 * q) * (2 * (int64_t)Ci) + 2 * c;   // G real part
+    const float* row1 = row0 + 2 * (int64_t)Ci;                                               // G imaginary part
+    gW[(((int64_t)o * Ci + c) * R + r) * M + m] = make_float2(row0[0] + row1[1], row1[0] - row0[1]);
+}
+
+// xh[m][n][c] = x[n,c] conj(u)^m (nn/field_conv.py:128-130): the explicit operand of the generic (non-2xFP16) gW-from-G path
+template <int B>
+__global__ void k_xhat(const float2* __restrict__ x, float2* __restrict__ xh, int64_t total) {
+    constexpr int M = 2 * B + 1;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float2 z = x[i];
+    const bool origin = (fabsf(z.x) < 1e-7f) && (fabsf(z.y) < 1e-7f);
+    const float ri = rsqrtf(z.x * z.x + z.y * z.y);
+    const float2 u = origin ? make_float2(1.f, 0.f) : make_float2(z.x * ri, z.y * ri);
+    float2 up = z, dn = z;
+    xh[(int64_t)B * total + i] = z;
+#pragma unroll
+    for (int k = 1; k <= B; ++k) {
+        up = cmul_conj(up, u);
+        dn = cmul(dn, u);
+        xh[(int64_t)(B + k) * total + i] = up;
+        xh[(int64_t)(B - k) * total + i] = dn;
+    }
+}
+
 // ----------------------------------------------------------------------------- softAngle chain rule
 // gxh is [N][M][Ci] complex (gradient w.r.t. xhat[n,c,m] = x conj(u)^m).  SURVEY.md appendix A.3:
 //   non-origin: h_m = conj(g_m) u^(1-m);  gx = u * ( sum_m Re h_m  - i sum_m (1-m) Im h_m )
@@ -268,6 +305,33 @@ static int choose_split(int64_t rows_m, int64_t kdim, int flags) {
 
 static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 
+// gW from G: 2B+1 products P_m[2RCo x 2Ci] = G_m^T Xh_m over the vertices.  Fast path: one batched 2xFP16 TN launch.
+struct GwPlan {
+    bool batched;          // the 2xFP16 batched launch is feasible
+    int split, n_main;
+    int64_t kps;
+    size_t xhat_ws;        // packed (batched) or explicit fp32 (generic) xhat operand
+    size_t parts;          // split partials (+ per-product GEMM workspace on the generic path)
+};
+static GwPlan gw_from_g_plan(const Dims& d, int flags) {
+    GwPlan g;
+    const int64_t Mr = 2 * (int64_t)d.R * d.Co;
+    const int64_t rows_eff = (int64_t)d.M * ((Mr + 127) / 128) * 128;
+    g.split = choose_split(rows_eff, d.N, flags);
+    g.n_main = 1;
+    g.kps = 0;
+    g.batched = (flags & FCB_GEMM_MASK) == FCB_GEMM_TC_2XF16 && (Mr % 4) == 0 &&
+                gemm_h_tn_plan(2 * d.Ci, d.N, g.split, &g.n_main, &g.kps);
+    if (g.batched) {
+        g.xhat_ws = gemm_h_tn_xhat_ws_bytes(d.Ci, d.N, d.M);
+        g.parts = g.split > 1 ? align_up((size_t)g.split * d.M * Mr * 2 * d.Ci * 4, 256) : 0;
+    } else {
+        g.xhat_ws = align_up((size_t)d.M * d.N * d.Ci * 8, 256);
+        g.parts = align_up(gemm_ws_bytes(Mr, 2 * d.Ci, d.N, 1, 1, g.split, flags & ~FCB_FLAG_A_PACKED), 256);
+    }
+    return g;
+}
+
 static size_t fwd_ws(const Dims& d) {
     return 256 /* max|contrib| slot */ + align_up((size_t)(4 * d.K * d.Co) * 4, 256) +
            max_sz(gemm_tc_ws_bytes(2 * d.Co, 2 * d.K, 1), gemm_h_ws_bytes(2 * d.Co, 2 * d.K, 1)) + 512;
@@ -280,15 +344,20 @@ static size_t gw_parts_bytes(const Dims& d, int flags) {
     return align_up(b > fp32_parts ? b : fp32_parts, 256) + 256;
 }
 
-static size_t bwd_ws(const Dims& d, bool need_contrib, int flags) {
+// from_g: no contrib from the forward -> the weight gradient is taken from G and xhat (gw_from_g_plan)
+static size_t bwd_ws(const Dims& d, bool from_g, int flags) {
     size_t s = 512;                                                         // max|contrib|, max|G| slots
     s += align_up((size_t)(4 * d.K * d.Co) * 4, 256);                       // Bt
     s += align_up((size_t)(4 * d.K * d.Co) * 4, 256);                       // P
-    s += gw_parts_bytes(d, flags);                                          // split-K partials (+ the packed gy operand)
+    if (from_g) {
+        const GwPlan g = gw_from_g_plan(d, flags);
+        s += g.xhat_ws + g.parts + 512;
+    } else {
+        s += gw_parts_bytes(d, flags);                                      // split-K partials (+ the packed gy operand)
+    }
     const size_t n_pad = (size_t)pk_rows_padded(d.N);                       // PK buffers hold whole 128-row tiles
     s += align_up(n_pad * d.Kt * 8, 256);                                   // G
     s += align_up((size_t)d.N * d.M * d.Ci * 8, 256);                       // gxh
-    if (need_contrib) s += align_up(n_pad * d.K * 8, 256);                  // recomputed contrib
     // packed operand of the tensor-core grad-x GEMM
     s += max_sz(gemm_tc_ws_bytes(2 * d.Ci, 2 * (int64_t)d.R * d.Co, d.M), gemm_h_ws_bytes(2 * d.Ci, 2 * (int64_t)d.R * d.Co, d.M));
     return s + 2048;
@@ -309,7 +378,7 @@ static bool pk_g_ok(const Dims& d) { return gemm_pk_grouped_ok(2 * d.Ci, 2 * (in
 static float* fwd_amax_slot(void* ws, float* user_slot, cudaStream_t st) {
     if (user_slot) return user_slot;
     float* slot = static_cast<float*>(ws);
-    cudaMemsetAsync(slot, 0, 4, st);
+    if (cudaMemsetAsync(slot, 0, 4, st) != cudaSuccess) return nullptr;
     return slot;
 }
 
@@ -327,38 +396,50 @@ static int contract_fwd(const Dims& d, const float* contrib, const float* amax, 
 }
 
 // contrib_packed / g_packed: contrib is (G will be) a PK buffer; gather_transpose(G, g_amax, g_packed) fills G either way.
+// contrib == nullptr: the forward kept nothing — the weight gradient comes from G and xhat (k_combine_gw_g), so the
+// backward neither stores nor recomputes the N x K contrib.
 template <typename GatherT>
 static int backward_common(const Dims& d, const float* x, const float* W, const float* gy, const float* contrib,
                            const float* contrib_amax, float* g_amax, GatherT&& gather_transpose, float* gx, float* gW,
                            Arena& ar, int flags, cudaStream_t st, bool contrib_packed = false, bool g_packed = false) {
     float* Bt = ar.take<float>((size_t)(4 * d.K * d.Co));
     float* P = ar.take<float>((size_t)(4 * d.K * d.Co));
-    const int gw_split = choose_split(2 * d.K, d.N, flags);
-    const size_t parts_bytes = gw_parts_bytes(d, flags);
+    const bool from_g = gW && !contrib;
+    const GwPlan gp = from_g ? gw_from_g_plan(d, flags) : GwPlan();
+    const int gw_split = from_g ? gp.split : choose_split(2 * d.K, d.N, flags);
+    const size_t parts_bytes = from_g ? gp.parts + 256 : gw_parts_bytes(d, flags);
+    void* xhat_ws = from_g ? static_cast<void*>(ar.take<char>(gp.xhat_ws + 256)) : nullptr;
     float* parts = reinterpret_cast<float*>(ar.take<char>(parts_bytes));
     float* G = ar.take<float>((size_t)pk_rows_padded(d.N) * d.Kt * 2);
     float* gxh = ar.take<float>((size_t)d.N * d.M * d.Ci * 2);
+    FCB_REQUIRE(ar.ok(), FCB_E_WORKSPACE, "bwd: workspace too small");
     const int64_t tot = d.K * d.Co;
-    if (gW) {
+    if (gW && !from_g) {
         // K4: P[2K x 2Co] = contrib_real^T @ gy_real, split over vertices, fixed-order reduction
         int rc = launch_gemm(contrib, gy, P, 2 * d.K, 2 * d.Co, d.N, 2 * d.K, 2 * d.Co, 2 * d.Co, 1, 1, 0, 0, 0, gw_split, parts,
                              parts_bytes, flags | (contrib_packed ? FCB_FLAG_A_PACKED : 0), contrib_amax, st);
         if (rc) return rc;
         FCB_LAUNCH("combine_gw", st, k_combine_gw<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, reinterpret_cast<float2*>(gW), d.Ci, d.Co, d.R, d.M));
     }
-    if (gx) {
+    if (gx || from_g) {
         // K5a: G[j][m][r][o] = sum_{e: src=j} conj(sten) gy[tgt]
-        cudaMemsetAsync(g_amax, 0, 4, st);
+        if (cudaMemsetAsync(g_amax, 0, 4, st) != cudaSuccess) {
+            set_error("bwd: cudaMemsetAsync failed");
+            return FCB_E_CUDA;
+        }
         int rc = gather_transpose(G, g_amax, g_packed);
         if (rc) return rc;
+    }
+    if (gx) {
         // K5b: gxh[:, m, :] = G[:, m, :] @ conj(W)[m]  (one real GEMM per m, batched)
         FCB_LAUNCH("pack_w_bwd", st, k_pack_w_bwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bt, d.Ci, d.Co, d.R, d.M));
         const int64_t Q2 = 2 * (int64_t)d.R * d.Co;
         const size_t tcb = max_sz(gemm_tc_ws_bytes(2 * d.Ci, Q2, d.M), gemm_h_ws_bytes(2 * d.Ci, Q2, d.M));
         void* tcw = ar.take<char>(tcb);
+        FCB_REQUIRE(ar.ok(), FCB_E_WORKSPACE, "bwd: workspace too small");
         int grouped = 0;     // all m in one pass over G (one long-K tensor-core pipeline) when the plan allows
-        rc = launch_gemm_grouped(G, Bt, gxh, d.N, 2 * d.Ci, Q2, d.M, flags | (g_packed ? FCB_FLAG_A_PACKED : 0), g_amax, tcw, tcb,
-                                 &grouped, st);
+        int rc = launch_gemm_grouped(G, Bt, gxh, d.N, 2 * d.Ci, Q2, d.M, flags | (g_packed ? FCB_FLAG_A_PACKED : 0), g_amax, tcw, tcb,
+                                     &grouped, st);
         if (rc) return rc;
         FCB_REQUIRE(grouped || !g_packed, FCB_E_ARG, "bwd: packed G but the grouped contraction did not run");
         if (!grouped) {
@@ -383,6 +464,43 @@ static int backward_common(const Dims& d, const float* x, const float* W, const 
             prof_end(st);
             FCB_CUDA_LAUNCH_CHECK("softangle_bwd");
         }
+    }
+    if (from_g) {
+        // K4': P[m][2RCo][2Ci] = G_m^T Xh_m, split over vertices, fixed-order reduction; G is read once more instead of contrib
+        const int64_t Mr = 2 * (int64_t)d.R * d.Co;
+        const int N2 = 2 * d.Ci;
+        if (gp.batched) {
+            int rc = launch_gemm_h_tn_xhat(G, x, P, Mr, d.Ci, d.B, d.N, gp.split, gp.kps, parts, gp.n_main, g_amax, xhat_ws,
+                                           gp.xhat_ws + 256, g_packed ? 1 : 0, st);
+            if (rc) return rc;
+            if (gp.split > 1) {
+                rc = launch_reduce_splits(parts, P, (int64_t)d.M * Mr, N2, N2, 0, 1, gp.split, st);
+                if (rc) return rc;
+            }
+        } else {
+            FCB_REQUIRE(!g_packed, FCB_E_ARG, "bwd: packed G but the batched weight-gradient product is not feasible");
+            float2* xh = static_cast<float2*>(xhat_ws);
+            const int64_t el = d.N * d.Ci;
+            const unsigned blocks = (unsigned)((el + 255) / 256);
+            const float2* x2 = reinterpret_cast<const float2*>(x);
+            prof_begin("xhat", st);
+            switch (d.B) {
+                case 0: k_xhat<0><<<blocks, 256, 0, st>>>(x2, xh, el); break;
+                case 1: k_xhat<1><<<blocks, 256, 0, st>>>(x2, xh, el); break;
+                case 2: k_xhat<2><<<blocks, 256, 0, st>>>(x2, xh, el); break;
+                case 3: k_xhat<3><<<blocks, 256, 0, st>>>(x2, xh, el); break;
+                case 4: k_xhat<4><<<blocks, 256, 0, st>>>(x2, xh, el); break;
+            }
+            prof_end(st);
+            FCB_CUDA_LAUNCH_CHECK("xhat");
+            for (int m = 0; m < d.M; ++m) {
+                int rc = launch_gemm(G + (int64_t)m * Mr, reinterpret_cast<const float*>(xh) + (int64_t)m * d.N * N2, P + (int64_t)m * Mr * N2,
+                                     Mr, N2, d.N, (int64_t)d.M * Mr, N2, N2, 1, 1, 0, 0, 0, gp.split, parts, parts_bytes,
+                                     flags & ~FCB_FLAG_A_PACKED, g_amax, st);
+                if (rc) return rc;
+            }
+        }
+        FCB_LAUNCH("combine_gw", st, k_combine_gw_g<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, reinterpret_cast<float2*>(gW), d.Ci, d.Co, d.R, d.M));
     }
     return FCB_OK;
 }
@@ -480,6 +598,7 @@ extern "C" int fcb_fwd_f32(const float* x, const float* W, const int32_t* rowptr
     FCB_REQUIRE(ws_bytes >= fwd_ws(d), FCB_E_WORKSPACE, "fwd: workspace too small");
     if (N == 0) return FCB_OK;
     float* amax = fwd_amax_slot(ws, contrib_absmax, st);
+    FCB_REQUIRE(amax, FCB_E_CUDA, "fwd: cudaMemsetAsync failed");
     rc = launch_aggregate(x, rowptr_tgt, rec_tgt, rot_tgt, contrib, N, Ci, band_limit, R, 0, amax, st);
     if (rc) return rc;
     return contract_fwd(d, contrib, amax, W, y, ws, ws_bytes, flags, st);
@@ -497,24 +616,20 @@ extern "C" int fcb_bwd_f32(const float* x, const float* W, const float* gy, cons
     FCB_REQUIRE(R >= 2, FCB_E_UNSUPPORTED, "bwd: n_rings must be >= 2");
     FCB_REQUIRE(x && W && gy && ws, FCB_E_ARG, "bwd: null pointer");
     FCB_REQUIRE(!gx || (rowptr_src && rec_src && rot_src), FCB_E_ARG, "bwd: grad x needs the by-source plan");
-    FCB_REQUIRE(!gW || contrib || (rowptr_tgt && rec_tgt && rot_tgt), FCB_E_ARG, "bwd: grad W needs contrib or the by-target plan");
+    FCB_REQUIRE(!gW || contrib || (rowptr_src && rec_src && rot_src), FCB_E_ARG, "bwd: grad W needs contrib or the by-source plan");
+    (void)rowptr_tgt; (void)rec_tgt; (void)rot_tgt;
     FCB_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(W), FCB_E_ALIGN, "bwd: pointers must be 16-byte aligned");
-    const bool recompute = gW && !contrib;
-    FCB_REQUIRE(ws_bytes >= bwd_ws(d, recompute, flags), FCB_E_WORKSPACE, "bwd: workspace too small");
+    const bool from_g = gW && !contrib;          // nothing kept by the forward: gW = xhat^H G, no recompute
+    FCB_REQUIRE(ws_bytes >= bwd_ws(d, from_g, flags), FCB_E_WORKSPACE, "bwd: workspace too small");
     if (N == 0) {
-        if (gW) cudaMemsetAsync(gW, 0, (size_t)d.K * d.Co * 8, st);
+        if (gW && cudaMemsetAsync(gW, 0, (size_t)d.K * d.Co * 8, st) != cudaSuccess) {
+            set_error("bwd: cudaMemsetAsync failed");
+            return FCB_E_CUDA;
+        }
         return FCB_OK;
     }
     Arena ar(ws, ws_bytes);
-    float* slots = ar.take<float>(128);          // [0] max|contrib| when recomputed here, [64] max|G|
-    if (recompute) {
-        float* c2 = ar.take<float>((size_t)d.N * d.K * 2);
-        cudaMemsetAsync(slots, 0, 4, st);
-        rc = launch_aggregate(x, rowptr_tgt, rec_tgt, rot_tgt, c2, N, Ci, band_limit, R, 0, slots, st);
-        if (rc) return rc;
-        contrib = c2;
-        contrib_absmax = slots;
-    }
+    float* slots = ar.take<float>(128);          // [64] max|G|
     auto gather = [&](float* G, float* g_amax, bool) {
         return launch_aggregate(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, g_amax, st);
     };
@@ -570,36 +685,32 @@ extern "C" int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, c
     FCB_REQUIRE((flags & FCB_GEMM_MASK) == FCB_GEMM_TC_2XF16, FCB_E_ARG, "bwd_pk: needs FCB_GEMM_TC_2XF16");
     FCB_REQUIRE(x && W && gy && ws, FCB_E_ARG, "bwd_pk: null pointer");
     FCB_REQUIRE(!gx || (rowptr_src && rec_src && rot_src && norm_src), FCB_E_ARG, "bwd_pk: grad x needs the by-source plan and its norm");
-    FCB_REQUIRE(!gW || (contrib_pk && contrib_scale) || (rowptr_tgt && rec_tgt && rot_tgt && norm_tgt), FCB_E_ARG,
-                "bwd_pk: grad W needs the packed contrib + its scale, or the by-target plan and its norm");
+    FCB_REQUIRE(!gW || (contrib_pk && contrib_scale) || (rowptr_src && rec_src && rot_src && norm_src), FCB_E_ARG,
+                "bwd_pk: grad W needs the packed contrib + its scale, or the by-source plan and its norm");
+    (void)rowptr_tgt; (void)rec_tgt; (void)rot_tgt; (void)norm_tgt;
     FCB_REQUIRE(pk_contrib_ok(d), FCB_E_UNSUPPORTED, "bwd_pk: shape not supported by the packed path (fcb_pk_supported)");
     FCB_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(W), FCB_E_ALIGN, "bwd_pk: pointers must be 16-byte aligned");
-    const bool recompute = gW && !(contrib_pk && contrib_scale);
-    FCB_REQUIRE(ws_bytes >= bwd_ws(d, recompute, flags), FCB_E_WORKSPACE, "bwd_pk: workspace too small");
+    const bool from_g = gW && !(contrib_pk && contrib_scale);
+    FCB_REQUIRE(ws_bytes >= bwd_ws(d, from_g, flags), FCB_E_WORKSPACE, "bwd_pk: workspace too small");
     if (N == 0) {
-        if (gW) cudaMemsetAsync(gW, 0, (size_t)d.K * d.Co * 8, st);
+        if (gW && cudaMemsetAsync(gW, 0, (size_t)d.K * d.Co * 8, st) != cudaSuccess) {
+            set_error("bwd_pk: cudaMemsetAsync failed");
+            return FCB_E_CUDA;
+        }
         return FCB_OK;
     }
     Arena ar(ws, ws_bytes);
-    float* slots = ar.take<float>(128);   // [0] contrib scale when recomputed here, [16] max|x|, [64] G scale / max|G|, [80] max|gy|
-    const float* contrib = static_cast<const float*>(contrib_pk);
-    if (recompute) {
-        float* c2 = ar.take<float>((size_t)pk_rows_padded(d.N) * d.K * 2);
-        rc = launch_absmax_f32(x, N, 2 * Ci, 2 * (int64_t)Ci, 1, 0, slots + 16, st);
-        if (rc) return rc;
-        rc = launch_aggregate_packed(x, rowptr_tgt, rec_tgt, rot_tgt, c2, N, Ci, band_limit, R, 0, slots + 16, norm_tgt, slots, st);
-        if (rc) return rc;
-        contrib = c2;
-        contrib_scale = slots;
-    }
-    const bool g_pk = pk_g_ok(d);
+    float* slots = ar.take<float>(128);   // [64] G scale / max|G|, [80] max|gy|
+    const float* contrib = from_g ? nullptr : static_cast<const float*>(contrib_pk);
+    if (from_g) contrib_scale = nullptr;
+    const bool g_pk = pk_g_ok(d) && (!from_g || gw_from_g_plan(d, flags).batched);
     auto gather = [&](float* G, float* g_amax, bool packed) {
         if (!packed) return launch_aggregate(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, g_amax, st);
         int r2 = launch_absmax_f32(gy, N, 2 * Co, 2 * (int64_t)Co, 1, 0, slots + 80, st);
         if (r2) return r2;
         return launch_aggregate_packed(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, slots + 80, norm_src, g_amax, st);
     };
-    return backward_common(d, x, W, gy, contrib, contrib_scale, slots + 64, gather, gx, gW, ar, flags, st, true, g_pk);
+    return backward_common(d, x, W, gy, contrib, contrib_scale, slots + 64, gather, gx, gW, ar, flags, st, !from_g, g_pk);
 }
 
 extern "C" int fcb_fwd_dense_f32(const float* x, const float* W, const float* sten, const int32_t* rowptr_tgt,
@@ -615,6 +726,7 @@ extern "C" int fcb_fwd_dense_f32(const float* x, const float* W, const float* st
     FCB_REQUIRE(ws_bytes >= fwd_ws(d), FCB_E_WORKSPACE, "fwd_dense: workspace too small");
     if (N == 0) return FCB_OK;
     float* amax = fwd_amax_slot(ws, contrib_absmax, st);
+    FCB_REQUIRE(amax, FCB_E_CUDA, "fwd_dense: cudaMemsetAsync failed");
     rc = launch_aggregate_dense(x, sten, rowptr_tgt, nbr_tgt, perm_tgt, contrib, N, Ci, band_limit, R, 0, amax, st);
     if (rc) return rc;
     return contract_fwd(d, contrib, amax, W, y, ws, ws_bytes, flags, st);
@@ -633,7 +745,10 @@ extern "C" int fcb_bwd_dense_f32(const float* x, const float* W, const float* gy
     FCB_REQUIRE(!gx || (sten && rowptr_src && nbr_src && perm_src), FCB_E_ARG, "bwd_dense: grad x needs the by-source plan");
     FCB_REQUIRE(ws_bytes >= bwd_ws(d, false, flags), FCB_E_WORKSPACE, "bwd_dense: workspace too small");
     if (N == 0) {
-        if (gW) cudaMemsetAsync(gW, 0, (size_t)d.K * d.Co * 8, st);
+        if (gW && cudaMemsetAsync(gW, 0, (size_t)d.K * d.Co * 8, st) != cudaSuccess) {
+            set_error("bwd_dense: cudaMemsetAsync failed");
+            return FCB_E_CUDA;
+        }
         return FCB_OK;
     }
     Arena ar(ws, ws_bytes);

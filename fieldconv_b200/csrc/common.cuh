@@ -134,6 +134,13 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
 int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
                      int64_t ldc, int split, int64_t k_per_split, float* parts, int n_main, const float* amax_a, void* bp_ws,
                      size_t bp_bytes, int a_packed, cudaStream_t st);
+// weight gradient from G: P[m][Mr][2Ci] = G_m^T Xh_m for all 2B+1 frequencies in one batched 2xFP16 TN launch (gemm_h.cu);
+// G = [Kv x M*Mr] fp32 or PK; the packed xhat operands are built from x.  gemm_h_tn_plan: accumulation plan of that launch.
+size_t gemm_h_tn_xhat_ws_bytes(int Ci, int64_t Kv, int M);
+int launch_gemm_h_tn_xhat(const float* G, const float* x, float* P, int64_t Mr, int Ci, int band_limit, int64_t Kv, int split,
+                          int64_t k_per_split, float* parts, int n_main, const float* amax_g, void* bp_ws, size_t bp_bytes,
+                          int a_packed, cudaStream_t st);
+bool gemm_h_tn_plan(int N, int64_t Kv, int split, int* n_main, int64_t* k_per_split);
 // whether the 2xFP16 kernels can consume PK operands for these shapes (same tests the dispatchers apply)
 bool gemm_pk_nn_ok(int N, int64_t K);
 bool gemm_pk_tn_ok(int64_t Mr, int N, int64_t Kv, int split);

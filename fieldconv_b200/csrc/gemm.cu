@@ -363,6 +363,19 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
     return rc;
 }
 
+// 2xFP16 TN accumulation plan for Kv vertices cut into `split` ranges, all N columns in one chunk (false: use the generic path)
+bool gemm_h_tn_plan(int N, int64_t Kv, int split, int* n_main, int64_t* k_per_split) {
+    if (N <= 0 || N > 256 || Kv <= 0 || split < 1) return false;
+    const int mode = FCB_GEMM_TC_2XF16;
+    int64_t kps = (Kv + split - 1) / split;
+    kps = (kps + tc_stage(mode) - 1) / tc_stage(mode) * tc_stage(mode);
+    int nm = 1;
+    if (tc_plan(N, kps / tc_kstep(mode), mode, 1, &nm) < N) return false;
+    *n_main = nm;
+    *k_per_split = kps;
+    return true;
+}
+
 // PK operands: the same feasibility tests the dispatchers above apply (shape only; the buffers are the library's own)
 bool gemm_pk_nn_ok(int N, int64_t K) {
     return (K % 64) == 0 && (N % 4) == 0 && use_tc(N, K, 0, 1, 1, FCB_GEMM_TC_2XF16);

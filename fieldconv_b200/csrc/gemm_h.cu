@@ -464,7 +464,10 @@ struct ParamsTN {
     int64_t Mr, Kv, lda, ldc, k_per_split, part_stride;
     int N, Npad, nb_atoms, stages, n_main, wide;
     int64_t a_tile_stride;     // PACKED: bytes between consecutive 128-vertex tiles of the PK buffer
-    int a_chunks;              // PACKED: 64-column chunks in the PK buffer (= Mr / 64)
+    int a_chunks;              // PACKED: 64-column chunks of ONE batch entry (= Mr / 64)
+    // batch (blockIdx.y): entry b reads the columns [b*Mr, (b+1)*Mr) of A (fp32: a_batch_off floats; PACKED: a_chunks
+    // chunks further), its own packed B operand and writes its own [Mr x N] block of C / of every split's partials
+    int64_t a_batch_off, bp_batch_stride, c_batch_stride;
     uint32_t tmem_cols;
 };
 
@@ -497,10 +500,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_tn(const ParamsTN p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int split = blockIdx.z;
+    const int batch = blockIdx.y;
     const int64_t kb = (int64_t)split * p.k_per_split;       // multiple of KV
     const int64_t ke = min(p.Kv, kb + p.k_per_split);
     const int nchunks = kb < ke ? (int)((ke - kb + KV - 1) / KV) : 0;
-    float* C = p.C + (int64_t)split * p.part_stride;
+    float* C = p.C + (int64_t)split * p.part_stride + (int64_t)batch * p.c_batch_stride;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -534,7 +538,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_tn(const ParamsTN p) {
             const int64_t m = m0 + 8 * f8;
             a_v[i] = v;
             a_cnt[i] = (int)max((int64_t)0, min((int64_t)8, p.Mr - m));
-            a_src[i] = p.A + (kb + v) * p.lda + m;
+            a_src[i] = p.A + (int64_t)batch * p.a_batch_off + (kb + v) * p.lda + m;
             a_off[i] = tn_off_h(v, f8, 2);
         }
         const bool cols_full = (m0 + BM <= p.Mr);
@@ -665,12 +669,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_tn(const ParamsTN p) {
         if (lane == 0) {
             const uint32_t bytes = 2u * b_plane;
             const int64_t img = (int64_t)b_plane;                          // fp16 elements per chunk image (hi + lo planes)
-            const __half* src = p.Bp + (kb / KV) * img;
+            const __half* src = p.Bp + (int64_t)batch * p.bp_batch_stride + (kb / KV) * img;
             // PACKED: column chunks c0, c0+1 of this CTA's 128 columns (the second may lie past the matrix end: its D
             // rows are never stored, so it is simply not loaded)
             const int c0 = (int)(m0 / PK_COLS);
             const int n_ca = (c0 + 1 < p.a_chunks) ? 2 : 1;
-            const uint8_t* a_base = reinterpret_cast<const uint8_t*>(p.A) + (int64_t)c0 * PK_BLOCK_BYTES;
+            const uint8_t* a_base = reinterpret_cast<const uint8_t*>(p.A) + ((int64_t)batch * p.a_chunks + c0) * PK_BLOCK_BYTES;
             uint32_t s = 0, ph = 1;
             for (int kc = 0; kc < nchunks; ++kc) {
                 mbar_wait(empty(s), ph);
@@ -725,6 +729,74 @@ __global__ void k_pack_b_h_tn(const float* __restrict__ B, __half* __restrict__ 
     __half* dst = Bp + c * 2 * plane + tn_off_h(v, f8, atoms) / 2;
     *reinterpret_cast<uint4*>(dst) = hi;
     *reinterpret_cast<uint4*>(dst + plane) = lo;
+}
+
+
+// ---- weight gradient from G (no contrib in the backward):  gW[o,c,r,m] = sum_j conj(xhat[j,c,m]) G[j,m,r,o]
+// (identity: sum_n conj(contrib[n,c,r,m]) gy[n,o] regrouped by source vertex, nn/field_conv.py:130-137 under autograd).
+// Per frequency m one TN product  P_m[2RCo x 2Ci] = G_m^T Xh_m  with Xh_m the real view of xhat[:, :, m]: the B operand
+// of batch entry m.  This kernel builds all M packed operands straight from x (gauge alignment xhat = x conj(u)^m,
+// utils/field.py:40-48 + nn/field_conv.py:128-130) — one thread per 16-byte piece (4 complex channels of one vertex).
+template <int BL>
+__global__ void __launch_bounds__(256) k_pack_xhat_tn(const float2* __restrict__ x, __half* __restrict__ Bp, int64_t Kv, int Ci,
+                                                      int atoms, int64_t nchunks, int64_t bp_batch_stride,
+                                                      const float* __restrict__ amax_b) {
+    constexpr int M = 2 * BL + 1;
+    const int u_per_row = atoms * 8;
+    const int64_t per_chunk = (int64_t)KV * u_per_row;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nchunks * per_chunk) return;
+    const int64_t c = i / per_chunk;
+    const int r = (int)(i - c * per_chunk);
+    const int v = r / u_per_row, f8 = r - v * u_per_row;
+    const int64_t vg = c * KV + v;
+    const float s = scale_of(amax_b);
+    F8 xm[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) zero8(xm[m]);
+    if (vg < Kv) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int ch = 4 * f8 + e;
+            if (ch < Ci) {
+                const float2 z = x[vg * Ci + ch];
+                const bool origin = (fabsf(z.x) < 1e-7f) && (fabsf(z.y) < 1e-7f);
+                const float ri = rsqrtf(z.x * z.x + z.y * z.y);
+                const float2 u = origin ? make_float2(1.f, 0.f) : make_float2(z.x * ri, z.y * ri);
+                float2 up = z, dn = z;
+                xm[BL].v[2 * e] = z.x; xm[BL].v[2 * e + 1] = z.y;
+#pragma unroll
+                for (int k = 1; k <= BL; ++k) {
+                    up = cmul_conj(up, u);        // z conj(u)^k
+                    dn = cmul(dn, u);             // z u^k = z conj(u)^(-k)
+                    xm[BL + k].v[2 * e] = up.x; xm[BL + k].v[2 * e + 1] = up.y;
+                    xm[BL - k].v[2 * e] = dn.x; xm[BL - k].v[2 * e + 1] = dn.y;
+                }
+            }
+        }
+    }
+    const int64_t plane = (int64_t)KV * atoms * 64;                       // fp16 elements per plane
+    __half* dst = Bp + c * 2 * plane + tn_off_h(v, f8, atoms) / 2;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        uint4 hi, lo;
+        split8(xm[m], s, hi, lo);
+        *reinterpret_cast<uint4*>(dst + m * bp_batch_stride) = hi;
+        *reinterpret_cast<uint4*>(dst + m * bp_batch_stride + plane) = lo;
+    }
+}
+
+// out (bit pattern of a non-negative float) = max(out, max_i |z_i| * (1 + 2^-20)): the bound on every real component of
+// xhat = z conj(u)^m.  out is pre-zeroed.
+__global__ void __launch_bounds__(256) k_absmax_modulus(const float2* __restrict__ z, int64_t n, uint32_t* __restrict__ out) {
+    float mx = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 v = __ldg(z + i);
+        mx = fmaxf(mx, sqrtf(v.x * v.x + v.y * v.y));
+    }
+    mx *= 1.000001f;
+    const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+    if ((threadIdx.x & 31) == 0 && w > *reinterpret_cast<volatile uint32_t*>(out)) atomicMax(out, w);
 }
 
 }  // namespace th
@@ -860,6 +932,64 @@ size_t gemm_h_tn_ws_bytes(int N, int64_t Kv) {
     return 256 + align_up((size_t)nchunks * 2 * th::KV * atoms * 128, 256) + 256;
 }
 
+// The TN launch proper.  batch > 1: entry b takes the columns [b*Mr, (b+1)*Mr) of A (whose rows are lda reals long; for a
+// packed A, lda = total real columns of the PK buffer), the packed B operand at Bp + b*bp_batch_stride and writes the
+// [Mr x N] block b of C (dense, ldc = N when batched) or of every split's partials [split][batch][Mr][N].
+static int launch_gemm_h_tn_packed_b(const float* A, const __half* Bp, const float* amax_b, int64_t bp_batch_stride, float* C,
+                                     int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldc, int batch, int split,
+                                     int64_t k_per_split, float* parts, int n_main, const float* amax_a, int a_packed,
+                                     cudaStream_t st);
+
+size_t gemm_h_tn_xhat_ws_bytes(int Ci, int64_t Kv, int M) {
+    const int npad = (2 * Ci + 15) / 16 * 16;
+    const int atoms = (npad + 63) / 64;
+    const int64_t nchunks = (Kv + th::KV - 1) / th::KV;
+    return 256 + align_up((size_t)M * nchunks * 2 * th::KV * atoms * 128, 256) + 256;
+}
+
+// P[m][2RCo][2Ci] (or the split partials) = G_m^T Xh_m for all m in ONE launch; G = [Kv x M*Mr] (fp32, or PK when a_packed)
+int launch_gemm_h_tn_xhat(const float* G, const float* x, float* P, int64_t Mr, int Ci, int band_limit, int64_t Kv, int split,
+                          int64_t k_per_split, float* parts, int n_main, const float* amax_g, void* bp_ws, size_t bp_bytes,
+                          int a_packed, cudaStream_t st) {
+    const int M = 2 * band_limit + 1;
+    const int N = 2 * Ci;
+    FCB_REQUIRE(G && x && P && bp_ws && amax_g, FCB_E_ARG, "gemm_h_tn_xhat: null pointer");
+    FCB_REQUIRE(bp_bytes >= gemm_h_tn_xhat_ws_bytes(Ci, Kv, M), FCB_E_WORKSPACE, "gemm_h_tn_xhat: packed-operand workspace too small");
+    FCB_REQUIRE(band_limit >= 0 && band_limit <= FCB_MAX_BAND_LIMIT, FCB_E_UNSUPPORTED, "gemm_h_tn_xhat: band_limit");
+    if (Mr == 0 || Kv == 0) return FCB_OK;
+    const int npad = (N + 15) / 16 * 16;
+    const int atoms = (npad + 63) / 64;
+    const int64_t nchunks = (Kv + th::KV - 1) / th::KV;
+    float* amax_b = static_cast<float*>(bp_ws);
+    __half* Bp = reinterpret_cast<__half*>(static_cast<char*>(bp_ws) + 256);
+    const int64_t bp_stride = nchunks * 2 * th::KV * atoms * 64;            // fp16 elements per batch entry
+    if (cudaMemsetAsync(amax_b, 0, 4, st) != cudaSuccess) {
+        set_error("gemm_h_tn_xhat: cudaMemsetAsync failed");
+        return FCB_E_CUDA;
+    }
+    {
+        int64_t blocks = (Kv * Ci + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        FCB_LAUNCH("absmax_mod", st, th::k_absmax_modulus<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float2*>(x), Kv * Ci,
+                                                                                       reinterpret_cast<uint32_t*>(amax_b)));
+        const int64_t items = nchunks * th::KV * atoms * 8;
+        const unsigned pb = (unsigned)((items + 255) / 256);
+        const float2* x2 = reinterpret_cast<const float2*>(x);
+        prof_begin("pack_xhat_tn", st);
+        switch (band_limit) {
+            case 0: th::k_pack_xhat_tn<0><<<pb, 256, 0, st>>>(x2, Bp, Kv, Ci, atoms, nchunks, bp_stride, amax_b); break;
+            case 1: th::k_pack_xhat_tn<1><<<pb, 256, 0, st>>>(x2, Bp, Kv, Ci, atoms, nchunks, bp_stride, amax_b); break;
+            case 2: th::k_pack_xhat_tn<2><<<pb, 256, 0, st>>>(x2, Bp, Kv, Ci, atoms, nchunks, bp_stride, amax_b); break;
+            case 3: th::k_pack_xhat_tn<3><<<pb, 256, 0, st>>>(x2, Bp, Kv, Ci, atoms, nchunks, bp_stride, amax_b); break;
+            default: th::k_pack_xhat_tn<4><<<pb, 256, 0, st>>>(x2, Bp, Kv, Ci, atoms, nchunks, bp_stride, amax_b); break;
+        }
+        prof_end(st);
+        FCB_CUDA_LAUNCH_CHECK("pack_xhat_tn");
+    }
+    return launch_gemm_h_tn_packed_b(G, Bp, amax_b, bp_stride, P, Mr, N, Kv, (int64_t)M * Mr, N, M, split, k_per_split, parts, n_main,
+                                     amax_g, a_packed, st);
+}
+
 int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
                      int64_t ldc, int split, int64_t k_per_split, float* parts, int n_main, const float* amax_a, void* bp_ws,
                      size_t bp_bytes, int a_packed, cudaStream_t st) {
@@ -886,18 +1016,34 @@ int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N
         if (items > 0)
             FCB_LAUNCH("pack_b_h_tn", st, th::k_pack_b_h_tn<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(B, Bp, Kv, N, nb_atoms, ldb, nchunks, amax_b));
     }
+    return launch_gemm_h_tn_packed_b(A, Bp, amax_b, 0, C, Mr, N, Kv, a_packed ? Mr : lda, ldc, 1, split, k_per_split, parts, n_main, amax_a,
+                                     a_packed, st);
+}
+
+static int launch_gemm_h_tn_packed_b(const float* A, const __half* Bp, const float* amax_b, int64_t bp_batch_stride, float* C,
+                                     int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldc, int batch, int split,
+                                     int64_t k_per_split, float* parts, int n_main, const float* amax_a, int a_packed,
+                                     cudaStream_t st) {
+    FCB_REQUIRE(batch >= 1 && batch <= 65535, FCB_E_ARG, "gemm_h_tn: bad batch");
+    FCB_REQUIRE(batch == 1 || ldc == N, FCB_E_ARG, "gemm_h_tn: a batched product writes dense [Mr x N] blocks");
+    if (a_packed) FCB_REQUIRE((lda % PK_COLS) == 0 && lda >= (int64_t)batch * Mr, FCB_E_ARG, "gemm_h_tn: packed A needs lda = total PK columns");
+    const int npad = (N + 15) / 16 * 16;
+    const int nb_atoms = (npad + 63) / 64;
     th::ParamsTN p;
     p.A = A; p.Bp = Bp;
     p.C = split > 1 ? parts : C;
     p.amax_a = amax_a; p.amax_b = amax_b;
-    p.Mr = Mr; p.Kv = Kv; p.lda = lda;
+    p.Mr = Mr; p.Kv = Kv; p.lda = a_packed ? 4 : lda;
     p.ldc = split > 1 ? N : ldc;
     p.k_per_split = k_per_split;
-    p.part_stride = split > 1 ? Mr * (int64_t)N : 0;
+    p.part_stride = split > 1 ? (int64_t)batch * Mr * (int64_t)N : 0;
+    p.c_batch_stride = Mr * (split > 1 ? (int64_t)N : ldc);
+    p.a_batch_off = Mr;
+    p.bp_batch_stride = bp_batch_stride;
     p.N = N; p.Npad = npad; p.nb_atoms = nb_atoms;
-    p.wide = ((lda % 8) == 0 && (reinterpret_cast<uintptr_t>(A) & 31u) == 0) ? 1 : 0;
+    p.wide = (!a_packed && (lda % 8) == 0 && (Mr % 8) == 0 && (reinterpret_cast<uintptr_t>(A) & 31u) == 0) ? 1 : 0;
     p.a_chunks = (int)(Mr / PK_COLS);
-    p.a_tile_stride = (int64_t)p.a_chunks * PK_BLOCK_BYTES;
+    p.a_tile_stride = (a_packed ? lda / PK_COLS : (int64_t)p.a_chunks) * PK_BLOCK_BYTES;
     FCB_REQUIRE(n_main >= 1 && npad * (n_main + 1) <= 512, FCB_E_ARG, "gemm_h_tn: accumulators do not fit TMEM");
     p.n_main = n_main;
     uint32_t cols = 32;
@@ -909,7 +1055,7 @@ int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N
     FCB_REQUIRE(stages >= 1, FCB_E_UNSUPPORTED, "gemm_h_tn: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
-    dim3 grid((unsigned)((Mr + th::BM - 1) / th::BM), 1, (unsigned)split);
+    dim3 grid((unsigned)((Mr + th::BM - 1) / th::BM), (unsigned)batch, (unsigned)split);
     // the opt-in shared-memory size is a per-device (per-context) function attribute: remember it per device
     static bool attr_set_dev[64] = {};
     bool attr_unknown_dev = false;

@@ -18,23 +18,14 @@ from torch import Tensor
 
 from . import _lib
 
-# contrib (N x K complex) is kept for the weight gradient when it is at most this many bytes AND at most a quarter
-# of the device memory that is free at the time of the forward; otherwise the backward recomputes it.
-SAVE_CONTRIB_BYTES = int(os.environ.get("FIELDCONV_B200_SAVE_CONTRIB_BYTES", str(24 << 30)))
+# The backward takes the weight gradient from G and xhat (gW[o,c,r,m] = sum_j conj(xhat[j,c,m]) G[j,m,r,o], csrc/api.cu
+# backward_common), so the forward keeps NOTHING of size N x K by default: no saved contrib, no recompute.
+# FIELDCONV_B200_SAVE_CONTRIB=1 restores the older behaviour (contrib saved by the forward, gW = contrib^H gy) for A/B runs.
+SAVE_CONTRIB = os.environ.get("FIELDCONV_B200_SAVE_CONTRIB", "0") == "1"
 
 
-_FREE_AT_FIRST_USE = {}
-
-
-def keep_contrib_default(nbytes, device):
-    if nbytes > SAVE_CONTRIB_BYTES:
-        return False
-    if nbytes <= (256 << 20):
-        return True
-    key = torch.device(device).index
-    if key not in _FREE_AT_FIRST_USE:            # queried once per device: cudaMemGetInfo is not free
-        _FREE_AT_FIRST_USE[key] = torch.cuda.mem_get_info(device)[0]
-    return nbytes <= _FREE_AT_FIRST_USE[key] // 4
+def keep_contrib_default(nbytes=0, device=None):
+    return SAVE_CONTRIB
 
 
 def _real(t):

@@ -252,8 +252,11 @@ class _PartitionedFieldConv(torch.autograd.Function):
         gx_ext = torch.empty(n_ext, ci, dtype=torch.complex64, device=dev) if need_gx else None
         gw = torch.empty_like(W) if need_gw else None
         have = contrib.numel() > 0
+        # no contrib kept: gW = sum over the SOURCE rows of conj(xhat) G, so the halo sources contribute their share too
+        gw_halo = torch.zeros_like(W) if (need_gw and not have and n_ext > n_own) else None
 
-        def rows(a, b, with_gw):
+        def rows(a, b, with_gw, gw_out=None):
+            gw_out = gw if gw_out is None else gw_out
             if b <= a or not (need_gx or with_gw):
                 return
             fl = flags | (0x100 if (have or not with_gw) else 0)
@@ -266,17 +269,20 @@ class _PartitionedFieldConv(torch.autograd.Function):
                       plan.rowptr_tgt[a:].data_ptr(), plan.rec_tgt.data_ptr(), plan.rot_tgt.data_ptr(),
                       plan.rowptr_src[a:].data_ptr(), plan.rec_src.data_ptr(), plan.rot_src.data_ptr(),
                       torch.view_as_real(gx_ext)[a:].data_ptr() if need_gx else 0,
-                      torch.view_as_real(gw).data_ptr() if with_gw else 0,
+                      torch.view_as_real(gw_out).data_ptr() if with_gw else 0,
                       b - a, ci, co, band_limit, plan.n_rings, flags, ws.data_ptr(), nbytes, _lib.stream_ptr())
 
         main = torch.cuda.current_stream(dev)
         comm = _comm_stream(dev)
         with torch.cuda.device(dev):
+            if need_gx or gw_halo is not None:
+                rows(n_own, n_ext, gw_halo is not None, gw_halo)   # partial grad-x (and grad-W share) of the halo sources
             if need_gx:
-                rows(n_own, n_ext, False)        # partial grad-x of the halo sources (targets are all owned)
                 halo_ready = torch.cuda.Event()
                 halo_ready.record(main)
             rows(0, n_own, need_gw)              # owned rows: grad-x and grad-W, overlaps the send below
+            if gw_halo is not None:
+                gw = gw + gw_halo
         gx_own = None
         if need_gx:
             gx_own = gx_ext[:n_own]

@@ -1,7 +1,7 @@
 #!/bin/bash
-# Lean A/B of the aggregation kernel's variants (FIELDCONV_B200_AGG_VARIANT=b0,b1,b2; code = 10*CTAs/SM + pipeline depth,
-# +100 = FAST arithmetic).  Parity of a variant: FIELDCONV_B200_AGG_VARIANT=... python tools/variant_probe.py
-#   gpurun --timeout 420 -- 'bash tools/gpu_variants.sh r01h'
+# Lean A/B of the aggregation kernel's variants.  FIELDCONV_B200_AGG_VARIANT=<b1 fp32>,<b1 packed>,<b2 fp32>,<b2 packed>;
+# code = 100*FAST + 10*(CTAs/SM) + MODE (aggregate_kernel.cuh).  Parity of every variant first (tools/variant_probe.py).
+#   gpurun --timeout 600 -- 'bash tools/gpu_variants.sh r02b'
 TAG=${1:-rXX}
 OUT=gpurun_out
 mkdir -p $OUT
@@ -11,14 +11,22 @@ run() {   # variant-string  layer_bench args...
   FIELDCONV_B200_AGG_VARIANT=$v timeout 100 python tools/layer_bench.py "$@" --tag "var$v"
 }
 {
-  # band limit 2, fp32 output (the cfg-2 bench path): default 31 vs depth 3 / FAST arithmetic
-  for v in 32,41,31 32,41,33 32,41,34 32,41,131 32,41,133 32,41,134 32,41,43 32,41,44; do run $v --side 284 --channels 48 --band 2 --rings 6; done
-  # band limit 2, packed output: default 22 vs out-of-line ring store at 3 CTAs/SM (packed wins at B=2 if this gets close to the fp32 kernel)
-  for v in 32,32,22 32,32,231 32,32,232 32,32,331; do run $v --side 284 --channels 48 --band 2 --rings 6 --precision 2xf16p; done
-  # band limit 1, packed output (1 M vertices, C=32): default 32 vs depth 3 / FAST
-  for v in 32,32,31 32,33,31 32,34,31 32,44,31 32,132,31 32,134,31; do run $v --side 1000 --channels 32 --band 1 --rings 6 --steps 5; done
-  # band limit 1, fp32 output: default 41 vs depth 3 / FAST
-  for v in 32,41,31 32,43,31 32,44,31 32,34,31 32,141,31 32,134,31; do run $v --side 1000 --channels 32 --band 1 --rings 6 --steps 5 --precision 2xf16; done
+  for v in 134 135 136 124 125 126 144 146; do
+    for prec in 2xf16 2xf16p; do
+      PROBE_PARITY_ONLY=1 PROBE_PRECISION=$prec FIELDCONV_B200_AGG_VARIANT=$v,$v,$v,$v timeout 100 python tools/variant_probe.py
+    done
+  done
+} > $OUT/${TAG}_variant_parity.jsonl 2> $OUT/${TAG}_variant_parity.err
+cat $OUT/${TAG}_variant_parity.jsonl | cut -c 1-400
+{
+  # band limit 2, fp32 output (the cfg-2 bench path)
+  for v in 134 135 136 124 125 126 31; do run 0,0,$v,0 --side 284 --channels 48 --band 2 --rings 6 --precision 2xf16; done
+  # band limit 2, packed output
+  for v in 22 134 135 136 124 125 126; do run 0,0,0,$v --side 284 --channels 48 --band 2 --rings 6 --precision 2xf16p; done
+  # band limit 1, fp32 output (1 M vertices, C=32)
+  for v in 134 135 136 144 146 41; do run $v,0,0,0 --side 1000 --channels 32 --band 1 --rings 6 --steps 5 --precision 2xf16; done
+  # band limit 1, packed output
+  for v in 134 135 136 144 146; do run 0,$v,0,0 --side 1000 --channels 32 --band 1 --rings 6 --steps 5 --precision 2xf16p; done
 } > $OUT/${TAG}_variants.jsonl 2> $OUT/${TAG}_variants.err
 python - <<PY
 import json
@@ -29,3 +37,12 @@ for l in open("$OUT/${TAG}_variants.jsonl"):
           {n: v for n, v in k.items() if n.startswith("aggregate")})
 PY
 tail -3 $OUT/${TAG}_variants.err
+if [ -n "$NCU" ]; then
+  FIELDCONV_B200_NCU=1 timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off \
+      -k regex:'k_aggregate' -o $OUT/${TAG}_full_1m_c32 -f \
+      python tools/layer_bench.py --side 1000 --channels 32 --band 1 --rings 6 --precision 2xf16 > $OUT/${TAG}_ncu_1m.log 2>&1
+  FIELDCONV_B200_NCU=1 timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off \
+      -k regex:'k_aggregate' -o $OUT/${TAG}_full_cfg2 -f \
+      python tools/layer_bench.py --side 284 --channels 48 --band 2 --rings 6 --precision 2xf16 > $OUT/${TAG}_ncu_cfg2.log 2>&1
+  ls -la $OUT/${TAG}_full*
+fi
