@@ -31,7 +31,8 @@ METRIC = "fieldconv_fwd_bwd_edges_per_sec"
 UNIT = "edges/s"
 B, R, C, N_BLOCKS, N_CLASSES = 2, 6, 48, 5, 8
 MESHES_PER_RANK, N_SIDE, DEG = 16, 71, 40.0
-CPU_SAMPLE_SIDE = 36            # bounded CPU sample: one FCResNetBlock on a 1296-vertex mesh
+WORKLOAD = "fcresnet5_c48_b2_r6_16x5k"
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # nominal: 148 SMs x 128 FP32 lanes x FMA at clocks.max.sm
 
 
 def peaks():
@@ -42,51 +43,145 @@ def peaks():
     return 6650.0, 1590.0, "fallback"
 
 
-# ----------------------------------------------------------------------------- reference arm (CPU port)
-def cpu_sample(steps, warmup, threads=None):
-    """One FCResNetBlock(48,48,B=2,R=6) fwd+bwd in the reference's formulation on a small mesh."""
+def base_config(world, precision):
+    """The workload description shared by both arms (the reference arm measures a bounded sample of exactly this)."""
+    return {"workload": WORKLOAD, "blocks": N_BLOCKS, "channels": C, "band_limit": B, "n_rings": R,
+            "meshes_per_gpu": MESHES_PER_RANK, "vertices_per_mesh": N_SIDE * N_SIDE, "edges_per_vertex": DEG,
+            "fieldconv_layers": 2 * N_BLOCKS, "precision": precision, "parallelism": "dp%d" % world,
+            "l2": "working set per step (>=0.9 GB of contrib per layer) exceeds the 126 MB L2; no explicit flush",
+            "step": "forward + backward + NCCL grad all-reduce (N>1) + Adam"}
+
+
+# ----------------------------------------------------------------------------- reference arm (the reference's CPU path)
+def host_threads():
+    """All host cores, explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers."""
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def _reference_ns():
+    """The UNMODIFIED reference (nn/field_conv.py etc.) when its tree is reachable (FIELDCONV_REFERENCE or
+    /root/reference — never on the GPU box), else None: the caller then times the oracle's port of the same formulation."""
+    try:
+        from oracle import ref_loader
+        if ref_loader.available():
+            return ref_loader.load()
+    except Exception:
+        pass
+    return None
+
+
+def cpu_block_sample(steps, warmup):
+    """Bounded sample of the bench workload on the host: ONE FCResNetBlock(48,48,B=2,R=6) fwd+bwd on ONE of the
+    5041-vertex meshes (1 of the 5 blocks x 1 of the 16 meshes of a step), in the reference's own formulation
+    (nn/fc_resnet_block.py:84-88 over nn/field_conv.py:104-137: per-edge product tensor, index-sum, broadcast filter)."""
     from fieldconv_b200.synthetic import random_features, torus_mesh
     from fieldconv_b200 import nn as fnn
     from oracle import restate
-    if threads:
-        torch.set_num_threads(threads)
-    mesh = torus_mesh(CPU_SAMPLE_SIDE, deg=DEG, seed=0)
+    mesh = torus_mesh(N_SIDE, deg=DEG, seed=0)
     e, sten, _, _, _ = restate.fc_precomp(mesh.logMag, mesh.logAng, mesh.w, mesh.supp_edges, mesh.xp, B, R, mesh.epsilon)
     torch.manual_seed(0)
-    blk = fnn.FCResNetBlock(C, C, B, R, 1)          # parameter container only (reference init); math is the oracle's
-    params = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in blk.state_dict().items()}
+    blk = fnn.FCResNetBlock(C, C, B, R, 1)          # parameter container only (reference init)
     x = random_features(mesh.num_nodes, C, seed=1)
     gy = random_features(mesh.num_nodes, C, seed=2, zero_frac=0)
+    ns = _reference_ns()
+    if ns is not None:
+        ref = ns.FCResNetBlock(C, C, B, R, 1)
+        ref.load_state_dict(blk.state_dict())
+        params = list(ref.parameters())
+
+        def run(xr):
+            return ref(xr, e, sten)
+        kind = "reference"
+    else:
+        pd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in blk.state_dict().items()}
+        params = list(pd.values())
+
+        def run(xr):
+            return restate.fc_resnet_block(xr, e, sten, pd, B, 1, refstyle=True)
+        kind = "port"
     times = []
     for it in range(warmup + steps):
         xr = x.clone().requires_grad_(True)
-        for v in params.values():
+        for v in params:
             v.grad = None
         t0 = time.perf_counter()
-        y = restate.fc_resnet_block(xr, e, sten, params, B, 1, refstyle=True)
+        y = run(xr)
         (y.real * gy.real + y.imag * gy.imag).sum().backward()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     edges = 2 * e.shape[0]                           # two FieldConv layers per block
-    return edges, times, mesh.num_nodes
+    sample = ("1 FCResNetBlock(48,48,B=2,R=6) fwd+bwd on one %d-vertex mesh of the batch (%d edge-convs/step; 1 of 5 blocks x 1 of "
+              "16 meshes), %s" % (mesh.num_nodes, edges, "unmodified reference nn/fc_resnet_block.py" if kind == "reference"
+                                  else "oracle/restate.py port of the reference formulation (reference tree not on this box)"))
+    return edges, times, kind, sample
+
+
+def cpu_cfg1_layer(threads, iters, warmup):
+    """one FieldConv layer fwd+bwd at BASELINE config 1 (5041 vertices, ~40 edges/vertex, C=32, B=1,
+    R=6, ftype=1) in the reference's formulation (nn/field_conv.py:104-137)."""
+    from fieldconv_b200.synthetic import random_features, torus_mesh
+    from fieldconv_b200 import nn as fnn
+    from oracle import restate
+    b1, c1 = 1, 32
+    torch.set_num_threads(threads)
+    mesh = torus_mesh(N_SIDE, deg=DEG, seed=0)
+    e, sten, _, _, _ = restate.fc_precomp(mesh.logMag, mesh.logAng, mesh.w, mesh.supp_edges, mesh.xp, b1, R, mesh.epsilon)
+    torch.manual_seed(0)
+    lay = fnn.FieldConv(c1, c1, b1, R, 1)
+    x = random_features(mesh.num_nodes, c1, seed=1)
+    gy = random_features(mesh.num_nodes, c1, seed=2, zero_frac=0)
+    ns = _reference_ns()
+    if ns is not None:
+        ref = ns.FieldConv(c1, c1, b1, R, 1)
+        ref.load_state_dict(lay.state_dict())
+        params = list(ref.parameters())
+
+        def run(xr):
+            return ref(xr, e, sten)
+    else:
+        params = [p.detach().clone().requires_grad_(True) for p in (lay.zonal, lay.spherical, lay.phase)]
+
+        def run(xr):
+            return restate.field_conv_refstyle(xr, e, sten, params[0], params[1], params[2], 1, b1)
+    ts = []
+    for it in range(warmup + iters):
+        xr = x.clone().requires_grad_(True)
+        for v in params:
+            v.grad = None
+        t0 = time.perf_counter()
+        y = run(xr)
+        (y.real * gy.real + y.imag * gy.imag).sum().backward()
+        if it >= warmup:
+            ts.append(time.perf_counter() - t0)
+    ts.sort()
+    ne = int(e.shape[0])
+    return {"threads": torch.get_num_threads(), "edges": ne, "min_s": ts[0], "median_s": ts[len(ts) // 2],
+            "edges_per_s": ne / ts[0], "kind": "reference" if ns is not None else "port"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    edges, times, n = cpu_sample(args.steps, args.warmup)
+    cores = host_threads()
+    edges, times, kind, sample = cpu_block_sample(args.steps, args.warmup)
     ms = 1e3 * sum(times) / len(times)
     val = edges / (ms * 1e-3)
-    sample = "1 FCResNetBlock(48,48,B=2,R=6) fwd+bwd on one %d-vertex mesh (%d edge-convs/step)" % (n, edges)
+    cfg1 = {"all_threads": cpu_cfg1_layer(cores, 5, 2), "one_thread": cpu_cfg1_layer(1, 2, 1),
+            "what": "BASELINE.md §3 / BASELINE.json configs[0]: one FieldConv(32,32,B=1,R=6) layer fwd+bwd, 5041 vertices"}
+    torch.set_num_threads(cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "fcresnet5_c48_b2_r6_16x5k (bounded CPU sample of it)", "sample": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "config": base_config(args.gpus, args.precision),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "host_cpu_count": os.cpu_count()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cfg1_layer": cfg1,
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -158,11 +253,37 @@ class ClockSampler:
                 "window": window}
 
 
-def algorithmic_bytes_aggregate(n, e, c, transpose=False):
-    """Per launch of k_aggregate: each array once — 24 B/edge of plan records
-    (16 B rec + 8 B rot), the feature rows read once (N*C*8), row pointers, and the N*R*C*M*8 B result written."""
-    m = 2 * B + 1
-    return e * 24 + (n + 1) * 4 + n * c * 8 + n * R * c * m * 8
+def contract_bytes_layer(n, e, ci, co, b, r):
+    """SURVEY.md §8(d) ALGORITHMIC bytes of one FieldConv layer, each array once, compact edge format, contrib / G never in
+    HBM: (forward, forward + backward)."""
+    m = 2 * b + 1
+    k = r * ci * m
+    fwd = e * 20 + (n + 1) * 4 + n * ci * 8 + n * co * 8 + co * k * 8
+    return fwd, fwd + e * 20 + e * 24 + n * (2 * ci + co) * 8 + 2 * co * k * 8
+
+
+def kernel_bytes(name, n, e, c, b, r):
+    """Kernel-level bytes of one launch at the cfg-2 layer shape (what THIS kernel must move given that contrib / G live in
+    HBM between kernels): plan records + feature rows + the N x 2K result for the aggregations, the A operand read once +
+    B + C for the contractions."""
+    m = 2 * b + 1
+    k2 = 2 * r * c * m                                  # real columns of contrib / G
+    if name.startswith("aggregate"):
+        return e * 24 + (n + 1) * 4 + n * c * 8 + n * k2 * 4
+    if name.startswith(("gemm_h_nn", "gemm_p_nn", "gemm_tc_nn", "gemm_nn")):
+        return n * k2 * 4 + k2 * 2 * c * 4 + n * 2 * c * 4
+    if name.startswith(("gemm_h_tn", "gemm_p_tn", "gemm_tc_tn", "gemm_tn")):
+        return n * k2 * 4 + n * 2 * c * 4 * m + k2 * 2 * c * 4
+    return None
+
+
+def ncu_reference():
+    """Counters of the committed `ncu --set full` capture of the same kernels at the cfg-2 layer shape (profiles/ncu_traffic.json,
+    written from profiles/*_ncu_full_summary.md): DRAM bytes per launch, issue-active %, FMA-pipe %, tensor-pipe %."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except (OSError, ValueError):
+        return {}
 
 
 def run_ours(args):
@@ -309,12 +430,21 @@ def run_ours(args):
         _lib.profile_enable(1 << 14)
     step(x_dev, plan, labels)
     barrier()
+    recs = _lib.profile_collect(1 << 14) if rank == 0 else []
+    del opt, net, params, plan, batch, x_dev, labels
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[3] inside the same run: NCCL parity of the vertex-partitioned layer (N >= 2) and the 4M-vertex
+    #      strong-scaling point of this N, so the driver's 1 -> 2 -> 4 -> 8 runs carry the whole curve
+    parity = partition_parity(world, rank, dev) if world > 1 and not args.skip_cfg4 else None
+    cfg4 = None
+    if not args.skip_cfg4:
+        cfg4 = measure_cfg4(args.cfg4_side, world, rank, dev, args.precision, steps=3, warmup=2, e2e=False)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     hbm, tf_sus, which = peaks()
-    recs = _lib.profile_collect(1 << 14)
     tot = {}
     for name, ms in recs:
         a = tot.setdefault(name, [0, 0.0])
@@ -323,67 +453,93 @@ def run_ours(args):
     lib_ms = sum(v[1] for v in tot.values())
     shares = {k: {"launches": v[0], "ms": round(v[1], 4), "share_of_step": round(v[1] / ms_step, 4)} for k, v in
               sorted(tot.items(), key=lambda kv: -kv[1][1])}
-    # dominant kernel among the FieldConv path's own kernels (the "lin_*" records are TangentLin's small GEMMs)
-    dominant = max(((k, v) for k, v in tot.items() if not k.startswith("lin_")), key=lambda kv: kv[1][1])[0]
+    # kernel families of the FieldConv path (the "lin_*" records are TangentLin's small GEMMs)
+    fam = {}
+    for k, v in tot.items():
+        if k.startswith("lin_"):
+            continue
+        f = "k_aggregate" if k.startswith("aggregate") else ("k_gemm_*_nn" if "_nn" in k and k.startswith("gemm") else
+                                                               ("k_gemm_*_tn" if "_tn" in k and k.startswith("gemm") else k))
+        a = fam.setdefault(f, [0, 0.0, []])
+        a[0] += v[0]
+        a[1] += v[1]
+        a[2].append(k)
+    dominant = max(fam.items(), key=lambda kv: kv[1][1])[0]
     m = 2 * B + 1
-    k_complex = R * C * m
-    avg_ms = tot[dominant][1] / tot[dominant][0]
-    if dominant.startswith("aggregate"):
-        per_launch = algorithmic_bytes_aggregate(n, e_kept, C)
-        roof = {"kernel": "k_aggregate" + ("<transpose>" if "_T" in dominant else "") + (" (packed fp16 output)" if dominant.endswith("_pk") else ""),
+    ncu = ncu_reference()
+    per_kernel = {}
+    for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1])[:6]:
+        kb = kernel_bytes(k, n, e_kept, C, B, R)
+        avg = v[1] / v[0]
+        ent = {"launches": v[0], "avg_launch_ms": round(avg, 4)}
+        if kb:
+            ent.update({"kernel_bytes_per_launch": kb, "GBps": round(kb / (avg * 1e-3) / 1e9, 1),
+                        "frac_of_hbm_peak": round(kb / (avg * 1e-3) / 1e9 / hbm, 4)})
+        if k in ncu.get("cfg2_layer", {}):
+            ent["ncu"] = ncu["cfg2_layer"][k]
+        per_kernel[k] = ent
+    fwd_b, all_b = contract_bytes_layer(n, e_kept, C, C, B, R)
+    contract_step = all_b * 2 * N_BLOCKS
+    d_launches, d_ms = fam[dominant][0], fam[dominant][1]
+    avg_ms = d_ms / d_launches
+    if dominant == "k_aggregate":
+        per_launch = kernel_bytes("aggregate", n, e_kept, C, B, R)
+        flops = 14.0 * C * m * e_kept
+        roof = {"kernel": "k_aggregate (forward + transposed launches: %s)" % ", ".join(sorted(fam[dominant][2])),
                 "bound": "hbm", "achieved": per_launch / (avg_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                 "algorithmic_bytes_per_launch": per_launch,
-                "algorithmic_tflops": 14.0 * C * m * e_kept / (avg_ms * 1e-3) / 1e12,
-                "note": "gather + segmented reduction: E*24 B of plan records, the feature rows once, the N x R*M*C complex "
-                        "result written once; ncu (profiles/) shows the kernel issue/FMA-pipe bound (65 % issue-active), "
-                        "the HBM fraction is the contract's figure"}
+                "fp32_pipe": {"achieved_tflops": flops / (avg_ms * 1e-3) / 1e12, "peak_tflops_nominal": FP32_PEAK_TFLOPS,
+                              "frac": flops / (avg_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
+                              "flops_per_launch": flops, "definition": "SURVEY.md §8(d): 14*Ci*M flops per edge"},
+                "note": "gather + segmented reduction; kernel-level bytes = E*24 B of plan records + the feature rows once + the "
+                        "N x 2K fp32 result written once.  The kernel is bound by FP32 instruction issue / the FMA pipe, not by "
+                        "HBM (see fp32_pipe and the ncu counters): the HBM fraction is reported because the contract asks for it"}
     else:
-        # contraction launches of one name share one shape family: the forward-shaped (N x 2K) @ (2K x 2Co) product;
-        # algorithmic bytes = the A operand read once + B + C written once
-        per_launch = n * 2 * k_complex * 4 + 2 * k_complex * 2 * C * 4 + n * 2 * C * 4
-        flops = 8.0 * n * k_complex * C
-        roof = {"kernel": "k_gemm (" + dominant + ")", "bound": "hbm", "achieved": per_launch / (avg_ms * 1e-3) / 1e9,
-                "peak": hbm, "unit": "GB/s", "algorithmic_bytes_per_launch": per_launch,
-                "fp32_tflops_achieved": flops / (avg_ms * 1e-3) / 1e12,
-                "note": ("tcgen05 contraction: reads the contrib operand once (HBM floor) — fp32 split into fp16 (hi, lo) planes "
-                         "by producer warps (gemm_h_*) or packed fp16 planes bulk-copied (gemm_p_*); %.0f flop/B"
-                         if dominant.startswith(("gemm_h", "gemm_p", "gemm_tc")) else
-                         "FP32-FMA contraction (arithmetic intensity %.0f flop/B): the binding resource is the FMA pipe, "
-                         "the HBM fraction is reported because the contract asks for it") % (flops / per_launch)}
+        per_launch = kernel_bytes(fam[dominant][2][0], n, e_kept, C, B, R) or 0
+        flops = 8.0 * n * R * C * m * C
+        roof = {"kernel": dominant + " (" + ", ".join(sorted(fam[dominant][2])) + ")", "bound": "hbm",
+                "achieved": per_launch / (avg_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                "algorithmic_bytes_per_launch": per_launch, "fp32_tflops_achieved": flops / (avg_ms * 1e-3) / 1e12,
+                "note": "tcgen05 contraction: reads its N x 2K operand once (HBM floor), 2xFP16 split operands"}
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["peak_source"] = which
     roof["avg_launch_ms"] = avg_ms
-    roof["launches_averaged"] = tot[dominant][0]
+    roof["launches_averaged"] = d_launches
+    roof["share_of_step"] = round(d_ms / ms_step, 4)
+    # the contract's own figure: §8(d) bytes of the whole step (contrib / G counted as on-chip) over the step time
+    roof["contract"] = {"bytes_per_step": contract_step, "bytes_per_edge_fwd_bwd": all_b / e_kept,
+                        "achieved_GBps": contract_step / (ms_step * 1e-3) / 1e9,
+                        "frac": contract_step / (ms_step * 1e-3) / 1e9 / hbm,
+                        "note": "SURVEY.md §8(d) algorithmic bytes x 10 layers / step time; the kernels actually move the N x 2K "
+                                "contrib / G through HBM between aggregation and contraction (see traffic)"}
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
-    # layer shape (profiles/ncu_traffic.json, written from profiles/*_ncu_full_summary.md), or null for kernels without one
+    # layer shape, for the dominant kernel and summed over one layer's forward + backward
     roof["traffic"] = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        if dominant in tr.get("cfg2_layer", {}):
-            roof["traffic"] = tr["cfg2_layer"][dominant]
-            roof["traffic_source"] = tr.get("source")
-    except (OSError, ValueError):
-        pass
+    key = fam[dominant][2][0]
+    if key in ncu.get("cfg2_layer", {}):
+        roof["traffic"] = ncu["cfg2_layer"][key].get("dram_bytes")
+        roof["ncu"] = {kk: ncu["cfg2_layer"][key].get(kk) for kk in ("issue_active_pct", "fma_pipe_pct", "tensor_pipe_pct", "dram_pct")}
+        roof["traffic_source"] = ncu.get("source")
+    if "layer_dram_bytes_fwd_bwd" in ncu:
+        roof["traffic_layer_fwd_bwd"] = ncu["layer_dram_bytes_fwd_bwd"]
+        roof["contract_bytes_layer_fwd_bwd"] = all_b
+    roof["per_kernel"] = per_kernel
 
-    # ---- CPU baseline on the box's host cores (bounded sample)
-    if args.skip_cpu_baseline:             # A/B runs of tools/*.sh only; the driver's command never passes this
-        cpu = None
-    else:
-        edges_c, times_c, n_c = cpu_sample(steps=2, warmup=1)
-        cpu_val = edges_c / (sum(times_c) / len(times_c))
-        cpu = {"value": cpu_val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "1 FCResNetBlock(48,48,B=2,R=6) fwd+bwd on one %d-vertex mesh, reference formulation "
-                         "(oracle/restate.py field_conv_refstyle), mean of 2 runs after 1 warm-up" % n_c}
+    # ---- CPU baseline on the box's host cores (bounded sample of the same workload, rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not args.skip_cpu_baseline:       # --skip-cpu-baseline: A/B runs of tools/*.sh only
+        cores = host_threads()
+        edges_c, times_c, kind_c, sample_c = cpu_block_sample(steps=2, warmup=1)
+        cpu = {"value": edges_c / (sum(times_c) / len(times_c)), "unit": UNIT, "cores": cores, "kind": kind_c,
+               "sample": sample_c + "; mean of 2 runs after 1 warm-up"}
 
+    cfg = base_config(world, args.precision)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "fcresnet5_c48_b2_r6_16x5k", "blocks": N_BLOCKS, "channels": C, "band_limit": B, "n_rings": R,
-                   "meshes_per_gpu": MESHES_PER_RANK, "vertices_per_gpu": n, "edges_per_gpu": e_kept,
-                   "fieldconv_layers": 2 * N_BLOCKS, "precision": args.precision, "parallelism": "dp%d" % world,
-                   "l2": "working set per step (>=0.9 GB of contrib per layer) exceeds the 126 MB L2; no explicit flush",
-                   "step": "forward + backward + NCCL grad all-reduce (N>1) + Adam"},
+        "config": cfg,
+        "measured": {"vertices_per_gpu": n, "edges_per_gpu": e_kept},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms, "includes": "H2D of x + raw mesh attributes from pinned memory, device plan build "
                                                    "(FCPrecomp + 2 CSR sorts), fwd+bwd+Adam, async D2H of the loss into pinned memory "
@@ -394,30 +550,93 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "kernel_shares": shares,
         "library_ms_per_step": lib_ms,
+        "partition_parity": parity,
+        "cfg4": cfg4,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("bench.py: the vertex-partitioned layer disagrees with the single-GPU layer: %s" % json.dumps(parity))
 
 
 # ----------------------------------------------------------------------------- cfg 4: one large mesh, vertex partition
-def run_partitioned(args):
-    """BASELINE.json configs[3]: a single side^2-vertex torus mesh (64 support edges/vertex), C=64, band_limit=1,
-    n_rings=6, one FCResNetBlock (2 FieldConv layers) + |x| -> Linear -> CE; vertex-partitioned across the ranks,
-    halo rows exchanged over NCCL/NVLink and overlapped with the interior rows; strong scaling."""
+def partition_parity(world, rank, dev):
+    """NCCL parity of the vertex-partitioned path (run by every rank, N >= 2): one FCResNetBlock(32,32,B=1,R=6) on a
+    ~100k-vertex mesh, partitioned across the ranks (halo exchange over NCCL, overlapped with the interior rows), against
+    the same block on the whole mesh on one GPU.  Matches nn/field_conv.py:130-134 (one-hop gather) of the reference.
+    Returns normwise relative errors (max-norm, L2) of y, grad x and the parameter gradients; ok = all <= 1e-5 (2e-5 for the
+    modReLU bias gradients, as in tests/test_gpu_parity.py)."""
     import torch.distributed as dist
     import fieldconv_b200 as fcb
-    from fieldconv_b200 import _lib
+    from fieldconv_b200.synthetic import random_features, torus_mesh
+    c, b, r, side = 32, 1, 6, 316
+    mesh = torus_mesh(side, deg=DEG, seed=5, device=dev)
+    n = mesh.num_nodes
+    torch.manual_seed(1)
+    blk = fcb.FCResNetBlock(c, c, b, r, 1).to(dev)
+    x = random_features(n, c, seed=11, device=dev)
+    gy = random_features(n, c, seed=12, zero_frac=0, device=dev)
+    part = fcb.partition_mesh(mesh, world, rank)
+    own = part.own_global
+    xo = x[own].contiguous().requires_grad_(True)
+    y = blk(xo, part)
+    y.backward(gy[own].contiguous())
+    fcb.allreduce_gradients(list(blk.parameters()))
+    y_all = torch.zeros(n, c, dtype=torch.complex64, device=dev)
+    gx_all = torch.zeros(n, c, dtype=torch.complex64, device=dev)
+    y_all[own] = y.detach()
+    gx_all[own] = xo.grad
+    for t in (y_all, gx_all):
+        dist.all_reduce(torch.view_as_real(t))
+    out = None
+    if rank == 0:
+        gp = {k: p.grad.detach().clone() for k, p in blk.named_parameters()}
+        for p in blk.parameters():
+            p.grad = None
+        plan = fcb.build_plan(mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp, mesh.w, r, mesh.epsilon)
+        xr = x.clone().requires_grad_(True)
+        y_ref = blk(xr, plan)
+        y_ref.backward(gy)
+
+        def rel(a, bb):
+            d = (a - bb).abs()
+            return max(float(d.max() / bb.abs().max().clamp_min(1e-30)),
+                       float(torch.linalg.vector_norm(d.reshape(-1)) / torch.linalg.vector_norm(bb.reshape(-1)).clamp_min(1e-30)))
+        errs = {"y": rel(y_all, y_ref.detach()), "gx": rel(gx_all, xr.grad)}
+        ok = errs["y"] <= 1e-5 and errs["gx"] <= 1e-5
+        worst_p, worst_b = 0.0, 0.0
+        for k, p in blk.named_parameters():
+            e = rel(gp[k], p.grad)
+            if "bias" in k:
+                worst_b = max(worst_b, e)
+            else:
+                worst_p = max(worst_p, e)
+        errs["param_grads"], errs["bias_grads"] = worst_p, worst_b
+        ok = ok and worst_p <= 1e-5 and worst_b <= 2e-5
+        out = {"ok": bool(ok), "rel_err": errs, "tolerance": 1e-5, "world": world, "vertices": n, "edges": plan.num_edges,
+               "halo_rows_rank0": part.n_halo, "interior_rows_rank0": part.n_interior,
+               "what": "FCResNetBlock(32,32,B=1,R=6) fwd+bwd, vertex-partitioned over NCCL vs the whole mesh on rank 0"}
+    flag = torch.tensor([1 if (out is None or out["ok"]) else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    torch.cuda.synchronize()
+    del mesh, part, blk
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_cfg4(side, world, rank, dev, precision, steps, warmup, e2e):
+    """BASELINE.json configs[3]: a single side^2-vertex torus mesh (64 support edges/vertex), C=64, band_limit=1,
+    n_rings=6, one FCResNetBlock (2 FieldConv layers) + |x| -> Linear -> CE; vertex-partitioned across the ranks,
+    halo rows exchanged over NCCL/NVLink and overlapped with the interior rows; strong scaling.  The process group is the
+    caller's.  Returns the record on rank 0 (None elsewhere)."""
+    import torch.distributed as dist
+    import fieldconv_b200 as fcb
+    from fieldconv_b200 import _lib, partition as fpart
     from fieldconv_b200.synthetic import random_features, torus_mesh
     c4, b4, r4, deg4 = 64, 1, 6, 64.0
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    mesh = torus_mesh(args.side, deg=deg4, seed=0, device=dev)
+    t_setup = time.perf_counter()
+    mesh = torus_mesh(side, deg=deg4, seed=0, device=dev)
     n_global = mesh.num_nodes
     part = fcb.partition_mesh(mesh, world, rank)
     del mesh
@@ -429,15 +648,15 @@ def run_partitioned(args):
         dist.all_reduce(t)
     e_global = int(t.item())
     torch.manual_seed(0)
-    blk = fcb.FCResNetBlock(c4, c4, b4, r4, 1, precision=args.precision).to(dev)
+    blk = fcb.FCResNetBlock(c4, c4, b4, r4, 1, precision=precision).to(dev)
     head = torch.nn.Linear(c4, N_CLASSES).to(dev)
     params = list(blk.parameters()) + list(head.parameters())
     opt = torch.optim.Adam(params, lr=0.01)
     x_own = random_features(n_global, c4, seed=1, device=dev)[part.own_global].contiguous()
     labels = torch.randint(0, N_CLASSES, (n_global,), device=dev, generator=torch.Generator(device=dev).manual_seed(0))
     labels = labels[part.own_global].contiguous()
-    host_x, host_lab = x_own.cpu().pin_memory(), labels.cpu().pin_memory()
     loss_fn = torch.nn.CrossEntropyLoss(reduction="sum")
+    setup_s = time.perf_counter() - t_setup
 
     def step(x, lab):
         opt.zero_grad(set_to_none=True)
@@ -459,74 +678,105 @@ def run_partitioned(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(x_own, labels)
     barrier()
-    t_begin = time.perf_counter()
     l0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(x_own, labels)
     ev1.record()
     barrier()
     launches = _lib.launch_count() - l0
-    ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
-    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / steps
     value = e_global * 2 / (ms_step * 1e-3)
+    rec = {"workload": "partitioned_mesh_%dx%d_c64_b1_r6_deg64" % (side, side), "vertices": n_global, "edges": e_global,
+           "fieldconv_layers": 2, "n_gpus": world, "scaling": "strong", "steps": steps, "warmup": warmup,
+           "ms_per_step": ms_step, "value": value, "unit": UNIT, "gpu_launches": launches, "setup_s": round(setup_s, 2),
+           "parallelism": "vertex-partition x%d + NCCL halo exchange overlapped with interior rows" % world,
+           "step": "forward + backward + halo exchanges + NCCL grad all-reduce + Adam",
+           "backward": "no contrib kept or recomputed: gW from G and xhat (csrc/api.cu backward_common)"}
+    if e2e:
+        host_x, host_lab = x_own.cpu().pin_memory(), labels.cpu().pin_memory()
 
-    def e2e_step():
-        return float(step(host_x.to(dev, non_blocking=True), host_lab.to(dev, non_blocking=True)).item())
-    e2e_step()
-    barrier()
-    n_e2e = max(2, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(n_e2e):
+        def e2e_step():
+            return float(step(host_x.to(dev, non_blocking=True), host_lab.to(dev, non_blocking=True)).item())
         e2e_step()
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_e2e
-    # one more step with per-launch CUDA events (every rank runs it: the step contains collectives)
+        barrier()
+        n_e2e = max(2, min(steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_e2e
+        rec["e2e"] = {"value": e_global * 2 / (e2e_ms * 1e-3), "unit": UNIT,
+                      "h2d_bytes_per_step": host_x.numel() * 8 + host_lab.numel() * 8, "d2h_bytes_per_step": 4,
+                      "ms_per_step": e2e_ms, "includes": "H2D of this rank's features + labels (pinned), step, D2H loss; "
+                                                         "the static partition/plan is built once"}
+    # exposed communication: events around the halo exchanges of one more step (every rank runs it: collectives inside)
+    fpart.HALO_TIMING = []
     if rank == 0:
         _lib.profile_enable(1 << 12)
     step(x_own, labels)
     barrier()
+    halo = fpart.collect_halo_timing()
+    fpart.HALO_TIMING = None
+    comm = torch.tensor([halo["exposed_ms"], halo["comm_ms"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(comm, op=dist.ReduceOp.MAX)
+    rec["halo"] = {"rows_rank0": part.n_halo, "owned_rank0": part.n_own, "interior_rank0": part.n_interior,
+                   "bytes_per_layer_per_direction_rank0": part.n_halo * c4 * 8,
+                   "exposed_ms_per_step_max_rank": float(comm[0].item()), "comm_ms_per_step_max_rank": float(comm[1].item()),
+                   "definition": "comm = device time of the halo send/recv on the side stream; exposed = time the compute stream "
+                                 "waited for it (CUDA events), summed over the 2 layers x 2 directions of one step"}
+    out = None
     if rank == 0:
-        hbm, _, which = peaks()
         tot = {}
         for name, ms in _lib.profile_collect(1 << 12):
             a = tot.setdefault(name, [0, 0.0])
             a[0] += 1
             a[1] += ms
-        shares = {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1])}
-        n_own = part.n_own
-        agg = tot.get("aggregate", [1, 0.0])
-        per_launch = e_local * 24 + (n_own + 1) * 4 + part.n_ext * c4 * 8 + n_own * r4 * c4 * (2 * b4 + 1) * 8
-        avg_ms = agg[1] / max(agg[0], 1)
-        roof = {"kernel": "k_aggregate", "bound": "hbm", "achieved": per_launch / max(avg_ms, 1e-9) / 1e6, "peak": hbm,
-                "unit": "GB/s", "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms, "peak_source": which,
-                "traffic": None}
-        roof["frac"] = roof["achieved"] / roof["peak"]
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": "partitioned_mesh_%dx%d_c64_b1_r6_deg64" % (args.side, args.side), "vertices": n_global,
-                           "edges": e_global, "fieldconv_layers": 2, "precision": args.precision,
-                           "parallelism": "vertex-partition x%d + NCCL halo exchange overlapped with interior rows" % world,
-                           "rank0": {"owned": part.n_own, "interior": part.n_interior, "halo": part.n_halo},
-                           "l2": "per-layer working set (>= 4 GB of contrib per rank) exceeds the 126 MB L2",
-                           "step": "forward + backward + halo exchanges + NCCL grad all-reduce + Adam"},
-                "e2e": {"value": e_global * 2 / (e2e_ms * 1e-3), "unit": UNIT,
-                        "h2d_bytes_per_step": host_x.numel() * 8 + host_lab.numel() * 8, "d2h_bytes_per_step": 4,
-                        "ms_per_step": e2e_ms, "includes": "H2D of this rank's features + labels (pinned), step, D2H loss; "
-                                                           "the static partition/plan is built once"},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_ms_rank0": shares}
+        rec["kernel_ms_rank0"] = {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1])}
+        out = rec
+    del blk, head, opt, params, plan, part, x_own, labels
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_partitioned(args):
+    """`--workload cfg4`: the cfg-4 record as the bench line itself."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    parity = partition_parity(world, rank, dev) if world > 1 else None
+    t_begin = time.perf_counter()
+    rec = measure_cfg4(args.side, world, rank, dev, args.precision, args.steps, args.warmup, e2e=True)
+    if rank == 0:
+        clocks = sampler.stop(t_begin, time.perf_counter())
+        e2e = rec.pop("e2e")
+        line = {"metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": rec["workload"], "vertices": rec["vertices"], "edges": rec["edges"], "fieldconv_layers": 2,
+                           "precision": args.precision, "parallelism": rec["parallelism"],
+                           "l2": "per-layer working set (GBs of G per rank) exceeds the 126 MB L2", "step": rec["step"]},
+                "e2e": e2e, "gpu_launches": rec["gpu_launches"], "clocks": clocks, "halo": rec["halo"],
+                "kernel_ms_rank0": rec["kernel_ms_rank0"], "partition_parity": parity}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("bench.py: partition parity failed: %s" % json.dumps(parity))
 
 
 def main():
@@ -541,6 +791,8 @@ def main():
                     help="cfg2 (default, the driver's line): FC-ResNet on a batch of 16 meshes per GPU, data parallel; "
                          "cfg4: one large mesh vertex-partitioned across the GPUs with NVLink halo exchange (strong scaling)")
     ap.add_argument("--side", type=int, default=2000, help="cfg4: the mesh has side^2 vertices (2000 -> 4M)")
+    ap.add_argument("--cfg4-side", type=int, default=2000, help="side of the cfg-4 sub-record's mesh inside the default run")
+    ap.add_argument("--skip-cfg4", action="store_true", help="kernel A/B runs only: omit the cfg-4 sub-record and the NCCL partition parity")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

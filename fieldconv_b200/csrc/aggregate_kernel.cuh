@@ -22,44 +22,28 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
 __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 
-// One decoded plan record as the edge loop consumes it (k_aggregate stages these in shared memory, once per record):
-// the complex factors come with their 90-degree rotations so that every complex product below is one FMUL2 + one FFMA2
-// with a broadcast scalar (a b = a.x (b.x, b.y) + a.y (-b.y, b.x)) instead of two FMUL + two FFMA.
-struct EdgeOps {
-    float2 wxp, iwxp;      // wxp (conjugated for the transposed operator, operand scale folded in) and i * wxp
-    float2 q0, miq0;       // e^{i theta} (conjugated when transposed) and -i * q0
-};
-
 // Frequencies 0 and +1 by complex products, the others by the three-term recurrence of a unit-modulus rotation,
 // z q^(m+1) = 2 Re(q) z q^m - z q^(m-1)  (and z conj(q) = 2 Re(q) z - z q exactly): one FFMA2 per new frequency.
 // Deviation from the product form: <= 4e-7 normwise at |m| = 2, 8e-7 at |m| = 3 (|q|^2 = 1 +- 5e-7 enters linearly),
-// inside the fp32 reference's own noise.
-// CM2: the three complex products as FMUL2 + FFMA2 pairs (fewer issue slots, 8 more FMA-pipe cycles per edge for the
-// rotated copy of q) instead of scalar FMUL / FFMA (experiment switch FIELDCONV_B200_AGG_CM2).
-template <int B, bool TRANSPOSE, bool CM2>
-__device__ __forceinline__ void edge_products(float2 z, const EdgeOps& e, float2* p) {
-    if (CM2) p[B] = __ffma2_rn(bc2(z.y), e.iwxp, __fmul2_rn(bc2(z.x), e.wxp));        // wxp * z
-    else p[B] = cmul(e.wxp, z);
+// inside the fp32 reference's own noise.  wxp and q0 arrive decoded for the direction (conjugated for the transposed
+// operator, the packed path's operand scale folded into wxp).  (Measured and dropped, r02c: the three complex products as
+// FMUL2 + FFMA2 pairs on pre-rotated operands — 3 fewer issue slots but 8 more FMA-pipe cycles per edge, no change in time.)
+template <int B, bool TRANSPOSE>
+__device__ __forceinline__ void edge_products(float2 z, float2 wxp, float2 q0, float2* p) {
+    p[B] = cmul(wxp, z);
     if (B == 0) return;
-    float2 q, iq;
+    float2 q;
     if (!TRANSPOSE) {
         // branch-free: at origin entries (|re|,|im| < 1e-7) the selects discard the inf/NaN of rsqrt(0)
         const bool origin = (fabsf(z.x) < 1e-7f) && (fabsf(z.y) < 1e-7f);
         const float ri = rsqrt_ftz(fmaf(z.x, z.x, z.y * z.y));
         const float ux = origin ? 1.f : z.x * ri;
         const float uy = origin ? 0.f : z.y * ri;
-        if (CM2) {
-            q = __ffma2_rn(bc2(uy), e.miq0, __fmul2_rn(bc2(ux), e.q0));                 // q0 * conj(u)
-            iq = __ffma2_rn(bc2(uy), e.q0, __fmul2_rn(bc2(ux), neg2(e.miq0)));          // i * q
-        } else {
-            q = cmul_conj(e.q0, make_float2(ux, uy));
-        }
+        q = cmul_conj(q0, make_float2(ux, uy));
     } else {
-        q = e.q0;
-        iq = neg2(e.miq0);
+        q = q0;
     }
-    if (CM2) p[B + 1] = __ffma2_rn(bc2(p[B].y), iq, __fmul2_rn(bc2(p[B].x), q));      // p0 * q
-    else p[B + 1] = cmul(p[B], q);
+    p[B + 1] = cmul(p[B], q);
     const float2 c2 = bc2(2.f * q.x);
     p[B - 1] = __ffma2_rn(c2, p[B], neg2(p[B + 1]));
 #pragma unroll
@@ -128,7 +112,7 @@ __device__ __forceinline__ void store_ring_packed(uint8_t* __restrict__ row_base
     }
 }
 
-constexpr int AGG_CAP = 768;           // plan records staged per CTA and chunk (36 KB of shared memory)
+constexpr int AGG_CAP = 768;           // plan records staged per CTA and chunk (24 KB of shared memory)
 
 // The two live rings sit in two fixed accumulator sets selected by ring
 // parity (ring r lives in acc[r & 1]), so sliding the two-ring window costs one store + one clear, no moves.
@@ -139,9 +123,9 @@ constexpr int AGG_CAP = 768;           // plan records staged per CTA and chunk 
 // MINB: minimum resident CTAs per SM the register allocation is held to (3 for band limits <= 2: 80 registers).
 //
 // Records: the CTA's plan records (one contiguous CSR range, ~11 rows x 40 edges at C = 48) are copied into shared
-// memory with coalesced loads first and DECODED once per record instead of once per lane and edge (EdgeOps: ring weights
-// of the even / odd accumulator set, conjugation of the transposed operator, the packed path's operand scale folded into
-// wxp, the rotated factors of the FFMA2 complex products); in the edge loop a record is three LDS.128 and the neighbour
+// memory with coalesced loads first and DECODED once per record instead of once per lane and edge (ring weights of the
+// even / odd accumulator set, conjugation of the transposed operator, the packed path's operand scale folded into
+// wxp); in the edge loop a record is two LDS.128 and the neighbour
 // id of the next edge is known without a global load, so the feature gather never waits on a record.  Ranges longer than
 // AGG_CAP records are staged chunk by chunk (any vertex degree).  The feature row of edge p+1 is in flight in registers
 // while edge p is accumulated.
@@ -150,7 +134,7 @@ constexpr int AGG_CAP = 768;           // plan records staged per CTA and chunk 
 // 0.386 / 0.319 ms; 1M vertices x C=32: 2.74 / 2.53 -> 2.43 / 2.10 ms.  Deeper feature prefetch (two edges ahead in
 // registers, or a four-deep cp.async ring in shared memory) measured 2-4 % slower: after staging the kernel is bound by
 // instruction issue and the FMA pipe (ncu r02b: issue-active 70 %, FMA pipe 59 %), not by gather latency.
-template <int B, bool TRANSPOSE, bool PACK, int MINB, bool CM2>
+template <int B, bool TRANSPOSE, bool PACK, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restrict__ feat, const int32_t* __restrict__ rowptr,
                                                       const int4* __restrict__ rec, const float2* __restrict__ rot,
                                                       float4* __restrict__ out, int64_t N, int C, int R,
@@ -165,8 +149,7 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
     const bool valid = row < N;
     float mx = 0.f;
     __shared__ int4 s_a[AGG_CAP];        // {nbr | f << 27, weight of the even ring set, weight of the odd ring set, -}
-    __shared__ float4 s_b[AGG_CAP];      // {wxp, i wxp}
-    __shared__ float4 s_c[AGG_CAP];      // {q0, -i q0}
+    __shared__ float4 s_b[AGG_CAP];      // {wxp, q0}: conjugated for the transposed operator, operand scale folded into wxp
 
     // PK addressing of this lane: first byte of its row inside (row tile, chunk 0, hi plane); real column of (ring 0, m = -B)
     uint8_t* pk_row = nullptr;
@@ -242,8 +225,7 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
             const float wx = __int_as_float(rc.z) * pk_s, wy = (TRANSPOSE ? -__int_as_float(rc.w) : __int_as_float(rc.w)) * pk_s;
             const float qx = rt.x, qy = TRANSPOSE ? -rt.y : rt.y;
             s_a[i] = make_int4(rc.x, __float_as_int(odd ? t : omt), __float_as_int(odd ? omt : t), 0);
-            s_b[i] = make_float4(wx, wy, -wy, wx);
-            s_c[i] = make_float4(qx, qy, qy, -qx);
+            s_b[i] = make_float4(wx, wy, qx, qy);
         }
         __syncthreads();
         const int a = max(p0, lo) - lo, b = min(p1, hi) - lo;      // this lane's edges inside the chunk
@@ -256,20 +238,15 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
                 const float4 v = vA;
                 vA = __ldg(row_of(min(i + 1, last)));
                 const int4 ra = s_a[i];
-                const float4 rb = s_b[i], rc4 = s_c[i];
+                const float4 rb = s_b[i];
                 const int f = (int)((uint32_t)ra.x >> NBR_BITS);
                 while (fcur < f) retire(fcur++);
-                EdgeOps eo;
-                eo.wxp = make_float2(rb.x, rb.y);
-                eo.iwxp = make_float2(rb.z, rb.w);
-                eo.q0 = make_float2(rc4.x, rc4.y);
-                eo.miq0 = make_float2(rc4.z, rc4.w);
                 const float2 w00 = bc2(__int_as_float(ra.y)), w11 = bc2(__int_as_float(ra.z));
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
                     const float2 z = ch ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
                     float2 pr[M];
-                    edge_products<B, TRANSPOSE, CM2>(z, eo, pr);
+                    edge_products<B, TRANSPOSE>(z, make_float2(rb.x, rb.y), make_float2(rb.z, rb.w), pr);
 #pragma unroll
                     for (int m = 0; m < M; ++m) {
                         acc0[ch][m] = __ffma2_rn(w00, pr[m], acc0[ch][m]);
@@ -299,13 +276,12 @@ static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const vo
     prof_begin(PACK ? (TRANSPOSE ? "aggregate_T_pk" : "aggregate_pk") : (TRANSPOSE ? "aggregate_T" : "aggregate"), st);
 #define FCB_AGG_ARGS <<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am, pk_feat_amax, pk_norm, pk_bound)
     // resident CTAs per SM: 3 (<= 85 registers) up to band limit 2, 2 beyond (the accumulators alone take 56+ registers)
-    static const bool cm2 = [] { const char* e = getenv("FIELDCONV_B200_AGG_CM2"); return e && atoi(e) != 0; }();
     switch (B) {
-        case 0: k_aggregate<0, TRANSPOSE, PACK, 3, false> FCB_AGG_ARGS; break;
-        case 1: if (cm2) k_aggregate<1, TRANSPOSE, PACK, 3, true> FCB_AGG_ARGS; else k_aggregate<1, TRANSPOSE, PACK, 3, false> FCB_AGG_ARGS; break;
-        case 2: if (cm2) k_aggregate<2, TRANSPOSE, PACK, 3, true> FCB_AGG_ARGS; else k_aggregate<2, TRANSPOSE, PACK, 3, false> FCB_AGG_ARGS; break;
-        case 3: k_aggregate<3, TRANSPOSE, PACK, 2, false> FCB_AGG_ARGS; break;
-        case 4: k_aggregate<4, TRANSPOSE, PACK, 2, false> FCB_AGG_ARGS; break;
+        case 0: k_aggregate<0, TRANSPOSE, PACK, 3> FCB_AGG_ARGS; break;
+        case 1: k_aggregate<1, TRANSPOSE, PACK, 3> FCB_AGG_ARGS; break;
+        case 2: k_aggregate<2, TRANSPOSE, PACK, 3> FCB_AGG_ARGS; break;
+        case 3: k_aggregate<3, TRANSPOSE, PACK, 2> FCB_AGG_ARGS; break;
+        case 4: k_aggregate<4, TRANSPOSE, PACK, 2> FCB_AGG_ARGS; break;
         default: set_error("aggregate: band_limit %d unsupported", B); return FCB_E_UNSUPPORTED;
     }
 #undef FCB_AGG_ARGS

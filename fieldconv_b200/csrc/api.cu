@@ -318,6 +318,10 @@ static GwPlan gw_from_g_plan(const Dims& d, int flags) {
     const int64_t Mr = 2 * (int64_t)d.R * d.Co;
     const int64_t rows_eff = (int64_t)d.M * ((Mr + 127) / 128) * 128;
     g.split = choose_split(rows_eff, d.N, flags);
+    if ((flags & FCB_GEMM_MASK) == FCB_GEMM_TC_2XF16) {        // wide outputs (2Ci > 128) leave room for fewer accumulators
+        const int64_t cap = gemm_h_tn_max_vertices_per_split(2 * d.Ci);
+        if (cap > 0 && (d.N + g.split - 1) / g.split > cap - 64) g.split = (int)((d.N + cap - 65) / (cap - 64));
+    }
     g.n_main = 1;
     g.kps = 0;
     g.batched = (flags & FCB_GEMM_MASK) == FCB_GEMM_TC_2XF16 && (Mr % 4) == 0 &&

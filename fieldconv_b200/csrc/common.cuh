@@ -141,6 +141,7 @@ int launch_gemm_h_tn_xhat(const float* G, const float* x, float* P, int64_t Mr, 
                           int64_t k_per_split, float* parts, int n_main, const float* amax_g, void* bp_ws, size_t bp_bytes,
                           int a_packed, cudaStream_t st);
 bool gemm_h_tn_plan(int N, int64_t Kv, int split, int* n_main, int64_t* k_per_split);
+int64_t gemm_h_tn_max_vertices_per_split(int N);
 // whether the 2xFP16 kernels can consume PK operands for these shapes (same tests the dispatchers apply)
 bool gemm_pk_nn_ok(int N, int64_t K);
 bool gemm_pk_tn_ok(int64_t Mr, int N, int64_t Kv, int split);

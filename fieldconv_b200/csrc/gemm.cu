@@ -369,11 +369,22 @@ bool gemm_h_tn_plan(int N, int64_t Kv, int split, int* n_main, int64_t* k_per_sp
     const int mode = FCB_GEMM_TC_2XF16;
     int64_t kps = (Kv + split - 1) / split;
     kps = (kps + tc_stage(mode) - 1) / tc_stage(mode) * tc_stage(mode);
-    int nm = 1;
-    if (tc_plan(N, kps / tc_kstep(mode), mode, 1, &nm) < N) return false;
+    // all N columns in one accumulator tile: (n_main + 1) * Npad TMEM columns, at most 400 accumulating MMAs each
+    const int npad = (N + 15) / 16 * 16;
+    const int avail = 512 / npad - 1;
+    const int64_t need = (kps / tc_kstep(mode) + 399) / 400;
+    if (avail < 1 || need > avail) return false;
+    int nm = avail < 3 ? avail : 3;
+    if (nm < need) nm = (int)need;
     *n_main = nm;
     *k_per_split = kps;
     return true;
+}
+// vertices one split of that product may cover (its accumulators are limited to 400 accumulating MMAs of 16 vertices)
+int64_t gemm_h_tn_max_vertices_per_split(int N) {
+    const int npad = (N + 15) / 16 * 16;
+    const int avail = 512 / npad - 1;
+    return avail < 1 ? 0 : (int64_t)(avail < 3 ? avail : 3) * 400 * 16;
 }
 
 // PK operands: the same feasibility tests the dispatchers above apply (shape only; the buffers are the library's own)

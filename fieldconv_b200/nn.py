@@ -10,6 +10,7 @@ Extra, keyword-only: ``precision=`` selects the contraction arithmetic, and ``fo
 a compact ``fieldconv_b200.Plan`` instead of (supp_edges, supp_sten) — the fast path.
 """
 import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -70,6 +71,28 @@ def _resolve_precision(precision, ci, co, n_rings, band_limit):
     return _lib.GEMM_SIMT_FP32
 
 
+# Dense-stencil plans (CSR orders of the caller's supp_edges), ONE per (supp_edges tensor, N), shared by every layer of the
+# network.  Keyed on the tensor OBJECT (id + in-place version) and validated through a weak reference, so an address the
+# caching allocator hands to the next batch can never match a stale entry; the entry dies with the tensor.
+_DENSE_PLANS = {}
+
+
+def shared_dense_plan(supp_edges, n):
+    key = (id(supp_edges), supp_edges._version, int(supp_edges.shape[0]), int(n))
+    hit = _DENSE_PLANS.get(key)
+    if hit is not None and hit[0]() is supp_edges:
+        return hit[1]
+    plan = build_dense_plan(supp_edges, n)
+    for k in [k for k in _DENSE_PLANS if k[0] == key[0]]:        # older versions / sizes of the same object
+        del _DENSE_PLANS[k]
+    _DENSE_PLANS[key] = (weakref.ref(supp_edges, lambda _r, k=key: _DENSE_PLANS.pop(k, None)), plan)
+    return plan
+
+
+def _param_versions(m):
+    return tuple(p._version for p in (m.zonal, m.spherical, m.phase))
+
+
 def fold_weights(zonal, spherical, phase, ftype, band_limit):
     """(zonal, spherical, phase) -> W (Co,Ci,R,2B+1) complex with y = sum contrib * W, i.e. the
     coefficient tensors of weightContribReal / Offset / Complex divided by 2B+1
@@ -105,7 +128,7 @@ def prefold(module):
         w = fold_weights(torch.stack([m.zonal for m in layers]), torch.stack([m.spherical for m in layers]),
                          torch.stack([m.phase for m in layers]), ftype, band_limit)
         for m, wi in zip(layers, w.unbind(0)):
-            m._prefolded = wi
+            m._prefolded = (wi, _param_versions(m))       # valid only while the parameters are unchanged
     lins = {}
     for m in module.modules():
         if isinstance(m, TangentLin):
@@ -114,7 +137,7 @@ def prefold(module):
         if len(layers) > 1:
             emb = _lin_embedding(torch.stack([m.Re for m in layers]), torch.stack([m.Im for m in layers]))
             for m, e in zip(layers, emb.unbind(0)):
-                m._preemb = e
+                m._preemb = (e, (m.Re._version, m.Im._version))
 
 
 def _lin_embedding(Re, Im):
@@ -147,21 +170,18 @@ class FieldConv(nn.Module):
             self.register_buffer("phase", torch.zeros(out_channels, in_channels, band_limit + 1))
         nn.init.xavier_uniform_(self.zonal)
         nn.init.xavier_uniform_(self.spherical)
-        self._dense_cache = None
         self._prefolded = None
 
     def weight(self):
-        w = self._prefolded
-        if w is not None:                 # handed over by prefold() for exactly one forward
-            self._prefolded = None
-            return w
+        pre, self._prefolded = self._prefolded, None
+        # handed over by prefold() for exactly one forward, and only while the parameters it was folded from are
+        # unchanged (a layer skipped in that forward must not run on pre-optimizer-step weights later)
+        if pre is not None and pre[1] == _param_versions(self):
+            return pre[0]
         return fold_weights(self.zonal, self.spherical, self.phase, self.ftype, self.B)
 
     def _dense_plan(self, supp_edges, n):
-        key = (supp_edges.data_ptr(), supp_edges.shape[0], supp_edges._version, n)
-        if self._dense_cache is None or self._dense_cache[0] != key:
-            self._dense_cache = (key, build_dense_plan(supp_edges, n))
-        return self._dense_cache[1]
+        return shared_dense_plan(supp_edges, n)
 
     def forward(self, x, supp_edges=None, supp_sten=None, *, plan=None):
         if isinstance(supp_edges, (Plan, DensePlan, MeshPartition)):
@@ -180,9 +200,18 @@ class FieldConv(nn.Module):
             w = torch.cat((w, torch.zeros_like(w[:, :1])), dim=1)
         if co % 2:
             w = torch.cat((w, torch.zeros_like(w[:1])), dim=0)
+        if supp_sten is not None:
+            if tuple(supp_sten.shape[1:]) != (self.R, 2 * self.B + 1):
+                raise ValueError("supp_sten must be (E, %d, %d), got %s" % (self.R, 2 * self.B + 1, tuple(supp_sten.shape)))
+            if supp_edges is not None and supp_sten.shape[0] != supp_edges.shape[0]:
+                raise ValueError("supp_sten has %d edges, supp_edges %d" % (supp_sten.shape[0], supp_edges.shape[0]))
         if plan is None and supp_sten is not None:
             # (supp_edges, supp_sten) straight from fieldconv_b200.FCPrecomp: use the compact plan it was expanded from
             plan = attached_plan(supp_edges, supp_sten, self.R, x.shape[0])
+        if plan is not None and x.shape[0] != plan.num_nodes:
+            # the reference raises an index error on a mismatched (features, mesh) pair; here it would be an out-of-bounds
+            # gather on the device
+            raise ValueError("x has %d rows, the plan was built for %d vertices" % (x.shape[0], plan.num_nodes))
         if plan is not None and not plan.dense:
             if plan.n_rings != self.R:
                 raise ValueError("plan was built for n_rings=%d, layer has %d" % (plan.n_rings, self.R))
@@ -193,9 +222,9 @@ class FieldConv(nn.Module):
             flags &= ~_lib.FLAG_PACKED
             if supp_sten is None:
                 raise ValueError("forward needs (supp_edges, supp_sten) or a compact plan")
-            if tuple(supp_sten.shape[1:]) != (self.R, 2 * self.B + 1):
-                raise ValueError("supp_sten must be (E, %d, %d)" % (self.R, 2 * self.B + 1))
             dplan = plan if plan is not None else self._dense_plan(supp_edges, x.shape[0])
+            if dplan.e_cap != supp_sten.shape[0]:
+                raise ValueError("the dense plan was built for %d edges, supp_sten has %d" % (dplan.e_cap, supp_sten.shape[0]))
             y = ops.field_conv_dense(x, w, supp_sten, dplan, flags)
         return y[:, :co] if co % 2 else y
 
@@ -218,7 +247,8 @@ class TangentLin(nn.Module):
 
     def forward(self, x):
         ci, co = self.in_channels, self.out_channels
-        emb, self._preemb = self._preemb, None                  # handed over by prefold() for exactly one forward
+        pre, self._preemb = self._preemb, None                  # handed over by prefold() for exactly one forward
+        emb = pre[0] if (pre is not None and pre[1] == (self.Re._version, self.Im._version)) else None
         if emb is None:
             emb = _lin_embedding(self.Re, self.Im)              # (2Ci, 2Co)
         xr = torch.view_as_real(x.contiguous()).reshape(x.shape[0], 2 * ci)

@@ -189,6 +189,22 @@ def halo_backward_add(g_own, g_halo, part):
 
 
 # ----------------------------------------------------------------------------- the partitioned layer (CUDA)
+# bench.py sets HALO_TIMING = [] for one step: every exchange then records (comm start, comm end, compute-stream wait start,
+# wait end) CUDA events; collect_halo_timing() turns them into the communication time and its exposed (non-overlapped) part
+HALO_TIMING = None
+
+
+def _timing_events():
+    return [torch.cuda.Event(enable_timing=True) for _ in range(4)] if HALO_TIMING is not None else None
+
+
+def collect_halo_timing():
+    torch.cuda.synchronize()
+    comm = sum(e[0].elapsed_time(e[1]) for e in (HALO_TIMING or []))
+    exposed = sum(e[2].elapsed_time(e[3]) for e in (HALO_TIMING or []))
+    return {"comm_ms": comm, "exposed_ms": exposed, "exchanges": len(HALO_TIMING or [])}
+
+
 class _PartitionedFieldConv(torch.autograd.Function):
     """FieldConv over the owned rows with the halo exchange overlapped:
        forward : [comm stream] halo rows of x      || [main] interior rows;  then boundary rows
@@ -209,10 +225,15 @@ class _PartitionedFieldConv(torch.autograd.Function):
         ready = torch.cuda.Event()
         ready.record(main)
         done = torch.cuda.Event()
+        tev = _timing_events()
         with torch.cuda.stream(comm):
             comm.wait_event(ready)
+            if tev:
+                tev[0].record(comm)
             halo = halo_forward(x_own, part)
             x_ext[n_own:].copy_(halo)
+            if tev:
+                tev[1].record(comm)
             done.record(comm)
         y = torch.empty(n_own, co, dtype=torch.complex64, device=dev)
         keep = ops.keep_contrib_default(n_own * k * 8, dev)
@@ -231,7 +252,12 @@ class _PartitionedFieldConv(torch.autograd.Function):
 
         with torch.cuda.device(dev):
             rows(0, n_int)                       # interior: every source is local
+            if tev:
+                tev[2].record(main)
             main.wait_event(done)
+            if tev:
+                tev[3].record(main)
+                HALO_TIMING.append(tev)
             rows(n_int, n_own)                   # boundary: needs the halo rows
         halo.record_stream(main)
         ctx.part, ctx.cfg = part, (band_limit, flags)
@@ -289,12 +315,22 @@ class _PartitionedFieldConv(torch.autograd.Function):
             back_done = torch.cuda.Event()
             own_ready = torch.cuda.Event()
             own_ready.record(main)
+            tev = _timing_events()
             with torch.cuda.stream(comm):
                 comm.wait_event(halo_ready)
                 comm.wait_event(own_ready)       # the adds below touch gx_own
+                if tev:
+                    tev[0].record(comm)
                 halo_backward_add(gx_own, gx_ext[n_own:], part)
+                if tev:
+                    tev[1].record(comm)
                 back_done.record(comm)
+            if tev:
+                tev[2].record(main)
             main.wait_event(back_done)
+            if tev:
+                tev[3].record(main)
+                HALO_TIMING.append(tev)
         return gx_own, gw, None, None, None
 
 
@@ -316,6 +352,8 @@ def partitioned_field_conv(layer, x_own, part):
     ci, co = layer.in_channels, layer.out_channels
     if ci % 2 or co % 2:
         raise ValueError("partitioned FieldConv needs even channel counts")
+    if x_own.shape[0] != part.n_own or x_own.shape[1] != ci:
+        raise ValueError("x_own must be (%d owned rows, %d channels), got %s" % (part.n_own, ci, tuple(x_own.shape)))
     flags = _resolve_precision(layer.precision, ci, co, layer.R, layer.B) & _lib.GEMM_MASK   # row sub-ranges: fp32 operand layout
     return _PartitionedFieldConv.apply(x_own, layer.weight(), part, layer.B, flags)
 

@@ -162,6 +162,46 @@ def test_prefold_tangent_lin_embedding_matches():
         assert torch.allclose(y, y_ref, rtol=1e-5, atol=1e-6)
     fcb.prefold(net)
     for m in net:
-        assert torch.equal(m._preemb, _lin_embedding(m.Re, m.Im))
-    g = torch.autograd.grad(sum(m._preemb.sum() for m in net), [m.Re for m in net])
+        assert torch.equal(m._preemb[0], _lin_embedding(m.Re, m.Im))
+    g = torch.autograd.grad(sum(m._preemb[0].sum() for m in net), [m.Re for m in net])
     assert all(torch.allclose(gi, torch.zeros_like(gi) + 2.0) for gi in g)   # every Re entry appears twice in E
+
+
+def test_prefold_handoff_goes_stale_with_the_parameters():
+    """A layer that did not run in the forward prefold() was called for must not use the pre-optimizer-step filter later
+    (ADVICE r1): the hand-over is tagged with the parameters' versions."""
+    torch.manual_seed(3)
+    net = torch.nn.ModuleList([fcb.FieldConv(4, 4, 1, 3, 1) for _ in range(2)])
+    fcb.prefold(net)
+    w_old = net[1]._prefolded[0].detach().clone()
+    with torch.no_grad():
+        net[1].zonal.add_(1.0)                      # what an optimizer step does
+    w = net[1].weight()                              # the stale hand-over is ignored and dropped
+    assert net[1]._prefolded is None
+    assert not torch.equal(w.detach(), w_old)
+    assert torch.equal(w, fcb.nn.fold_weights(net[1].zonal, net[1].spherical, net[1].phase, 1, 1))
+    assert torch.equal(net[0].weight().detach(), fcb.nn.fold_weights(net[0].zonal, net[0].spherical, net[0].phase, 1, 1).detach())
+
+
+def test_shared_dense_plan_cache_is_keyed_on_the_tensor_object():
+    """the dense-path plan cache must not be fooled by a recycled device address — it keys on the tensor object
+    (validated through a weak reference) and one plan serves every layer."""
+    from fieldconv_b200 import nn as fnn
+    calls = []
+    orig = fnn.build_dense_plan
+    fnn.build_dense_plan = lambda e, n: calls.append((id(e), n)) or ("plan", len(calls))
+    try:
+        fnn._DENSE_PLANS.clear()
+        e1 = torch.zeros(5, 2, dtype=torch.long)
+        p1 = fnn.shared_dense_plan(e1, 4)
+        assert fnn.shared_dense_plan(e1, 4) is p1 and len(calls) == 1          # shared across layers / calls
+        e2 = torch.zeros(5, 2, dtype=torch.long)                                 # same shape, same contents, another object
+        assert fnn.shared_dense_plan(e2, 4) is not p1 and len(calls) == 2
+        e1.add_(1)                                                               # in-place edit bumps the version
+        assert fnn.shared_dense_plan(e1, 4) is not p1 and len(calls) == 3
+        del e1, e2
+        import gc
+        gc.collect()
+        assert not fnn._DENSE_PLANS                                              # entries die with their tensors
+    finally:
+        fnn.build_dense_plan = orig
