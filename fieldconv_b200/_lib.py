@@ -16,6 +16,8 @@ FLAG_HAVE_CONTRIB = 0x100
 # Python-level only (ops.py): run the layer through fcb_fwd_pk_f32 / fcb_bwd_pk_f32 (packed fp16 operand planes written by
 # the aggregation kernels, bulk-copied by the contraction kernels); never passed to the library
 FLAG_PACKED = 0x200
+# Python-level only: run the forward through fcb_fwd_fused_f32 (band_limit <= 1: contrib never leaves the SM)
+FLAG_FUSED = 0x400
 
 _P = ctypes.c_void_p
 _I64 = ctypes.c_int64
@@ -43,6 +45,8 @@ SIGNATURES = {
     "fcb_pk_contrib_bytes": [_I64, _I, _I, _I, _PSZ],
     "fcb_fwd_pk_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_bwd_pk_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_fwd_fused_workspace_bytes": [_I, _I, _I, _I, _PSZ],
+    "fcb_fwd_fused_f32": [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_aggregate_f32": [_P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _P],
     "fcb_gemm_workspace_bytes": [_I64, _I, _I64, _I, _I, _I, _I, _PSZ],
     "fcb_gemm_tc_feasible": [_I, _I64, _I, _I, _I],
@@ -79,6 +83,8 @@ def load():
             fn.restype = ctypes.c_int
         lib.fcb_pk_supported.argtypes = [_I64, _I, _I, _I, _I]
         lib.fcb_pk_supported.restype = ctypes.c_int
+        lib.fcb_fused_supported.argtypes = [_I, _I, _I, _I]
+        lib.fcb_fused_supported.restype = ctypes.c_int
         lib.fcb_last_error.argtypes = []
         lib.fcb_last_error.restype = ctypes.c_char_p
         lib.fcb_launch_count.argtypes = []
@@ -109,6 +115,11 @@ def tc_feasible(n, k, trans_a=0, split_k=1, flags=GEMM_TC_3XTF32):
 def pk_supported(n, ci, co, band_limit, n_rings):
     """Whether the packed-operand path (fcb_fwd_pk_f32 / fcb_bwd_pk_f32) takes this layer shape."""
     return bool(load().fcb_pk_supported(int(n), int(ci), int(co), int(band_limit), int(n_rings)))
+
+
+def fused_supported(ci, co, band_limit, n_rings):
+    """Whether the fused forward (fcb_fwd_fused_f32) takes this layer shape."""
+    return bool(load().fcb_fused_supported(int(ci), int(co), int(band_limit), int(n_rings)))
 
 
 def ptr(t):

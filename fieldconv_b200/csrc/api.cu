@@ -717,6 +717,27 @@ extern "C" int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, c
     return backward_common(d, x, W, gy, contrib, contrib_scale, slots + 64, gather, gx, gW, ar, flags, st, !from_g, g_pk);
 }
 
+// ------------------------------------------------------------------ fused forward (band_limit <= 1)
+extern "C" int fcb_fused_supported(int Ci, int Co, int band_limit, int R) { return fused_fwd_ok(Ci, Co, band_limit, R) ? 1 : 0; }
+
+extern "C" int fcb_fwd_fused_workspace_bytes(int Ci, int Co, int band_limit, int R, size_t* bytes) {
+    FCB_REQUIRE(bytes, FCB_E_ARG, "fwd_fused_workspace: null");
+    FCB_REQUIRE(fused_fwd_ok(Ci, Co, band_limit, R), FCB_E_UNSUPPORTED, "fwd_fused_workspace: shape not supported (fcb_fused_supported)");
+    *bytes = fused_fwd_ws_bytes(Ci, Co, band_limit, R);
+    return FCB_OK;
+}
+
+extern "C" int fcb_fwd_fused_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
+                                 const float* rot_tgt, const float* norm_tgt, float* y, int64_t N, int64_t n_feat_rows, int Ci,
+                                 int Co, int band_limit, int R, void* ws, size_t ws_bytes, void* stream) {
+    Dims d;
+    int rc = check_dims("fwd_fused", N, Ci, Co, band_limit, R, &d);
+    if (rc) return rc;
+    FCB_REQUIRE(n_feat_rows >= N, FCB_E_ARG, "fwd_fused: n_feat_rows must be >= N");
+    return launch_fused_fwd(x, W, rowptr_tgt, rec_tgt, rot_tgt, norm_tgt, y, N, n_feat_rows, Ci, Co, band_limit, R, ws, ws_bytes,
+                            static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int fcb_fwd_dense_f32(const float* x, const float* W, const float* sten, const int32_t* rowptr_tgt,
                                  const int32_t* nbr_tgt, const int32_t* perm_tgt, float* y, float* contrib,
                                  float* contrib_absmax, int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws,

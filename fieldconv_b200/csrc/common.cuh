@@ -142,6 +142,11 @@ int launch_gemm_h_tn_xhat(const float* G, const float* x, float* P, int64_t Mr, 
                           int a_packed, cudaStream_t st);
 bool gemm_h_tn_plan(int N, int64_t Kv, int split, int* n_main, int64_t* k_per_split);
 int64_t gemm_h_tn_max_vertices_per_split(int N);
+// fused forward for band_limit <= 1 (fused_fwd.cu)
+bool fused_fwd_ok(int Ci, int Co, int B, int R);
+size_t fused_fwd_ws_bytes(int Ci, int Co, int B, int R);
+int launch_fused_fwd(const float* x, const float* W, const int32_t* rowptr, const void* rec, const float* rot, const float* norm,
+                     float* y, int64_t N, int64_t n_feat, int Ci, int Co, int B, int R, void* ws, size_t ws_bytes, cudaStream_t st);
 // whether the 2xFP16 kernels can consume PK operands for these shapes (same tests the dispatchers apply)
 bool gemm_pk_nn_ok(int N, int64_t K);
 bool gemm_pk_tn_ok(int64_t Mr, int N, int64_t Kv, int split);

@@ -32,6 +32,19 @@ _PRECISIONS = {"fp32": _lib.GEMM_SIMT_FP32, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32
 PACKED_POLICY = os.environ.get("FIELDCONV_B200_PACKED", "auto")
 
 
+# FIELDCONV_B200_FUSED=1: the fused forward (gather -> shared-memory tile -> tcgen05, csrc/fused_fwd.cu) wherever the shape
+# is supported (band_limit <= 1, Ci % 32 == 0, Co <= 128) and nothing of size N x K has to be kept; =0: never.
+FUSED_POLICY = os.environ.get("FIELDCONV_B200_FUSED", "0")
+
+
+def fused_flags(flags, plan, ci, co, band_limit, n_rings):
+    if FUSED_POLICY != "1" or (flags & _lib.GEMM_MASK) != _lib.GEMM_TC_2XF16 or ops.SAVE_CONTRIB:
+        return flags
+    if getattr(plan, "norms", None) is None or not _lib.fused_supported(ci, co, band_limit, n_rings):
+        return flags
+    return flags | _lib.FLAG_FUSED
+
+
 def _packed_by_default(band_limit):
     if PACKED_POLICY == "0":
         return False
@@ -217,6 +230,8 @@ class FieldConv(nn.Module):
                 raise ValueError("plan was built for n_rings=%d, layer has %d" % (plan.n_rings, self.R))
             flags = packed_flags(flags, plan, x.shape[0], x.shape[1], w.shape[0], self.B, self.R, self.precision == "2xf16p",
                                  auto=self.precision == "auto")
+            if self.precision in ("auto", "2xf16", "2xf16p"):
+                flags = fused_flags(flags, plan, x.shape[1], w.shape[0], self.B, self.R)
             y = ops.field_conv(x, w, plan, self.B, flags)
         else:
             flags &= ~_lib.FLAG_PACKED

@@ -60,8 +60,17 @@ def fc_fwd(x: Tensor, W: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: T
     co = W.shape[0]
     k = n_rings * ci * (2 * band_limit + 1)
     packed = bool(flags & _lib.FLAG_PACKED)
-    cflags = flags & ~_lib.FLAG_PACKED
+    fused = bool(flags & _lib.FLAG_FUSED) and not keep_contrib
+    cflags = flags & ~(_lib.FLAG_PACKED | _lib.FLAG_FUSED)
     y = torch.empty(n, co, dtype=torch.complex64, device=x.device)
+    if fused:      # band_limit <= 1: one kernel, contrib never exists in device memory (csrc/fused_fwd.cu)
+        nbytes = _lib.query_bytes("fcb_fwd_fused_workspace_bytes", ci, co, band_limit, n_rings)
+        ws = _ws(nbytes, x.device)
+        with torch.cuda.device(x.device):
+            _lib.call("fcb_fwd_fused_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
+                      rot_tgt.data_ptr(), norms.data_ptr(), _real(y).data_ptr(), n, n, ci, co, band_limit, n_rings,
+                      ws.data_ptr(), nbytes, _lib.stream_ptr())
+        return y, torch.empty(0, dtype=torch.complex64, device=x.device), torch.zeros(1, dtype=torch.float32, device=x.device)
     # rows padded to whole 128-row tiles: the packed (PK) layout needs them, the fp32 layout ignores the tail
     contrib = torch.empty(_padded_rows(n), k, dtype=torch.complex64, device=x.device)
     cmax = torch.zeros(1, dtype=torch.float32, device=x.device)     # max|contrib| (or its bound): operand scale of the 2xFP16 contraction
@@ -98,7 +107,7 @@ def fc_bwd(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, cmax: Tensor, rowp
     n, ci = x.shape
     co = W.shape[0]
     packed = bool(flags & _lib.FLAG_PACKED)
-    cflags = flags & ~_lib.FLAG_PACKED
+    cflags = flags & ~(_lib.FLAG_PACKED | _lib.FLAG_FUSED)
     gx = torch.empty_like(x) if need_gx else torch.empty(0, dtype=x.dtype, device=x.device)
     gw = torch.empty_like(W) if need_gw else torch.empty(0, dtype=W.dtype, device=x.device)
     have_contrib = contrib.numel() > 0
@@ -157,8 +166,8 @@ def field_conv(x, W, plan, band_limit, flags=0, keep_contrib=None):
         keep_contrib = keep_contrib_default(n * plan.n_rings * ci * (2 * band_limit + 1) * 8, x.device)
     norms = getattr(plan, "norms", None)
     if norms is None:
-        if flags & _lib.FLAG_PACKED:
-            raise RuntimeError("fieldconv_b200: the packed path needs a plan built by build_plan (plan.norms)")
+        if flags & (_lib.FLAG_PACKED | _lib.FLAG_FUSED):
+            raise RuntimeError("fieldconv_b200: the packed / fused paths need a plan built by build_plan (plan.norms)")
         norms = torch.zeros(2, dtype=torch.float32, device=x.device)
     y, _, _ = fc_fwd(x, W, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src, plan.rot_src, norms,
                      band_limit, plan.n_rings, flags, bool(keep_contrib))

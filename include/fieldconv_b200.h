@@ -165,6 +165,19 @@ int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, const void* 
                    const float* rot_src, const float* norm_src, float* gx, float* gW, int64_t N, int Ci, int Co,
                    int band_limit, int R, int flags, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Fused forward (band_limit <= 1): gather -> shared-memory operand tile -> tcgen05 contraction in ONE kernel; the
+ * N x K `contrib` of nn/field_conv.py:130-134 never exists in device memory (csrc/fused_fwd.cu).  Same arguments as
+ * fcb_fwd_pk_f32 minus the contrib buffers; norm_tgt = fcb_plan_norm of the by-target order; n_feat_rows = rows of x
+ * (>= N; larger when the N target rows gather from halo rows behind them, fieldconv_b200/partition.py).  The backward of a layer run
+ * this way is fcb_bwd_f32 / fcb_bwd_pk_f32 with contrib == NULL (gW from G and xhat).
+ * fcb_fused_supported: 1 when the shape is taken (band_limit <= 1, Ci a multiple of 32, Co even and <= 128, at most 400
+ * accumulating MMAs per TMEM accumulator), else 0 — use fcb_fwd_f32 / fcb_fwd_pk_f32. */
+int fcb_fused_supported(int Ci, int Co, int band_limit, int R);
+int fcb_fwd_fused_workspace_bytes(int Ci, int Co, int band_limit, int R, size_t* bytes);
+int fcb_fwd_fused_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
+                      const float* norm_tgt, float* y, int64_t N, int64_t n_feat_rows, int Ci, int Co, int band_limit, int R,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ dense-stencil forward/backward
  * Exact drop-in for arbitrary supp_sten (E,R,M) complex (nn/field_conv.py:114-116), any number
  * of non-zero rings per edge.  Same outputs as above. */

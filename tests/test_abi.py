@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_binding_covers_header():
-    bound = set(_lib.SIGNATURES) | {"fcb_last_error", "fcb_launch_count", "fcb_pk_supported", "fcb_gemm_tc_feasible"}
+    bound = set(_lib.SIGNATURES) | {"fcb_last_error", "fcb_launch_count", "fcb_pk_supported", "fcb_gemm_tc_feasible", "fcb_fused_supported"}
     assert set(header_symbols()) <= bound
 
 
@@ -80,6 +80,18 @@ def test_tensor_core_accumulation_plan():
     assert _lib.tc_feasible(256, 7680, flags=3)       # two 128-column chunks, two pairs each
     assert _lib.tc_feasible(96, 80000, trans_a=1, split_k=26, flags=3)
     assert not _lib.tc_feasible(64, 10 ** 6, flags=3)
+
+
+def test_fused_forward_shape_support():
+    # host-side predicate only: band_limit <= 1, Ci a multiple of 32, Co even and <= 128, <= 400 accumulating MMAs
+    assert _lib.fused_supported(32, 32, 1, 6) and _lib.fused_supported(64, 64, 1, 6) and _lib.fused_supported(128, 128, 1, 6)
+    assert _lib.fused_supported(32, 16, 0, 2) and _lib.fused_supported(64, 48, 1, 2)
+    assert not _lib.fused_supported(48, 48, 1, 6)          # Ci not a multiple of 32
+    assert not _lib.fused_supported(32, 32, 2, 6)          # band_limit 2: the ring burst does not fit shared memory
+    assert not _lib.fused_supported(256, 256, 1, 6)        # 576 accumulating MMAs / Co too wide for one TMEM tile
+    assert _lib.query_bytes("fcb_fwd_fused_workspace_bytes", 32, 32, 1, 6) >= 18 * 2 * 64 * 64 * 2
+    with pytest.raises(RuntimeError, match="not supported"):
+        _lib.query_bytes("fcb_fwd_fused_workspace_bytes", 48, 48, 2, 6)
 
 
 def test_packed_path_shape_support_and_sizes():

@@ -69,6 +69,8 @@ def test_weight_gradient_from_g_matches_contrib_path(name, precision):
                           g["w"].to(DEV), g["R"], g["epsilon"])
     W = restate.fold_weights(g["zonal"], g["spherical"], g["phase"], g["ftype"], g["B"]).to(DEV)
     flags = fnn._PRECISIONS[precision]
+    if g["ci"] % 2 or g["co"] % 2:
+        pytest.skip("the raw op needs even channel counts (the module pads)")
     if flags & _lib.FLAG_PACKED and not _lib.pk_supported(g["x"].shape[0], g["ci"], g["co"], g["B"], g["R"]):
         pytest.skip("packed path does not support this shape")
     outs = []

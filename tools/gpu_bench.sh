@@ -8,8 +8,8 @@ export PYTHONUNBUFFERED=1
 timeout 900 python -m pytest tests -m gpu -q -x -rf --tb=short -p no:cacheprovider > $OUT/${TAG}_pytest.log 2>&1
 echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
 tail -12 $OUT/${TAG}_pytest.log
-/usr/bin/time -v timeout 900 python bench.py ${BENCH_ARGS} > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
-echo "bench exit $?"; grep -E "Elapsed|Maximum resident" $OUT/${TAG}_bench.err; tail -5 $OUT/${TAG}_bench.err | cut -c 1-600
+T0=$(date +%s); timeout 900 python bench.py ${BENCH_ARGS} > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+echo "bench exit $? wall $(( $(date +%s) - T0 )) s"; tail -5 $OUT/${TAG}_bench.err | cut -c 1-600
 python - <<PY
 import json
 try:
