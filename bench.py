@@ -475,7 +475,7 @@ def run_ours(args):
         if kb:
             ent.update({"kernel_bytes_per_launch": kb, "GBps": round(kb / (avg * 1e-3) / 1e9, 1),
                         "frac_of_hbm_peak": round(kb / (avg * 1e-3) / 1e9 / hbm, 4)})
-        if k in ncu.get("cfg2_layer", {}):
+        if isinstance(ncu.get("cfg2_layer", {}).get(k), dict):
             ent["ncu"] = ncu["cfg2_layer"][k]
         per_kernel[k] = ent
     fwd_b, all_b = contract_bytes_layer(n, e_kept, C, C, B, R)
@@ -516,9 +516,13 @@ def run_ours(args):
     # layer shape, for the dominant kernel and summed over one layer's forward + backward
     roof["traffic"] = None
     key = fam[dominant][2][0]
-    if key in ncu.get("cfg2_layer", {}):
-        roof["traffic"] = ncu["cfg2_layer"][key].get("dram_bytes")
-        roof["ncu"] = {kk: ncu["cfg2_layer"][key].get(kk) for kk in ("issue_active_pct", "fma_pipe_pct", "tensor_pipe_pct", "dram_pct")}
+    ent = ncu.get("cfg2_layer", {}).get(key)
+    if isinstance(ent, dict):
+        roof["traffic"] = ent.get("dram_bytes")
+        roof["ncu"] = {kk: ent.get(kk) for kk in ("issue_active_pct", "fma_pipe_pct", "tensor_pipe_pct", "dram_pct")}
+        roof["traffic_source"] = ncu.get("source")
+    elif ent is not None:
+        roof["traffic"] = ent
         roof["traffic_source"] = ncu.get("source")
     if "layer_dram_bytes_fwd_bwd" in ncu:
         roof["traffic_layer_fwd_bwd"] = ncu["layer_dram_bytes_fwd_bwd"]

@@ -85,7 +85,7 @@ def test_tensor_core_accumulation_plan():
 def test_fused_forward_shape_support():
     # host-side predicate only: band_limit <= 1, Ci a multiple of 32, Co even and <= 128, <= 400 accumulating MMAs
     assert _lib.fused_supported(32, 32, 1, 6) and _lib.fused_supported(64, 64, 1, 6) and _lib.fused_supported(128, 128, 1, 6)
-    assert _lib.fused_supported(32, 16, 0, 2) and _lib.fused_supported(64, 48, 1, 2)
+    assert _lib.fused_supported(32, 16, 1, 2) and _lib.fused_supported(64, 48, 1, 2)
     assert not _lib.fused_supported(48, 48, 1, 6)          # Ci not a multiple of 32
     assert not _lib.fused_supported(32, 32, 2, 6)          # band_limit 2: the ring burst does not fit shared memory
     assert not _lib.fused_supported(256, 256, 1, 6)        # 576 accumulating MMAs / Co too wide for one TMEM tile

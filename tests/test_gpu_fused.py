@@ -27,7 +27,7 @@ def _run(mesh, ci, co, B, R, flags, ftype=1, seed=0, scale=1.0):
     return m, x, gy, y
 
 
-@pytest.mark.parametrize("n_side,ci,co,B,R,ftype", [(71, 32, 32, 1, 6, 1), (30, 64, 64, 1, 6, 0), (24, 32, 16, 0, 2, 2),
+@pytest.mark.parametrize("n_side,ci,co,B,R,ftype", [(71, 32, 32, 1, 6, 1), (30, 64, 64, 1, 6, 0), (24, 32, 16, 1, 2, 2),
                                                      (20, 128, 128, 1, 6, 1), (26, 64, 48, 1, 3, 1), (17, 32, 2, 1, 2, 1)])
 def test_fused_forward_vs_fp64_oracle(n_side, ci, co, B, R, ftype):
     assert _lib.fused_supported(ci, co, B, R)

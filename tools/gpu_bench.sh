@@ -5,7 +5,7 @@ TAG=${1:-rXX}
 OUT=gpurun_out
 mkdir -p $OUT
 export PYTHONUNBUFFERED=1
-timeout 900 python -m pytest tests -m gpu -q -x -rf --tb=short -p no:cacheprovider > $OUT/${TAG}_pytest.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -rf --tb=short -p no:cacheprovider > $OUT/${TAG}_pytest.log 2>&1
 echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
 tail -12 $OUT/${TAG}_pytest.log
 T0=$(date +%s); timeout 900 python bench.py ${BENCH_ARGS} > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
