@@ -17,7 +17,8 @@
 //               swizzled) through a shared-memory ring with cp.async.bulk (TMA engine) and issues the MMAs of every completed
 //               ring:  [main | cross] += A_hi [W_hi | W_lo]  (one MMA of width 2 Npad),  cross += A_lo W_hi  — the 2xFP16
 //               scheme of gemm_h.cu, fp32 accumulators in TMEM, at most 400 accumulating MMAs per accumulator.
-//   all warps   epilogue: tcgen05.ld of the two accumulator blocks, sum, 1/(s_A s_W), 64-byte stores of y.
+//   warps 0-3   epilogue (one warp per TMEM lane quarter; the other aggregation warps exit when their rows are done):
+//               tcgen05.ld of the two accumulator blocks, sum, 1/(s_A s_W), 64-byte stores of y.
 // C_in > 32 runs as C_in/32 passes over the rows' edge lists (the K order is pass-major), accumulating into the same TMEM tile.
 // The operand scale s_A comes from the a-priori bound max|contrib| <= sqrt(2) max|x| max_i sum_{e->i} |wxp_e| (plan norm,
 // fc_precomp.py:87 makes the row mass <= 1), folded into wxp per edge, exactly as the packed-operand path does.
@@ -56,6 +57,24 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+}
+
+// wait with back-off: the few warps that outlive their rows must not compete for issue slots with the working ones
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(128);
+    }
 }
 
 __device__ __forceinline__ void mma_f16_m64(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -228,6 +247,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_fused_fwd(const Params p) {
             }
             while (fcur < p.R) retire(fcur++);
         }
+        if (warp >= 4) return;       // the epilogue needs one warp per TMEM lane quarter: everyone else is done
     } else if (tid == AGG_THREADS) {
         // ------------------------------------------------------------------ filter loader + MMA issuer (one thread)
         const int stages_total = p.passes * p.R;
@@ -280,18 +300,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_fused_fwd(const Params p) {
         tc_commit(tmem_full);
     }
     __syncwarp();
-    // ---------------------------------------------------------------------- epilogue (all 32 warps)
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    {
+    // ---------------------------------------------------------------------- epilogue (warps 0-3: one per TMEM lane quarter)
+    if (warp < 4) {
+        mbar_wait_sleep(tmem_full, 0);
+        tc_fence_after();
         const float inv = __uint_as_float((254u - sf) << 23) * inv_scale_of(p.w_amax);
-        const int q = warp & 3, part = warp >> 2;       // TMEM lane quarter, column slice
+        const int q = warp;                             // TMEM lane quarter
         const int rl = 16 * q + lane;                   // D row of this thread (M = 64: rows 16q..16q+15 sit on lanes 0..15)
         const int64_t row = row0 + rl;
         const int groups = p.Npad / 16;
         const int n2 = 2 * p.Co;
         const uint32_t lane_base = tmem_d + ((uint32_t)(32 * q) << 16);
-        for (int g = part; g < groups; g += 8) {
+        for (int g = 0; g < groups; ++g) {
             uint32_t r0[16], r1[16];
             tc_ld16(lane_base + (uint32_t)(16 * g), r0);
             tc_ld16(lane_base + (uint32_t)(p.Npad + 16 * g), r1);
@@ -316,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_fused_fwd(const Params p) {
         }
     }
     tc_fence_before();
-    __syncthreads();
+    asm volatile("bar.sync 1, 160;" ::: "memory");      // warps 0-3 (TMEM reads done) and warp 31 (owner of the allocation)
     if (warp == 31) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(p.tmem_cols) : "memory");
     }

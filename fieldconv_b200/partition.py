@@ -236,12 +236,22 @@ class _PartitionedFieldConv(torch.autograd.Function):
                 tev[1].record(comm)
             done.record(comm)
         y = torch.empty(n_own, co, dtype=torch.complex64, device=dev)
-        keep = ops.keep_contrib_default(n_own * k * 8, dev)
-        contrib = torch.empty(n_own, k, dtype=torch.complex64, device=dev)
+        fused = bool(flags & _lib.FLAG_FUSED)
+        flags &= ~_lib.FLAG_FUSED
+        keep = ops.keep_contrib_default(n_own * k * 8, dev) and not fused
+        contrib = torch.empty((0 if fused else n_own), k, dtype=torch.complex64, device=dev)
         cmax = torch.zeros(1, dtype=torch.float32, device=dev)      # max|contrib| over both row ranges (atomic max)
 
         def rows(a, b):
             if b <= a:
+                return
+            if fused:      # band_limit <= 1: gather -> shared-memory tile -> tcgen05 in one kernel, no contrib buffer at all
+                nbytes = _lib.query_bytes("fcb_fwd_fused_workspace_bytes", ci, co, band_limit, plan.n_rings)
+                ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+                _lib.call("fcb_fwd_fused_f32", torch.view_as_real(x_ext).data_ptr(), torch.view_as_real(W).data_ptr(),
+                          plan.rowptr_tgt[a:].data_ptr(), plan.rec_tgt.data_ptr(), plan.rot_tgt.data_ptr(),
+                          plan.norms.data_ptr(), torch.view_as_real(y)[a:].data_ptr(), b - a, n_ext, ci, co, band_limit,
+                          plan.n_rings, ws.data_ptr(), nbytes, _lib.stream_ptr())
                 return
             nbytes = _lib.query_bytes("fcb_fwd_workspace_bytes", b - a, ci, co, band_limit, plan.n_rings, flags)
             ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
@@ -346,7 +356,7 @@ def _comm_stream(dev):
 
 def partitioned_field_conv(layer, x_own, part):
     """`layer` is a fieldconv_b200.FieldConv; x_own (n_own, Ci) complex64 in the partition's local order."""
-    from .nn import _resolve_precision
+    from .nn import _resolve_precision, fused_flags
     if part.plan is None or part.plan.n_rings != layer.R:
         part.build_plan(layer.R)
     ci, co = layer.in_channels, layer.out_channels
@@ -355,6 +365,8 @@ def partitioned_field_conv(layer, x_own, part):
     if x_own.shape[0] != part.n_own or x_own.shape[1] != ci:
         raise ValueError("x_own must be (%d owned rows, %d channels), got %s" % (part.n_own, ci, tuple(x_own.shape)))
     flags = _resolve_precision(layer.precision, ci, co, layer.R, layer.B) & _lib.GEMM_MASK   # row sub-ranges: fp32 operand layout
+    if layer.precision in ("auto", "2xf16", "2xf16p"):
+        flags = fused_flags(flags, part.plan, ci, co, layer.B, layer.R)
     return _PartitionedFieldConv.apply(x_own, layer.weight(), part, layer.B, flags)
 
 

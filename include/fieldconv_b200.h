@@ -165,6 +165,17 @@ int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, const void* 
                    const float* rot_src, const float* norm_src, float* gx, float* gW, int64_t N, int Ci, int Co,
                    int band_limit, int R, int flags, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Support-graph construction (transforms/support_graph.py:56-59 of the reference: radius(pos, pos, epsilon,
+ * max_num_neighbors=512), self loops included, rows (query j, found i) grouped by j).  Two passes over a hashed uniform grid
+ * of cell size r (csrc/radius.cu): fcb_radius_count builds the grid in `workspace` and writes counts[N] (capped at
+ * max_neighbors); the caller turns them into offsets[N+1] (exclusive scan, int64) and calls fcb_radius_fill with the SAME
+ * workspace, which writes edges[E x 2] int64.  (ox, oy, oz) = lower corner of the bounding box of pos (N x 3 float32). */
+int fcb_radius_workspace_bytes(int64_t N, size_t* bytes);
+int fcb_radius_count(const float* pos, int64_t N, float r, int max_neighbors, float ox, float oy, float oz, int32_t* counts,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int fcb_radius_fill(const float* pos, int64_t N, float r, int max_neighbors, float ox, float oy, float oz,
+                    const int64_t* offsets, int64_t* edges, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Fused forward (band_limit <= 1): gather -> shared-memory operand tile -> tcgen05 contraction in ONE kernel; the
  * N x K `contrib` of nn/field_conv.py:130-134 never exists in device memory (csrc/fused_fwd.cu).  Same arguments as
  * fcb_fwd_pk_f32 minus the contrib buffers; norm_tgt = fcb_plan_norm of the by-target order; n_feat_rows = rows of x
