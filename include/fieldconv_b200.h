@@ -165,6 +165,17 @@ int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, const void* 
                    const float* rot_src, const float* norm_src, float* gx, float* gW, int64_t N, int Ci, int Co,
                    int band_limit, int R, int flags, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- TransField / LiftBlock aggregations (nn/trans_field.py:96-110 of the reference; csrc/lift.cu).  x: (N, Ci) float32
+ * scalar features; lift_sten: (E, R, 2) complex64 (frequencies 0 and 1 of FCPrecomp's stencil) in the caller's edge order;
+ * the CSR orders come from fcb_plan_build_dense.  agg: (N, Ci+1, R) complex64 — channels 0..Ci-1 hold
+ * sum_{e->i} x[src] s1[e,r], channel Ci the channel-independent sum_{e->i} s1[e,r]; mag: (N, Ci, R) float32 =
+ * sum_{e->i} x[src] softAbs(s0[e,r]).  The backward is the adjoint with respect to x over the by-source order. */
+int fcb_lift_aggregate_f32(const float* x, const float* lift_sten, const int32_t* rowptr_tgt, const int32_t* nbr_tgt,
+                           const int32_t* perm_tgt, float* agg, float* mag, int64_t N, int Ci, int R, void* stream);
+int fcb_lift_aggregate_bwd_f32(const float* g_agg, const float* g_mag, const float* lift_sten, const int32_t* rowptr_src,
+                               const int32_t* nbr_src, const int32_t* perm_src, float* gx, int64_t N, int Ci, int R,
+                               void* stream);
+
 /* ---- Support-graph construction (transforms/support_graph.py:56-59 of the reference: radius(pos, pos, epsilon,
  * max_num_neighbors=512), self loops included, rows (query j, found i) grouped by j).  Two passes over a hashed uniform grid
  * of cell size r (csrc/radius.cu): fcb_radius_count builds the grid in `workspace` and writes counts[N] (capped at

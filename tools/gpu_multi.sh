@@ -9,7 +9,7 @@ mkdir -p $OUT
 export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 if [ -z "$SKIP_TESTS" ]; then
-  timeout 300 python -m pytest tests/test_gpu_partition.py -m gpu -q -rs --tb=short -p no:cacheprovider > $OUT/${TAG}_pytest_partition_n2.log 2>&1
+  timeout 600 python -m pytest tests -m gpu -q -rs --tb=short -p no:cacheprovider > $OUT/${TAG}_pytest_partition_n2.log 2>&1
   echo "pytest exit $?" >> $OUT/${TAG}_pytest_partition_n2.log
   tail -5 $OUT/${TAG}_pytest_partition_n2.log | cut -c 1-300
 fi
