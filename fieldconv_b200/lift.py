@@ -47,31 +47,31 @@ def _(x, lift_sten, rowptr_tgt, nbr_tgt, perm_tgt, rowptr_src, nbr_src, perm_src
 
 
 @torch.library.custom_op("fieldconv_b200::lift_aggregate_bwd", mutates_args=())
-def lift_aggregate_bwd(g_agg: Tensor, g_mag: Tensor, lift_sten: Tensor, rowptr_src: Tensor, nbr_src: Tensor,
+def lift_aggregate_bwd(g_agg: Tensor, g_mag: Tensor, agg: Tensor, lift_sten: Tensor, rowptr_src: Tensor, nbr_src: Tensor,
                        perm_src: Tensor) -> Tensor:
-    g_agg, g_mag, lift_sten = g_agg.contiguous(), g_mag.contiguous(), lift_sten.contiguous()
+    g_agg, g_mag, agg, lift_sten = g_agg.contiguous(), g_mag.contiguous(), agg.contiguous(), lift_sten.contiguous()
     n, c1, r = g_agg.shape
     gx = torch.empty(n, c1 - 1, dtype=torch.float32, device=g_agg.device)
     with torch.cuda.device(g_agg.device):
         _lib.call("fcb_lift_aggregate_bwd_f32", torch.view_as_real(g_agg).data_ptr(), g_mag.data_ptr(),
-                  torch.view_as_real(lift_sten).data_ptr(), rowptr_src.data_ptr(), nbr_src.data_ptr(), perm_src.data_ptr(),
+                  torch.view_as_real(agg).data_ptr(), torch.view_as_real(lift_sten).data_ptr(), rowptr_src.data_ptr(), nbr_src.data_ptr(), perm_src.data_ptr(),
                   gx.data_ptr(), n, c1 - 1, r, _lib.stream_ptr())
     return gx
 
 
 @lift_aggregate_bwd.register_fake
-def _(g_agg, g_mag, lift_sten, rowptr_src, nbr_src, perm_src):
+def _(g_agg, g_mag, agg, lift_sten, rowptr_src, nbr_src, perm_src):
     return g_mag.new_empty(g_agg.shape[0], g_agg.shape[1] - 1)
 
 
 def _la_setup(ctx, inputs, output):
-    ctx.save_for_backward(inputs[1], inputs[5], inputs[6], inputs[7])
+    ctx.save_for_backward(inputs[1], inputs[5], inputs[6], inputs[7], output[0])
     ctx.shape = (inputs[0].shape[0], inputs[0].shape[1], inputs[1].shape[1])
     ctx.set_materialize_grads(False)
 
 
 def _la_backward(ctx, g_agg, g_mag):
-    lift_sten, rowptr_src, nbr_src, perm_src = ctx.saved_tensors
+    lift_sten, rowptr_src, nbr_src, perm_src, agg = ctx.saved_tensors
     if not ctx.needs_input_grad[0] or (g_agg is None and g_mag is None):
         return (None,) * 8
     n, ci, r = ctx.shape
@@ -79,7 +79,7 @@ def _la_backward(ctx, g_agg, g_mag):
         g_agg = torch.zeros(n, ci + 1, r, dtype=torch.complex64, device=lift_sten.device)
     if g_mag is None:
         g_mag = torch.zeros(n, ci, r, dtype=torch.float32, device=lift_sten.device)
-    return (lift_aggregate_bwd(g_agg, g_mag, lift_sten, rowptr_src, nbr_src, perm_src),) + (None,) * 7
+    return (lift_aggregate_bwd(g_agg, g_mag, agg, lift_sten, rowptr_src, nbr_src, perm_src),) + (None,) * 7
 
 
 lift_aggregate.register_autograd(_la_backward, setup_context=_la_setup)
@@ -116,8 +116,7 @@ class TransField(nn.Module):
         agg, mag = lift_aggregate(x.float(), lift_sten, dp.rowptr_tgt, dp.nbr_tgt, dp.perm_tgt, dp.rowptr_src, dp.nbr_src,
                                   dp.perm_src)
         ci = self.in_channels
-        # contribAng = -sum (x_j - x_i) s1 = x_i S1 - sum x_j s1  (nn/trans_field.py:104-106)
-        a_ring = x.float()[..., None] * agg[:, ci:ci + 1, :] - agg[:, :ci, :]                      # (N, Ci, R) complex
+        a_ring = -agg[:, :ci, :]                 # contribAng = -sum (x_j - x_i) s1  (nn/trans_field.py:104-106), (N, Ci, R) complex
         a = torch.einsum("ncr,ocr->noc", a_ring, self.zonalAng.to(a_ring.dtype))                    # :12 / :19 before softAngle
         m = torch.einsum("ncr,ocr->noc", mag, self.zonalMag).abs()                                   # softAbsolute(:14 / :21)
         origin = (a.real.abs() < 1e-7) & (a.imag.abs() < 1e-7)                                       # utils/field.py:14-16

@@ -141,3 +141,19 @@ def with_edge_cases(mesh, isolated=(), duplicate=0, shuffle_seed=None, far=0):
         e, r, t, xp = e[perm], r[perm], t[perm], xp[perm]
     out.supp_edges, out.logMag, out.logAng, out.xp = e.contiguous(), r.contiguous(), t.contiguous(), xp.contiguous()
     return out
+
+
+def skewed_degree(mesh, seed=0, isolated_frac=0.1, exponent=3.0):
+    """A degree-skewed variant of a synthetic mesh: every target keeps each of its incoming edges with its own probability
+    p_i = u_i^exponent (u_i uniform), and `isolated_frac` of the targets lose all of them — power-law-like in-degrees with
+    many empty rows and a few full ones.  Self loops go through the same lottery."""
+    out = types.SimpleNamespace(**vars(mesh))
+    g = torch.Generator().manual_seed(seed)
+    n = mesh.num_nodes
+    p = torch.rand(n, generator=g) ** exponent
+    p[torch.rand(n, generator=g) < isolated_frac] = 0.0
+    p[torch.rand(n, generator=g) < 0.02] = 1.0
+    keep = (torch.rand(mesh.supp_edges.shape[0], generator=g) < p[mesh.supp_edges[:, 1].cpu()]).to(mesh.supp_edges.device)
+    for k in ("supp_edges", "logMag", "logAng", "xp"):
+        setattr(out, k, getattr(mesh, k)[keep].contiguous())
+    return out

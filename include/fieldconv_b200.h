@@ -168,11 +168,12 @@ int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, const void* 
 /* ---- TransField / LiftBlock aggregations (nn/trans_field.py:96-110 of the reference; csrc/lift.cu).  x: (N, Ci) float32
  * scalar features; lift_sten: (E, R, 2) complex64 (frequencies 0 and 1 of FCPrecomp's stencil) in the caller's edge order;
  * the CSR orders come from fcb_plan_build_dense.  agg: (N, Ci+1, R) complex64 — channels 0..Ci-1 hold
- * sum_{e->i} x[src] s1[e,r], channel Ci the channel-independent sum_{e->i} s1[e,r]; mag: (N, Ci, R) float32 =
- * sum_{e->i} x[src] softAbs(s0[e,r]).  The backward is the adjoint with respect to x over the by-source order. */
+ * sum_{e->i} (x[src] - x[i]) s1[e,r] (= -contribAng), channel Ci the channel-independent sum_{e->i} s1[e,r]; mag: (N, Ci, R)
+ * float32 = sum_{e->i} x[src] softAbs(s0[e,r]).  The backward is the adjoint with respect to x (by-source order; `agg` is
+ * the forward's output, read for its channel Ci). */
 int fcb_lift_aggregate_f32(const float* x, const float* lift_sten, const int32_t* rowptr_tgt, const int32_t* nbr_tgt,
                            const int32_t* perm_tgt, float* agg, float* mag, int64_t N, int Ci, int R, void* stream);
-int fcb_lift_aggregate_bwd_f32(const float* g_agg, const float* g_mag, const float* lift_sten, const int32_t* rowptr_src,
+int fcb_lift_aggregate_bwd_f32(const float* g_agg, const float* g_mag, const float* agg, const float* lift_sten, const int32_t* rowptr_src,
                                const int32_t* nbr_src, const int32_t* perm_src, float* gx, int64_t N, int Ci, int R,
                                void* stream);
 

@@ -140,6 +140,57 @@ def test_synthetic_mesh_vs_fp64_oracle(n_side, ci, co, B, R, ftype, precision):
         assert_close_normwise(m.phase.grad, gp_ref[2].float(), TOL, "grad phase")
 
 
+@pytest.mark.parametrize("n_side,ci,co,B,R,ftype", [
+    (83, 128, 128, 2, 6, 1),      # BASELINE configs[2] at FULL size: 6889 vertices, C=128, band_limit 2 (tensor-core regime)
+    (22, 16, 16, 1, 2, 1),        # configs[4] corners: C=16, n_rings 2
+    (18, 64, 64, 3, 2, 1),        # band_limit 3, n_rings 2
+    (14, 256, 256, 1, 2, 0),      # C=256
+    (16, 64, 64, 3, 6, 2),        # band_limit 3, n_rings 6, complex filters
+    (20, 32, 64, 2, 6, 1),        # C_in != C_out
+])
+def test_sweep_corner_layers_vs_fp64_oracle(n_side, ci, co, B, R, ftype):
+    """Full-size cfg 3 and the corners of the cfg-5 sweep (C in {16, 64, 256}, band_limit 3, n_rings 2) as whole layers
+    (forward, grad x, parameter gradients) against the fp64 oracle, default precision."""
+    mesh = torus_mesh(n_side, deg=40.0, seed=3, device=DEV)
+    torch.manual_seed(0)
+    m = fcb.FieldConv(ci, co, B, R, ftype).to(DEV)
+    plan = fcb.build_plan(mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp, mesh.w, R, mesh.epsilon)
+    x = random_features(mesh.num_nodes, ci, seed=2, device=DEV).requires_grad_(True)
+    gy = random_features(mesh.num_nodes, co, seed=3, zero_frac=0, device=DEV)
+    y = m(x, plan)
+    (y.real * gy.real + y.imag * gy.imag).sum().backward()
+    y_ref, gx_ref, gp_ref = _oracle_layer(mesh, x, m, gy)
+    assert_close_normwise(y, y_ref.to(torch.complex64), TOL, "y")
+    assert_close_normwise(x.grad, gx_ref.to(torch.complex64), TOL, "grad x")
+    assert_close_normwise(m.zonal.grad, gp_ref[0].float(), TOL, "grad zonal")
+    assert_close_normwise(m.spherical.grad, gp_ref[1].float(), TOL, "grad spherical")
+    if ftype == 1:
+        assert_close_normwise(m.phase.grad, gp_ref[2].float(), TOL, "grad phase")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "auto", "2xf16p"])
+def test_degree_skewed_mesh(precision):
+    """Power-law in-degrees with many isolated rows and a few very long rows (longer than the 768 plan records a CTA of the
+    aggregation kernel stages at once): rows of one warp differ in length and in where their rings end."""
+    from fieldconv_b200.synthetic import skewed_degree
+    mesh = skewed_degree(torus_mesh(36, deg=120.0, seed=7, device=DEV), seed=11)
+    deg = torch.bincount(mesh.supp_edges[:, 1], minlength=mesh.num_nodes)
+    assert int((deg == 0).sum()) > 50 and int(deg.max()) > 100 and float(deg.float().std()) > 20
+    ci = co = 32
+    torch.manual_seed(0)
+    m = fcb.FieldConv(ci, co, 1, 6, 1, precision=precision).to(DEV)
+    plan = fcb.build_plan(mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp, mesh.w, 6, mesh.epsilon)
+    x = random_features(mesh.num_nodes, ci, seed=2, device=DEV).requires_grad_(True)
+    gy = random_features(mesh.num_nodes, co, seed=3, zero_frac=0, device=DEV)
+    y = m(x, plan)
+    (y.real * gy.real + y.imag * gy.imag).sum().backward()
+    y_ref, gx_ref, gp_ref = _oracle_layer(mesh, x, m, gy)
+    assert_close_normwise(y, y_ref.to(torch.complex64), TOL, "y")
+    assert_close_normwise(x.grad, gx_ref.to(torch.complex64), TOL, "grad x")
+    assert_close_normwise(m.zonal.grad, gp_ref[0].float(), TOL, "grad zonal")
+    assert float(y[deg == 0].abs().max()) == 0.0
+
+
 def test_bitwise_determinism():
     """The segmented reduction and the split reductions use fixed orders: two runs agree bit for bit
     (the reference's scatter_add uses float atomics on CUDA and does not)."""
