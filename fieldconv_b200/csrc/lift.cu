@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(256) k_lift_aggregate_T(const float2* __restri
     if (t >= N * Ci) return;
     const int64_t row = t / Ci;
     const int c = (int)(t - row * Ci);
-    float acc = 0.f;
+    // the out-edge sum and the own-row term nearly cancel (gradient of the per-edge differences x_j - x_i): accumulate in
+    // double — this kernel is tiny (N x Ci threads), the precision matters more than the FP64 rate
+    double acc = 0.0;
     const int p1 = rowptr[row + 1];
     for (int p = rowptr[row]; p < p1; ++p) {
         const int64_t e = perm[p];
@@ -81,18 +83,15 @@ __global__ void __launch_bounds__(256) k_lift_aggregate_T(const float2* __restri
         for (int r = 0; r < R; ++r) {
             const float2 s0 = s[2 * r], s1 = s[2 * r + 1];
             const float2 g = ga[r];
-            acc = fmaf(g.x, s1.x, acc);
-            acc = fmaf(g.y, s1.y, acc);
-            acc = fmaf(gm[r], soft_abs_c(s0), acc);
+            acc += (double)g.x * s1.x + (double)g.y * s1.y + (double)gm[r] * soft_abs_c(s0);
         }
     }
-    float own = 0.f;
+    double own = 0.0;
     for (int r = 0; r < R; ++r) {
         const float2 g = g_agg[(row * C1 + c) * R + r], s = s1sum[row * s1_stride + r];
-        own = fmaf(g.x, s.x, own);
-        own = fmaf(g.y, s.y, own);
+        own += (double)g.x * s.x + (double)g.y * s.y;
     }
-    gx[t] = acc - own;
+    gx[t] = (float)(acc - own);
 }
 
 }  // namespace fcb

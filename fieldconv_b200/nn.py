@@ -45,6 +45,9 @@ def fused_flags(flags, plan, ci, co, band_limit, n_rings):
     return flags | _lib.FLAG_FUSED
 
 
+LIN_POLICY = os.environ.get("FIELDCONV_B200_LIN", "2xf16")
+
+
 def _packed_by_default(band_limit):
     if PACKED_POLICY == "0":
         return False
@@ -252,8 +255,9 @@ class TangentLin(nn.Module):
         if precision not in _PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
         self.in_channels, self.out_channels = in_channels, out_channels
-        # "auto": scaled fp16-pair tensor cores (fp32-grade, 5e-6); the library falls back to FP32 FMA where no plan fits
-        self.gemm_flags = _lib.GEMM_TC_2XF16 if precision == "auto" else (_PRECISIONS[precision] & _lib.GEMM_MASK)
+        # "auto": FIELDCONV_B200_LIN selects "2xf16" (scaled fp16-pair tensor cores, fp32-grade 5e-6; the library falls back to
+        # FP32 FMA where no plan fits) or "fp32" (FP32-FMA kernel: one launch instead of absmax + pack + GEMM)
+        self.gemm_flags = _PRECISIONS[LIN_POLICY] if precision == "auto" else (_PRECISIONS[precision] & _lib.GEMM_MASK)
         self._preemb = None
         self.Re = Parameter(torch.empty(out_channels, in_channels))
         self.Im = Parameter(torch.empty(out_channels, in_channels))
