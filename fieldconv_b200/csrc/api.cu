@@ -336,9 +336,18 @@ static GwPlan gw_from_g_plan(const Dims& d, int flags) {
     return g;
 }
 
+// workspace of the forward contraction: packed filter (+ the split-K partials of a wide output, 2 Co > 128)
+static size_t fwd_gemm_ws(const Dims& d) {
+    return max_sz(gemm_tc_ws_bytes(2 * d.Co, 2 * d.K, 1), gemm_h_ws_bytes(2 * d.Co, 2 * d.K, 1) + gemm_h_nn_parts_bytes(d.N, 2 * d.Co, 2 * d.K, 1));
+}
+// workspace of the grad-x contraction (grouped, or one product per frequency when 2 Ci is wide)
+static size_t gx_gemm_ws(const Dims& d) {
+    const int64_t Q2 = 2 * (int64_t)d.R * d.Co;
+    return max_sz(gemm_tc_ws_bytes(2 * d.Ci, Q2, d.M), gemm_h_ws_bytes(2 * d.Ci, Q2, d.M) + gemm_h_nn_parts_bytes(d.N, 2 * d.Ci, Q2, d.M));
+}
+
 static size_t fwd_ws(const Dims& d) {
-    return 256 /* max|contrib| slot */ + align_up((size_t)(4 * d.K * d.Co) * 4, 256) +
-           max_sz(gemm_tc_ws_bytes(2 * d.Co, 2 * d.K, 1), gemm_h_ws_bytes(2 * d.Co, 2 * d.K, 1)) + 512;
+    return 256 /* max|contrib| slot */ + align_up((size_t)(4 * d.K * d.Co) * 4, 256) + fwd_gemm_ws(d) + 512;
 }
 
 static size_t gw_parts_bytes(const Dims& d, int flags) {
@@ -363,7 +372,7 @@ static size_t bwd_ws(const Dims& d, bool from_g, int flags) {
     s += align_up(n_pad * d.Kt * 8, 256);                                   // G
     s += align_up((size_t)d.N * d.M * d.Ci * 8, 256);                       // gxh
     // packed operand of the tensor-core grad-x GEMM
-    s += max_sz(gemm_tc_ws_bytes(2 * d.Ci, 2 * (int64_t)d.R * d.Co, d.M), gemm_h_ws_bytes(2 * d.Ci, 2 * (int64_t)d.R * d.Co, d.M));
+    s += gx_gemm_ws(d);
     return s + 2048;
 }
 
@@ -394,7 +403,7 @@ static int contract_fwd(const Dims& d, const float* contrib, const float* amax, 
     float* Bw = ar.take<float>((size_t)(4 * d.K * d.Co));
     const int64_t tot = d.K * d.Co;
     FCB_LAUNCH("pack_w_fwd", st, k_pack_w_fwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bw, d.Ci, d.Co, d.R, d.M));
-    const size_t tcb = max_sz(gemm_tc_ws_bytes(2 * d.Co, 2 * d.K, 1), gemm_h_ws_bytes(2 * d.Co, 2 * d.K, 1));
+    const size_t tcb = fwd_gemm_ws(d);
     void* tcw = ar.take<char>(tcb);
     return launch_gemm(contrib, Bw, y, d.N, 2 * d.Co, 2 * d.K, 2 * d.K, 2 * d.Co, 2 * d.Co, 0, 1, 0, 0, 0, 1, tcw, tcb, flags, amax, st);
 }
@@ -438,7 +447,7 @@ static int backward_common(const Dims& d, const float* x, const float* W, const 
         // K5b: gxh[:, m, :] = G[:, m, :] @ conj(W)[m]  (one real GEMM per m, batched)
         FCB_LAUNCH("pack_w_bwd", st, k_pack_w_bwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bt, d.Ci, d.Co, d.R, d.M));
         const int64_t Q2 = 2 * (int64_t)d.R * d.Co;
-        const size_t tcb = max_sz(gemm_tc_ws_bytes(2 * d.Ci, Q2, d.M), gemm_h_ws_bytes(2 * d.Ci, Q2, d.M));
+        const size_t tcb = gx_gemm_ws(d);
         void* tcw = ar.take<char>(tcb);
         FCB_REQUIRE(ar.ok(), FCB_E_WORKSPACE, "bwd: workspace too small");
         int grouped = 0;     // all m in one pass over G (one long-K tensor-core pipeline) when the plan allows

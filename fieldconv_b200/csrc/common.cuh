@@ -122,7 +122,8 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
                 void* ws, size_t ws_bytes, int flags, const float* a_amax, cudaStream_t st);
 size_t gemm_tc_ws_bytes(int N, int64_t K, int batch);
 // 2xFP16 tensor-core kernels (gemm_h.cu).  a_amax: device float holding max|A| (from the kernel that produced A).
-int gemm_h_plan_nn(int N, int64_t ksteps, int* n_pairs);
+int gemm_h_plan_nn(int N, int64_t ksteps, int* n_pairs, int* split_k = nullptr);   // split_k: wide outputs (N > 128) allowed
+size_t gemm_h_nn_parts_bytes(int64_t M, int N, int64_t K, int batch);              // split-K partials of the wide-output plan
 size_t gemm_h_ws_bytes(int N, int64_t K, int batch);
 size_t gemm_h_tn_ws_bytes(int N, int64_t Kv);
 float* gemm_h_amax_slot(void* ws);      // scratch float inside a gemm_h workspace for max|A| computed by the dispatcher
@@ -130,7 +131,8 @@ int launch_absmax_f32(const float* p, int64_t rows, int cols, int64_t ld, int ba
 // a_packed != 0: A is a PK buffer (lda / sa ignored; NN: M x kgroups*K, TN: Kv x Mr) and amax_a the scale it was packed with
 int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int n_pairs, int kgroups,
-                     const float* amax_a, void* ws, size_t ws_bytes, int a_packed, cudaStream_t st);
+                     const float* amax_a, void* ws, size_t ws_bytes, int a_packed, cudaStream_t st, int split_k = 1,
+                     float* parts = nullptr);
 int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
                      int64_t ldc, int split, int64_t k_per_split, float* parts, int n_main, const float* amax_a, void* bp_ws,
                      size_t bp_bytes, int a_packed, cudaStream_t st);

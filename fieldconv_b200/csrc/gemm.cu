@@ -198,9 +198,18 @@ static int64_t tc_ksteps(int64_t K, int trans_a, int split_k, int mode) {
 }
 
 // accumulation plan of the selected tensor-core kernel: column-chunk width (0: not feasible) and accumulator count
-static int tc_plan(int N, int64_t ksteps, int mode, int trans_a, int* n_acc) {
-    if (mode == FCB_GEMM_TC_2XF16) return trans_a ? gemm_tc_plan(N, ksteps, FCB_GEMM_TC_3XTF32, n_acc) : gemm_h_plan_nn(N, ksteps, n_acc);
+static int tc_plan(int N, int64_t ksteps, int mode, int trans_a, int* n_acc, int* split = nullptr) {
+    int dummy = 1;
+    if (mode == FCB_GEMM_TC_2XF16) return trans_a ? gemm_tc_plan(N, ksteps, FCB_GEMM_TC_3XTF32, n_acc) : gemm_h_plan_nn(N, ksteps, n_acc, split ? split : &dummy);
     return gemm_tc_plan(N, ksteps, mode, n_acc);
+}
+
+// split-K partials of the 2xFP16 NN kernel's wide-output plan (N > 128): [split][batch][M][chunk] floats, else 0
+size_t gemm_h_nn_parts_bytes(int64_t M, int N, int64_t K, int batch) {
+    int n_pairs = 1, split = 1;
+    const int chunk = gemm_h_plan_nn(N, tc_ksteps(K, 0, 1, FCB_GEMM_TC_2XF16), &n_pairs, &split);
+    if (chunk <= 0 || split <= 1) return 0;
+    return align_up((size_t)split * batch * M * chunk * 4, 256);
 }
 
 // tensor cores are used when the mode asks for them and the accumulation plan fits TMEM (gemm_tc_plan)
@@ -214,7 +223,8 @@ static bool use_tc(int N, int64_t K, int trans_a, int batch, int split_k, int fl
 
 size_t gemm_ws_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags) {
     const bool h = (flags & FCB_GEMM_MASK) == FCB_GEMM_TC_2XF16;
-    if (use_tc(N, K, trans_a, batch, split_k, flags) && !trans_a) return h ? gemm_h_ws_bytes(N, K, batch) : gemm_tc_ws_bytes(N, K, batch);
+    if (use_tc(N, K, trans_a, batch, split_k, flags) && !trans_a)
+        return h ? gemm_h_ws_bytes(N, K, batch) + gemm_h_nn_parts_bytes(M, N, K, batch) : gemm_tc_ws_bytes(N, K, batch);
     const size_t parts = split_k > 1 ? align_up((size_t)split_k * batch * M * N * 4, 256) : 0;
     if (use_tc(N, K, trans_a, batch, split_k, flags) && trans_a)
         return parts + (h ? gemm_h_tn_ws_bytes(N, K) : gemm_tc_tn_ws_bytes(N, K));   // + packed B
@@ -282,10 +292,14 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
     }
     if (use_tc(N, K, trans_a, batch, split_k, flags) && !trans_a && (ldc % 4) == 0 && (sc % 4) == 0 && aligned16(C) &&
         (!h || ((lda % 4) == 0 && (sa % 4) == 0 && aligned16(A)))) {
-        int n_main = 1;
-        const int chunk = tc_plan(N, tc_ksteps(K, 0, 1, mode), mode, 0, &n_main);
+        int n_main = 1, h_split = 1;
+        const int chunk = tc_plan(N, tc_ksteps(K, 0, 1, mode), mode, 0, &n_main, &h_split);
+        float* h_parts = nullptr;
         if (h) {
-            FCB_REQUIRE(ws && ws_bytes >= gemm_h_ws_bytes(N, K, batch), FCB_E_WORKSPACE, "gemm: workspace too small (fcb_gemm_workspace_bytes)");
+            const size_t parts_b = gemm_h_nn_parts_bytes(M, N, K, batch);
+            FCB_REQUIRE(ws && ws_bytes >= gemm_h_ws_bytes(N, K, batch) + parts_b, FCB_E_WORKSPACE, "gemm: workspace too small (fcb_gemm_workspace_bytes)");
+            if (parts_b) h_parts = reinterpret_cast<float*>(static_cast<char*>(ws) + gemm_h_ws_bytes(N, K, batch));
+            if (!h_parts) h_split = 1;
             if (M == 0) return FCB_OK;
             if (!a_amax) {       // operand maximum not supplied by the producer of A: one extra pass over A
                 float* slot = gemm_h_amax_slot(ws);
@@ -299,7 +313,7 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
         for (int n0 = 0; n0 < N; n0 += chunk) {      // column chunks (one unless N is wide): same A, offset B and C
             const int nc = N - n0 < chunk ? N - n0 : chunk;
             int rc = h ? launch_gemm_h_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, n_main, 1, a_amax, ws, ws_bytes,
-                                          packed ? 1 : 0, st)
+                                          packed ? 1 : 0, st, h_split, h_parts)
                        : launch_gemm_tc_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, mode, n_main, 1, ws,
                                            ws_bytes, st);
             if (rc) return rc;

@@ -166,6 +166,12 @@ struct Params {
                                // products into its own accumulator and lands in C columns [g*N, (g+1)*N)
     int wide;                  // rows are 32-byte aligned: 256-bit loads
     int64_t a_tile_stride;     // PACKED: bytes between consecutive 128-row tiles of the PK buffer
+    // split-K (blockIdx.z, kgroups == 1 only): split z contracts the chunks [z * cps, min(nchunks, (z + 1) * cps)) and writes
+    // its [M x N] partial at C + z * part_stride (ldc = N); the caller sums the partials in split order (deterministic).
+    // Used for WIDE outputs (128 < N <= 256): all N columns in one accumulator pair (512 TMEM columns) and the K range cut
+    // so that no accumulator takes more than 400 accumulating MMAs — A is read ONCE instead of once per 128-column chunk.
+    int cps;
+    int64_t part_stride;
     uint32_t tmem_cols;
 };
 
@@ -195,9 +201,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int batch = blockIdx.y;
+    const int kc_begin = (int)blockIdx.z * p.cps;
+    const int n_kc = min(p.nchunks, kc_begin + p.cps) - kc_begin;       // chunks of this CTA (>= 1 by construction)
     const float* A = p.A + batch * p.sa;
     const __half* Bp = p.Bp + batch * p.bp_batch_stride;
-    float* C = p.C + batch * p.sc;
+    float* C = p.C + batch * p.sc + (int64_t)blockIdx.z * p.part_stride;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -240,7 +248,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
         const bool wide = p.wide != 0;
         F8 v[PAIRED ? 4 : PF][UN];
         auto issue = [&](int kc, F8(&dst)[UN]) {
-            const int64_t k0 = (int64_t)kc * KC;
+            const int64_t k0 = (int64_t)(kc_begin + kc) * KC;
             if (k0 + KC <= p.K) {                        // full chunk (CTA-uniform)
 #pragma unroll
                 for (int i = 0; i < UN; ++i) {
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
             if (++ps == (uint32_t)S) { ps = 0; pph ^= 1u; }
         };
         if (PAIRED) {
-            const int n = p.nchunks;
+            const int n = n_kc;
             if (0 < n) issue(0, v[0]);
             if (1 < n) issue(1, v[1]);
             for (int kc = 0; kc < n; kc += 4) {          // slots 0,1 hold chunks kc, kc+1; slots 2,3 take kc+2, kc+3
@@ -293,13 +301,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
         } else {
 #pragma unroll
         for (int u = 0; u < PF - 1; ++u)
-            if (u < p.nchunks) issue(u, v[u]);
-        for (int kc = 0; kc < p.nchunks; kc += PF) {
+            if (u < n_kc) issue(u, v[u]);
+        for (int kc = 0; kc < n_kc; kc += PF) {
 #pragma unroll
             for (int u = 0; u < PF; ++u) {
                 const int k = kc + u;
-                if (k < p.nchunks) {
-                    if (k + PF - 1 < p.nchunks) issue(k + PF - 1, v[(u + PF - 1) % PF]);
+                if (k < n_kc) {
+                    if (k + PF - 1 < n_kc) issue(k + PF - 1, v[(u + PF - 1) % PF]);
                     commit(v[u]);
                 }
             }
@@ -358,16 +366,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
         // descriptors only — see gemm_tc.cu)
         if (lane == 0) {
             const uint32_t npad = (uint32_t)p.Npad;
-            const uint32_t idesc1 = make_idesc_f16(p.Npad), idesc2 = make_idesc_f16(2 * p.Npad);
+            const uint32_t idesc1 = make_idesc_f16(p.Npad), idesc2 = 2 * p.Npad <= 256 ? make_idesc_f16(2 * p.Npad) : 0u;
             const uint64_t a_hi_d = make_desc_k_sw128(a_hi0), a_lo_d = make_desc_k_sw128(a_lo0);
             const uint64_t b_hi_d = make_desc_k_sw128(b0), b_lo_d = make_desc_k_sw128(b0 + b_plane);
             const uint64_t a_step = (uint64_t)(A_PLANE >> 4), b_step = (uint64_t)((2 * b_plane) >> 4);
             const uint32_t n_pairs = (uint32_t)p.n_pairs;
+            const bool merged = 2 * p.Npad <= 256;                  // one MMA of width 2 Npad for [main | cross], else two of width Npad
             uint32_t s = 0, ph = 0;
             uint32_t pr = 0, d_pair = tmem_d, first = n_pairs;       // the first n_pairs k-steps overwrite their pair
             const bool grouped = p.kgroups > 1;
             uint32_t g_left = (uint32_t)p.cpg, d_grp = tmem_d;
-            for (int kc = 0; kc < p.nchunks; ++kc) {
+            for (int kc = 0; kc < n_kc; ++kc) {
                 if (!PACKED) mbar_wait(full_a(s), ph);
                 mbar_wait(full_b(s), ph);
                 tc_fence_after();
@@ -382,7 +391,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
                         tc_mma_f16(d_grp, a_hi + adv, b_lo + adv, idesc1, 1u);
                         continue;
                     }
-                    tc_mma_f16(d_pair, a_hi + adv, b_hi + adv, idesc2, first ? 0u : 1u);    // [main | cross] (+)= A_hi [B_hi | B_lo]
+                    if (merged) {
+                        tc_mma_f16(d_pair, a_hi + adv, b_hi + adv, idesc2, first ? 0u : 1u);    // [main | cross] (+)= A_hi [B_hi | B_lo]
+                    } else {
+                        tc_mma_f16(d_pair, a_hi + adv, b_hi + adv, idesc1, first ? 0u : 1u);           // main (+)= A_hi B_hi
+                        tc_mma_f16(d_pair + npad, a_hi + adv, b_lo + adv, idesc1, first ? 0u : 1u);    // cross (+)= A_hi B_lo
+                    }
                     tc_mma_f16(d_pair + npad, a_lo + adv, b_hi + adv, idesc1, 1u);          // cross += A_lo B_hi
                     if (first) --first;
                     if (++pr == n_pairs) { pr = 0; d_pair = tmem_d; } else d_pair += 2 * npad;
@@ -398,11 +412,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
         // ------------------------------------------------------------------ B loader (one thread, TMA bulk copies)
         if (lane == 0) {
             const uint32_t bytes = 2u * b_plane;
-            const __half* src = Bp;
             const int64_t src_step = (int64_t)2 * p.Npad * KC;
-            const uint8_t* a_src = reinterpret_cast<const uint8_t*>(p.A) + (int64_t)blockIdx.x * p.a_tile_stride;
+            const __half* src = Bp + (int64_t)kc_begin * src_step;
+            const uint8_t* a_src = reinterpret_cast<const uint8_t*>(p.A) + (int64_t)blockIdx.x * p.a_tile_stride +
+                                   (int64_t)kc_begin * PK_BLOCK_BYTES;
             uint32_t s = 0, ph = 1;
-            for (int kc = 0; kc < p.nchunks; ++kc) {
+            for (int kc = 0; kc < n_kc; ++kc) {
                 mbar_wait(empty(s), ph);
                 mbar_expect_tx(full_b(s), PACKED ? bytes + PK_BLOCK_BYTES : bytes);
                 bulk_copy_g2s(b0 + s * 2 * b_plane, src, bytes, full_b(s));
@@ -804,10 +819,23 @@ __global__ void __launch_bounds__(256) k_absmax_modulus(const float2* __restrict
 // ------------------------------------------------------------------------------------------------------------ host side
 constexpr int64_t H_MAX_ACC_MMAS = 400;
 
-// NN: column-chunk width + number of (main, cross) accumulator pairs for `ksteps` k-steps of 16 reals (0: not feasible)
-int gemm_h_plan_nn(int N, int64_t ksteps, int* n_pairs_out) {
+// NN: column-chunk width, number of (main, cross) accumulator pairs the k-steps of 16 reals are dealt over, and the number of
+// K ranges (split-K CTAs) for `ksteps` k-steps (0: not feasible).  N <= 128: one CTA per row tile, up to 512 / (2 Npad) pairs.
+// Wider outputs: chunks of up to 256 columns, ONE pair filling the 512 TMEM columns, and the K range cut so that no
+// accumulator takes more than 400 accumulating MMAs — A is read once per 256 columns instead of once per 128.
+int gemm_h_plan_nn(int N, int64_t ksteps, int* n_pairs_out, int* split_out) {
     if (N <= 0) return 0;
+    if (split_out) *split_out = 1;
     const int64_t need = (ksteps + H_MAX_ACC_MMAS - 1) / H_MAX_ACC_MMAS;
+    if (N > 128 && split_out) {
+        const int nchunks_col = (N + 255) / 256;
+        int nc = (N + nchunks_col - 1) / nchunks_col;
+        nc = (nc + 15) / 16 * 16;
+        if (nc > 256) nc = 256;
+        *n_pairs_out = 1;
+        *split_out = (int)(need < 1 ? 1 : need);
+        return nc;
+    }
     const int widths[3] = {128, 64, 32};
     for (int w : widths) {
         const int nc = N < w ? N : w;
@@ -841,10 +869,11 @@ int launch_absmax_f32(const float* p, int64_t rows, int cols, int64_t ld, int ba
 
 int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int n_pairs, int kgroups,
-                     const float* amax_a, void* ws, size_t ws_bytes, int a_packed, cudaStream_t st) {
+                     const float* amax_a, void* ws, size_t ws_bytes, int a_packed, cudaStream_t st, int split_k, float* parts) {
     FCB_REQUIRE(A && B && C && ws && amax_a, FCB_E_ARG, "gemm_h: null pointer");
     FCB_REQUIRE(M >= 0 && N > 0 && K > 0 && batch >= 1 && batch <= 65535, FCB_E_ARG, "gemm_h: bad sizes");
-    FCB_REQUIRE(N <= 128, FCB_E_UNSUPPORTED, "gemm_h: N=%d > 128 not supported by one accumulator pair", N);
+    FCB_REQUIRE(N <= 256, FCB_E_UNSUPPORTED, "gemm_h: N=%d > 256 not supported by one accumulator pair", N);
+    FCB_REQUIRE(split_k >= 1 && split_k <= 65535 && (split_k == 1 || (parts && kgroups == 1)), FCB_E_ARG, "gemm_h: bad split-K arguments");
     if (a_packed) {
         FCB_REQUIRE(batch == 1 && (K % th::KC) == 0 && (reinterpret_cast<uintptr_t>(A) & 127u) == 0, FCB_E_ARG,
                     "gemm_h: a packed A operand needs batch == 1, K %% 64 == 0 and a 128-byte aligned buffer");
@@ -879,6 +908,16 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
     p.kgroups = kgroups; p.cpg = nchunks;
     p.wide = ((lda % 8) == 0 && (sa % 8) == 0 && (reinterpret_cast<uintptr_t>(A) & 31u) == 0) ? 1 : 0;
     p.a_tile_stride = (int64_t)nchunks * kgroups * PK_BLOCK_BYTES;
+    if (split_k > nchunks) split_k = nchunks;
+    p.cps = (nchunks * kgroups + split_k - 1) / split_k;
+    split_k = (nchunks * kgroups + p.cps - 1) / p.cps;          // no empty K range
+    p.part_stride = 0;
+    if (split_k > 1) {                                          // partials [split][batch][M][N]
+        p.C = parts;
+        p.ldc = N;
+        p.sc = M * (int64_t)N;
+        p.part_stride = (int64_t)batch * M * N;
+    }
     int cols_needed;
     if (kgroups > 1) {
         p.K = K * kgroups;
@@ -895,7 +934,7 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
     const size_t stage_bytes = 2 * th::A_PLANE + 2 * (size_t)npad * 128;
     int stages = (int)((220 * 1024 - 2048) / stage_bytes);
     if (stages > 6) stages = 6;
-    if (stages > p.nchunks) stages = p.nchunks < 1 ? 1 : p.nchunks;
+    if (stages > p.cps) stages = p.cps < 1 ? 1 : p.cps;
     FCB_REQUIRE(stages >= 1, FCB_E_UNSUPPORTED, "gemm_h: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = stages * stage_bytes + 1024 /*align slack*/ + 8 * (3 * stages + 2) + 64;
@@ -915,12 +954,13 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
         }
         attr_set = true;
     }
-    dim3 grid((unsigned)((M + th::BM - 1) / th::BM), (unsigned)batch);
+    dim3 grid((unsigned)((M + th::BM - 1) / th::BM), (unsigned)batch, (unsigned)split_k);
     // FIELDCONV_B200_GEMM_PAIRED=1: paired chunk loads in the fp32-operand producers (experiment switch, read once)
     static const bool paired = [] { const char* e = getenv("FIELDCONV_B200_GEMM_PAIRED"); return e && atoi(e) != 0; }();
     if (a_packed) FCB_LAUNCH("gemm_p_nn", st, (th::k_gemm_h_nn<true, false><<<grid, th::THREADS, smem, st>>>(p)));
     else if (paired) FCB_LAUNCH("gemm_h_nn", st, (th::k_gemm_h_nn<false, true><<<grid, th::THREADS, smem, st>>>(p)));
     else FCB_LAUNCH("gemm_h_nn", st, (th::k_gemm_h_nn<false, false><<<grid, th::THREADS, smem, st>>>(p)));
+    if (split_k > 1) return launch_reduce_splits(parts, C, M, N, ldc, sc, batch, split_k, st);
     return FCB_OK;
 }
 
