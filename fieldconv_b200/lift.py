@@ -117,8 +117,10 @@ class TransField(nn.Module):
                                   dp.perm_src)
         ci = self.in_channels
         a_ring = -agg[:, :ci, :]                 # contribAng = -sum (x_j - x_i) s1  (nn/trans_field.py:104-106), (N, Ci, R) complex
-        a = torch.einsum("ncr,ocr->noc", a_ring, self.zonalAng.to(a_ring.dtype))                    # :12 / :19 before softAngle
-        m = torch.einsum("ncr,ocr->noc", mag, self.zonalMag).abs()                                   # softAbsolute(:14 / :21)
+        # the reference's own broadcast-multiply-and-sum over the rings (elementwise kernels + a reduction: plain fp32
+        # adds, no library GEMM whose reduction order / precision mode could differ from the reference's)
+        a = (a_ring[:, None] * self.zonalAng[None]).sum(dim=3)                                       # :12 / :19 before softAngle
+        m = (mag[:, None] * self.zonalMag[None]).sum(dim=3).abs()                                    # softAbsolute(:14 / :21)
         origin = (a.real.abs() < 1e-7) & (a.imag.abs() < 1e-7)                                       # utils/field.py:14-16
         mod = a.abs()
         unit = torch.where(origin, torch.ones_like(a), a / torch.where(origin, torch.ones_like(mod), mod))
