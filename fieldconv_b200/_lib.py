@@ -37,6 +37,8 @@ SIGNATURES = {
     "fcb_precomp_expand_f32": [_P, _P, _P, _F, _I64, _I64, _I, _I, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P],
     "fcb_fwd_workspace_bytes": [_I64, _I, _I, _I, _I, _I, _PSZ],
     "fcb_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_fwd_act_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_fwd_act_pk_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_bwd_workspace_bytes": [_I64, _I, _I, _I, _I, _I, _PSZ],
     "fcb_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_fwd_dense_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],

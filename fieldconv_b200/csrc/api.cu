@@ -210,6 +210,30 @@ __global__ void k_modrelu_fwd(const float2* __restrict__ x, const float* __restr
     y[i] = out;
 }
 
+// z = y (+ res) in place, act = modReLU(z, bias): the stand-alone form of the block epilogue for the contraction paths that
+// cannot fuse it (FP32-FMA, 3xTF32, split / chunked 2xFP16 products)
+__global__ void k_res_modrelu(float2* __restrict__ y, const float2* __restrict__ res, const float* __restrict__ bias,
+                              float2* __restrict__ act, int64_t total, int C) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float2 z = y[i];
+    if (res) {
+        const float2 r = res[i];
+        z.x += r.x; z.y += r.y;
+        y[i] = z;
+    }
+    if (!act) return;
+    const bool origin = (fabsf(z.x) < 1e-7f) && (fabsf(z.y) < 1e-7f);
+    float2 out = z;
+    if (!origin) {
+        const float n2 = z.x * z.x + z.y * z.y;
+        const float ri = rsqrtf(n2);
+        const float s = fmaxf(n2 * ri + bias[i % C], 0.f) * ri;
+        out = make_float2(s * z.x, s * z.y);
+    }
+    act[i] = out;
+}
+
 constexpr int MR_ROWS = 256;  // rows per block slab in the backward bias reduction
 
 // gx = u (s' Re t + i (s/rho) Im t), t = conj(u) g ; gb_c = sum_n s' Re t   
@@ -395,8 +419,20 @@ static float* fwd_amax_slot(void* ws, float* user_slot, cudaStream_t st) {
     return slot;
 }
 
+static int apply_epilogue(const Dims& d, float* y, const GemmEpilogue* epi, cudaStream_t st) {
+    const int64_t tot = d.N * d.Co;
+    if (tot == 0 || (!epi->res && !epi->act)) return FCB_OK;
+    FCB_REQUIRE(epi->ld == 2 * (int64_t)d.Co, FCB_E_ARG, "fwd: the block epilogue needs dense (N, Co) residual / activation buffers");
+    FCB_LAUNCH("res_modrelu", st, k_res_modrelu<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+                                      reinterpret_cast<float2*>(y), reinterpret_cast<const float2*>(epi->res), epi->bias,
+                                      reinterpret_cast<float2*>(epi->act), tot, d.Co));
+    return FCB_OK;
+}
+
+// epi (optional): y receives z = contraction (+ res), epi->act = modReLU(z, bias) — fused into the 2xFP16 kernel's epilogue
+// when the product is a single un-split launch, else applied by k_res_modrelu right after
 static int contract_fwd(const Dims& d, const float* contrib, const float* amax, const float* W, float* y, void* ws,
-                        size_t ws_bytes, int flags, cudaStream_t st) {
+                        size_t ws_bytes, int flags, cudaStream_t st, const GemmEpilogue* epi = nullptr) {
     FCB_REQUIRE(ws_bytes >= fwd_ws(d), FCB_E_WORKSPACE, "fwd: workspace too small");
     Arena ar(ws, ws_bytes);
     ar.take<char>(256);      // the max|contrib| slot (fwd_amax_slot)
@@ -405,7 +441,11 @@ static int contract_fwd(const Dims& d, const float* contrib, const float* amax, 
     FCB_LAUNCH("pack_w_fwd", st, k_pack_w_fwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bw, d.Ci, d.Co, d.R, d.M));
     const size_t tcb = fwd_gemm_ws(d);
     void* tcw = ar.take<char>(tcb);
-    return launch_gemm(contrib, Bw, y, d.N, 2 * d.Co, 2 * d.K, 2 * d.K, 2 * d.Co, 2 * d.Co, 0, 1, 0, 0, 0, 1, tcw, tcb, flags, amax, st);
+    int fused = 0;
+    int rc = launch_gemm(contrib, Bw, y, d.N, 2 * d.Co, 2 * d.K, 2 * d.K, 2 * d.Co, 2 * d.Co, 0, 1, 0, 0, 0, 1, tcw, tcb, flags, amax, st,
+                         epi, &fused);
+    if (rc || !epi || fused) return rc;
+    return apply_epilogue(d, y, epi, st);
 }
 
 // contrib_packed / g_packed: contrib is (G will be) a PK buffer; gather_transpose(G, g_amax, g_packed) fills G either way.
@@ -597,9 +637,9 @@ extern "C" int fcb_bwd_workspace_bytes(int64_t N, int Ci, int Co, int band_limit
     return FCB_OK;
 }
 
-extern "C" int fcb_fwd_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
-                           const float* rot_tgt, float* y, float* contrib, float* contrib_absmax, int64_t N, int Ci, int Co,
-                           int band_limit, int R, int flags, void* ws, size_t ws_bytes, void* stream) {
+static int fwd_impl(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt, float* y,
+                    float* contrib, float* contrib_absmax, int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws,
+                    size_t ws_bytes, void* stream, const GemmEpilogue* epi) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Dims d;
     int rc = check_dims("fwd", N, Ci, Co, band_limit, R, &d);
@@ -614,7 +654,34 @@ extern "C" int fcb_fwd_f32(const float* x, const float* W, const int32_t* rowptr
     FCB_REQUIRE(amax, FCB_E_CUDA, "fwd: cudaMemsetAsync failed");
     rc = launch_aggregate(x, rowptr_tgt, rec_tgt, rot_tgt, contrib, N, Ci, band_limit, R, 0, amax, st);
     if (rc) return rc;
-    return contract_fwd(d, contrib, amax, W, y, ws, ws_bytes, flags, st);
+    return contract_fwd(d, contrib, amax, W, y, ws, ws_bytes, flags, st, epi);
+}
+
+extern "C" int fcb_fwd_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
+                           const float* rot_tgt, float* y, float* contrib, float* contrib_absmax, int64_t N, int Ci, int Co,
+                           int band_limit, int R, int flags, void* ws, size_t ws_bytes, void* stream) {
+    return fwd_impl(x, W, rowptr_tgt, rec_tgt, rot_tgt, y, contrib, contrib_absmax, N, Ci, Co, band_limit, R, flags, ws, ws_bytes,
+                    stream, nullptr);
+}
+
+static int make_epilogue(const float* res, const float* bias, float* act, int Co, GemmEpilogue* e) {
+    FCB_REQUIRE((bias == nullptr) == (act == nullptr), FCB_E_ARG, "fwd_act: bias and act go together");
+    FCB_REQUIRE((!res || aligned16(res)) && (!act || aligned16(act)), FCB_E_ALIGN, "fwd_act: res / act must be 16-byte aligned");
+    e->res = res; e->bias = bias; e->act = act; e->ld = 2 * (int64_t)Co;
+    return FCB_OK;
+}
+
+// Block epilogue fused into the layer (nn/fc_resnet_block.py:84-88): y = conv(x) + res (res may be NULL),
+// act = modReLU(y, bias) (nn/tangent_nonlin.py:24-35; bias / act may both be NULL).  Otherwise as fcb_fwd_f32.
+extern "C" int fcb_fwd_act_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
+                               const float* rot_tgt, float* y, float* contrib, float* contrib_absmax, const float* res,
+                               const float* bias, float* act, int64_t N, int Ci, int Co, int band_limit, int R, int flags,
+                               void* ws, size_t ws_bytes, void* stream) {
+    GemmEpilogue e;
+    int rc = make_epilogue(res, bias, act, Co, &e);
+    if (rc) return rc;
+    return fwd_impl(x, W, rowptr_tgt, rec_tgt, rot_tgt, y, contrib, contrib_absmax, N, Ci, Co, band_limit, R, flags, ws, ws_bytes,
+                    stream, &e);
 }
 
 extern "C" int fcb_bwd_f32(const float* x, const float* W, const float* gy, const float* contrib,
@@ -664,10 +731,9 @@ extern "C" int fcb_pk_contrib_bytes(int64_t N, int Ci, int band_limit, int R, si
     return FCB_OK;
 }
 
-extern "C" int fcb_fwd_pk_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
-                              const float* rot_tgt, const float* norm_tgt, float* y, void* contrib_pk, float* contrib_scale,
-                              int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws, size_t ws_bytes,
-                              void* stream) {
+static int fwd_pk_impl(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
+                       const float* norm_tgt, float* y, void* contrib_pk, float* contrib_scale, int64_t N, int Ci, int Co,
+                       int band_limit, int R, int flags, void* ws, size_t ws_bytes, void* stream, const GemmEpilogue* epi) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Dims d;
     int rc = check_dims("fwd_pk", N, Ci, Co, band_limit, R, &d);
@@ -683,7 +749,26 @@ extern "C" int fcb_fwd_pk_f32(const float* x, const float* W, const int32_t* row
     if (rc) return rc;
     rc = launch_aggregate_packed(x, rowptr_tgt, rec_tgt, rot_tgt, contrib_pk, N, Ci, band_limit, R, 0, x_amax, norm_tgt, contrib_scale, st);
     if (rc) return rc;
-    return contract_fwd(d, static_cast<const float*>(contrib_pk), contrib_scale, W, y, ws, ws_bytes, flags | FCB_FLAG_A_PACKED, st);
+    return contract_fwd(d, static_cast<const float*>(contrib_pk), contrib_scale, W, y, ws, ws_bytes, flags | FCB_FLAG_A_PACKED, st, epi);
+}
+
+extern "C" int fcb_fwd_pk_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
+                              const float* rot_tgt, const float* norm_tgt, float* y, void* contrib_pk, float* contrib_scale,
+                              int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws, size_t ws_bytes,
+                              void* stream) {
+    return fwd_pk_impl(x, W, rowptr_tgt, rec_tgt, rot_tgt, norm_tgt, y, contrib_pk, contrib_scale, N, Ci, Co, band_limit, R, flags, ws,
+                       ws_bytes, stream, nullptr);
+}
+
+extern "C" int fcb_fwd_act_pk_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
+                                  const float* rot_tgt, const float* norm_tgt, float* y, void* contrib_pk, float* contrib_scale,
+                                  const float* res, const float* bias, float* act, int64_t N, int Ci, int Co, int band_limit,
+                                  int R, int flags, void* ws, size_t ws_bytes, void* stream) {
+    GemmEpilogue e;
+    int rc = make_epilogue(res, bias, act, Co, &e);
+    if (rc) return rc;
+    return fwd_pk_impl(x, W, rowptr_tgt, rec_tgt, rot_tgt, norm_tgt, y, contrib_pk, contrib_scale, N, Ci, Co, band_limit, R, flags, ws,
+                       ws_bytes, stream, &e);
 }
 
 extern "C" int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, const void* contrib_pk,

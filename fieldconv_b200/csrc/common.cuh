@@ -98,6 +98,17 @@ constexpr uint32_t PK_BLOCK_BYTES = 2 * PK_PLANE_BYTES;         // hi + lo
 static inline int64_t pk_rows_padded(int64_t rows) { return (rows + PK_ROWS - 1) / PK_ROWS * PK_ROWS; }
 static inline size_t pk_bytes(int64_t rows, int64_t cols) { return (size_t)(pk_rows_padded(rows) / PK_ROWS) * (size_t)(cols / PK_COLS) * PK_BLOCK_BYTES; }
 
+// Optional fused epilogue of the forward contraction: C receives z = A B (+ res), act = modReLU(z, bias)
+// (nn/fc_resnet_block.py:84-88, nn/tangent_nonlin.py:24-35).  Applied inside the 2xFP16 kernel's TMEM -> register epilogue
+// when the product is one un-split launch; launch_gemm reports through *fused whether it was, so the caller can run the
+// stand-alone kernel otherwise.
+struct GemmEpilogue {
+    const float* res;      // [M x N], row stride ld, or nullptr
+    const float* bias;     // N / 2 floats, or nullptr (no activation output)
+    float* act;            // [M x N], row stride ld
+    int64_t ld;
+};
+
 // internal entry points shared between translation units
 int sort_pairs(uint32_t* k_in, uint32_t* v_in, uint32_t* k_out, uint32_t* v_out, int64_t n, int bits,
                void* ws, size_t ws_bytes, cudaStream_t st);
@@ -119,7 +130,8 @@ size_t gemm_ws_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int sp
 // flags & FCB_FLAG_A_PACKED: A is a PK buffer (only with FCB_GEMM_TC_2XF16, batch == 1 and gemm_pk_*_ok shapes)
 int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                 int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k,
-                void* ws, size_t ws_bytes, int flags, const float* a_amax, cudaStream_t st);
+                void* ws, size_t ws_bytes, int flags, const float* a_amax, cudaStream_t st, const GemmEpilogue* epi = nullptr,
+                int* epi_fused = nullptr);
 size_t gemm_tc_ws_bytes(int N, int64_t K, int batch);
 // 2xFP16 tensor-core kernels (gemm_h.cu).  a_amax: device float holding max|A| (from the kernel that produced A).
 int gemm_h_plan_nn(int N, int64_t ksteps, int* n_pairs, int* split_k = nullptr);   // split_k: wide outputs (N > 128) allowed
@@ -132,7 +144,7 @@ int launch_absmax_f32(const float* p, int64_t rows, int cols, int64_t ld, int ba
 int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int n_pairs, int kgroups,
                      const float* amax_a, void* ws, size_t ws_bytes, int a_packed, cudaStream_t st, int split_k = 1,
-                     float* parts = nullptr);
+                     float* parts = nullptr, const GemmEpilogue* epi = nullptr);
 int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
                      int64_t ldc, int split, int64_t k_per_split, float* parts, int n_main, const float* amax_a, void* bp_ws,
                      size_t bp_bytes, int a_packed, cudaStream_t st);

@@ -279,8 +279,9 @@ int launch_gemm_grouped(const float* A, const float* Bm, float* C, int64_t M, in
 
 int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                 int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k, void* ws,
-                size_t ws_bytes, int flags, const float* a_amax, cudaStream_t st) {
+                size_t ws_bytes, int flags, const float* a_amax, cudaStream_t st, const GemmEpilogue* epi, int* epi_fused) {
     FCB_REQUIRE(A && Bm && C, FCB_E_ARG, "gemm: null pointer");
+    if (epi_fused) *epi_fused = 0;
     FCB_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 1 && split_k >= 1, FCB_E_ARG, "gemm: bad sizes");
     const int mode = flags & FCB_GEMM_MASK;
     const bool h = mode == FCB_GEMM_TC_2XF16;
@@ -310,10 +311,13 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
                 a_amax = slot;
             }
         }
+        // the block epilogue rides along when the product is ONE un-split 2xFP16 launch
+        const bool fuse_epi = h && epi && chunk >= N && h_split == 1 && batch == 1;
+        if (fuse_epi && epi_fused) *epi_fused = 1;
         for (int n0 = 0; n0 < N; n0 += chunk) {      // column chunks (one unless N is wide): same A, offset B and C
             const int nc = N - n0 < chunk ? N - n0 : chunk;
             int rc = h ? launch_gemm_h_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, n_main, 1, a_amax, ws, ws_bytes,
-                                          packed ? 1 : 0, st, h_split, h_parts)
+                                          packed ? 1 : 0, st, h_split, h_parts, fuse_epi ? epi : nullptr)
                        : launch_gemm_tc_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, mode, n_main, 1, ws,
                                            ws_bytes, st);
             if (rc) return rc;

@@ -172,6 +172,12 @@ struct Params {
     // so that no accumulator takes more than 400 accumulating MMAs — A is read ONCE instead of once per 128-column chunk.
     int cps;
     int64_t part_stride;
+    // fused block epilogue (kgroups == 1, split-K off): C receives z = A B (+ epi_res), epi_act = modReLU(z, epi_bias) —
+    // nn/fc_resnet_block.py:84-88 with nn/tangent_nonlin.py:24-35 applied in the TMEM -> register epilogue
+    const float* epi_res;      // optional [M x N] residual (row stride epi_ld)
+    const float* epi_bias;     // N / 2 modReLU biases (one per complex output channel), nullptr: no activation output
+    float* epi_act;            // [M x N] activated output (row stride epi_ld)
+    int64_t epi_ld;
     uint32_t tmem_cols;
 };
 
@@ -346,6 +352,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
             }
 #pragma unroll
             for (int e = 0; e < 16; ++e) acc[e] = acc[e] * inv_a * inv_b;
+            if (p.epi_res && m < p.M) {
+                const float* rsrc = p.epi_res + m * p.epi_ld + 16 * g;
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (16 * g + e < p.N) acc[e] += __ldg(rsrc + e);
+            }
+            if (p.epi_act && m < p.M) {
+                // modReLU on the 8 complex values of this piece: y = relu(|z| + b_c) z / |z|, origin entries passed through
+                float* adst = p.epi_act + m * p.epi_ld + 16 * g;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int n = 16 * g + 2 * j;
+                    if (n + 1 < p.N) {
+                        const float zx = acc[2 * j], zy = acc[2 * j + 1];
+                        const bool origin = (fabsf(zx) < 1e-7f) && (fabsf(zy) < 1e-7f);
+                        const float n2 = zx * zx + zy * zy;
+                        const float ri = rsqrtf(n2);
+                        const float sc = fmaxf(n2 * ri + __ldg(p.epi_bias + (n >> 1)), 0.f) * ri;
+                        *reinterpret_cast<float2*>(adst + 2 * j) = origin ? make_float2(zx, zy) : make_float2(sc * zx, sc * zy);
+                    }
+                }
+            }
             if (m < p.M) {
                 float* dst = C + m * p.ldc + (int64_t)kg * p.N + 16 * g;
 #pragma unroll
@@ -869,7 +897,8 @@ int launch_absmax_f32(const float* p, int64_t rows, int cols, int64_t ld, int ba
 
 int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int n_pairs, int kgroups,
-                     const float* amax_a, void* ws, size_t ws_bytes, int a_packed, cudaStream_t st, int split_k, float* parts) {
+                     const float* amax_a, void* ws, size_t ws_bytes, int a_packed, cudaStream_t st, int split_k, float* parts,
+                     const GemmEpilogue* epi) {
     FCB_REQUIRE(A && B && C && ws && amax_a, FCB_E_ARG, "gemm_h: null pointer");
     FCB_REQUIRE(M >= 0 && N > 0 && K > 0 && batch >= 1 && batch <= 65535, FCB_E_ARG, "gemm_h: bad sizes");
     FCB_REQUIRE(N <= 256, FCB_E_UNSUPPORTED, "gemm_h: N=%d > 256 not supported by one accumulator pair", N);
@@ -912,6 +941,11 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
     p.cps = (nchunks * kgroups + split_k - 1) / split_k;
     split_k = (nchunks * kgroups + p.cps - 1) / p.cps;          // no empty K range
     p.part_stride = 0;
+    p.epi_res = nullptr; p.epi_bias = nullptr; p.epi_act = nullptr; p.epi_ld = 0;
+    if (epi) {
+        FCB_REQUIRE(split_k == 1 && kgroups == 1 && batch == 1 && (N & 1) == 0, FCB_E_ARG, "gemm_h: the fused epilogue needs one un-split product");
+        p.epi_res = epi->res; p.epi_bias = epi->bias; p.epi_act = epi->act; p.epi_ld = epi->ld;
+    }
     if (split_k > 1) {                                          // partials [split][batch][M][N]
         p.C = parts;
         p.ldc = N;

@@ -46,6 +46,8 @@ def fused_flags(flags, plan, ci, co, band_limit, n_rings):
 
 
 LIN_POLICY = os.environ.get("FIELDCONV_B200_LIN", "2xf16")
+# FIELDCONV_B200_BLOCK_EPILOGUE=0: FCResNetBlock runs TangentNonLin / the residual add as separate kernels (A/B switch)
+BLOCK_EPILOGUE = os.environ.get("FIELDCONV_B200_BLOCK_EPILOGUE", "1")
 
 
 def _packed_by_default(band_limit):
@@ -247,6 +249,25 @@ class FieldConv(nn.Module):
         return y[:, :co] if co % 2 else y
 
 
+def _fused_block_ok(plan, supp_sten):
+    """The block epilogue (modReLU, residual) rides in the layer's contraction kernel on the compact-plan path."""
+    return BLOCK_EPILOGUE == "1" and isinstance(plan, Plan) and not plan.dense and not ops.SAVE_CONTRIB
+
+
+def _conv_act(layer, x, plan, bias, res):
+    """modReLU(layer(x) + res, bias) through the fused-epilogue op; shapes / flags resolved as in FieldConv.forward."""
+    ci, co = layer.in_channels, layer.out_channels
+    if ci % 2 or co % 2 or x.shape[1] != ci:
+        return None                                   # odd channel counts take the padded, unfused route
+    if x.shape[0] != plan.num_nodes:
+        raise ValueError("x has %d rows, the plan was built for %d vertices" % (x.shape[0], plan.num_nodes))
+    if plan.n_rings != layer.R:
+        raise ValueError("plan was built for n_rings=%d, layer has %d" % (plan.n_rings, layer.R))
+    flags = _resolve_precision(layer.precision, ci, co, layer.R, layer.B)
+    flags = packed_flags(flags, plan, x.shape[0], ci, co, layer.B, layer.R, layer.precision == "2xf16p", auto=layer.precision == "auto")
+    return ops.field_conv_act(x, layer.weight(), plan, layer.B, bias, res, flags)
+
+
 class TangentLin(nn.Module):
     """nn/tangent_lin.py:12-29 — y = x @ (Re + i Im)^T, carried as one real GEMM on the interleaved storage."""
 
@@ -306,6 +327,15 @@ class FCResNetBlock(nn.Module):
     def forward(self, x, supp_edges=None, supp_sten=None, *, plan=None):
         if isinstance(supp_edges, (Plan, DensePlan, MeshPartition)):
             plan, supp_edges = supp_edges, None
+        if supp_sten is not None and plan is None:
+            plan = attached_plan(supp_edges, supp_sten, self.conv1.R, x.shape[0])
+        if _fused_block_ok(plan, supp_sten) and x.is_cuda and FUSED_POLICY != "1":
+            # nonlin1 and (residual add + nonlin2) run in the epilogue of conv1's / conv2's contraction kernel
+            h = _conv_act(self.conv1, x, plan, self.nonlin1.bias, None)
+            if h is not None:
+                out = _conv_act(self.conv2, h, plan, self.nonlin2.bias, self.res(x))
+                if out is not None:
+                    return out
         h = self.nonlin1(self.conv1(x, supp_edges, supp_sten, plan=plan))
         h = self.conv2(h, supp_edges, supp_sten, plan=plan)
         return self.nonlin2(self.res(x) + h)

@@ -159,6 +159,97 @@ def _fc_backward(ctx, gy, _gcontrib, _gcmax):
 fc_fwd.register_autograd(_fc_backward, setup_context=_fc_setup)
 
 
+# --------------------------------------------------------------------------- layer + block epilogue in one op
+@torch.library.custom_op("fieldconv_b200::fc_fwd_act", mutates_args=())
+def fc_fwd_act(x: Tensor, W: Tensor, res: Tensor, bias: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: Tensor,
+               rowptr_src: Tensor, rec_src: Tensor, rot_src: Tensor, norms: Tensor, band_limit: int, n_rings: int, flags: int,
+               has_res: bool) -> Tuple[Tensor, Tensor]:
+    """(act, z) with z = FieldConv(x) (+ res) and act = modReLU(z, bias): nn/fc_resnet_block.py:84-88 with the TangentNonLin
+    (and the residual add) applied in the contraction kernel's epilogue (fcb_fwd_act_f32 / fcb_fwd_act_pk_f32).  Nothing of
+    size N x K is kept: the backward is modrelu_bwd + fc_bwd with gW from G and xhat."""
+    _check(x, "x")
+    _check(W, "W")
+    x, W = x.contiguous(), W.contiguous()
+    n, ci = x.shape
+    co = W.shape[0]
+    k = n_rings * ci * (2 * band_limit + 1)
+    packed = bool(flags & _lib.FLAG_PACKED)
+    cflags = flags & ~(_lib.FLAG_PACKED | _lib.FLAG_FUSED)
+    z = torch.empty(n, co, dtype=torch.complex64, device=x.device)
+    act = torch.empty(n, co, dtype=torch.complex64, device=x.device)
+    b = bias.reshape(-1).contiguous().float()
+    r_ptr = 0
+    if has_res:
+        _check(res, "res")
+        res = res.contiguous()
+        r_ptr = _real(res).data_ptr()
+    contrib = torch.empty(_padded_rows(n), k, dtype=torch.complex64, device=x.device)      # transient: freed on return
+    cmax = torch.zeros(1, dtype=torch.float32, device=x.device)
+    nbytes = _lib.query_bytes("fcb_fwd_workspace_bytes", n, ci, co, band_limit, n_rings, cflags)
+    ws = _ws(nbytes, x.device)
+    with torch.cuda.device(x.device):
+        if packed:
+            _lib.call("fcb_fwd_act_pk_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
+                      rot_tgt.data_ptr(), norms.data_ptr(), _real(z).data_ptr(), _real(contrib).data_ptr(), cmax.data_ptr(),
+                      r_ptr, b.data_ptr(), _real(act).data_ptr(), n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes,
+                      _lib.stream_ptr())
+        else:
+            _lib.call("fcb_fwd_act_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
+                      rot_tgt.data_ptr(), _real(z).data_ptr(), _real(contrib).data_ptr(), cmax.data_ptr(), r_ptr, b.data_ptr(),
+                      _real(act).data_ptr(), n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes, _lib.stream_ptr())
+    return act, z
+
+
+@fc_fwd_act.register_fake
+def _(x, W, res, bias, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, has_res):
+    return x.new_empty(x.shape[0], W.shape[0]), x.new_empty(x.shape[0], W.shape[0])
+
+
+def _fa_setup(ctx, inputs, output):
+    x, W, res, bias, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, has_res = inputs
+    ctx.save_for_backward(x, W, bias, output[1], rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms)
+    ctx.cfg = (band_limit, n_rings, flags, has_res)
+    ctx.set_materialize_grads(False)
+
+
+def _fa_backward(ctx, g_act, g_z):
+    x, W, bias, z, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms = ctx.saved_tensors
+    band_limit, n_rings, flags, has_res = ctx.cfg
+    if g_act is None and g_z is None:
+        return (None,) * 15
+    gb = None
+    gz = g_z
+    if g_act is not None:
+        gz_a, gbv = modrelu_bwd(z, bias, g_act.contiguous())
+        gz = gz_a if gz is None else gz + gz_a
+        gb = gbv.reshape(bias.shape)
+    empty = torch.empty(0, dtype=torch.complex64, device=x.device)
+    cm = torch.zeros(1, dtype=torch.float32, device=x.device)
+    gx, gw = fc_bwd(x, W, gz, empty, cm, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings,
+                    flags & ~_lib.FLAG_FUSED, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+    return (gx if ctx.needs_input_grad[0] else None, gw if ctx.needs_input_grad[1] else None,
+            gz if (has_res and ctx.needs_input_grad[2]) else None, gb if ctx.needs_input_grad[3] else None) + (None,) * 11
+
+
+fc_fwd_act.register_autograd(_fa_backward, setup_context=_fa_setup)
+
+
+def field_conv_act(x, W, plan, band_limit, bias, res=None, flags=0):
+    """modReLU(FieldConv(x) + res, bias) for the compact plan, the block epilogue fused into the layer; differentiable w.r.t.
+    x, W, res and bias.  Returns the activated output."""
+    norms = getattr(plan, "norms", None)
+    if norms is None:
+        if flags & _lib.FLAG_PACKED:
+            raise RuntimeError("fieldconv_b200: the packed path needs a plan built by build_plan (plan.norms)")
+        norms = torch.zeros(2, dtype=torch.float32, device=x.device)
+    has_res = res is not None
+    if not has_res:
+        res = torch.empty(0, dtype=torch.complex64, device=x.device)
+    act, _ = fc_fwd_act(x, W, res, bias, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src, plan.rot_src,
+                        norms, band_limit, plan.n_rings, flags, has_res)
+    return act
+
+
 def field_conv(x, W, plan, band_limit, flags=0, keep_contrib=None):
     """y = FieldConv(x) for the compact plan; differentiable w.r.t. x and W.  flags may carry _lib.FLAG_PACKED."""
     n, ci = x.shape

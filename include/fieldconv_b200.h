@@ -165,6 +165,21 @@ int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, const void* 
                    const float* rot_src, const float* norm_src, float* gx, float* gW, int64_t N, int Ci, int Co,
                    int band_limit, int R, int flags, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- FCResNetBlock epilogue fused into the layer (nn/fc_resnet_block.py:84-88 of the reference):
+ *   y   = FieldConv(x) + res        (res: (N, Co) complex64 — the TangentLin residual nn/tangent_lin.py:27-29 — or NULL)
+ *   act = modReLU(y, bias)          (nn/tangent_nonlin.py:24-35; bias: Co floats; bias and act may both be NULL)
+ * Same arguments as fcb_fwd_f32 / fcb_fwd_pk_f32 plus (res, bias, act).  With the 2xFP16 contraction and an output of at
+ * most 128 real columns the epilogue runs inside the contraction kernel (TMEM -> registers -> two stores); otherwise one
+ * pointwise kernel follows.  y keeps the PRE-activation values (what the modReLU backward needs). */
+int fcb_fwd_act_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
+                    float* y, float* contrib, float* contrib_absmax, const float* res, const float* bias, float* act,
+                    int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* workspace, size_t workspace_bytes,
+                    void* stream);
+int fcb_fwd_act_pk_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
+                       const float* norm_tgt, float* y, void* contrib_pk, float* contrib_scale, const float* res,
+                       const float* bias, float* act, int64_t N, int Ci, int Co, int band_limit, int R, int flags,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- TransField / LiftBlock aggregations (nn/trans_field.py:96-110 of the reference; csrc/lift.cu).  x: (N, Ci) float32
  * scalar features; lift_sten: (E, R, 2) complex64 (frequencies 0 and 1 of FCPrecomp's stencil) in the caller's edge order;
  * the CSR orders come from fcb_plan_build_dense.  agg: (N, Ci+1, R) complex64 — channels 0..Ci-1 hold

@@ -104,6 +104,43 @@ def test_block_matches_reference():
             assert_close_normwise(p.grad, g["g." + k], 2e-5 if "bias" in k else TOL, mode + ": grad " + k)
 
 
+@pytest.mark.parametrize("c,B,precision", [(48, 2, "auto"), (32, 1, "auto"), (16, 1, "fp32"), (128, 1, "auto"), (32, 1, "3xtf32")])
+def test_block_epilogue_fused_matches_separate_kernels(c, B, precision, monkeypatch):
+    """FCResNetBlock with nonlin1 / (residual + nonlin2) applied in the contraction kernels' epilogue (fcb_fwd_act_*) against the
+    same block with TangentNonLin and the add as separate kernels: outputs, grad x and every parameter gradient; and the
+    fused run must not launch the stand-alone modReLU forward where the 2xFP16 kernel can carry the epilogue."""
+    from fieldconv_b200 import _lib, nn as fnn
+    mesh = torus_mesh(26, deg=40.0, seed=8, device=DEV)
+    plan = fcb.build_plan(mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp, mesh.w, 6, mesh.epsilon)
+    torch.manual_seed(3)
+    blk = fcb.FCResNetBlock(c, c, B, 6, 1, precision=precision).to(DEV)
+    with torch.no_grad():
+        blk.nonlin1.bias.uniform_(-0.3, 0.3)
+        blk.nonlin2.bias.uniform_(-0.3, 0.3)
+    gy = random_features(mesh.num_nodes, c, seed=5, zero_frac=0, device=DEV)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setattr(fnn, "BLOCK_EPILOGUE", mode)
+        blk.zero_grad()
+        x = random_features(mesh.num_nodes, c, seed=4, device=DEV).requires_grad_(True)
+        _lib.profile_enable(512)
+        y = blk(x, plan)
+        (y.real * gy.real + y.imag * gy.imag).sum().backward()
+        torch.cuda.synchronize()
+        names = [n for n, _ in _lib.profile_collect(512)]
+        res[mode] = (names, y.detach(), x.grad, {k: p.grad.clone() for k, p in blk.named_parameters()})
+    assert "modrelu_fwd" in res["0"][0]
+    assert "modrelu_fwd" not in res["1"][0]
+    if precision == "auto":          # one un-split 2xFP16 launch carries the epilogue: no pointwise kernel at all
+        assert "res_modrelu" not in res["1"][0], res["1"][0]
+    else:                            # paths that cannot fuse run ONE pointwise kernel instead of add + modReLU
+        assert "res_modrelu" in res["1"][0]
+    assert_close_normwise(res["1"][1], res["0"][1], 2e-6, "block y")
+    assert_close_normwise(res["1"][2], res["0"][2], 2e-6, "block grad x")
+    for k in res["0"][3]:
+        assert_close_normwise(res["1"][3][k], res["0"][3][k], 5e-6, "grad " + k)
+
+
 def _oracle_layer(mesh, x, m, gy, dtype=torch.complex128):
     """fp64 folded-form oracle on the CPU for a synthetic mesh."""
     B, R = m.B, m.R
