@@ -491,8 +491,9 @@ static int backward_common(const Dims& d, const float* x, const float* W, const 
         void* tcw = ar.take<char>(tcb);
         FCB_REQUIRE(ar.ok(), FCB_E_WORKSPACE, "bwd: workspace too small");
         int grouped = 0;     // all m in one pass over G (one long-K tensor-core pipeline) when the plan allows
+        // 2xFP16 grouped product: the softAngle chain rule runs in its epilogue (grouped == 2) — gxhat never reaches memory
         int rc = launch_gemm_grouped(G, Bt, gxh, d.N, 2 * d.Ci, Q2, d.M, flags | (g_packed ? FCB_FLAG_A_PACKED : 0), g_amax, tcw, tcb,
-                                     &grouped, st);
+                                     &grouped, st, x, gx);
         if (rc) return rc;
         FCB_REQUIRE(grouped || !g_packed, FCB_E_ARG, "bwd: packed G but the grouped contraction did not run");
         if (!grouped) {
@@ -505,7 +506,7 @@ static int backward_common(const Dims& d, const float* x, const float* W, const 
         const float2* x2 = reinterpret_cast<const float2*>(x);
         const float2* g2 = reinterpret_cast<const float2*>(gxh);
         float2* o2 = reinterpret_cast<float2*>(gx);
-        if (el > 0) {
+        if (el > 0 && grouped != 2) {
             prof_begin("softangle_bwd", st);
             switch (d.B) {
                 case 0: k_softangle_bwd<0><<<blocks, 256, 0, st>>>(x2, g2, o2, d.N, d.Ci); break;

@@ -144,7 +144,7 @@ int launch_absmax_f32(const float* p, int64_t rows, int cols, int64_t ld, int ba
 int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int n_pairs, int kgroups,
                      const float* amax_a, void* ws, size_t ws_bytes, int a_packed, cudaStream_t st, int split_k = 1,
-                     float* parts = nullptr, const GemmEpilogue* epi = nullptr);
+                     float* parts = nullptr, const GemmEpilogue* epi = nullptr, const float* sa_x = nullptr, float* sa_gx = nullptr);
 int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
                      int64_t ldc, int split, int64_t k_per_split, float* parts, int n_main, const float* amax_a, void* bp_ws,
                      size_t bp_bytes, int a_packed, cudaStream_t st);
@@ -178,7 +178,10 @@ int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N
                       void* ws, size_t ws_bytes, cudaStream_t st);
 // grad-x contraction gxh[:, m, :] = G[:, m, :] @ Bt[m] for all m in one pass over G when the tensor-core plan allows
 // (returns FCB_OK and sets *done = 1), otherwise leaves *done = 0 for the caller to use the batched path
+// sa_x / sa_gx (optional, 2xFP16 grouped product only): the softAngle chain rule runs in the epilogue and writes grad x
+// ([M x N/2] complex) instead of C; *done = 2 then
 int launch_gemm_grouped(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t Kg, int groups, int flags,
-                        const float* a_amax, void* ws, size_t ws_bytes, int* done, cudaStream_t st);
+                        const float* a_amax, void* ws, size_t ws_bytes, int* done, cudaStream_t st, const float* sa_x = nullptr,
+                        float* sa_gx = nullptr);
 
 }  // namespace fcb

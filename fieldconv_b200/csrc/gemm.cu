@@ -241,7 +241,7 @@ int launch_reduce_splits(const float* partials, float* C, int64_t M, int N, int6
 
 // A = [M x groups*Kg] row-major (lda = groups*Kg), Bm = groups matrices [Kg x N] back to back, C = [M x groups*N].
 int launch_gemm_grouped(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t Kg, int groups, int flags,
-                        const float* a_amax, void* ws, size_t ws_bytes, int* done, cudaStream_t st) {
+                        const float* a_amax, void* ws, size_t ws_bytes, int* done, cudaStream_t st, const float* sa_x, float* sa_gx) {
     *done = 0;
     const int mode = flags & FCB_GEMM_MASK;
     if (!mode_is_tc(mode) || groups < 2) return FCB_OK;
@@ -261,9 +261,10 @@ int launch_gemm_grouped(const float* A, const float* Bm, float* C, int64_t M, in
             if (rc) return rc;
             a_amax = slot;
         }
+        const bool sa = sa_gx && sa_x && groups >= 3 && groups <= 7 && (groups & 1) && (N % 8) == 0 && aligned16(sa_x) && aligned16(sa_gx);
         int rc = launch_gemm_h_nn(A, Bm, C, M, N, Kg, groups * Kg, N, groups * (int64_t)N, 1, 0, Kg * N, 0, 1, groups, a_amax, ws,
-                                  ws_bytes, packed ? 1 : 0, st);
-        if (rc == FCB_OK) *done = 1;
+                                  ws_bytes, packed ? 1 : 0, st, 1, nullptr, nullptr, sa ? sa_x : nullptr, sa ? sa_gx : nullptr);
+        if (rc == FCB_OK) *done = sa ? 2 : 1;
         return rc;
     }
     const int64_t chunks = Kg / 32;

@@ -178,8 +178,66 @@ struct Params {
     const float* epi_bias;     // N / 2 modReLU biases (one per complex output channel), nullptr: no activation output
     float* epi_act;            // [M x N] activated output (row stride epi_ld)
     int64_t epi_ld;
+    // fused softAngle chain rule (grouped-K mode, kgroups = 2 * sa_band + 1): the k-group accumulators ARE gxhat[:, m, :] of one
+    // row, so the epilogue turns them into grad x directly (utils/field.py:40-48) — gxhat never
+    // goes to memory and k_softangle_bwd is not launched.  sa_x / sa_gx: [M x N/2] complex, row stride N floats.
+    const float* sa_x;
+    float* sa_gx;
+    int sa_band;
     uint32_t tmem_cols;
 };
+
+// gx of 4 complex channels from their gxhat accumulators: non-origin  h_m = conj(g_m) u^(1-m),  gx = u (sum Re h_m - i sum (1-m) Im h_m);
+// origin  gx = sum_m g_m
+template <int BL>
+__device__ __forceinline__ void softangle_epilogue(uint32_t lane_base, int npad, int blk, float inv, const float* __restrict__ xrow,
+                                                   float* __restrict__ grow) {
+    constexpr int M = 2 * BL + 1;
+    uint32_t r[M][8];
+#pragma unroll
+    for (int kg = 0; kg < M; ++kg) tc_ld8(lane_base + (uint32_t)(kg * npad + 8 * blk), r[kg]);
+    tc_ld_wait();
+    if (!xrow) return;
+    const float4 xa = __ldg(reinterpret_cast<const float4*>(xrow + 8 * blk)), xb = __ldg(reinterpret_cast<const float4*>(xrow + 8 * blk) + 1);
+    const float2 zs[4] = {make_float2(xa.x, xa.y), make_float2(xa.z, xa.w), make_float2(xb.x, xb.y), make_float2(xb.z, xb.w)};
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float2 g[M];
+#pragma unroll
+        for (int kg = 0; kg < M; ++kg) g[kg] = make_float2(__uint_as_float(r[kg][2 * c]) * inv, __uint_as_float(r[kg][2 * c + 1]) * inv);
+        const float2 z = zs[c];
+        const bool origin = (fabsf(z.x) < 1e-7f) && (fabsf(z.y) < 1e-7f);
+        float2 out;
+        if (origin) {
+            out = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int kg = 0; kg < M; ++kg) { out.x += g[kg].x; out.y += g[kg].y; }
+        } else {
+            const float ri = rsqrtf(z.x * z.x + z.y * z.y);
+            const float2 u = make_float2(z.x * ri, z.y * ri);
+            float a = 0.f, b = 0.f;
+            {
+                const float2 h = cmul(make_float2(g[BL].x, -g[BL].y), u);
+                a += h.x; b -= h.y;
+            }
+            float2 pos = u, neg = u;
+#pragma unroll
+            for (int k = 1; k <= BL; ++k) {
+                pos = cmul(pos, u);              // u^(1+k)
+                neg = cmul_conj(neg, u);         // u^(1-k)
+                const float2 hm = cmul(make_float2(g[BL - k].x, -g[BL - k].y), pos);   // m = -k
+                const float2 hp = cmul(make_float2(g[BL + k].x, -g[BL + k].y), neg);   // m = +k
+                a += hm.x + hp.x;
+                b -= (float)(1 + k) * hm.y + (float)(1 - k) * hp.y;
+            }
+            out = cmul(u, make_float2(a, b));
+        }
+        o[2 * c] = out.x; o[2 * c + 1] = out.y;
+    }
+    *reinterpret_cast<float4*>(grow + 8 * blk) = make_float4(o[0], o[1], o[2], o[3]);
+    *(reinterpret_cast<float4*>(grow + 8 * blk) + 1) = make_float4(o[4], o[5], o[6], o[7]);
+}
 
 // PACKED: A is a PK buffer (common.cuh) — the (hi, lo) planes of every 64-column chunk are already the swizzled tile
 // images, so the loader thread brings them in with two 16 KB bulk copies per stage on the stage's `full_b` barrier and
@@ -330,6 +388,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
         const bool grouped = p.kgroups > 1;
         const int items = groups * (grouped ? p.kgroups : 1);       // (k-group, 16-column group) pairs
         const uint32_t lane_base = tmem_d + ((uint32_t)(32 * q) << 16);
+        if (grouped && p.sa_gx) {
+            // grad x straight from the k-group accumulators (N % 8 == 0 guaranteed by the launcher)
+            const float inv = inv_a * inv_b;
+            const float* xrow = m < p.M ? p.sa_x + m * (int64_t)p.N : nullptr;
+            float* grow = p.sa_gx + m * (int64_t)p.N;
+            for (int blk = part; blk < p.N / 8; blk += N_PROD_WARPS / 4) {
+                switch (p.sa_band) {
+                    case 1: softangle_epilogue<1>(lane_base, p.Npad, blk, inv, xrow, grow); break;
+                    case 2: softangle_epilogue<2>(lane_base, p.Npad, blk, inv, xrow, grow); break;
+                    default: softangle_epilogue<3>(lane_base, p.Npad, blk, inv, xrow, grow); break;
+                }
+            }
+        } else
         for (int it = part; it < items; it += N_PROD_WARPS / 4) {
             const int kg = it / groups, g = it - kg * groups;
             uint32_t r[16];
@@ -354,24 +425,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
             for (int e = 0; e < 16; ++e) acc[e] = acc[e] * inv_a * inv_b;
             if (p.epi_res && m < p.M) {
                 const float* rsrc = p.epi_res + m * p.epi_ld + 16 * g;
+                if (16 * g + 15 < p.N) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    if (16 * g + e < p.N) acc[e] += __ldg(rsrc + e);
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 r4 = __ldg(reinterpret_cast<const float4*>(rsrc) + c4);
+                        acc[4 * c4] += r4.x; acc[4 * c4 + 1] += r4.y; acc[4 * c4 + 2] += r4.z; acc[4 * c4 + 3] += r4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (16 * g + e < p.N) acc[e] += __ldg(rsrc + e);
+                }
             }
             if (p.epi_act && m < p.M) {
                 // modReLU on the 8 complex values of this piece: y = relu(|z| + b_c) z / |z|, origin entries passed through
                 float* adst = p.epi_act + m * p.epi_ld + 16 * g;
+                float a[16];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int n = 16 * g + 2 * j;
-                    if (n + 1 < p.N) {
-                        const float zx = acc[2 * j], zy = acc[2 * j + 1];
-                        const bool origin = (fabsf(zx) < 1e-7f) && (fabsf(zy) < 1e-7f);
-                        const float n2 = zx * zx + zy * zy;
-                        const float ri = rsqrtf(n2);
-                        const float sc = fmaxf(n2 * ri + __ldg(p.epi_bias + (n >> 1)), 0.f) * ri;
-                        *reinterpret_cast<float2*>(adst + 2 * j) = origin ? make_float2(zx, zy) : make_float2(sc * zx, sc * zy);
-                    }
+                    const float zx = acc[2 * j], zy = acc[2 * j + 1];
+                    const bool origin = (fabsf(zx) < 1e-7f) && (fabsf(zy) < 1e-7f);
+                    const float n2 = zx * zx + zy * zy;
+                    const float ri = rsqrtf(n2);
+                    const float sc = fmaxf(n2 * ri + (n + 1 < p.N ? __ldg(p.epi_bias + (n >> 1)) : 0.f), 0.f) * ri;
+                    a[2 * j] = origin ? zx : sc * zx;
+                    a[2 * j + 1] = origin ? zy : sc * zy;
+                }
+                if (16 * g + 15 < p.N) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4)
+                        *reinterpret_cast<float4*>(adst + 4 * c4) = make_float4(a[4 * c4], a[4 * c4 + 1], a[4 * c4 + 2], a[4 * c4 + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (16 * g + e < p.N) adst[e] = a[e];
                 }
             }
             if (m < p.M) {
@@ -898,7 +986,7 @@ int launch_absmax_f32(const float* p, int64_t rows, int cols, int64_t ld, int ba
 int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int n_pairs, int kgroups,
                      const float* amax_a, void* ws, size_t ws_bytes, int a_packed, cudaStream_t st, int split_k, float* parts,
-                     const GemmEpilogue* epi) {
+                     const GemmEpilogue* epi, const float* sa_x, float* sa_gx) {
     FCB_REQUIRE(A && B && C && ws && amax_a, FCB_E_ARG, "gemm_h: null pointer");
     FCB_REQUIRE(M >= 0 && N > 0 && K > 0 && batch >= 1 && batch <= 65535, FCB_E_ARG, "gemm_h: bad sizes");
     FCB_REQUIRE(N <= 256, FCB_E_UNSUPPORTED, "gemm_h: N=%d > 256 not supported by one accumulator pair", N);
@@ -942,6 +1030,12 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
     split_k = (nchunks * kgroups + p.cps - 1) / p.cps;          // no empty K range
     p.part_stride = 0;
     p.epi_res = nullptr; p.epi_bias = nullptr; p.epi_act = nullptr; p.epi_ld = 0;
+    p.sa_x = nullptr; p.sa_gx = nullptr; p.sa_band = 0;
+    if (sa_gx) {
+        FCB_REQUIRE(sa_x && kgroups >= 3 && kgroups <= 7 && (kgroups & 1) && (N % 8) == 0 && aligned16(sa_x) && aligned16(sa_gx), FCB_E_ARG,
+                    "gemm_h: the fused softAngle epilogue needs the grouped product of band limit 1..3 and N %% 8 == 0");
+        p.sa_x = sa_x; p.sa_gx = sa_gx; p.sa_band = (kgroups - 1) / 2;
+    }
     if (epi) {
         FCB_REQUIRE(split_k == 1 && kgroups == 1 && batch == 1 && (N & 1) == 0, FCB_E_ARG, "gemm_h: the fused epilogue needs one un-split product");
         p.epi_res = epi->res; p.epi_bias = epi->bias; p.epi_act = epi->act; p.epi_ld = epi->ld;
