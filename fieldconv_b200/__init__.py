@@ -5,6 +5,7 @@
 from .plan import DensePlan, Plan, build_dense_plan, build_plan  # noqa: F401
 from .partition import MeshPartition, allreduce_gradients, partition_mesh  # noqa: F401
 from .transforms import FCPrecomp, SupportGraph, farthest_point_sample, radius_graph  # noqa: F401
+from .echo import ECHO, ECHOBlock  # noqa: F401
 from .lift import LiftBlock, TransField  # noqa: F401
 from .nn import FCResNetBlock, FieldConv, TangentLin, TangentNonLin, fold_weights, prefold  # noqa: F401
 

@@ -51,6 +51,8 @@ SIGNATURES = {
     "fcb_fwd_fused_f32": [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_lift_aggregate_f32": [_P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
     "fcb_lift_aggregate_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
+    "fcb_echo_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _P],
+    "fcb_echo_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _P],
     "fcb_radius_workspace_bytes": [_I64, _PSZ],
     "fcb_radius_count": [_P, _I64, _F, _I, _F, _F, _F, _P, _P, _SZ, _P],
     "fcb_radius_fill": [_P, _I64, _F, _I, _F, _F, _F, _P, _P, _P, _SZ, _P],

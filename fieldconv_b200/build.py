@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfieldconv_b200.so")
 SOURCES = ["aggregate.cu", "aggregate_t.cu", "aggregate_pk.cu", "aggregate_pk_t.cu", "api.cu", "plan.cu", "gemm.cu", "gemm_tc.cu",
-           "gemm_h.cu", "fused_fwd.cu", "radius.cu", "lift.cu"]
+           "gemm_h.cu", "fused_fwd.cu", "radius.cu", "lift.cu", "echo.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -192,6 +192,19 @@ int fcb_lift_aggregate_bwd_f32(const float* g_agg, const float* g_mag, const flo
                                const int32_t* nbr_src, const int32_t* perm_src, float* gx, int64_t N, int Ci, int R,
                                void* stream);
 
+/* ---- ECHO descriptors (nn/echo.py:94-148 of the reference; csrc/echo.cu).  x: (N, C) complex64 tangent features; ln, wxp:
+ * (E,) complex64 as returned by FCPrecomp (transforms/fc_precomp.py:77,92) in the caller's edge order; CSR orders from
+ * fcb_plan_build_dense; dmap: the (2 n_bins + 1)^2 raster-cell -> bin table of nn/echo.py:11-27 (int32); hdim = number of
+ * bins (n_bins 1..3).  hist: (N, C, hdim) complex64 accumulated histogram (kept for the backward); out: (N, C, hdim)
+ * float32 = softAbs(hist).  Deterministic (one thread per histogram, fixed edge order); no host sync.  The backward
+ * returns grad x for a real upstream gradient g_out of `out`. */
+int fcb_echo_fwd_f32(const float* x, const float* ln, const float* wxp, const int32_t* rowptr_tgt, const int32_t* nbr_tgt,
+                     const int32_t* perm_tgt, const int32_t* dmap, float* hist, float* out, int64_t N, int C, int n_bins,
+                     int hdim, void* stream);
+int fcb_echo_bwd_f32(const float* x, const float* ln, const float* wxp, const int32_t* rowptr_src, const int32_t* nbr_src,
+                     const int32_t* perm_src, const int32_t* dmap, const float* hist, const float* g_out, float* gx,
+                     int64_t N, int C, int n_bins, int hdim, void* stream);
+
 /* ---- Support-graph construction (transforms/support_graph.py:56-59 of the reference: radius(pos, pos, epsilon,
  * max_num_neighbors=512), self loops included, rows (query j, found i) grouped by j).  Two passes over a hashed uniform grid
  * of cell size r (csrc/radius.cu): fcb_radius_count builds the grid in `workspace` and writes counts[N] (capped at

@@ -142,12 +142,41 @@ def make_lift(name, n_side, deg, ci, co, B, R, ftype, seed):
     print(name, "N", d.num_nodes, "E", e.shape[0], "|y|max", float(y.abs().max()))
 
 
+ECHO_CASES = [
+    # name, n_side, deg, C, n_bins, B, R (of the FCPrecomp call that produces ln / wxp)
+    ("echo_nb2", 8, 14.0, 4, 2, 1, 6),
+    ("echo_nb3", 7, 12.0, 6, 3, 2, 4),
+]
+
+
+def make_echo(name, n_side, deg, c, n_bins, B, R, seed):
+    """ECHO descriptors (nn/echo.py:94-148) on FCPrecomp's (supp_edges, ln, wxp) — SURVEY.md §8(f) F2."""
+    ns = ref_loader.load()
+    d = syn.torus_mesh(n_side, deg=deg, seed=seed, tile=4)
+    g = torch.Generator().manual_seed(seed)
+    keep = d.supp_edges[:, 1] != 3                      # an isolated target
+    for k in ("supp_edges", "logMag", "logAng", "xp"):
+        setattr(d, k, getattr(d, k)[keep])
+    e, _, ln, wxp = ns.FCPrecomp(B, R, float(d.epsilon))(d)
+    x = torch.complex(torch.randn(d.num_nodes, c, generator=g), torch.randn(d.num_nodes, c, generator=g))
+    x[torch.rand(x.shape, generator=g) < 0.08] = 0.0
+    echo = ns.ECHO(c, n_bins)
+    xr = x.clone().requires_grad_(True)
+    y = echo(xr, e, ln, wxp)
+    gy = torch.randn(y.shape, generator=g)
+    (y * gy).sum().backward()
+    out = dict(n=np.int64(d.num_nodes), c=np.int64(c), n_bins=np.int64(n_bins), hdim=np.int64(echo.hdim), supp_edges=_np(e),
+               ln=_np(ln), wxp=_np(wxp), x=_np(x), gy=_np(gy), y=_np(y), gx=_np(xr.grad), dMap=_np(echo.dMap))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+    print(name, "N", d.num_nodes, "E", e.shape[0], "hdim", echo.hdim, "|y|max", float(y.abs().max()))
+
+
 def main():
     import sys
     if not ref_loader.available():
         raise SystemExit("reference tree not present; golden vectors can only be generated in the build container")
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
-    only = sys.argv[1] if len(sys.argv) > 1 else "all"      # "all" | "fc" | "lift"
+    only = sys.argv[1] if len(sys.argv) > 1 else "all"      # "all" | "fc" | "lift" | "echo"
     if only in ("all", "fc"):
         for i, c in enumerate(CASES):
             make_case(*c, seed=100 + i)
@@ -155,6 +184,9 @@ def main():
     if only in ("all", "lift"):
         for i, c in enumerate(LIFT_CASES):
             make_lift(*c, seed=200 + i)
+    if only in ("all", "echo"):
+        for i, c in enumerate(ECHO_CASES):
+            make_echo(*c, seed=300 + i)
 
 
 if __name__ == "__main__":

@@ -85,6 +85,8 @@ def load():
         softAngle=ref_field.softAngle,
         TransField=ref_nn.TransField,
         LiftBlock=ref_nn.LiftBlock,
+        ECHO=ref_nn.ECHO,
+        ECHOBlock=ref_nn.ECHOBlock,
     )
     _cache["ns"] = ns
     return ns

@@ -119,3 +119,16 @@ def test_trans_field_restatements_match_reference(name):
         if g["ftype"] == 1:
             assert_close_normwise(ps[2].grad, g["g_phase"], 10 * tol, fn.__name__ + " g_phase")
     assert float(g["y"][5].abs().max()) == 0.0            # the isolated target
+
+
+@pytest.mark.parametrize("name", golden_names("echo_"))
+def test_echo_restatement_matches_reference(name):
+    """oracle/restate.py echo_refstyle (nn/echo.py:94-148) against outputs and autograd gradients of the unmodified reference."""
+    g = load_golden(name)
+    x = g["x"].clone().requires_grad_(True)
+    y = restate.echo_refstyle(x, g["supp_edges"], g["ln"], g["wxp"], g["n_bins"])
+    (y * g["gy"]).sum().backward()
+    d_map, dim = restate.echo_disk_map(g["n_bins"])
+    assert dim == g["hdim"] and torch.equal(d_map, g["dMap"])
+    assert float((y.detach() - g["y"]).abs().max()) <= 2e-6 * float(g["y"].abs().max())
+    assert float((x.grad - g["gx"]).abs().max()) <= 2e-6 * float(g["gx"].abs().max())
