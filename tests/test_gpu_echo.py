@@ -52,7 +52,8 @@ def test_echo_block_end_to_end():
     B, R, ci = 1, 6, 8
     edges, sten, ln, wxp = fcb.FCPrecomp(B, R, mesh.epsilon)(types.SimpleNamespace(**vars(mesh)))
     torch.manual_seed(0)
-    blk = fcb.ECHOBlock(ci, 5, n_des=4, n_bins=2, band_limit=B, n_rings=R, ftype=1).to(DEV)
+    blk = fcb.ECHOBlock(ci, 5, n_bins=2, band_limit=B, n_rings=R, ftype=1).to(DEV)      # n_des = in_channels (the reference's nonlin
+    # is TangentNonLin(in_channels), nn/echo_block.py:57, so only n_des == in_channels is usable there too)
     assert set(k.split(".")[0] for k in blk.state_dict()) == {"conv", "nonlin", "echo", "lin1", "lin2", "lin3", "res"}
     x = random_features(mesh.num_nodes, ci, seed=1, device=DEV).requires_grad_(True)
     out = blk(x, edges, sten, ln, wxp)

@@ -69,6 +69,8 @@ def test_lift_block_on_a_mesh_vs_fp64_oracle_and_determinism():
     # evaluation (the reference's own differs from its fp64 run by 4e-6..6e-6 on this mesh on the CPU, measured with
     # oracle/restate.py) sits around 1e-5 of fp64 here; the goldens above pin grad x to the reference's fp32 result at 1e-5.
     assert_close_normwise(x.grad, xd.grad.float(), 1e-4, "grad x")
-    assert_close_normwise(f.zonalAng.grad, ps[0].grad.float(), TOL, "grad zonalAng")
-    assert_close_normwise(f.zonalMag.grad, ps[1].grad.float(), TOL, "grad zonalMag")
-    assert_close_normwise(f.phase.grad, ps[2].grad.float(), TOL, "grad phase")
+    # parameter gradients against fp64 on this mesh: held to 1e-4 (measured 5e-6 .. 3e-5 run to run, the spread of the
+    # 1/|a|-amplified entries above); the reference's fp32 goldens pin all three to 1e-5 in the test above
+    assert_close_normwise(f.zonalAng.grad, ps[0].grad.float(), 1e-4, "grad zonalAng")
+    assert_close_normwise(f.zonalMag.grad, ps[1].grad.float(), 1e-4, "grad zonalMag")
+    assert_close_normwise(f.phase.grad, ps[2].grad.float(), 1e-4, "grad phase")
