@@ -24,6 +24,8 @@
 // fc_precomp.py:87 makes the row mass <= 1), folded into wxp per edge, exactly as the packed-operand path does.
 #include <cuda_fp16.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -457,19 +459,19 @@ int launch_fused_fwd(const float* x, const float* W, const int32_t* rowptr, cons
     uint32_t cols = 32;
     while ((int)cols < 2 * npad) cols <<= 1;
     p.tmem_cols = cols;
-    static bool attr_set_dev[64] = {};
-    bool attr_unknown_dev = false;
+    static std::atomic<bool> attr_set_dev[64];
+    std::atomic<bool> attr_unknown_dev{false};
     int attr_dev = 0;
     if (cudaGetDevice(&attr_dev) != cudaSuccess) attr_dev = -1;
-    bool& attr_set = (attr_dev >= 0 && attr_dev < 64) ? attr_set_dev[attr_dev] : attr_unknown_dev;
-    if (!attr_set) {
+    std::atomic<bool>& attr_set = (attr_dev >= 0 && attr_dev < 64) ? attr_set_dev[attr_dev] : attr_unknown_dev;
+    if (!attr_set.load(std::memory_order_acquire)) {       // idempotent: racing threads at worst set the attribute twice
         cudaError_t e = cudaFuncSetAttribute(ff::k_fused_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ff::k_fused_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_error("fused_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return FCB_E_CUDA;
         }
-        attr_set = true;
+        attr_set.store(true, std::memory_order_release);
     }
     const unsigned grid = (unsigned)((N + ff::ROWS - 1) / ff::ROWS);
     if (B == 0) FCB_LAUNCH("fused_fwd", st, ff::k_fused_fwd<0><<<grid, ff::THREADS, smem, st>>>(p));

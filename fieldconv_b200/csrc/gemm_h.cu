@@ -28,6 +28,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -1067,12 +1069,12 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
     p.stages = stages;
     const size_t smem = stages * stage_bytes + 1024 /*align slack*/ + 8 * (3 * stages + 2) + 64;
     // the opt-in shared-memory size is a per-device (per-context) function attribute: remember it per device
-    static bool attr_set_dev[64] = {};
-    bool attr_unknown_dev = false;
+    static std::atomic<bool> attr_set_dev[64];
+    std::atomic<bool> attr_unknown_dev{false};
     int attr_dev = 0;
     if (cudaGetDevice(&attr_dev) != cudaSuccess) attr_dev = -1;
-    bool& attr_set = (attr_dev >= 0 && attr_dev < 64) ? attr_set_dev[attr_dev] : attr_unknown_dev;
-    if (!attr_set) {
+    std::atomic<bool>& attr_set = (attr_dev >= 0 && attr_dev < 64) ? attr_set_dev[attr_dev] : attr_unknown_dev;
+    if (!attr_set.load(std::memory_order_acquire)) {       // idempotent: racing threads at worst set the attribute twice
         cudaError_t e = cudaFuncSetAttribute(th::k_gemm_h_nn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(th::k_gemm_h_nn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(th::k_gemm_h_nn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1080,7 +1082,7 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
             set_error("gemm_h: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return FCB_E_CUDA;
         }
-        attr_set = true;
+        attr_set.store(true, std::memory_order_release);
     }
     dim3 grid((unsigned)((M + th::BM - 1) / th::BM), (unsigned)batch, (unsigned)split_k);
     // FIELDCONV_B200_GEMM_PAIRED=1: paired chunk loads in the fp32-operand producers (experiment switch, read once)
@@ -1225,19 +1227,19 @@ static int launch_gemm_h_tn_packed_b(const float* A, const __half* Bp, const flo
     const size_t smem = stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
     dim3 grid((unsigned)((Mr + th::BM - 1) / th::BM), (unsigned)batch, (unsigned)split);
     // the opt-in shared-memory size is a per-device (per-context) function attribute: remember it per device
-    static bool attr_set_dev[64] = {};
-    bool attr_unknown_dev = false;
+    static std::atomic<bool> attr_set_dev[64];
+    std::atomic<bool> attr_unknown_dev{false};
     int attr_dev = 0;
     if (cudaGetDevice(&attr_dev) != cudaSuccess) attr_dev = -1;
-    bool& attr_set = (attr_dev >= 0 && attr_dev < 64) ? attr_set_dev[attr_dev] : attr_unknown_dev;
-    if (!attr_set) {
+    std::atomic<bool>& attr_set = (attr_dev >= 0 && attr_dev < 64) ? attr_set_dev[attr_dev] : attr_unknown_dev;
+    if (!attr_set.load(std::memory_order_acquire)) {       // idempotent: racing threads at worst set the attribute twice
         cudaError_t e = cudaFuncSetAttribute(th::k_gemm_h_tn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(th::k_gemm_h_tn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_error("gemm_h_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return FCB_E_CUDA;
         }
-        attr_set = true;
+        attr_set.store(true, std::memory_order_release);
     }
     if (a_packed) FCB_LAUNCH("gemm_p_tn", st, th::k_gemm_h_tn<true><<<grid, th::THREADS, smem, st>>>(p));
     else FCB_LAUNCH("gemm_h_tn", st, th::k_gemm_h_tn<false><<<grid, th::THREADS, smem, st>>>(p));

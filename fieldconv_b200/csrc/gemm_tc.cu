@@ -20,6 +20,8 @@
 //   warp 17    B operand: the weights are pre-packed (k_pack_b_tc) into the exact shared-memory image of every
 //              stage, so one cp.async.bulk (TMA engine, mbarrier complete_tx) per stage brings hi and lo planes in.
 // Shared-memory ring of S stages: {A_hi 16 KB, A_lo 16 KB, B_hi, B_lo (Npad*128 B each)}.
+#include <atomic>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -697,18 +699,18 @@ int launch_gemm_tc_nn(const float* A, const float* B, float* C, int64_t M, int N
     p.stages = stages;
     const size_t smem = stages * stage_bytes + 1024 /*align slack*/ + 8 * (3 * stages + 2) + 64;
     // the opt-in shared-memory size is a per-device (per-context) function attribute: remember it per device
-    static bool attr_set_dev[64] = {};
-    bool attr_unknown_dev = false;
+    static std::atomic<bool> attr_set_dev[64];
+    std::atomic<bool> attr_unknown_dev{false};
     int attr_dev = 0;
     if (cudaGetDevice(&attr_dev) != cudaSuccess) attr_dev = -1;
-    bool& attr_set = (attr_dev >= 0 && attr_dev < 64) ? attr_set_dev[attr_dev] : attr_unknown_dev;
-    if (!attr_set) {
+    std::atomic<bool>& attr_set = (attr_dev >= 0 && attr_dev < 64) ? attr_set_dev[attr_dev] : attr_unknown_dev;
+    if (!attr_set.load(std::memory_order_acquire)) {       // idempotent: racing threads at worst set the attribute twice
         cudaError_t e = cudaFuncSetAttribute(tc::k_gemm_tc_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return FCB_E_CUDA;
         }
-        attr_set = true;
+        attr_set.store(true, std::memory_order_release);
     }
     dim3 grid((unsigned)((M + tc::BM - 1) / tc::BM), (unsigned)batch);
     FCB_LAUNCH("gemm_tc_nn", st, tc::k_gemm_tc_nn<<<grid, tc::THREADS, smem, st>>>(p));
@@ -765,18 +767,18 @@ int launch_gemm_tc_tn(const float* A, const float* B, float* C, int64_t Mr, int 
     const size_t smem = stages * stage_bytes + 1024 + 8 * (3 * stages + 2) + 64;
     dim3 grid((unsigned)((Mr + tc::BM - 1) / tc::BM), 1, (unsigned)split);
     // the opt-in shared-memory size is a per-device (per-context) function attribute: remember it per device
-    static bool attr_set_dev[64] = {};
-    bool attr_unknown_dev = false;
+    static std::atomic<bool> attr_set_dev[64];
+    std::atomic<bool> attr_unknown_dev{false};
     int attr_dev = 0;
     if (cudaGetDevice(&attr_dev) != cudaSuccess) attr_dev = -1;
-    bool& attr_set = (attr_dev >= 0 && attr_dev < 64) ? attr_set_dev[attr_dev] : attr_unknown_dev;
-    if (!attr_set) {
+    std::atomic<bool>& attr_set = (attr_dev >= 0 && attr_dev < 64) ? attr_set_dev[attr_dev] : attr_unknown_dev;
+    if (!attr_set.load(std::memory_order_acquire)) {       // idempotent: racing threads at worst set the attribute twice
         cudaError_t e = cudaFuncSetAttribute(tc::k_gemm_tc_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
             set_error("gemm_tc_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return FCB_E_CUDA;
         }
-        attr_set = true;
+        attr_set.store(true, std::memory_order_release);
     }
     FCB_LAUNCH("gemm_tc_tn", st, tc::k_gemm_tc_tn<<<grid, tc::THREADS, smem, st>>>(p));
     return FCB_OK;

@@ -73,6 +73,10 @@ def packed_flags(flags, plan, n, ci, co, band_limit, n_rings, explicit, auto=Fal
     return flags
 
 
+import functools
+
+
+@functools.lru_cache(maxsize=None)
 def _resolve_precision(precision, ci, co, n_rings, band_limit):
     """"auto": error-compensated tensor cores — operands as scaled fp16 (hi, lo) pairs ("2xf16", fastest), else
     3xTF32 — when the library's accumulation plan (column chunks x TMEM accumulators, at most 400 accumulating MMAs

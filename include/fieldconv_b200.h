@@ -10,8 +10,11 @@
  * Conventions
  *  - every pointer is a DEVICE pointer unless stated otherwise; complex = interleaved
  *    (re, im) float pairs exactly like torch.complex64; all buffers are owned by the caller;
- *  - the library allocates nothing, keeps no state except a thread-local error string, never
- *    synchronises: all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *  - the library allocates no device memory and never synchronises: all work is enqueued on `stream` (a cudaStream_t
+ *    passed as void*).  Its only process state: a thread-local error string, an atomic launch counter
+ *    (fcb_launch_count), per-device atomic "opt-in shared-memory attribute already set" flags (idempotent), and the
+ *    optional per-launch timing facility fcb_profile_* (a debugging aid: NOT thread-safe, creates CUDA events — leave it
+ *    off in concurrent use);
  *  - return 0 on success, a negative FCB_E_* code on failure (fcb_last_error() explains);
  *  - feature rows must be 16-byte aligned: channel counts must be even (pad with a zero
  *    channel otherwise — the Python layer does this).
