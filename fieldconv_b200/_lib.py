@@ -16,6 +16,8 @@ FLAG_HAVE_CONTRIB = 0x100
 # Python-level only (ops.py): run the layer through fcb_fwd_pk_f32 / fcb_bwd_pk_f32 (packed fp16 operand planes written by
 # the aggregation kernels, bulk-copied by the contraction kernels); never passed to the library
 FLAG_PACKED = 0x200
+# Python-level only: backward through fcb_bwd_pk_f32 with a packed G even when the forward kept the fp32 contrib layout
+FLAG_PACKED_G = 0x800
 # Python-level only: run the forward through fcb_fwd_fused_f32 (band_limit <= 1: contrib never leaves the SM)
 FLAG_FUSED = 0x400
 

@@ -787,7 +787,8 @@ extern "C" int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, c
     FCB_REQUIRE(!gW || (contrib_pk && contrib_scale) || (rowptr_src && rec_src && rot_src && norm_src), FCB_E_ARG,
                 "bwd_pk: grad W needs the packed contrib + its scale, or the by-source plan and its norm");
     (void)rowptr_tgt; (void)rec_tgt; (void)rot_tgt; (void)norm_tgt;
-    FCB_REQUIRE(pk_contrib_ok(d), FCB_E_UNSUPPORTED, "bwd_pk: shape not supported by the packed path (fcb_pk_supported)");
+    FCB_REQUIRE(!(contrib_pk && contrib_scale) || pk_contrib_ok(d), FCB_E_UNSUPPORTED,
+                "bwd_pk: shape not supported by the packed path (fcb_pk_supported)");
     FCB_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(W), FCB_E_ALIGN, "bwd_pk: pointers must be 16-byte aligned");
     const bool from_g = gW && !(contrib_pk && contrib_scale);
     FCB_REQUIRE(ws_bytes >= bwd_ws(d, from_g, flags), FCB_E_WORKSPACE, "bwd_pk: workspace too small");

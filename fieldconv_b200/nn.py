@@ -46,6 +46,8 @@ def fused_flags(flags, plan, ci, co, band_limit, n_rings):
 
 
 LIN_POLICY = os.environ.get("FIELDCONV_B200_LIN", "2xf16")
+# FIELDCONV_B200_PACKED_G=0: band_limit 2 keeps the fp32 G layout in the backward too (A/B switch)
+PACKED_G_POLICY = os.environ.get("FIELDCONV_B200_PACKED_G", "1")
 # FIELDCONV_B200_BLOCK_EPILOGUE=0: FCResNetBlock runs TangentNonLin / the residual add as separate kernels (A/B switch)
 BLOCK_EPILOGUE = os.environ.get("FIELDCONV_B200_BLOCK_EPILOGUE", "1")
 
@@ -62,9 +64,15 @@ def packed_flags(flags, plan, n, ci, co, band_limit, n_rings, explicit, auto=Fal
     precision="auto" follows the measured policy above."""
     want = bool(flags & _lib.FLAG_PACKED) or (auto and _packed_by_default(band_limit) and (flags & _lib.GEMM_MASK) == _lib.GEMM_TC_2XF16)
     flags &= ~_lib.FLAG_PACKED
-    if not want:
-        return flags
     ok = getattr(plan, "norms", None) is not None and _lib.pk_supported(n, ci, co, band_limit, n_rings)
+    if not want:
+        # band_limit 2 under "auto": fp32 contrib in the forward (the packing store costs the aggregation more than the
+        # contraction gains), packed G in the backward, where TWO contractions read it (measured r02c at the cfg-2 layer:
+        # transposed aggregation +0.056 ms, grouped grad-x -0.053 ms, weight gradient -0.039 ms)
+        if auto and ok and band_limit == 2 and PACKED_POLICY != "0" and PACKED_G_POLICY == "1" and \
+                (flags & _lib.GEMM_MASK) == _lib.GEMM_TC_2XF16 and not ops.SAVE_CONTRIB:
+            flags |= _lib.FLAG_PACKED_G
+        return flags
     if ok:
         return flags | _lib.FLAG_PACKED
     if explicit:

@@ -61,7 +61,7 @@ def fc_fwd(x: Tensor, W: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: T
     k = n_rings * ci * (2 * band_limit + 1)
     packed = bool(flags & _lib.FLAG_PACKED)
     fused = bool(flags & _lib.FLAG_FUSED) and not keep_contrib
-    cflags = flags & ~(_lib.FLAG_PACKED | _lib.FLAG_FUSED)
+    cflags = flags & ~(_lib.FLAG_PACKED | _lib.FLAG_FUSED | _lib.FLAG_PACKED_G)
     y = torch.empty(n, co, dtype=torch.complex64, device=x.device)
     if fused:      # band_limit <= 1: one kernel, contrib never exists in device memory (csrc/fused_fwd.cu)
         nbytes = _lib.query_bytes("fcb_fwd_fused_workspace_bytes", ci, co, band_limit, n_rings)
@@ -106,11 +106,13 @@ def fc_bwd(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, cmax: Tensor, rowp
     x, W, gy = x.contiguous(), W.contiguous(), gy.contiguous()
     n, ci = x.shape
     co = W.shape[0]
-    packed = bool(flags & _lib.FLAG_PACKED)
-    cflags = flags & ~(_lib.FLAG_PACKED | _lib.FLAG_FUSED)
+    have_contrib = contrib.numel() > 0
+    # FLAG_PACKED_G: the forward ran the fp32 operand layout, the backward packs G (only meaningful when no fp32 contrib
+    # was kept: the packed entry point cannot read one)
+    packed = bool(flags & _lib.FLAG_PACKED) or (bool(flags & _lib.FLAG_PACKED_G) and not have_contrib)
+    cflags = flags & ~(_lib.FLAG_PACKED | _lib.FLAG_FUSED | _lib.FLAG_PACKED_G)
     gx = torch.empty_like(x) if need_gx else torch.empty(0, dtype=x.dtype, device=x.device)
     gw = torch.empty_like(W) if need_gw else torch.empty(0, dtype=W.dtype, device=x.device)
-    have_contrib = contrib.numel() > 0
     nbytes = _lib.query_bytes("fcb_bwd_workspace_bytes", n, ci, co, band_limit, n_rings,
                               cflags | (_lib.FLAG_HAVE_CONTRIB if have_contrib else 0))
     ws = _ws(nbytes, x.device)
@@ -174,7 +176,7 @@ def fc_fwd_act(x: Tensor, W: Tensor, res: Tensor, bias: Tensor, rowptr_tgt: Tens
     co = W.shape[0]
     k = n_rings * ci * (2 * band_limit + 1)
     packed = bool(flags & _lib.FLAG_PACKED)
-    cflags = flags & ~(_lib.FLAG_PACKED | _lib.FLAG_FUSED)
+    cflags = flags & ~(_lib.FLAG_PACKED | _lib.FLAG_FUSED | _lib.FLAG_PACKED_G)
     z = torch.empty(n, co, dtype=torch.complex64, device=x.device)
     act = torch.empty(n, co, dtype=torch.complex64, device=x.device)
     b = bias.reshape(-1).contiguous().float()
@@ -239,7 +241,7 @@ def field_conv_act(x, W, plan, band_limit, bias, res=None, flags=0):
     x, W, res and bias.  Returns the activated output."""
     norms = getattr(plan, "norms", None)
     if norms is None:
-        if flags & _lib.FLAG_PACKED:
+        if flags & (_lib.FLAG_PACKED | _lib.FLAG_PACKED_G):
             raise RuntimeError("fieldconv_b200: the packed path needs a plan built by build_plan (plan.norms)")
         norms = torch.zeros(2, dtype=torch.float32, device=x.device)
     has_res = res is not None
@@ -257,7 +259,7 @@ def field_conv(x, W, plan, band_limit, flags=0, keep_contrib=None):
         keep_contrib = keep_contrib_default(n * plan.n_rings * ci * (2 * band_limit + 1) * 8, x.device)
     norms = getattr(plan, "norms", None)
     if norms is None:
-        if flags & (_lib.FLAG_PACKED | _lib.FLAG_FUSED):
+        if flags & (_lib.FLAG_PACKED | _lib.FLAG_FUSED | _lib.FLAG_PACKED_G):
             raise RuntimeError("fieldconv_b200: the packed / fused paths need a plan built by build_plan (plan.norms)")
         norms = torch.zeros(2, dtype=torch.float32, device=x.device)
     y, _, _ = fc_fwd(x, W, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src, plan.rot_src, norms,

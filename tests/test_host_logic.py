@@ -76,7 +76,12 @@ def test_packed_path_selection_policy(monkeypatch):
     f16 = _lib.GEMM_TC_2XF16
     monkeypatch.setattr(fnn, "PACKED_POLICY", "auto")
     assert fnn.packed_flags(f16, FakePlan(), 5041, 32, 32, 1, 6, False, auto=True) == f16 | _lib.FLAG_PACKED
-    assert fnn.packed_flags(f16, FakePlan(), 80656, 48, 48, 2, 6, False, auto=True) == f16          # band_limit 2: unpacked
+    # band_limit 2: fp32 contrib in the forward, packed G in the backward (two contractions read it)
+    assert fnn.packed_flags(f16, FakePlan(), 80656, 48, 48, 2, 6, False, auto=True) == f16 | _lib.FLAG_PACKED_G
+    monkeypatch.setattr(fnn, "PACKED_G_POLICY", "0")
+    assert fnn.packed_flags(f16, FakePlan(), 80656, 48, 48, 2, 6, False, auto=True) == f16
+    monkeypatch.setattr(fnn, "PACKED_G_POLICY", "1")
+    assert fnn.packed_flags(f16, FakePlan(), 80656, 48, 48, 3, 6, False, auto=True) == f16          # band_limit 3: not measured, unpacked
     assert fnn.packed_flags(f16, NoNorms(), 5041, 32, 32, 1, 6, False, auto=True) == f16            # plan without norms
     assert fnn.packed_flags(f16, FakePlan(), 144, 6, 6, 1, 3, False, auto=True) == f16              # 108 columns: unsupported
     assert fnn.packed_flags(f16, FakePlan(), 5041, 32, 32, 1, 6, False, auto=False) == f16          # explicit "2xf16" stays unpacked
