@@ -283,12 +283,23 @@ __global__ void __launch_bounds__(256) k_modrelu_bwd(const float2* __restrict__ 
     }
 }
 
-__global__ void k_colsum_parts(const float* __restrict__ part, float* __restrict__ out, int64_t nparts, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// out[c] = sum_p part[p][c]: 32 lanes of a block share a channel group, lane l of column c sums the slabs l, l + 32, ...,
+// the 32 sums are added in lane order (fixed order).
+__global__ void __launch_bounds__(1024) k_colsum_parts(const float* __restrict__ part, float* __restrict__ out, int64_t nparts, int C) {
+    __shared__ float red[32][33];
+    const int cx = threadIdx.x & 31, l = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
     float s = 0.f;
-    for (int64_t p = 0; p < nparts; ++p) s += part[p * C + c];
-    out[c] = s;
+    if (c < C)
+        for (int64_t p = l; p < nparts; p += 32) s += part[p * C + c];
+    red[l][cx] = s;
+    __syncthreads();
+    if (l == 0 && c < C) {
+        float t = red[0][cx];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) t += red[j][cx];
+        out[c] = t;
+    }
 }
 
 // ----------------------------------------------------------------------------- layer drivers
@@ -909,6 +920,6 @@ extern "C" int fcb_modrelu_bwd_f32(const float* x, const float* bias, const floa
                                                           reinterpret_cast<const float2*>(gy),
                                                           reinterpret_cast<float2*>(gx), parts, N, C));
     }
-    FCB_LAUNCH("colsum_parts", st, k_colsum_parts<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(parts, gb, slabs, C));
+    FCB_LAUNCH("colsum_parts", st, k_colsum_parts<<<(unsigned)((C + 31) / 32), 1024, 0, st>>>(parts, gb, slabs, C));
     return FCB_OK;
 }

@@ -117,13 +117,18 @@ __global__ void __launch_bounds__(256) k_absmax(const float* __restrict__ p, int
     if (flat4) {       // contiguous and 16-byte aligned: float4 sweep
         const int64_t n4 = (int64_t)batch * rows * cols / 4;
         const float4* q = reinterpret_cast<const float4*>(p);
-        for (int64_t i = t0; i < n4; i += nt) {
-            const float4 v = __ldg(q + i);
+        auto take = [&](const float4 v) {
             mx = max(mx, __float_as_uint(fabsf(v.x)));
             mx = max(mx, __float_as_uint(fabsf(v.y)));
             mx = max(mx, __float_as_uint(fabsf(v.z)));
             mx = max(mx, __float_as_uint(fabsf(v.w)));
+        };
+        int64_t i = t0;
+        for (; i + 3 * nt < n4; i += 4 * nt) {      // four independent loads in flight per thread
+            const float4 v0 = __ldg(q + i), v1 = __ldg(q + i + nt), v2 = __ldg(q + i + 2 * nt), v3 = __ldg(q + i + 3 * nt);
+            take(v0); take(v1); take(v2); take(v3);
         }
+        for (; i < n4; i += nt) take(__ldg(q + i));
     } else {
         const int64_t per = rows * cols, tot = per * batch;
         for (int64_t i = t0; i < tot; i += nt) {
@@ -168,6 +173,8 @@ struct Params {
                                // products into its own accumulator and lands in C columns [g*N, (g+1)*N)
     int wide;                  // rows are 32-byte aligned: 256-bit loads
     int64_t a_tile_stride;     // PACKED: bytes between consecutive 128-row tiles of the PK buffer
+    int rows_per_tile;         // fp32 A: rows a CTA owns (<= BM, multiple of 8); BM for a PK operand
+    int reverse;               // row tiles taken last first
     // split-K (blockIdx.z, kgroups == 1 only): split z contracts the chunks [z * cps, min(nchunks, (z + 1) * cps)) and writes
     // its [M x N] partial at C + z * part_stride (ldc = N); the caller sums the partials in split order (deterministic).
     // Used for WIDE outputs (128 < N <= 256): all N columns in one accumulator pair (512 TMEM columns) and the K range cut
@@ -265,7 +272,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(sm + (tmem_slot - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    // Row tiles are taken LAST FIRST: the operand was just written front to back by the aggregation kernel, so its tail is
+    // what the (write-back) L2 still holds when this kernel starts.
+    const int64_t tile_x = p.reverse ? (int64_t)(gridDim.x - 1u - blockIdx.x) : (int64_t)blockIdx.x;
+    const int64_t m0 = tile_x * p.rows_per_tile;
+    const int64_t m_end = min(p.M, m0 + p.rows_per_tile);
     const int batch = blockIdx.y;
     const int kc_begin = (int)blockIdx.z * p.cps;
     const int n_kc = min(p.nchunks, kc_begin + p.cps) - kc_begin;       // chunks of this CTA (>= 1 by construction)
@@ -304,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
             const int idx = t + N_PROD * i;
             const int row = idx >> 3, j = idx & 7;          // 8 units of 8 reals per row and stage
             const int64_t m = m0 + row;
-            src[i] = (m < p.M) ? (A + m * p.lda + 8 * j) : nullptr;
+            src[i] = (m < m_end) ? (A + m * p.lda + 8 * j) : nullptr;
             kcol[i] = 8 * j;
             off[i] = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
         }
@@ -393,7 +404,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
         if (grouped && p.sa_gx) {
             // grad x straight from the k-group accumulators (N % 8 == 0 guaranteed by the launcher)
             const float inv = inv_a * inv_b;
-            const float* xrow = m < p.M ? p.sa_x + m * (int64_t)p.N : nullptr;
+            const float* xrow = m < m_end ? p.sa_x + m * (int64_t)p.N : nullptr;
             float* grow = p.sa_gx + m * (int64_t)p.N;
             for (int blk = part; blk < p.N / 8; blk += N_PROD_WARPS / 4) {
                 switch (p.sa_band) {
@@ -425,7 +436,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
             }
 #pragma unroll
             for (int e = 0; e < 16; ++e) acc[e] = acc[e] * inv_a * inv_b;
-            if (p.epi_res && m < p.M) {
+            if (p.epi_res && m < m_end) {
                 const float* rsrc = p.epi_res + m * p.epi_ld + 16 * g;
                 if (16 * g + 15 < p.N) {
 #pragma unroll
@@ -439,7 +450,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
                         if (16 * g + e < p.N) acc[e] += __ldg(rsrc + e);
                 }
             }
-            if (p.epi_act && m < p.M) {
+            if (p.epi_act && m < m_end) {
                 // modReLU on the 8 complex values of this piece: y = relu(|z| + b_c) z / |z|, origin entries passed through
                 float* adst = p.epi_act + m * p.epi_ld + 16 * g;
                 float a[16];
@@ -464,7 +475,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
                         if (16 * g + e < p.N) adst[e] = a[e];
                 }
             }
-            if (m < p.M) {
+            if (m < m_end) {
                 float* dst = C + m * p.ldc + (int64_t)kg * p.N + 16 * g;
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
@@ -532,7 +543,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
             const uint32_t bytes = 2u * b_plane;
             const int64_t src_step = (int64_t)2 * p.Npad * KC;
             const __half* src = Bp + (int64_t)kc_begin * src_step;
-            const uint8_t* a_src = reinterpret_cast<const uint8_t*>(p.A) + (int64_t)blockIdx.x * p.a_tile_stride +
+            const uint8_t* a_src = reinterpret_cast<const uint8_t*>(p.A) + tile_x * p.a_tile_stride +
                                    (int64_t)kc_begin * PK_BLOCK_BYTES;
             uint32_t s = 0, ph = 1;
             for (int kc = 0; kc < n_kc; ++kc) {
@@ -922,12 +933,25 @@ __global__ void __launch_bounds__(256) k_pack_xhat_tn(const float2* __restrict__
 // out (bit pattern of a non-negative float) = max(out, max_i |z_i| * (1 + 2^-20)): the bound on every real component of
 // xhat = z conj(u)^m.  out is pre-zeroed.
 __global__ void __launch_bounds__(256) k_absmax_modulus(const float2* __restrict__ z, int64_t n, uint32_t* __restrict__ out) {
-    float mx = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float2 v = __ldg(z + i);
-        mx = fmaxf(mx, sqrtf(v.x * v.x + v.y * v.y));
+    float m2 = 0.f;      // max |z|^2; the square root is monotone, one per thread at the end
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+    if (((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(z) & 15u) == 0)) {
+        const float4* q = reinterpret_cast<const float4*>(z);
+        const int64_t n2 = n >> 1;
+        auto take = [&](const float4 v) { m2 = fmaxf(m2, fmaxf(v.x * v.x + v.y * v.y, v.z * v.z + v.w * v.w)); };
+        int64_t i = t0;
+        for (; i + 3 * nt < n2; i += 4 * nt) {
+            const float4 v0 = __ldg(q + i), v1 = __ldg(q + i + nt), v2 = __ldg(q + i + 2 * nt), v3 = __ldg(q + i + 3 * nt);
+            take(v0); take(v1); take(v2); take(v3);
+        }
+        for (; i < n2; i += nt) take(__ldg(q + i));
+    } else {
+        for (int64_t i = t0; i < n; i += nt) {
+            const float2 v = __ldg(z + i);
+            m2 = fmaxf(m2, v.x * v.x + v.y * v.y);
+        }
     }
-    mx *= 1.000001f;
+    float mx = sqrtf(m2) * 1.000001f;
     const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
     if ((threadIdx.x & 31) == 0 && w > *reinterpret_cast<volatile uint32_t*>(out)) atomicMax(out, w);
 }
@@ -1084,7 +1108,20 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
         }
         attr_set.store(true, std::memory_order_release);
     }
-    dim3 grid((unsigned)((M + th::BM - 1) / th::BM), (unsigned)batch, (unsigned)split_k);
+    // fp32 operand: the row range is cut into equal tiles of <= 128 rows so that the grid fills whole waves of 148 CTAs (a
+    // 128-row MMA on fewer valid rows costs tensor time the kernel has to spare; the DRAM-bound loads shrink with the rows).
+    // A PK operand is tiled in 128-row images by its producer.
+    static const bool ragged = [] { const char* e = getenv("FIELDCONV_B200_GEMM_RAGGED"); return !e || atoi(e) != 0; }();
+    static const bool reverse = [] { const char* e = getenv("FIELDCONV_B200_GEMM_REVERSE"); return !e || atoi(e) != 0; }();
+    p.reverse = reverse ? 1 : 0;
+    p.rows_per_tile = th::BM;
+    if (!a_packed && ragged && batch == 1 && split_k == 1) {
+        const int64_t tiles = (M + th::BM - 1) / th::BM;
+        const int64_t ctas = (tiles + 147) / 148 * 148;
+        int64_t rpt = ((M + ctas - 1) / ctas + 7) / 8 * 8;
+        if (tiles > 148 && rpt >= 96 && rpt < th::BM) p.rows_per_tile = (int)rpt;
+    }
+    dim3 grid((unsigned)((M + p.rows_per_tile - 1) / p.rows_per_tile), (unsigned)batch, (unsigned)split_k);
     // FIELDCONV_B200_GEMM_PAIRED=1: paired chunk loads in the fp32-operand producers (experiment switch, read once)
     static const bool paired = [] { const char* e = getenv("FIELDCONV_B200_GEMM_PAIRED"); return e && atoi(e) != 0; }();
     if (a_packed) FCB_LAUNCH("gemm_p_nn", st, (th::k_gemm_h_nn<true, false><<<grid, th::THREADS, smem, st>>>(p)));

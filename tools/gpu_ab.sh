@@ -1,21 +1,16 @@
 #!/bin/bash
-# Lean A/B call: full parity suite with the current defaults, then the cfg-2 bench under the candidate settings.
-#   gpurun --timeout 600 -- 'bash tools/gpu_ab.sh r01g'
-TAG=${1:-rXX}
+# A/B of environment switches on the default bench (no cfg 4, no CPU baseline): one line per setting.
+#   gpurun --timeout 900 -- 'bash tools/gpu_ab.sh r02r "FIELDCONV_B200_GEMM_RAGGED=0" "FIELDCONV_B200_GEMM_REVERSE=0"'
+TAG=${1:-rXX}; shift
 OUT=gpurun_out
 mkdir -p $OUT
-export PYTHONUNBUFFERED=1
-timeout 300 python -m pytest tests -m gpu -q -rf --tb=short -p no:cacheprovider > $OUT/${TAG}_pytest.log 2>&1
-echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
-tail -6 $OUT/${TAG}_pytest.log | cut -c 1-300
-timeout 200 python bench.py --skip-cpu-baseline > $OUT/${TAG}_bench_default.json 2> $OUT/${TAG}_bench_default.err
-FIELDCONV_B200_AGG_OCC3_MAX_B=2 timeout 200 python bench.py --skip-cpu-baseline > $OUT/${TAG}_bench_occ3b2.json 2> $OUT/${TAG}_bench_occ3b2.err
-timeout 200 python bench.py --skip-cpu-baseline --precision 2xf16p > $OUT/${TAG}_bench_packed.json 2> $OUT/${TAG}_bench_packed.err
-FIELDCONV_B200_AGG_OCC3_MAX_B=2 timeout 200 python bench.py --skip-cpu-baseline --precision 2xf16p > $OUT/${TAG}_bench_packed_occ3b2.json 2> $OUT/${TAG}_bench_packed_occ3b2.err
-for f in default occ3b2 packed packed_occ3b2; do echo "== $f"; cut -c 1-260 $OUT/${TAG}_bench_$f.json; tail -2 $OUT/${TAG}_bench_$f.err; done
-{
-  FIELDCONV_B200_AGG_OCC3_MAX_B=2 timeout 100 python tools/layer_bench.py --side 284 --channels 48 --band 2 --rings 6 --tag occ3b2
-  FIELDCONV_B200_AGG_OCC3_MAX_B=2 timeout 100 python tools/layer_bench.py --side 284 --channels 48 --band 2 --rings 6 --precision 2xf16p --tag occ3b2
-  FIELDCONV_B200_AGG_OCC3_MAX_B=2 timeout 100 python tools/layer_bench.py --side 83 --channels 128 --band 2 --rings 6 --graph --tag occ3b2
-} > $OUT/${TAG}_layers_ab.jsonl 2> $OUT/${TAG}_layers_ab.err
-cut -c 1-600 $OUT/${TAG}_layers_ab.jsonl; tail -3 $OUT/${TAG}_layers_ab.err
+run() {
+  env "$@" python bench.py --skip-cfg4 --skip-cpu-baseline 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print(json.dumps({'env': sys.argv[1:], 'ms_per_step': d['ms_per_step'], 'e2e_ms': d['e2e']['ms_per_step'], 'kernels_ms': {k: v['ms'] for k, v in d['kernel_shares'].items()}}))" "$@"
+}
+: > $OUT/${TAG}_ab.jsonl
+run X=0 | tee -a $OUT/${TAG}_ab.jsonl
+for s in "$@"; do run $s | tee -a $OUT/${TAG}_ab.jsonl; done
+run X=0 | tee -a $OUT/${TAG}_ab.jsonl
