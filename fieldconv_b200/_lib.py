@@ -39,16 +39,17 @@ SIGNATURES = {
     "fcb_precomp_expand_f32": [_P, _P, _P, _F, _I64, _I64, _I, _I, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P],
     "fcb_fwd_workspace_bytes": [_I64, _I, _I, _I, _I, _I, _PSZ],
     "fcb_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
-    "fcb_fwd_act_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
-    "fcb_fwd_act_pk_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_bound_f32": [_P, _I64, _P, _P],
+    "fcb_fwd_act_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_fwd_act_pk_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_bwd_workspace_bytes": [_I64, _I, _I, _I, _I, _I, _PSZ],
-    "fcb_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_fwd_dense_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_bwd_dense_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_plan_norm": [_P, _P, _I64, _P, _P],
     "fcb_pk_contrib_bytes": [_I64, _I, _I, _I, _PSZ],
-    "fcb_fwd_pk_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
-    "fcb_bwd_pk_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_fwd_pk_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "fcb_bwd_pk_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_fwd_fused_workspace_bytes": [_I, _I, _I, _I, _PSZ],
     "fcb_fwd_fused_f32": [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _I, _I, _P, _SZ, _P],
     "fcb_lift_aggregate_f32": [_P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
@@ -61,12 +62,12 @@ SIGNATURES = {
     "fcb_aggregate_f32": [_P, _P, _P, _P, _P, _I64, _I, _I, _I, _I, _P],
     "fcb_gemm_workspace_bytes": [_I64, _I, _I64, _I, _I, _I, _I, _PSZ],
     "fcb_gemm_tc_feasible": [_I, _I64, _I, _I, _I],
-    "fcb_gemm_f32": [_P, _P, _P, _I64, _I, _I64, _I64, _I64, _I64, _I, _I, _I64, _I64, _I64, _I, _P, _SZ, _I, _P],
+    "fcb_gemm_f32": [_P, _P, _P, _I64, _I, _I64, _I64, _I64, _I64, _I, _I, _I64, _I64, _I64, _I, _P, _P, _P, _SZ, _I, _P],
     "fcb_sort_workspace_bytes": [_I64, _PSZ],
     "fcb_sort_pairs_u32": [_P, _P, _P, _P, _I64, _I, _P, _SZ, _P],
     "fcb_modrelu_fwd_f32": [_P, _P, _P, _I64, _I, _P],
     "fcb_modrelu_bwd_workspace_bytes": [_I64, _I, _PSZ],
-    "fcb_modrelu_bwd_f32": [_P, _P, _P, _P, _P, _I64, _I, _P, _SZ, _P],
+    "fcb_modrelu_bwd_f32": [_P, _P, _P, _P, _P, _P, _I64, _I, _P, _SZ, _P],
     "fcb_profile_enable": [_I],
     "fcb_profile_disable": [],
     "fcb_profile_collect": [ctypes.c_char_p, _SZ, ctypes.POINTER(ctypes.c_float), _I, ctypes.POINTER(_I)],
@@ -135,6 +136,18 @@ def fused_supported(ci, co, band_limit, n_rings):
 
 def ptr(t):
     return 0 if t is None else t.data_ptr()
+
+
+class Bounds(ctypes.Structure):
+    """struct fcb_bounds of the header: optional operand bounds (device pointers to one float, 0 = not available)."""
+    _fields_ = [("x", ctypes.c_void_p), ("gy", ctypes.c_void_p), ("act", ctypes.c_void_p)]
+
+
+def bounds(x=None, gy=None, act=None):
+    """-> argument for a `const fcb_bounds*` parameter (None when nothing is known: the library then computes what it needs)."""
+    if x is None and gy is None and act is None:
+        return None
+    return ctypes.byref(Bounds(ptr(x) or None, ptr(gy) or None, ptr(act) or None))
 
 
 def stream_ptr():

@@ -213,25 +213,34 @@ __global__ void k_modrelu_fwd(const float2* __restrict__ x, const float* __restr
 // z = y (+ res) in place, act = modReLU(z, bias): the stand-alone form of the block epilogue for the contraction paths that
 // cannot fuse it (FP32-FMA, 3xTF32, split / chunked 2xFP16 products)
 __global__ void k_res_modrelu(float2* __restrict__ y, const float2* __restrict__ res, const float* __restrict__ bias,
-                              float2* __restrict__ act, int64_t total, int C) {
+                              float2* __restrict__ act, int64_t total, int C, uint32_t* __restrict__ act_bound) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    float2 z = y[i];
-    if (res) {
-        const float2 r = res[i];
-        z.x += r.x; z.y += r.y;
-        y[i] = z;
+    float mod = 0.f;                 // |act_i| (the whole warp stays for the reduction below)
+    if (i < total) {
+        float2 z = y[i];
+        if (res) {
+            const float2 r = res[i];
+            z.x += r.x; z.y += r.y;
+            y[i] = z;
+        }
+        if (act) {
+            const bool origin = (fabsf(z.x) < 1e-7f) && (fabsf(z.y) < 1e-7f);
+            float2 out = z;
+            mod = 2e-7f;
+            if (!origin) {
+                const float n2 = z.x * z.x + z.y * z.y;
+                const float ri = rsqrtf(n2);
+                mod = fmaxf(n2 * ri + bias[i % C], 0.f);
+                const float s = mod * ri;
+                out = make_float2(s * z.x, s * z.y);
+            }
+            act[i] = out;
+        }
     }
-    if (!act) return;
-    const bool origin = (fabsf(z.x) < 1e-7f) && (fabsf(z.y) < 1e-7f);
-    float2 out = z;
-    if (!origin) {
-        const float n2 = z.x * z.x + z.y * z.y;
-        const float ri = rsqrtf(n2);
-        const float s = fmaxf(n2 * ri + bias[i % C], 0.f) * ri;
-        out = make_float2(s * z.x, s * z.y);
+    if (act && act_bound) {
+        const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(mod * 1.000001f));
+        if ((threadIdx.x & 31) == 0 && w > *reinterpret_cast<volatile uint32_t*>(act_bound)) atomicMax(act_bound, w);
     }
-    act[i] = out;
 }
 
 constexpr int MR_ROWS = 256;  // rows per block slab in the backward bias reduction
@@ -239,17 +248,20 @@ constexpr int MR_ROWS = 256;  // rows per block slab in the backward bias reduct
 // gx = u (s' Re t + i (s/rho) Im t), t = conj(u) g ; gb_c = sum_n s' Re t   
 __global__ void __launch_bounds__(256) k_modrelu_bwd(const float2* __restrict__ x, const float* __restrict__ bias,
                                                      const float2* __restrict__ gy, float2* __restrict__ gx,
-                                                     float* __restrict__ gb_part, int64_t N, int C) {
+                                                     float* __restrict__ gb_part, int64_t N, int C, uint32_t* __restrict__ gx_bound) {
     extern __shared__ float red[];   // [lanes_per_col][C]
     const int rl_count = max(1, 256 / C);
     const int rl = threadIdx.x / C, c = threadIdx.x - rl * C;
     const int64_t r0 = (int64_t)blockIdx.x * MR_ROWS;
     float part = 0.f;
+    float gmx = 0.f;                             // max |component| of what this thread writes to gx
     if (rl < rl_count) {
         for (int cc = c; cc < C; cc += 256) {   // C > 256: a thread strides channels
             const float bc = bias[cc];
             float acc = 0.f;
-            for (int64_t r = r0 + rl; r < min(N, r0 + MR_ROWS); r += rl_count) {
+            const int64_t r_end = min(N, r0 + MR_ROWS);
+#pragma unroll 4
+            for (int64_t r = r0 + rl; r < r_end; r += rl_count) {
                 const int64_t i = r * C + cc;
                 const float2 z = x[i];
                 const float2 g = gy[i];
@@ -268,9 +280,17 @@ __global__ void __launch_bounds__(256) k_modrelu_bwd(const float2* __restrict__ 
                     acc += sp * t.x;
                 }
                 gx[i] = out;
+                gmx = fmaxf(gmx, fmaxf(fabsf(out.x), fabsf(out.y)));
             }
             if (C > 256) gb_part[(int64_t)blockIdx.x * C + cc] = acc; else part = acc;
         }
+    }
+    __shared__ uint32_t s_mx;                    // block maximum first: one global atomic per block
+    if (gx_bound) {
+        if (threadIdx.x == 0) s_mx = 0u;
+        __syncthreads();
+        const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(gmx));
+        if ((threadIdx.x & 31) == 0 && w != 0u) atomicMax(&s_mx, w);
     }
     if (C <= 256) {
         if (rl < rl_count) red[rl * C + c] = part;
@@ -280,7 +300,10 @@ __global__ void __launch_bounds__(256) k_modrelu_bwd(const float2* __restrict__ 
             for (int k = 0; k < rl_count; ++k) s += red[k * C + threadIdx.x];
             gb_part[(int64_t)blockIdx.x * C + threadIdx.x] = s;
         }
+    } else {
+        __syncthreads();
     }
+    if (gx_bound && threadIdx.x == 0 && s_mx > *reinterpret_cast<volatile uint32_t*>(gx_bound)) atomicMax(gx_bound, s_mx);
 }
 
 // out[c] = sum_p part[p][c]: 32 lanes of a block share a channel group, lane l of column c sums the slabs l, l + 32, ...,
@@ -436,7 +459,7 @@ static int apply_epilogue(const Dims& d, float* y, const GemmEpilogue* epi, cuda
     FCB_REQUIRE(epi->ld == 2 * (int64_t)d.Co, FCB_E_ARG, "fwd: the block epilogue needs dense (N, Co) residual / activation buffers");
     FCB_LAUNCH("res_modrelu", st, k_res_modrelu<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
                                       reinterpret_cast<float2*>(y), reinterpret_cast<const float2*>(epi->res), epi->bias,
-                                      reinterpret_cast<float2*>(epi->act), tot, d.Co));
+                                      reinterpret_cast<float2*>(epi->act), tot, d.Co, reinterpret_cast<uint32_t*>(epi->act_bound)));
     return FCB_OK;
 }
 
@@ -465,7 +488,8 @@ static int contract_fwd(const Dims& d, const float* contrib, const float* amax, 
 template <typename GatherT>
 static int backward_common(const Dims& d, const float* x, const float* W, const float* gy, const float* contrib,
                            const float* contrib_amax, float* g_amax, GatherT&& gather_transpose, float* gx, float* gW,
-                           Arena& ar, int flags, cudaStream_t st, bool contrib_packed = false, bool g_packed = false) {
+                           Arena& ar, int flags, cudaStream_t st, bool contrib_packed = false, bool g_packed = false,
+                           const float* x_bound = nullptr) {
     float* Bt = ar.take<float>((size_t)(4 * d.K * d.Co));
     float* P = ar.take<float>((size_t)(4 * d.K * d.Co));
     const bool from_g = gW && !contrib;
@@ -536,7 +560,7 @@ static int backward_common(const Dims& d, const float* x, const float* W, const 
         const int N2 = 2 * d.Ci;
         if (gp.batched) {
             int rc = launch_gemm_h_tn_xhat(G, x, P, Mr, d.Ci, d.B, d.N, gp.split, gp.kps, parts, gp.n_main, g_amax, xhat_ws,
-                                           gp.xhat_ws + 256, g_packed ? 1 : 0, st);
+                                           gp.xhat_ws + 256, g_packed ? 1 : 0, st, x_bound);
             if (rc) return rc;
             if (gp.split > 1) {
                 rc = launch_reduce_splits(parts, P, (int64_t)d.M * Mr, N2, N2, 0, 1, gp.split, st);
@@ -676,10 +700,16 @@ extern "C" int fcb_fwd_f32(const float* x, const float* W, const int32_t* rowptr
                     stream, nullptr);
 }
 
-static int make_epilogue(const float* res, const float* bias, float* act, int Co, GemmEpilogue* e) {
+static int make_epilogue(const float* res, const float* bias, float* act, int Co, const fcb_bounds* bounds, cudaStream_t st,
+                         GemmEpilogue* e) {
     FCB_REQUIRE((bias == nullptr) == (act == nullptr), FCB_E_ARG, "fwd_act: bias and act go together");
     FCB_REQUIRE((!res || aligned16(res)) && (!act || aligned16(act)), FCB_E_ALIGN, "fwd_act: res / act must be 16-byte aligned");
     e->res = res; e->bias = bias; e->act = act; e->ld = 2 * (int64_t)Co;
+    e->act_bound = (bounds && act) ? bounds->act : nullptr;
+    if (e->act_bound && cudaMemsetAsync(e->act_bound, 0, 4, st) != cudaSuccess) {
+        set_error("fwd_act: cudaMemsetAsync failed");
+        return FCB_E_CUDA;
+    }
     return FCB_OK;
 }
 
@@ -687,10 +717,10 @@ static int make_epilogue(const float* res, const float* bias, float* act, int Co
 // act = modReLU(y, bias) (nn/tangent_nonlin.py:24-35; bias / act may both be NULL).  Otherwise as fcb_fwd_f32.
 extern "C" int fcb_fwd_act_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
                                const float* rot_tgt, float* y, float* contrib, float* contrib_absmax, const float* res,
-                               const float* bias, float* act, int64_t N, int Ci, int Co, int band_limit, int R, int flags,
-                               void* ws, size_t ws_bytes, void* stream) {
+                               const float* bias, float* act, const fcb_bounds* bounds, int64_t N, int Ci, int Co, int band_limit,
+                               int R, int flags, void* ws, size_t ws_bytes, void* stream) {
     GemmEpilogue e;
-    int rc = make_epilogue(res, bias, act, Co, &e);
+    int rc = make_epilogue(res, bias, act, Co, bounds, static_cast<cudaStream_t>(stream), &e);
     if (rc) return rc;
     return fwd_impl(x, W, rowptr_tgt, rec_tgt, rot_tgt, y, contrib, contrib_absmax, N, Ci, Co, band_limit, R, flags, ws, ws_bytes,
                     stream, &e);
@@ -699,8 +729,8 @@ extern "C" int fcb_fwd_act_f32(const float* x, const float* W, const int32_t* ro
 extern "C" int fcb_bwd_f32(const float* x, const float* W, const float* gy, const float* contrib,
                            const float* contrib_absmax, const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
                            const int32_t* rowptr_src, const void* rec_src, const float* rot_src, float* gx, float* gW,
-                           int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws, size_t ws_bytes,
-                           void* stream) {
+                           const fcb_bounds* bounds, int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws,
+                           size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Dims d;
     int rc = check_dims("bwd", N, Ci, Co, band_limit, R, &d);
@@ -725,7 +755,8 @@ extern "C" int fcb_bwd_f32(const float* x, const float* W, const float* gy, cons
     auto gather = [&](float* G, float* g_amax, bool) {
         return launch_aggregate(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, g_amax, st);
     };
-    return backward_common(d, x, W, gy, contrib, contrib_absmax, slots + 64, gather, gx, gW, ar, flags, st);
+    return backward_common(d, x, W, gy, contrib, contrib_absmax, slots + 64, gather, gx, gW, ar, flags, st, false, false,
+                           bounds ? bounds->x : nullptr);
 }
 
 // ------------------------------------------------------------------ packed-operand (PK) variants
@@ -745,7 +776,8 @@ extern "C" int fcb_pk_contrib_bytes(int64_t N, int Ci, int band_limit, int R, si
 
 static int fwd_pk_impl(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
                        const float* norm_tgt, float* y, void* contrib_pk, float* contrib_scale, int64_t N, int Ci, int Co,
-                       int band_limit, int R, int flags, void* ws, size_t ws_bytes, void* stream, const GemmEpilogue* epi) {
+                       int band_limit, int R, int flags, void* ws, size_t ws_bytes, void* stream, const GemmEpilogue* epi,
+                       const float* x_bound) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Dims d;
     int rc = check_dims("fwd_pk", N, Ci, Co, band_limit, R, &d);
@@ -756,9 +788,13 @@ static int fwd_pk_impl(const float* x, const float* W, const int32_t* rowptr_tgt
     FCB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(W), FCB_E_ALIGN, "fwd_pk: pointers must be 16-byte aligned");
     FCB_REQUIRE(ws_bytes >= fwd_ws(d), FCB_E_WORKSPACE, "fwd_pk: workspace too small");
     if (N == 0) return FCB_OK;
-    float* x_amax = static_cast<float*>(ws) + 16;          // inside the 256-byte scalar area at the head of the workspace
-    rc = launch_absmax_f32(x, N, 2 * Ci, 2 * (int64_t)Ci, 1, 0, x_amax, st);
-    if (rc) return rc;
+    const float* x_amax = x_bound;                         // supplied by the producer of x, else one pass over x
+    if (!x_amax) {
+        float* slot = static_cast<float*>(ws) + 16;        // inside the 256-byte scalar area at the head of the workspace
+        rc = launch_absmax_f32(x, N, 2 * Ci, 2 * (int64_t)Ci, 1, 0, slot, st);
+        if (rc) return rc;
+        x_amax = slot;
+    }
     rc = launch_aggregate_packed(x, rowptr_tgt, rec_tgt, rot_tgt, contrib_pk, N, Ci, band_limit, R, 0, x_amax, norm_tgt, contrib_scale, st);
     if (rc) return rc;
     return contract_fwd(d, static_cast<const float*>(contrib_pk), contrib_scale, W, y, ws, ws_bytes, flags | FCB_FLAG_A_PACKED, st, epi);
@@ -766,28 +802,28 @@ static int fwd_pk_impl(const float* x, const float* W, const int32_t* rowptr_tgt
 
 extern "C" int fcb_fwd_pk_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
                               const float* rot_tgt, const float* norm_tgt, float* y, void* contrib_pk, float* contrib_scale,
-                              int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws, size_t ws_bytes,
-                              void* stream) {
+                              const fcb_bounds* bounds, int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws,
+                              size_t ws_bytes, void* stream) {
     return fwd_pk_impl(x, W, rowptr_tgt, rec_tgt, rot_tgt, norm_tgt, y, contrib_pk, contrib_scale, N, Ci, Co, band_limit, R, flags, ws,
-                       ws_bytes, stream, nullptr);
+                       ws_bytes, stream, nullptr, bounds ? bounds->x : nullptr);
 }
 
 extern "C" int fcb_fwd_act_pk_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
                                   const float* rot_tgt, const float* norm_tgt, float* y, void* contrib_pk, float* contrib_scale,
-                                  const float* res, const float* bias, float* act, int64_t N, int Ci, int Co, int band_limit,
-                                  int R, int flags, void* ws, size_t ws_bytes, void* stream) {
+                                  const float* res, const float* bias, float* act, const fcb_bounds* bounds, int64_t N, int Ci,
+                                  int Co, int band_limit, int R, int flags, void* ws, size_t ws_bytes, void* stream) {
     GemmEpilogue e;
-    int rc = make_epilogue(res, bias, act, Co, &e);
+    int rc = make_epilogue(res, bias, act, Co, bounds, static_cast<cudaStream_t>(stream), &e);
     if (rc) return rc;
     return fwd_pk_impl(x, W, rowptr_tgt, rec_tgt, rot_tgt, norm_tgt, y, contrib_pk, contrib_scale, N, Ci, Co, band_limit, R, flags, ws,
-                       ws_bytes, stream, &e);
+                       ws_bytes, stream, &e, bounds ? bounds->x : nullptr);
 }
 
 extern "C" int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, const void* contrib_pk,
                               const float* contrib_scale, const int32_t* rowptr_tgt, const void* rec_tgt,
                               const float* rot_tgt, const float* norm_tgt, const int32_t* rowptr_src, const void* rec_src,
-                              const float* rot_src, const float* norm_src, float* gx, float* gW, int64_t N, int Ci, int Co,
-                              int band_limit, int R, int flags, void* ws, size_t ws_bytes, void* stream) {
+                              const float* rot_src, const float* norm_src, float* gx, float* gW, const fcb_bounds* bounds,
+                              int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Dims d;
     int rc = check_dims("bwd_pk", N, Ci, Co, band_limit, R, &d);
@@ -817,14 +853,25 @@ extern "C" int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, c
     const bool g_pk = pk_g_ok(d) && (!from_g || gw_from_g_plan(d, flags).batched);
     auto gather = [&](float* G, float* g_amax, bool packed) {
         if (!packed) return launch_aggregate(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, g_amax, st);
-        int r2 = launch_absmax_f32(gy, N, 2 * Co, 2 * (int64_t)Co, 1, 0, slots + 80, st);
-        if (r2) return r2;
-        return launch_aggregate_packed(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, slots + 80, norm_src, g_amax, st);
+        const float* gy_amax = bounds ? bounds->gy : nullptr;       // supplied by the producer of gy, else one pass over gy
+        if (!gy_amax) {
+            int r2 = launch_absmax_f32(gy, N, 2 * Co, 2 * (int64_t)Co, 1, 0, slots + 80, st);
+            if (r2) return r2;
+            gy_amax = slots + 80;
+        }
+        return launch_aggregate_packed(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, gy_amax, norm_src, g_amax, st);
     };
-    return backward_common(d, x, W, gy, contrib, contrib_scale, slots + 64, gather, gx, gW, ar, flags, st, !from_g, g_pk);
+    return backward_common(d, x, W, gy, contrib, contrib_scale, slots + 64, gather, gx, gW, ar, flags, st, !from_g, g_pk,
+                           bounds ? bounds->x : nullptr);
 }
 
 // ------------------------------------------------------------------ fused forward (band_limit <= 1)
+// ------------------------------------------------------------------ operand bounds
+extern "C" int fcb_bound_f32(const float* z, int64_t n_complex, float* bound_out, void* stream) {
+    FCB_REQUIRE(bound_out && n_complex >= 0 && (z || n_complex == 0), FCB_E_ARG, "bound: bad arguments");
+    return launch_bound_modulus(z, n_complex, bound_out, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int fcb_fused_supported(int Ci, int Co, int band_limit, int R) { return fused_fwd_ok(Ci, Co, band_limit, R) ? 1 : 0; }
 
 extern "C" int fcb_fwd_fused_workspace_bytes(int Ci, int Co, int band_limit, int R, size_t* bytes) {
@@ -906,9 +953,13 @@ extern "C" int fcb_modrelu_bwd_workspace_bytes(int64_t N, int C, size_t* bytes) 
     return FCB_OK;
 }
 
-extern "C" int fcb_modrelu_bwd_f32(const float* x, const float* bias, const float* gy, float* gx, float* gb, int64_t N,
-                                   int C, void* ws, size_t ws_bytes, void* stream) {
+extern "C" int fcb_modrelu_bwd_f32(const float* x, const float* bias, const float* gy, float* gx, float* gb, float* gx_bound,
+                                   int64_t N, int C, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (gx_bound && cudaMemsetAsync(gx_bound, 0, 4, st) != cudaSuccess) {
+        set_error("modrelu_bwd: cudaMemsetAsync failed");
+        return FCB_E_CUDA;
+    }
     FCB_REQUIRE(x && bias && gy && gx && gb && ws && N >= 0 && C > 0, FCB_E_ARG, "modrelu_bwd: bad arguments");
     const int64_t slabs = (N + MR_ROWS - 1) / MR_ROWS;
     FCB_REQUIRE(ws_bytes >= (size_t)(slabs + 1) * C * 4, FCB_E_WORKSPACE, "modrelu_bwd: workspace too small");
@@ -918,7 +969,8 @@ extern "C" int fcb_modrelu_bwd_f32(const float* x, const float* bias, const floa
         const size_t smem = C <= 256 ? (size_t)rl_count * C * 4 : 0;
         FCB_LAUNCH("modrelu_bwd", st, k_modrelu_bwd<<<(unsigned)slabs, 256, smem, st>>>(reinterpret_cast<const float2*>(x), bias,
                                                           reinterpret_cast<const float2*>(gy),
-                                                          reinterpret_cast<float2*>(gx), parts, N, C));
+                                                          reinterpret_cast<float2*>(gx), parts, N, C,
+                                                          reinterpret_cast<uint32_t*>(gx_bound)));
     }
     FCB_LAUNCH("colsum_parts", st, k_colsum_parts<<<(unsigned)((C + 31) / 32), 1024, 0, st>>>(parts, gb, slabs, C));
     return FCB_OK;

@@ -107,6 +107,7 @@ struct GemmEpilogue {
     const float* bias;     // N / 2 floats, or nullptr (no activation output)
     float* act;            // [M x N], row stride ld
     int64_t ld;
+    float* act_bound;      // nullable: max_i |act_i| (complex modulus) is atomically folded into it (pre-zeroed by the caller)
 };
 
 // internal entry points shared between translation units
@@ -131,7 +132,7 @@ size_t gemm_ws_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int sp
 int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                 int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k,
                 void* ws, size_t ws_bytes, int flags, const float* a_amax, cudaStream_t st, const GemmEpilogue* epi = nullptr,
-                int* epi_fused = nullptr);
+                int* epi_fused = nullptr, const float* b_amax = nullptr);
 size_t gemm_tc_ws_bytes(int N, int64_t K, int batch);
 // 2xFP16 tensor-core kernels (gemm_h.cu).  a_amax: device float holding max|A| (from the kernel that produced A).
 int gemm_h_plan_nn(int N, int64_t ksteps, int* n_pairs, int* split_k = nullptr);   // split_k: wide outputs (N > 128) allowed
@@ -147,13 +148,15 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
                      float* parts = nullptr, const GemmEpilogue* epi = nullptr, const float* sa_x = nullptr, float* sa_gx = nullptr);
 int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
                      int64_t ldc, int split, int64_t k_per_split, float* parts, int n_main, const float* amax_a, void* bp_ws,
-                     size_t bp_bytes, int a_packed, cudaStream_t st);
+                     size_t bp_bytes, int a_packed, cudaStream_t st, const float* b_bound = nullptr);
 // weight gradient from G: P[m][Mr][2Ci] = G_m^T Xh_m for all 2B+1 frequencies in one batched 2xFP16 TN launch (gemm_h.cu);
 // G = [Kv x M*Mr] fp32 or PK; the packed xhat operands are built from x.  gemm_h_tn_plan: accumulation plan of that launch.
 size_t gemm_h_tn_xhat_ws_bytes(int Ci, int64_t Kv, int M);
 int launch_gemm_h_tn_xhat(const float* G, const float* x, float* P, int64_t Mr, int Ci, int band_limit, int64_t Kv, int split,
                           int64_t k_per_split, float* parts, int n_main, const float* amax_g, void* bp_ws, size_t bp_bytes,
-                          int a_packed, cudaStream_t st);
+                          int a_packed, cudaStream_t st, const float* x_bound = nullptr);
+// out = max_i |z_i| (1 + 2^-20) over n complex numbers (the bound the operand-scale logic accepts for z and for xhat)
+int launch_bound_modulus(const float* z, int64_t n, float* out, cudaStream_t st);
 bool gemm_h_tn_plan(int N, int64_t Kv, int split, int* n_main, int64_t* k_per_split);
 int64_t gemm_h_tn_max_vertices_per_split(int N);
 // fused forward for band_limit <= 1 (fused_fwd.cu)

@@ -314,7 +314,8 @@ int launch_gemm_grouped(const float* A, const float* Bm, float* C, int64_t M, in
 
 int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                 int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k, void* ws,
-                size_t ws_bytes, int flags, const float* a_amax, cudaStream_t st, const GemmEpilogue* epi, int* epi_fused) {
+                size_t ws_bytes, int flags, const float* a_amax, cudaStream_t st, const GemmEpilogue* epi, int* epi_fused,
+                const float* b_amax) {
     FCB_REQUIRE(A && Bm && C, FCB_E_ARG, "gemm: null pointer");
     if (epi_fused) *epi_fused = 0;
     FCB_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 1 && split_k >= 1, FCB_E_ARG, "gemm: bad sizes");
@@ -380,7 +381,7 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
         for (int n0 = 0; n0 < N; n0 += chunk) {
             const int nc = N - n0 < chunk ? N - n0 : chunk;
             int rc = h ? launch_gemm_h_tn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, split_k, kps_tc, partials, n_main, a_amax, bp_ws,
-                                          bp_bytes, packed ? 1 : 0, st)
+                                          bp_bytes, packed ? 1 : 0, st, b_amax)
                        : launch_gemm_tc_tn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, split_k, kps_tc, partials, mode, n_main,
                                            bp_ws, bp_bytes, st);
             if (rc) return rc;
@@ -467,12 +468,12 @@ extern "C" int fcb_gemm_workspace_bytes(int64_t M, int N, int64_t K, int trans_a
 
 extern "C" int fcb_gemm_f32(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda,
                             int64_t ldb, int64_t ldc, int trans_a, int batch, int64_t stride_a, int64_t stride_b,
-                            int64_t stride_c, int split_k, void* workspace, size_t workspace_bytes, int flags,
-                            void* stream) {
+                            int64_t stride_c, int split_k, const float* a_bound, const float* b_bound, void* workspace,
+                            size_t workspace_bytes, int flags, void* stream) {
     fcb::prof_scope_lin(true);
     const int rc = fcb::launch_gemm(A, B, C, M, N, K, lda, ldb, ldc, trans_a, batch, stride_a, stride_b, stride_c, split_k,
-                                    workspace, workspace_bytes, flags & ~fcb::FCB_FLAG_A_PACKED, nullptr,
-                                    static_cast<cudaStream_t>(stream));
+                                    workspace, workspace_bytes, flags & ~fcb::FCB_FLAG_A_PACKED, a_bound,
+                                    static_cast<cudaStream_t>(stream), nullptr, nullptr, b_bound);
     fcb::prof_scope_lin(false);
     return rc;
 }

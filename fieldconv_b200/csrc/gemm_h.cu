@@ -187,6 +187,7 @@ struct Params {
     const float* epi_bias;     // N / 2 modReLU biases (one per complex output channel), nullptr: no activation output
     float* epi_act;            // [M x N] activated output (row stride epi_ld)
     int64_t epi_ld;
+    uint32_t* epi_bound;       // nullable: bit pattern of max_i |act_i| (modulus), folded in with atomicMax
     // fused softAngle chain rule (grouped-K mode, kgroups = 2 * sa_band + 1): the k-group accumulators ARE gxhat[:, m, :] of one
     // row, so the epilogue turns them into grad x directly (utils/field.py:40-48) — gxhat never
     // goes to memory and k_softangle_bwd is not launched.  sa_x / sa_gx: [M x N/2] complex, row stride N floats.
@@ -413,7 +414,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
                     default: softangle_epilogue<3>(lane_base, p.Npad, blk, inv, xrow, grow); break;
                 }
             }
-        } else
+        } else {
+        float act_mx = 0.f;          // largest modulus this thread wrote to epi_act
         for (int it = part; it < items; it += N_PROD_WARPS / 4) {
             const int kg = it / groups, g = it - kg * groups;
             uint32_t r[16];
@@ -461,9 +463,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
                     const bool origin = (fabsf(zx) < 1e-7f) && (fabsf(zy) < 1e-7f);
                     const float n2 = zx * zx + zy * zy;
                     const float ri = rsqrtf(n2);
-                    const float sc = fmaxf(n2 * ri + (n + 1 < p.N ? __ldg(p.epi_bias + (n >> 1)) : 0.f), 0.f) * ri;
+                    const float mod = fmaxf(n2 * ri + (n + 1 < p.N ? __ldg(p.epi_bias + (n >> 1)) : 0.f), 0.f);     // |act| of a non-origin entry
+                    const float sc = mod * ri;
                     a[2 * j] = origin ? zx : sc * zx;
                     a[2 * j + 1] = origin ? zy : sc * zy;
+                    act_mx = fmaxf(act_mx, origin ? 2e-7f : mod);
                 }
                 if (16 * g + 15 < p.N) {
 #pragma unroll
@@ -489,6 +493,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
                     }
                 }
             }
+        }
+        if (p.epi_bound) {
+            const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(act_mx * 1.000001f));
+            if (lane == 0 && w > *reinterpret_cast<volatile uint32_t*>(p.epi_bound)) atomicMax(p.epi_bound, w);
+        }
         }
     } else if (warp == N_PROD_WARPS) {
         // ------------------------------------------------------------------ MMA issuer (one thread; counters and pre-built
@@ -1009,6 +1018,19 @@ int launch_absmax_f32(const float* p, int64_t rows, int cols, int64_t ld, int ba
     return th::launch_absmax(p, rows, cols, ld, batch, stride, out, st);
 }
 
+int launch_bound_modulus(const float* z, int64_t n, float* out, cudaStream_t st) {
+    if (cudaMemsetAsync(out, 0, 4, st) != cudaSuccess) {
+        set_error("bound_modulus: cudaMemsetAsync failed");
+        return FCB_E_CUDA;
+    }
+    if (n <= 0) return FCB_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    FCB_LAUNCH("absmax_mod", st, th::k_absmax_modulus<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float2*>(z), n,
+                                                                                   reinterpret_cast<uint32_t*>(out)));
+    return FCB_OK;
+}
+
 int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int n_pairs, int kgroups,
                      const float* amax_a, void* ws, size_t ws_bytes, int a_packed, cudaStream_t st, int split_k, float* parts,
@@ -1055,7 +1077,7 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
     p.cps = (nchunks * kgroups + split_k - 1) / split_k;
     split_k = (nchunks * kgroups + p.cps - 1) / p.cps;          // no empty K range
     p.part_stride = 0;
-    p.epi_res = nullptr; p.epi_bias = nullptr; p.epi_act = nullptr; p.epi_ld = 0;
+    p.epi_res = nullptr; p.epi_bias = nullptr; p.epi_act = nullptr; p.epi_ld = 0; p.epi_bound = nullptr;
     p.sa_x = nullptr; p.sa_gx = nullptr; p.sa_band = 0;
     if (sa_gx) {
         FCB_REQUIRE(sa_x && kgroups >= 3 && kgroups <= 7 && (kgroups & 1) && (N % 8) == 0 && aligned16(sa_x) && aligned16(sa_gx), FCB_E_ARG,
@@ -1065,6 +1087,7 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
     if (epi) {
         FCB_REQUIRE(split_k == 1 && kgroups == 1 && batch == 1 && (N & 1) == 0, FCB_E_ARG, "gemm_h: the fused epilogue needs one un-split product");
         p.epi_res = epi->res; p.epi_bias = epi->bias; p.epi_act = epi->act; p.epi_ld = epi->ld;
+        p.epi_bound = epi->act ? reinterpret_cast<uint32_t*>(epi->act_bound) : nullptr;
     }
     if (split_k > 1) {                                          // partials [split][batch][M][N]
         p.C = parts;
@@ -1157,7 +1180,7 @@ size_t gemm_h_tn_xhat_ws_bytes(int Ci, int64_t Kv, int M) {
 // P[m][2RCo][2Ci] (or the split partials) = G_m^T Xh_m for all m in ONE launch; G = [Kv x M*Mr] (fp32, or PK when a_packed)
 int launch_gemm_h_tn_xhat(const float* G, const float* x, float* P, int64_t Mr, int Ci, int band_limit, int64_t Kv, int split,
                           int64_t k_per_split, float* parts, int n_main, const float* amax_g, void* bp_ws, size_t bp_bytes,
-                          int a_packed, cudaStream_t st) {
+                          int a_packed, cudaStream_t st, const float* x_bound) {
     const int M = 2 * band_limit + 1;
     const int N = 2 * Ci;
     FCB_REQUIRE(G && x && P && bp_ws && amax_g, FCB_E_ARG, "gemm_h_tn_xhat: null pointer");
@@ -1167,18 +1190,15 @@ int launch_gemm_h_tn_xhat(const float* G, const float* x, float* P, int64_t Mr, 
     const int npad = (N + 15) / 16 * 16;
     const int atoms = (npad + 63) / 64;
     const int64_t nchunks = (Kv + th::KV - 1) / th::KV;
-    float* amax_b = static_cast<float*>(bp_ws);
+    const float* amax_b = x_bound;                  // max_i |x_i|: supplied, else one pass over x
     __half* Bp = reinterpret_cast<__half*>(static_cast<char*>(bp_ws) + 256);
     const int64_t bp_stride = nchunks * 2 * th::KV * atoms * 64;            // fp16 elements per batch entry
-    if (cudaMemsetAsync(amax_b, 0, 4, st) != cudaSuccess) {
-        set_error("gemm_h_tn_xhat: cudaMemsetAsync failed");
-        return FCB_E_CUDA;
+    if (!amax_b) {
+        int rc = launch_bound_modulus(x, Kv * Ci, static_cast<float*>(bp_ws), st);
+        if (rc) return rc;
+        amax_b = static_cast<const float*>(bp_ws);
     }
     {
-        int64_t blocks = (Kv * Ci + 255) / 256;
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        FCB_LAUNCH("absmax_mod", st, th::k_absmax_modulus<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float2*>(x), Kv * Ci,
-                                                                                       reinterpret_cast<uint32_t*>(amax_b)));
         const int64_t items = nchunks * th::KV * atoms * 8;
         const unsigned pb = (unsigned)((items + 255) / 256);
         const float2* x2 = reinterpret_cast<const float2*>(x);
@@ -1199,7 +1219,7 @@ int launch_gemm_h_tn_xhat(const float* G, const float* x, float* P, int64_t Mr, 
 
 int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
                      int64_t ldc, int split, int64_t k_per_split, float* parts, int n_main, const float* amax_a, void* bp_ws,
-                     size_t bp_bytes, int a_packed, cudaStream_t st) {
+                     size_t bp_bytes, int a_packed, cudaStream_t st, const float* b_bound) {
     FCB_REQUIRE(A && B && C && bp_ws && amax_a, FCB_E_ARG, "gemm_h_tn: null pointer");
     FCB_REQUIRE(N > 0 && N <= 256 && split >= 1 && split <= 65535, FCB_E_UNSUPPORTED, "gemm_h_tn: unsupported shape");
     if (a_packed) {
@@ -1214,11 +1234,14 @@ int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N
     const int npad = (N + 15) / 16 * 16;
     const int nb_atoms = (npad + 63) / 64;
     const int64_t nchunks = (Kv + th::KV - 1) / th::KV;
-    float* amax_b = static_cast<float*>(bp_ws);
+    const float* amax_b = b_bound;                  // bound supplied by the producer of B, else one pass over it
     __half* Bp = reinterpret_cast<__half*>(static_cast<char*>(bp_ws) + 256);
     {
-        int rc = th::launch_absmax(B, Kv, N, ldb, 1, 0, amax_b, st);
-        if (rc) return rc;
+        if (!amax_b) {
+            int rc = th::launch_absmax(B, Kv, N, ldb, 1, 0, static_cast<float*>(bp_ws), st);
+            if (rc) return rc;
+            amax_b = static_cast<const float*>(bp_ws);
+        }
         const int64_t items = nchunks * th::KV * nb_atoms * 8;
         if (items > 0)
             FCB_LAUNCH("pack_b_h_tn", st, th::k_pack_b_h_tn<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(B, Bp, Kv, N, nb_atoms, ldb, nchunks, amax_b));

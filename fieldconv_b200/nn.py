@@ -303,6 +303,10 @@ class TangentLin(nn.Module):
         emb = pre[0] if (pre is not None and pre[1] == (self.Re._version, self.Im._version)) else None
         if emb is None:
             emb = _lin_embedding(self.Re, self.Im)              # (2Ci, 2Co)
+        if ci % 2 == 0 and co % 2 == 0 and x.is_cuda and x.dtype == torch.complex64:
+            x = x.contiguous()
+            xb = ops.bound_of(x) if ops._uses_bounds(self.gemm_flags) else None     # the A-operand scale; shared with the conv
+            return ops.tangent_lin(x, emb.contiguous(), self.gemm_flags, xb)
         xr = torch.view_as_real(x.contiguous()).reshape(x.shape[0], 2 * ci)
         if (2 * ci) % 4 or (2 * co) % 4:                         # GEMM wants 16-byte rows
             pad_i, pad_o = (2 * ci) % 4, (2 * co) % 4

@@ -11,7 +11,7 @@ with ordinary differentiable torch ops (tiny tensors), so parameter gradients fl
 gW through autograd exactly as in the reference (nn/field_conv.py:10-33).
 """
 import os
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -26,6 +26,46 @@ SAVE_CONTRIB = os.environ.get("FIELDCONV_B200_SAVE_CONTRIB", "0") == "1"
 
 def keep_contrib_default(nbytes=0, device=None):
     return SAVE_CONTRIB
+
+
+# ---------------------------------------------------------------------------- operand bounds (struct fcb_bounds)
+# The 2xFP16 tensor-core paths scale an operand by a power of two taken from a bound of its largest magnitude.  The kernels
+# that WRITE a tensor can report that bound for free (the fused block epilogue for the activation, the modReLU backward for
+# the gradient it returns); it travels with the tensor object as an attribute, tagged with the tensor's version counter,
+# and the consumers hand it to the library instead of letting every call take its own pass over the operand.  A tensor
+# without a bound gets ONE pass (bound_of) shared by all its consumers.  FIELDCONV_B200_BOUNDS=0: every call computes its own.
+BOUNDS = os.environ.get("FIELDCONV_B200_BOUNDS", "1") == "1"
+
+
+def set_bound(t, b):
+    """Attach to t the device scalar b >= max_i |t_i| (complex modulus / largest |component|) its producer reported."""
+    if BOUNDS and b is not None:
+        t._fcb_bound = (b, t._version)
+    return t
+
+
+def peek_bound(t):
+    rec = getattr(t, "_fcb_bound", None) if BOUNDS else None
+    if rec is not None and rec[1] == t._version and rec[0].device == t.device:
+        return rec[0]
+    return None
+
+
+def bound_of(t):
+    """The bound attached to the complex64 tensor t, computed (one pass, fcb_bound_f32) and attached when there is none."""
+    if not BOUNDS or not t.is_cuda or t.dtype != torch.complex64 or not t.is_contiguous():
+        return None
+    b = peek_bound(t)
+    if b is None:
+        b = torch.empty(1, dtype=torch.float32, device=t.device)
+        with torch.cuda.device(t.device):
+            _lib.call("fcb_bound_f32", _real(t).data_ptr(), t.numel(), b.data_ptr(), _lib.stream_ptr())
+        set_bound(t, b)
+    return b
+
+
+def _uses_bounds(flags):
+    return BOUNDS and (flags & _lib.GEMM_MASK) == _lib.GEMM_TC_2XF16
 
 
 def _real(t):
@@ -51,7 +91,7 @@ def _padded_rows(n):
 @torch.library.custom_op("fieldconv_b200::fc_fwd", mutates_args=())
 def fc_fwd(x: Tensor, W: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: Tensor, rowptr_src: Tensor,
            rec_src: Tensor, rot_src: Tensor, norms: Tensor, band_limit: int, n_rings: int, flags: int,
-           keep_contrib: bool) -> Tuple[Tensor, Tensor, Tensor]:
+           keep_contrib: bool, x_bound: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
     # the by-source plan tensors are unused here; they are inputs so autograd can hand them to fc_bwd
     _check(x, "x")
     _check(W, "W")
@@ -80,7 +120,7 @@ def fc_fwd(x: Tensor, W: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: T
         if packed:
             _lib.call("fcb_fwd_pk_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
                       rot_tgt.data_ptr(), norms.data_ptr(), _real(y).data_ptr(), _real(contrib).data_ptr(), cmax.data_ptr(),
-                      n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes, _lib.stream_ptr())
+                      _lib.bounds(x=x_bound), n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes, _lib.stream_ptr())
         else:
             _lib.call("fcb_fwd_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
                       rot_tgt.data_ptr(), _real(y).data_ptr(), _real(contrib).data_ptr(), cmax.data_ptr(), n, ci, co,
@@ -91,7 +131,8 @@ def fc_fwd(x: Tensor, W: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: T
 
 
 @fc_fwd.register_fake
-def _(x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, keep_contrib):
+def _(x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, keep_contrib,
+      x_bound=None):
     n, ci = x.shape
     k = n_rings * ci * (2 * band_limit + 1)
     return (x.new_empty(n, W.shape[0]), x.new_empty((_padded_rows(n), k) if keep_contrib else (0,)),
@@ -101,7 +142,7 @@ def _(x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, b
 @torch.library.custom_op("fieldconv_b200::fc_bwd", mutates_args=())
 def fc_bwd(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, cmax: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: Tensor,
            rowptr_src: Tensor, rec_src: Tensor, rot_src: Tensor, norms: Tensor, band_limit: int, n_rings: int, flags: int,
-           need_gx: bool, need_gw: bool) -> Tuple[Tensor, Tensor]:
+           need_gx: bool, need_gw: bool, x_bound: Optional[Tensor] = None, gy_bound: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     _check(gy, "grad_output")
     x, W, gy = x.contiguous(), W.contiguous(), gy.contiguous()
     n, ci = x.shape
@@ -116,46 +157,50 @@ def fc_bwd(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, cmax: Tensor, rowp
     nbytes = _lib.query_bytes("fcb_bwd_workspace_bytes", n, ci, co, band_limit, n_rings,
                               cflags | (_lib.FLAG_HAVE_CONTRIB if have_contrib else 0))
     ws = _ws(nbytes, x.device)
+    bnd = _lib.bounds(x=x_bound, gy=gy_bound)
     with torch.cuda.device(x.device):
         if packed:
             _lib.call("fcb_bwd_pk_f32", _real(x).data_ptr(), _real(W).data_ptr(), _real(gy).data_ptr(),
                       _real(contrib).data_ptr() if have_contrib else 0, cmax.data_ptr() if have_contrib else 0,
                       rowptr_tgt.data_ptr(), rec_tgt.data_ptr(), rot_tgt.data_ptr(), norms[0:].data_ptr(),
                       rowptr_src.data_ptr(), rec_src.data_ptr(), rot_src.data_ptr(), norms[1:].data_ptr(),
-                      _real(gx).data_ptr() if need_gx else 0, _real(gw).data_ptr() if need_gw else 0,
+                      _real(gx).data_ptr() if need_gx else 0, _real(gw).data_ptr() if need_gw else 0, bnd,
                       n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes, _lib.stream_ptr())
         else:
             _lib.call("fcb_bwd_f32", _real(x).data_ptr(), _real(W).data_ptr(), _real(gy).data_ptr(),
                       _real(contrib).data_ptr() if have_contrib else 0, cmax.data_ptr() if have_contrib else 0,
                       rowptr_tgt.data_ptr(), rec_tgt.data_ptr(), rot_tgt.data_ptr(),
                       rowptr_src.data_ptr(), rec_src.data_ptr(), rot_src.data_ptr(),
-                      _real(gx).data_ptr() if need_gx else 0, _real(gw).data_ptr() if need_gw else 0,
+                      _real(gx).data_ptr() if need_gx else 0, _real(gw).data_ptr() if need_gw else 0, bnd,
                       n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes, _lib.stream_ptr())
     return gx, gw
 
 
 @fc_bwd.register_fake
 def _(x, W, gy, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags,
-      need_gx, need_gw):
+      need_gx, need_gw, x_bound=None, gy_bound=None):
     return (torch.empty_like(x) if need_gx else x.new_empty(0)), (torch.empty_like(W) if need_gw else W.new_empty(0))
 
 
 def _fc_setup(ctx, inputs, output):
-    x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, keep = inputs
+    x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, keep, x_bound = inputs
     _, contrib, cmax = output
     ctx.save_for_backward(x, W, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms)
+    ctx.x_bound = x_bound            # a 1-element device scalar, not part of the graph
     ctx.cfg = (band_limit, n_rings, flags)
     ctx.set_materialize_grads(False)      # no N*K zero tensor for the unused contrib output
 
 
 def _fc_backward(ctx, gy, _gcontrib, _gcmax):
     if gy is None:
-        return (None,) * 13
+        return (None,) * 14
     x, W, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms = ctx.saved_tensors
     band_limit, n_rings, flags = ctx.cfg
+    gy = gy.contiguous()
     gx, gw = fc_bwd(x, W, gy, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit,
-                    n_rings, flags, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
-    return (gx if ctx.needs_input_grad[0] else None, gw if ctx.needs_input_grad[1] else None) + (None,) * 11
+                    n_rings, flags, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.x_bound,
+                    peek_bound(gy) if _uses_bounds(flags) else None)
+    return (gx if ctx.needs_input_grad[0] else None, gw if ctx.needs_input_grad[1] else None) + (None,) * 12
 
 
 fc_fwd.register_autograd(_fc_backward, setup_context=_fc_setup)
@@ -165,10 +210,11 @@ fc_fwd.register_autograd(_fc_backward, setup_context=_fc_setup)
 @torch.library.custom_op("fieldconv_b200::fc_fwd_act", mutates_args=())
 def fc_fwd_act(x: Tensor, W: Tensor, res: Tensor, bias: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: Tensor,
                rowptr_src: Tensor, rec_src: Tensor, rot_src: Tensor, norms: Tensor, band_limit: int, n_rings: int, flags: int,
-               has_res: bool) -> Tuple[Tensor, Tensor]:
-    """(act, z) with z = FieldConv(x) (+ res) and act = modReLU(z, bias): nn/fc_resnet_block.py:84-88 with the TangentNonLin
-    (and the residual add) applied in the contraction kernel's epilogue (fcb_fwd_act_f32 / fcb_fwd_act_pk_f32).  Nothing of
-    size N x K is kept: the backward is modrelu_bwd + fc_bwd with gW from G and xhat."""
+               has_res: bool, x_bound: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """(act, z, bound) with z = FieldConv(x) (+ res) and act = modReLU(z, bias): nn/fc_resnet_block.py:84-88 with the
+    TangentNonLin (and the residual add) applied in the contraction kernel's epilogue (fcb_fwd_act_f32 / fcb_fwd_act_pk_f32);
+    bound = max_i |act_i|, reported by that epilogue.  Nothing of size N x K is kept: the backward is modrelu_bwd + fc_bwd with
+    gW from G and xhat."""
     _check(x, "x")
     _check(W, "W")
     x, W = x.contiguous(), W.contiguous()
@@ -187,50 +233,61 @@ def fc_fwd_act(x: Tensor, W: Tensor, res: Tensor, bias: Tensor, rowptr_tgt: Tens
         r_ptr = _real(res).data_ptr()
     contrib = torch.empty(_padded_rows(n), k, dtype=torch.complex64, device=x.device)      # transient: freed on return
     cmax = torch.zeros(1, dtype=torch.float32, device=x.device)
+    act_bound = torch.empty(1, dtype=torch.float32, device=x.device)
     nbytes = _lib.query_bytes("fcb_fwd_workspace_bytes", n, ci, co, band_limit, n_rings, cflags)
     ws = _ws(nbytes, x.device)
+    bnd = _lib.bounds(x=x_bound, act=act_bound)
     with torch.cuda.device(x.device):
         if packed:
             _lib.call("fcb_fwd_act_pk_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
                       rot_tgt.data_ptr(), norms.data_ptr(), _real(z).data_ptr(), _real(contrib).data_ptr(), cmax.data_ptr(),
-                      r_ptr, b.data_ptr(), _real(act).data_ptr(), n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes,
+                      r_ptr, b.data_ptr(), _real(act).data_ptr(), bnd, n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes,
                       _lib.stream_ptr())
         else:
             _lib.call("fcb_fwd_act_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
                       rot_tgt.data_ptr(), _real(z).data_ptr(), _real(contrib).data_ptr(), cmax.data_ptr(), r_ptr, b.data_ptr(),
-                      _real(act).data_ptr(), n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes, _lib.stream_ptr())
-    return act, z
+                      _real(act).data_ptr(), bnd, n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes, _lib.stream_ptr())
+    return act, z, act_bound
 
 
 @fc_fwd_act.register_fake
-def _(x, W, res, bias, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, has_res):
-    return x.new_empty(x.shape[0], W.shape[0]), x.new_empty(x.shape[0], W.shape[0])
+def _(x, W, res, bias, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, has_res,
+      x_bound=None):
+    return x.new_empty(x.shape[0], W.shape[0]), x.new_empty(x.shape[0], W.shape[0]), x.new_empty(1, dtype=torch.float32)
 
 
 def _fa_setup(ctx, inputs, output):
-    x, W, res, bias, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, has_res = inputs
+    (x, W, res, bias, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, has_res,
+     x_bound) = inputs
     ctx.save_for_backward(x, W, bias, output[1], rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms)
+    ctx.x_bound = x_bound
     ctx.cfg = (band_limit, n_rings, flags, has_res)
     ctx.set_materialize_grads(False)
 
 
-def _fa_backward(ctx, g_act, g_z):
+def _fa_backward(ctx, g_act, g_z, _g_bound):
     x, W, bias, z, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms = ctx.saved_tensors
     band_limit, n_rings, flags, has_res = ctx.cfg
     if g_act is None and g_z is None:
-        return (None,) * 15
+        return (None,) * 16
     gb = None
     gz = g_z
+    gz_bound = None
     if g_act is not None:
-        gz_a, gbv = modrelu_bwd(z, bias, g_act.contiguous())
-        gz = gz_a if gz is None else gz + gz_a
+        gz_a, gbv, gzb = modrelu_bwd(z, bias, g_act.contiguous())
+        if gz is None:
+            gz, gz_bound = gz_a, gzb
+            set_bound(gz, gzb)        # the residual branch's backward receives this very tensor
+        else:
+            gz = gz + gz_a
         gb = gbv.reshape(bias.shape)
     empty = torch.empty(0, dtype=torch.complex64, device=x.device)
     cm = torch.zeros(1, dtype=torch.float32, device=x.device)
     gx, gw = fc_bwd(x, W, gz, empty, cm, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings,
-                    flags & ~_lib.FLAG_FUSED, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+                    flags & ~_lib.FLAG_FUSED, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.x_bound,
+                    gz_bound if _uses_bounds(flags) else None)
     return (gx if ctx.needs_input_grad[0] else None, gw if ctx.needs_input_grad[1] else None,
-            gz if (has_res and ctx.needs_input_grad[2]) else None, gb if ctx.needs_input_grad[3] else None) + (None,) * 11
+            gz if (has_res and ctx.needs_input_grad[2]) else None, gb if ctx.needs_input_grad[3] else None) + (None,) * 12
 
 
 fc_fwd_act.register_autograd(_fa_backward, setup_context=_fa_setup)
@@ -247,9 +304,20 @@ def field_conv_act(x, W, plan, band_limit, bias, res=None, flags=0):
     has_res = res is not None
     if not has_res:
         res = torch.empty(0, dtype=torch.complex64, device=x.device)
-    act, _ = fc_fwd_act(x, W, res, bias, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src, plan.rot_src,
-                        norms, band_limit, plan.n_rings, flags, has_res)
-    return act
+    x = x.contiguous()
+    act, _, act_bound = fc_fwd_act(x, W, res, bias, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src,
+                                   plan.rot_src, norms, band_limit, plan.n_rings, flags, has_res, _x_bound_for(x, W, flags))
+    return set_bound(act, act_bound)
+
+
+def _x_bound_for(x, W, flags):
+    """Bound of the layer input when some kernel of this layer will need it: the packed forward (operand scale of contrib)
+    or the weight gradient (operand scale of xhat)."""
+    if not _uses_bounds(flags):
+        return None
+    if (flags & _lib.FLAG_PACKED) or (torch.is_grad_enabled() and W.requires_grad):
+        return bound_of(x)
+    return peek_bound(x)
 
 
 def field_conv(x, W, plan, band_limit, flags=0, keep_contrib=None):
@@ -262,8 +330,9 @@ def field_conv(x, W, plan, band_limit, flags=0, keep_contrib=None):
         if flags & (_lib.FLAG_PACKED | _lib.FLAG_FUSED | _lib.FLAG_PACKED_G):
             raise RuntimeError("fieldconv_b200: the packed / fused paths need a plan built by build_plan (plan.norms)")
         norms = torch.zeros(2, dtype=torch.float32, device=x.device)
+    x = x.contiguous()
     y, _, _ = fc_fwd(x, W, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src, plan.rot_src, norms,
-                     band_limit, plan.n_rings, flags, bool(keep_contrib))
+                     band_limit, plan.n_rings, flags, bool(keep_contrib), _x_bound_for(x, W, flags))
     return y
 
 
@@ -366,23 +435,25 @@ def _(x, bias):
 
 
 @torch.library.custom_op("fieldconv_b200::modrelu_bwd", mutates_args=())
-def modrelu_bwd(x: Tensor, bias: Tensor, gy: Tensor) -> Tuple[Tensor, Tensor]:
+def modrelu_bwd(x: Tensor, bias: Tensor, gy: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (gx, gb, bound of gx: its largest |component|, reported by the kernel)"""
     x, gy = x.contiguous(), gy.contiguous()
     b = bias.reshape(-1).contiguous().float()
     n, c = x.shape
     gx = torch.empty_like(x)
     gb = torch.empty(c, dtype=torch.float32, device=x.device)
+    gx_bound = torch.empty(1, dtype=torch.float32, device=x.device)
     nbytes = _lib.query_bytes("fcb_modrelu_bwd_workspace_bytes", n, c)
     ws = _ws(nbytes, x.device)
     with torch.cuda.device(x.device):
         _lib.call("fcb_modrelu_bwd_f32", _real(x).data_ptr(), b.data_ptr(), _real(gy).data_ptr(), _real(gx).data_ptr(),
-                  gb.data_ptr(), n, c, ws.data_ptr(), nbytes, _lib.stream_ptr())
-    return gx, gb
+                  gb.data_ptr(), gx_bound.data_ptr(), n, c, ws.data_ptr(), nbytes, _lib.stream_ptr())
+    return gx, gb, gx_bound
 
 
 @modrelu_bwd.register_fake
 def _(x, bias, gy):
-    return torch.empty_like(x), x.new_empty(x.shape[1], dtype=torch.float32)
+    return torch.empty_like(x), x.new_empty(x.shape[1], dtype=torch.float32), x.new_empty(1, dtype=torch.float32)
 
 
 def _mr_setup(ctx, inputs, output):
@@ -391,19 +462,15 @@ def _mr_setup(ctx, inputs, output):
 
 def _mr_backward(ctx, gy):
     x, bias = ctx.saved_tensors
-    gx, gb = modrelu_bwd(x, bias, gy)
-    return gx, gb.reshape(bias.shape)
+    gx, gb, gxb = modrelu_bwd(x, bias, gy)
+    return set_bound(gx, gxb), gb.reshape(bias.shape)
 
 
 modrelu.register_autograd(_mr_backward, setup_context=_mr_setup)
 
 
 # --------------------------------------------------------------------------- real GEMM (TangentLin)
-@torch.library.custom_op("fieldconv_b200::gemm", mutates_args=())
-def gemm(a: Tensor, b: Tensor, trans_a: bool, flags: int = 0) -> Tensor:
-    """C = A @ B (trans_a False, A is MxK) or A^T @ B (trans_a True, A is KxM); fp32, row-major."""
-    _check(a, "a", torch.float32)
-    _check(b, "b", torch.float32)
+def _gemm_call(a, b, trans_a, flags, a_bound=None, b_bound=None):
     a, b = a.contiguous(), b.contiguous()
     if trans_a:
         k, m = a.shape
@@ -419,12 +486,23 @@ def gemm(a: Tensor, b: Tensor, trans_a: bool, flags: int = 0) -> Tensor:
     ws = _ws(nbytes, a.device)
     with torch.cuda.device(a.device):
         _lib.call("fcb_gemm_f32", a.data_ptr(), b.data_ptr(), c.data_ptr(), m, n, k, a.shape[1], n, n,
-                  1 if trans_a else 0, 1, 0, 0, 0, split, ws.data_ptr(), nbytes, flags, _lib.stream_ptr())
+                  1 if trans_a else 0, 1, 0, 0, 0, split, _lib.ptr(a_bound) or None, _lib.ptr(b_bound) or None, ws.data_ptr(), nbytes,
+                  flags, _lib.stream_ptr())
     return c
 
 
+@torch.library.custom_op("fieldconv_b200::gemm", mutates_args=())
+def gemm(a: Tensor, b: Tensor, trans_a: bool, flags: int = 0, a_bound: Optional[Tensor] = None,
+         b_bound: Optional[Tensor] = None) -> Tensor:
+    """C = A @ B (trans_a False, A is MxK) or A^T @ B (trans_a True, A is KxM); fp32, row-major.  a_bound / b_bound: device
+    scalars >= max|A|, max|B| when their producer knows them (struct fcb_bounds of the header)."""
+    _check(a, "a", torch.float32)
+    _check(b, "b", torch.float32)
+    return _gemm_call(a, b, trans_a, flags, a_bound, b_bound)
+
+
 @gemm.register_fake
-def _(a, b, trans_a, flags=0):
+def _(a, b, trans_a, flags=0, a_bound=None, b_bound=None):
     return a.new_empty(a.shape[1] if trans_a else a.shape[0], b.shape[1])
 
 
@@ -440,7 +518,51 @@ def _gemm_backward(ctx, gc):
         raise RuntimeError("fieldconv_b200::gemm: backward of the transposed form is not needed")
     ga = gemm(gc, b.t().contiguous(), False, ctx.flags) if ctx.needs_input_grad[0] else None
     gb = gemm(a, gc, True, ctx.flags) if ctx.needs_input_grad[1] else None
-    return ga, gb, None, None
+    return ga, gb, None, None, None, None
 
 
 gemm.register_autograd(_gemm_backward, setup_context=_gemm_setup)
+
+
+# --------------------------------------------------------------------------- TangentLin on complex tensors
+@torch.library.custom_op("fieldconv_b200::tangent_lin", mutates_args=())
+def tangent_lin(x: Tensor, emb: Tensor, flags: int, x_bound: Optional[Tensor] = None) -> Tensor:
+    """y = x @ (Re + i Im)^T (nn/tangent_lin.py:27-29) as ONE real GEMM on the interleaved storage: [x_re, x_im] @ emb with emb
+    the (2Ci, 2Co) real embedding of the weight.  Ci and Co even (16-byte rows).  Taking and returning the complex tensors
+    themselves lets the backward see the very gradient tensor its producer attached a bound to (set_bound)."""
+    _check(x, "x")
+    _check(emb, "emb", torch.float32)
+    x = x.contiguous()
+    n, ci = x.shape
+    yr = _gemm_call(_real(x).reshape(n, 2 * ci), emb, False, flags, x_bound, None)
+    return torch.view_as_complex(yr.reshape(n, emb.shape[1] // 2, 2))
+
+
+@tangent_lin.register_fake
+def _(x, emb, flags, x_bound=None):
+    return x.new_empty(x.shape[0], emb.shape[1] // 2)
+
+
+def _tl_setup(ctx, inputs, output):
+    x, emb, flags, x_bound = inputs
+    ctx.save_for_backward(x, emb)
+    ctx.flags, ctx.x_bound = flags, x_bound
+
+
+def _tl_backward(ctx, gy):
+    x, emb = ctx.saved_tensors
+    gy = gy.contiguous()
+    n, ci = x.shape
+    co = emb.shape[1] // 2
+    gyb = bound_of(gy) if _uses_bounds(ctx.flags) else None      # attached by the producer of gy, else ONE pass for both products
+    gyr = _real(gy).reshape(n, 2 * co)
+    gx = gemb = None
+    if ctx.needs_input_grad[0]:
+        gxr = _gemm_call(gyr, emb.t().contiguous(), False, ctx.flags, gyb, None)
+        gx = torch.view_as_complex(gxr.reshape(n, ci, 2))
+    if ctx.needs_input_grad[1]:
+        gemb = _gemm_call(_real(x.contiguous()).reshape(n, 2 * ci), gyr, True, ctx.flags, ctx.x_bound, gyb)
+    return gx, gemb, None, None
+
+
+tangent_lin.register_autograd(_tl_backward, setup_context=_tl_setup)

@@ -305,7 +305,7 @@ class _PartitionedFieldConv(torch.autograd.Function):
                       plan.rowptr_tgt[a:].data_ptr(), plan.rec_tgt.data_ptr(), plan.rot_tgt.data_ptr(),
                       plan.rowptr_src[a:].data_ptr(), plan.rec_src.data_ptr(), plan.rot_src.data_ptr(),
                       torch.view_as_real(gx_ext)[a:].data_ptr() if need_gx else 0,
-                      torch.view_as_real(gw_out).data_ptr() if with_gw else 0,
+                      torch.view_as_real(gw_out).data_ptr() if with_gw else 0, None,
                       b - a, ci, co, band_limit, plan.n_rings, flags, ws.data_ptr(), nbytes, _lib.stream_ptr())
 
         main = torch.cuda.current_stream(dev)

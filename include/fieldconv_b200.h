@@ -108,6 +108,25 @@ int fcb_precomp_expand_f32(const int64_t* edges_ji, const float* log_mag, const 
                            float* supp_sten, float* ln, float* wxp, void* workspace, size_t workspace_bytes,
                            void* stream);
 
+/* ------------------------------------------------------------------ operand bounds (optional)
+ * The tensor-core paths scale every fp32 operand by a power of two taken from an upper bound of its largest magnitude.
+ * For the intermediates (contrib, G) the kernel that writes them tracks the bound for free; for an operand that comes
+ * from OUTSIDE a call — the layer input x, the output gradient gy, the operands of fcb_gemm_f32 — the library otherwise
+ * spends one extra pass over it, per call.  A caller that runs a whole block knows better: the same x feeds the
+ * convolution, the residual TangentLin and both their backwards, and the kernels that write the next layer's input can
+ * report its bound as they go.  Every pointer is a device pointer to ONE float and may be NULL (= not available); an
+ * upper bound within a factor of ~2 of the true maximum costs no accuracy (the scale is a power of two).
+ *   x    in : >= max_i |x_i|, complex modulus, over every row of x the call may gather
+ *   gy   in : >= the largest |real or imaginary part| of gy
+ *   act  out: max_i |act_i| (modulus) of the activation fcb_fwd_act_* writes — the `x` bound of the next layer
+ * fcb_bound_f32 computes the modulus bound of n complex numbers (what a caller uses when no producer reported one). */
+typedef struct fcb_bounds {
+    const float* x;
+    const float* gy;
+    float* act;
+} fcb_bounds;
+int fcb_bound_f32(const float* z, int64_t n_complex, float* bound_out, void* stream);
+
 /* ------------------------------------------------------------------ forward (K1 + K2)
  * Replaces nn/field_conv.py:128-137 (+ utils/field.py:40-48, + the weightContrib* reduction
  * :10-33 given the folded weight W[o,c,r,m] = coeff/(2B+1)):
@@ -131,16 +150,17 @@ int fcb_fwd_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const
  *   gW[o,c,r,m] = sum_n conj(contrib[n,r,c,m]) gy[n,o]     (deterministic split reduction)
  *   gx          = softAngle chain rule applied to the transposed gather over the by-source
  *                 CSR of gy Wh conj(sten)                   
- * contrib may be NULL: it is then recomputed from x with the by-target plan (which must be
- * given).  contrib_absmax: the slot filled by the forward (any upper bound of max|contrib| within
- * a factor 2^10 works), or NULL — the 2xFP16 mode then spends one extra pass over contrib on it.
- * gW is complex (Co,Ci,R,M); either of gx / gW may be NULL to skip it. */
+ * contrib may be NULL (the forward kept nothing): the weight gradient is then taken from the transposed aggregation G
+ * and xhat,  gW[o,c,r,m] = sum_j conj(xhat[j,c,m]) G[j,m,r,o]  (the same sum regrouped by source vertex; needs the
+ * by-source plan) — nothing of size N x K is stored or recomputed.  contrib_absmax: the slot filled by the forward (any
+ * upper bound of max|contrib| within a factor 2^10 works), or NULL — the 2xFP16 mode then spends one extra pass over
+ * contrib on it.  bounds (may be NULL): see fcb_bounds.  gW is complex (Co,Ci,R,M); either of gx / gW may be NULL. */
 int fcb_bwd_workspace_bytes(int64_t N, int Ci, int Co, int band_limit, int R, int flags, size_t* bytes);
 int fcb_bwd_f32(const float* x, const float* W, const float* gy, const float* contrib,
                 const float* contrib_absmax, const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
                 const int32_t* rowptr_src, const void* rec_src, const float* rot_src,
-                float* gx, float* gW, int64_t N, int Ci, int Co, int band_limit, int R, int flags,
-                void* workspace, size_t workspace_bytes, void* stream);
+                float* gx, float* gW, const fcb_bounds* bounds, int64_t N, int Ci, int Co, int band_limit, int R,
+                int flags, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ packed-operand variants (FCB_GEMM_TC_2XF16 only)
  * Same results as fcb_fwd_f32 / fcb_bwd_f32 (nn/field_conv.py:128-137 and its autograd), different intermediate
@@ -160,13 +180,14 @@ int fcb_pk_supported(int64_t N, int Ci, int Co, int band_limit, int R);
 int fcb_pk_contrib_bytes(int64_t N, int Ci, int band_limit, int R, size_t* bytes);
 int fcb_fwd_pk_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
                    const float* rot_tgt, const float* norm_tgt, float* y, void* contrib_pk, float* contrib_scale,
-                   int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* workspace,
-                   size_t workspace_bytes, void* stream);
+                   const fcb_bounds* bounds, int64_t N, int Ci, int Co, int band_limit, int R, int flags,
+                   void* workspace, size_t workspace_bytes, void* stream);
 int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, const void* contrib_pk,
                    const float* contrib_scale, const int32_t* rowptr_tgt, const void* rec_tgt,
                    const float* rot_tgt, const float* norm_tgt, const int32_t* rowptr_src, const void* rec_src,
-                   const float* rot_src, const float* norm_src, float* gx, float* gW, int64_t N, int Ci, int Co,
-                   int band_limit, int R, int flags, void* workspace, size_t workspace_bytes, void* stream);
+                   const float* rot_src, const float* norm_src, float* gx, float* gW, const fcb_bounds* bounds,
+                   int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* workspace,
+                   size_t workspace_bytes, void* stream);
 
 /* ---- FCResNetBlock epilogue fused into the layer (nn/fc_resnet_block.py:84-88 of the reference):
  *   y   = FieldConv(x) + res        (res: (N, Co) complex64 — the TangentLin residual nn/tangent_lin.py:27-29 — or NULL)
@@ -176,12 +197,12 @@ int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, const void* 
  * pointwise kernel follows.  y keeps the PRE-activation values (what the modReLU backward needs). */
 int fcb_fwd_act_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
                     float* y, float* contrib, float* contrib_absmax, const float* res, const float* bias, float* act,
-                    int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* workspace, size_t workspace_bytes,
-                    void* stream);
+                    const fcb_bounds* bounds, int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* workspace,
+                    size_t workspace_bytes, void* stream);
 int fcb_fwd_act_pk_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
                        const float* norm_tgt, float* y, void* contrib_pk, float* contrib_scale, const float* res,
-                       const float* bias, float* act, int64_t N, int Ci, int Co, int band_limit, int R, int flags,
-                       void* workspace, size_t workspace_bytes, void* stream);
+                       const float* bias, float* act, const fcb_bounds* bounds, int64_t N, int Ci, int Co, int band_limit,
+                       int R, int flags, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- TransField / LiftBlock aggregations (nn/trans_field.py:96-110 of the reference; csrc/lift.cu).  x: (N, Ci) float32
  * scalar features; lift_sten: (E, R, 2) complex64 (frequencies 0 and 1 of FCPrecomp's stencil) in the caller's edge order;
@@ -253,7 +274,9 @@ int fcb_aggregate_f32(const float* feat, const int32_t* rowptr, const void* rec,
  * B is KxN row-major; batch >= 1 with element strides; split_k >= 1 writes per-split partials into
  * the workspace and reduces them in a fixed order (deterministic).  flags & FCB_GEMM_MASK selects
  * the FP32-FMA kernel or a tcgen05 tensor-core kernel (3xTF32 / TF32 / 2xFP16) when its accumulation plan fits.
- * The workspace size comes from fcb_gemm_workspace_bytes with the same arguments. */
+ * The workspace size comes from fcb_gemm_workspace_bytes with the same arguments.
+ * a_bound / b_bound (device floats, may be NULL): upper bounds of max|A|, max|B| for the 2xFP16 operand scales (see
+ * fcb_bounds); used for the operands the kernel would otherwise take a pass over (A; B of a transposed product). */
 int fcb_gemm_workspace_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags,
                              size_t* bytes);
 /* 1 if fcb_gemm_f32 with these flags would run on the tensor cores inside the fp32 parity budget (the
@@ -261,8 +284,8 @@ int fcb_gemm_workspace_bytes(int64_t M, int N, int64_t K, int trans_a, int batch
 int fcb_gemm_tc_feasible(int N, int64_t K, int trans_a, int split_k, int flags);
 int fcb_gemm_f32(const float* A, const float* B, float* C, int64_t M, int N, int64_t K,
                  int64_t lda, int64_t ldb, int64_t ldc, int trans_a, int batch, int64_t stride_a,
-                 int64_t stride_b, int64_t stride_c, int split_k, void* workspace, size_t workspace_bytes,
-                 int flags, void* stream);
+                 int64_t stride_b, int64_t stride_c, int split_k, const float* a_bound, const float* b_bound,
+                 void* workspace, size_t workspace_bytes, int flags, void* stream);
 /* Stable LSD radix sort of (key,value) uint32 pairs on the low `bits` bits of the key.
  * Result lands in keys_out/vals_out; keys_in/vals_in are clobbered. */
 int fcb_sort_workspace_bytes(int64_t n, size_t* bytes);
@@ -272,10 +295,11 @@ int fcb_sort_pairs_u32(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out,
 /* ------------------------------------------------------------------ block epilogue pieces
  * TangentNonLin / modReLU, nn/tangent_nonlin.py:24-35: y = relu(|x|+b_c) x/|x|, origin entries
  * passed through.  Backward returns gx and per-block partial bias gradients reduced in fixed
- * order into gb (C floats). */
+ * order into gb (C floats); gx_bound (device float, may be NULL) receives the largest |component| of gx — the `gy`
+ * bound of the layer whose output gradient gx is (fcb_bounds). */
 int fcb_modrelu_fwd_f32(const float* x, const float* bias, float* y, int64_t N, int C, void* stream);
 int fcb_modrelu_bwd_workspace_bytes(int64_t N, int C, size_t* bytes);
-int fcb_modrelu_bwd_f32(const float* x, const float* bias, const float* gy, float* gx, float* gb,
+int fcb_modrelu_bwd_f32(const float* x, const float* bias, const float* gy, float* gx, float* gb, float* gx_bound,
                         int64_t N, int C, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

@@ -63,7 +63,7 @@ def test_null_pointer_calls_are_rejected_without_touching_the_gpu():
     rc = lib.fcb_plan_build(None, None, None, None, None, None, 1.0, 10, 10, 1, None, None, None, None,
                             None, None, None, None, None, 0, None)
     assert rc == -5      # n_rings = 1 is unsupported (the reference divides by n_rings-1)
-    rc = lib.fcb_gemm_f32(None, None, None, 4, 4, 4, 4, 4, 4, 0, 1, 0, 0, 0, 1, None, 0, 0, None)
+    rc = lib.fcb_gemm_f32(None, None, None, 4, 4, 4, 4, 4, 4, 0, 1, 0, 0, 0, 1, None, None, None, 0, 0, None)
     assert rc == -1
 
 
@@ -104,7 +104,7 @@ def test_packed_path_shape_support_and_sizes():
     nbytes = _lib.query_bytes("fcb_pk_contrib_bytes", n, ci, b, r)
     assert nbytes == 1024 * (r * ci * 3) * 8               # same bytes as the fp32 layout, rows padded to 128
     lib = _lib.load()
-    rc = lib.fcb_fwd_pk_f32(None, None, None, None, None, None, None, None, None, 10, 32, 32, 1, 6, 3, None, 0, None)
+    rc = lib.fcb_fwd_pk_f32(None, None, None, None, None, None, None, None, None, None, 10, 32, 32, 1, 6, 3, None, 0, None)
     assert rc == -1
     rc = lib.fcb_plan_norm(None, None, 10, None, None)
     assert rc == -1

@@ -141,6 +141,65 @@ def test_block_epilogue_fused_matches_separate_kernels(c, B, precision, monkeypa
         assert_close_normwise(res["1"][3][k], res["0"][3][k], 5e-6, "grad " + k)
 
 
+@pytest.mark.parametrize("c,B", [(48, 2), (32, 1)])
+def test_operand_bounds_reported_by_producers_and_shared_by_consumers(c, B, monkeypatch):
+    """struct fcb_bounds: (1) the bounds the kernels report equal the true maxima; (2) a two-block stack run with the bounds
+    travelling along the tensors matches the run where every call takes its own pass over its operands; (3) with the
+    bounds the step launches fewer operand-maximum passes."""
+    from fieldconv_b200 import _lib, ops
+    mesh = torus_mesh(26, deg=40.0, seed=8, device=DEV)
+    plan = fcb.build_plan(mesh.supp_edges, mesh.logMag, mesh.logAng, mesh.xp, mesh.w, 6, mesh.epsilon)
+    n = mesh.num_nodes
+    torch.manual_seed(3)
+    blocks = torch.nn.ModuleList([fcb.FCResNetBlock(c, c, B, 6, 1).to(DEV) for _ in range(2)])
+    with torch.no_grad():
+        for blk in blocks:
+            blk.nonlin1.bias.uniform_(-0.3, 0.3)
+            blk.nonlin2.bias.uniform_(-0.3, 0.3)
+    # (1) producers: the activation bound of the fused epilogue, the gradient bound of the modReLU backward, fcb_bound_f32
+    x = random_features(n, c, seed=4, device=DEV)
+    h = blocks[0](x, plan)
+    hb = ops.peek_bound(h)
+    assert hb is not None, "the fused block epilogue did not attach a bound to its output"
+    true = float(h.detach().abs().max())
+    assert true <= float(hb) <= true * (1 + 1e-5) + 1e-30
+    z = random_features(n, c, seed=6, zero_frac=0, device=DEV)
+    g = random_features(n, c, seed=7, zero_frac=0, device=DEV)
+    gz, _, gzb = ops.modrelu_bwd(z, blocks[0].nonlin1.bias.detach(), g)
+    true = float(torch.view_as_real(gz).abs().max())
+    assert float(gzb) == pytest.approx(true, rel=1e-6)
+    xb = ops.bound_of(x)
+    true = float(x.abs().max())
+    assert true <= float(xb) <= true * (1 + 1e-5)
+    assert ops.bound_of(x) is xb, "the bound is cached on the tensor"
+    x2 = x.clone()
+    ops.set_bound(x2, xb)
+    x2.mul_(2.0)
+    assert ops.peek_bound(x2) is None, "an in-place update must invalidate the attached bound"
+    # (2) + (3)
+    gy = random_features(n, c, seed=5, zero_frac=0, device=DEV)
+    res = {}
+    for mode in (True, False):
+        monkeypatch.setattr(ops, "BOUNDS", mode)
+        blocks.zero_grad()
+        xin = random_features(n, c, seed=4, device=DEV).requires_grad_(True)
+        _lib.profile_enable(2048)
+        y = xin
+        for blk in blocks:
+            y = blk(y, plan)
+        (y.real * gy.real + y.imag * gy.imag).sum().backward()
+        torch.cuda.synchronize()
+        names = [k for k, _ in _lib.profile_collect(2048)]
+        passes = sum(1 for k in names if k in ("absmax_mod", "lin_absmax_mod"))
+        big = [k for k in names if k in ("absmax", "lin_absmax")]
+        res[mode] = (passes, len(big), y.detach(), xin.grad, {k: p.grad.clone() for k, p in blocks.named_parameters()})
+    assert res[True][0] + res[True][1] < res[False][0] + res[False][1], (res[True][:2], res[False][:2])
+    assert_close_normwise(res[True][2], res[False][2], 2e-6, "y")
+    assert_close_normwise(res[True][3], res[False][3], 2e-6, "grad x")
+    for k in res[False][4]:
+        assert_close_normwise(res[True][4][k], res[False][4][k], 5e-6, "grad " + k)
+
+
 def _oracle_layer(mesh, x, m, gy, dtype=torch.complex128):
     """fp64 folded-form oracle on the CPU for a synthetic mesh."""
     B, R = m.B, m.R

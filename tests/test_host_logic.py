@@ -210,3 +210,19 @@ def test_shared_dense_plan_cache_is_keyed_on_the_tensor_object():
         assert not fnn._DENSE_PLANS                                              # entries die with their tensors
     finally:
         fnn.build_dense_plan = orig
+
+
+def test_operand_bound_travels_with_the_tensor_and_dies_with_an_inplace_update():
+    """ops.set_bound / peek_bound (struct fcb_bounds): the bound a producer reported is an attribute of the tensor object,
+    tagged with the tensor's version counter; any in-place write makes it stale, and there is no CPU computation of one."""
+    from fieldconv_b200 import ops
+    t = torch.randn(5, 3, dtype=torch.complex64)
+    assert ops.peek_bound(t) is None
+    assert ops.bound_of(t) is None                       # CPU tensor: no bound, no fallback computation
+    b = torch.tensor([4.0])
+    assert ops.set_bound(t, b) is t
+    assert ops.peek_bound(t) is b
+    t.add_(1.0)
+    assert ops.peek_bound(t) is None
+    u = t.clone()
+    assert ops.peek_bound(u) is None                     # a copy is a new tensor: no inherited attribute

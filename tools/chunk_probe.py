@@ -53,7 +53,7 @@ def main():
 
     def gemm(a, bb, src, ws, stream):
         _lib.call("fcb_gemm_f32", src.data_ptr(), wmat.data_ptr(), y.data_ptr() + 4 * a * 2 * c, bb - a, 2 * c, k2, k2, 2 * c, 2 * c,
-                  0, 1, 0, 0, 0, 1, ws.data_ptr(), ws.numel(), flags, stream.cuda_stream)
+                  0, 1, 0, 0, 0, 1, None, None, ws.data_ptr(), ws.numel(), flags, stream.cuda_stream)
 
     def timed(fn):
         for _ in range(3):
