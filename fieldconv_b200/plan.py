@@ -1,6 +1,8 @@
 """Edge plans (K0): the device-side replacement of FCPrecomp's arithmetic and of the grouping
 that scatter_add / autograd perform implicitly in the reference (transforms/fc_precomp.py:53-97,
 nn/field_conv.py:134).  Built once per mesh, shared by every FieldConv layer, forward and backward."""
+import os
+
 import torch
 
 from . import _lib
@@ -66,7 +68,16 @@ def ring_radii(n_rings, device):
     return torch.sqrt(torch.div(torch.arange(n_rings, device=device), n_rings - 1)).float().contiguous()
 
 
-def build_plan(supp_edges, logMag, logAng, xp, w, n_rings, epsilon, num_nodes=None):
+def _validate_edges(supp_edges, n):
+    """The reference fails with an index error on an edge endpoint outside [0, N) (nn/field_conv.py:130-134); the plan
+    kernels drop such edges instead, so a corrupted or mis-offset batched supp_edges would silently become a smaller stencil.
+    One reduction + host sync: opt-in (validate=True or FIELDCONV_B200_VALIDATE=1)."""
+    if supp_edges.numel() and bool(((supp_edges < 0) | (supp_edges >= n)).any()):
+        bad = int(((supp_edges < 0) | (supp_edges >= n)).any(dim=1).sum())
+        raise IndexError("fieldconv_b200: %d of %d supp_edges rows have an endpoint outside [0, %d)" % (bad, supp_edges.shape[0], n))
+
+
+def build_plan(supp_edges, logMag, logAng, xp, w, n_rings, epsilon, num_nodes=None, validate=None):
     """Compact plan from the attributes the reference's offline transforms store on `data`
     (supp_edges, logMag, logAng, xp, w — transforms/compute_log_xport.py:36-50) and FCPrecomp's
     (n_rings, epsilon).  Reproduces fc_precomp.py:67-95 on the device."""
@@ -80,6 +91,8 @@ def build_plan(supp_edges, logMag, logAng, xp, w, n_rings, epsilon, num_nodes=No
     n = int(w.shape[0]) if num_nodes is None else int(num_nodes)
     e = int(supp_edges.shape[0])
     edges = supp_edges.to(torch.int64).contiguous()
+    if validate or (validate is None and os.environ.get("FIELDCONV_B200_VALIDATE", "0") == "1"):
+        _validate_edges(edges, n)
     lm, la = logMag.contiguous(), logAng.contiguous()
     xpc = xp.to(torch.complex64).contiguous()
     wv = w.reshape(-1).contiguous()

@@ -93,6 +93,18 @@ def test_plan_empty_and_all_filtered():
     assert y.shape == (7, 6) and float(y.detach().abs().max()) == 0.0     # no in-edges -> y = 0 (field_conv.py:134 dim_size=N)
 
 
+def test_plan_validate_rejects_out_of_range_endpoints():
+    """The reference raises an index error on an endpoint outside [0, N) (nn/field_conv.py:130-134); build_plan(validate=True)
+    does the same instead of dropping the edge."""
+    w = torch.ones(7, 1, device=DEV)
+    e = torch.tensor([[0, 1], [2, 7], [6, 6]], device=DEV)
+    args = (torch.full((3,), 0.3, device=DEV), torch.zeros(3, device=DEV), torch.ones(3, dtype=torch.complex64, device=DEV), w, 6, 1.0)
+    with pytest.raises(IndexError):
+        fcb.build_plan(e, *args, validate=True)
+    assert fcb.build_plan(e, *args).num_edges == 2            # default: the edge is dropped (documented)
+    assert fcb.build_plan(e[[0, 2]], *[a[[0, 2]] if a.ndim == 1 and a.shape[0] == 3 else a for a in args], validate=True).num_edges == 2
+
+
 @pytest.mark.parametrize("m,n,k,trans", [(1, 4, 4, 0), (130, 96, 72, 0), (257, 20, 1000, 0), (1000, 64, 36, 0),
                                          (300, 96, 4000, 1), (2880, 96, 20000, 1), (64, 256, 515, 1), (5, 12, 7, 1)])
 def test_gemm_matches_fp64(m, n, k, trans):
