@@ -102,7 +102,8 @@ def test_plan_validate_rejects_out_of_range_endpoints():
     with pytest.raises(IndexError):
         fcb.build_plan(e, *args, validate=True)
     assert fcb.build_plan(e, *args).num_edges == 2            # default: the edge is dropped (documented)
-    assert fcb.build_plan(e[[0, 2]], *[a[[0, 2]] if a.ndim == 1 and a.shape[0] == 3 else a for a in args], validate=True).num_edges == 2
+    ok = [a[[0, 2]] if (torch.is_tensor(a) and a.ndim == 1 and a.shape[0] == 3) else a for a in args]
+    assert fcb.build_plan(e[[0, 2]], *ok, validate=True).num_edges == 2
 
 
 @pytest.mark.parametrize("m,n,k,trans", [(1, 4, 4, 0), (130, 96, 72, 0), (257, 20, 1000, 0), (1000, 64, 36, 0),
