@@ -577,6 +577,223 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------ NN, short K
+// C[M x N] = A B for K <= 128 (TangentLin: K = 2 Ci): the whole contraction of a row tile is one or two chunks, so the
+// per-CTA fixed costs of k_gemm_h_nn (barrier set-up, TMEM allocation, the first B fetch, an un-overlapped epilogue) would be
+// most of its time.  Persistent form: one CTA per SM walks over row tiles; the packed B operand (<= 2 chunks) is fetched ONCE
+// and stays in shared memory; two operand stages and TWO accumulator sets in TMEM, so that
+//   warps 0-7   (producers) load / split / store the fp32 rows of tile t+1,
+//   warp  8     (one thread) issues the MMAs of tile t+1 as soon as its stage is full and an accumulator set is free,
+//   warps 9-12  (epilogue, one per TMEM lane quarter) drain tile t — all at the same time.
+constexpr int SK_PROD_WARPS = 8;
+constexpr int SK_PROD = SK_PROD_WARPS * 32;
+constexpr int SK_THREADS = (SK_PROD_WARPS + 1 + 4) * 32;
+constexpr int SK_UNITS = 4;          // 16-byte output units per producer thread and chunk (128 rows x 8 units / 256 threads)
+
+struct ParamsSK {
+    const float* A;
+    const __half* Bp;          // packed B (k_pack_b_h): [chunk][plane][Npad][64 fp16]
+    float* C;
+    const float *amax_a, *amax_b;
+    int64_t M, K, lda, ldc;
+    int N, Npad, nchunks, wide;
+    int rows_per_tile;         // <= BM, multiple of 8
+    int64_t tiles;
+    uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(SK_THREADS, 1) k_gemm_h_nn_small(const ParamsSK p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw);
+    const int NC = p.nchunks;
+    const uint32_t b_plane = (uint32_t)p.Npad * 128u;
+    const uint32_t a_stage = (uint32_t)NC * 2u * A_PLANE;           // [chunk][hi | lo]
+    // layout: B[NC][hi | lo] | A[2 stages] | barriers
+    const uint32_t b0 = base, a0 = base + (uint32_t)NC * 2u * b_plane;
+    const uint32_t bars = a0 + 2u * a_stage;
+    const uint32_t b_full = bars;
+    auto a_full = [&](int s) { return bars + 8u * (1 + s); };
+    auto a_empty = [&](int s) { return bars + 8u * (3 + s); };
+    auto t_full = [&](int s) { return bars + 8u * (5 + s); };
+    auto t_empty = [&](int s) { return bars + 8u * (7 + s); };
+    const uint32_t tmem_slot = bars + 8u * 9;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(sm + (tmem_slot - base));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(b_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(a_full(s), SK_PROD_WARPS);
+            mbar_init(a_empty(s), 1);
+            mbar_init(t_full(s), 1);
+            mbar_init(t_empty(s), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == SK_PROD_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot_ptr;
+    const uint32_t acc_cols = 2u * (uint32_t)p.Npad;                // [main | cross] of one accumulator set
+
+    if (warp < SK_PROD_WARPS) {
+        // ------------------------------------------------------------------ producers
+        const int t = threadIdx.x;
+        uint32_t off[SK_UNITS];
+        int urow[SK_UNITS], ucol[SK_UNITS];
+#pragma unroll
+        for (int i = 0; i < SK_UNITS; ++i) {
+            const int idx = t + SK_PROD * i;
+            const int row = idx >> 3, j = idx & 7;
+            urow[i] = row;
+            ucol[i] = 8 * j;
+            off[i] = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
+        }
+        const float s_a = scale_of(p.amax_a);
+        uint8_t* const a_base = sm + (a0 - base);
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+            const int st = it & 1;
+            const int64_t m0 = tile * p.rows_per_tile;
+            const int64_t m_end = min(p.M, m0 + p.rows_per_tile);
+            F8 v[2][SK_UNITS];                                      // every load of the tile in flight before the first split
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (c >= NC) break;
+#pragma unroll
+                for (int i = 0; i < SK_UNITS; ++i) {
+                    const int64_t m = m0 + urow[i];
+                    const int64_t k = (int64_t)c * KC + ucol[i];
+                    zero8(v[c][i]);
+                    if (m < m_end && k < p.K) {
+                        const float* src = p.A + m * p.lda + k;
+                        if (k + 8 <= p.K) {
+                            if (p.wide) ld256(src, v[c][i]);
+                            else ld2x128(src, v[c][i]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (k + e < p.K) v[c][i].v[e] = src[e];
+                        }
+                    }
+                }
+            }
+            mbar_wait(a_empty(st), (uint32_t)(((it >> 1) & 1) ^ 1));
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (c >= NC) break;
+#pragma unroll
+                for (int i = 0; i < SK_UNITS; ++i) {
+                    uint4 hi, lo;
+                    split8(v[c][i], s_a, hi, lo);
+                    uint8_t* dst = a_base + st * a_stage + (uint32_t)c * 2u * A_PLANE + off[i];
+                    *reinterpret_cast<uint4*>(dst) = hi;
+                    *reinterpret_cast<uint4*>(dst + A_PLANE) = lo;
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full(st));
+        }
+    } else if (warp == SK_PROD_WARPS) {
+        // ------------------------------------------------------------------ B fetch (once) + MMA issue (one thread)
+        if (lane == 0) {
+            const uint32_t b_bytes = (uint32_t)NC * 2u * b_plane;
+            mbar_expect_tx(b_full, b_bytes);
+            for (int c = 0; c < NC; ++c)
+                bulk_copy_g2s(b0 + (uint32_t)c * 2u * b_plane, p.Bp + (int64_t)c * 2 * p.Npad * KC, 2u * b_plane, b_full);
+            mbar_wait(b_full, 0);
+            const uint32_t npad = (uint32_t)p.Npad;
+            const bool merged = 2 * p.Npad <= 256;
+            const uint32_t idesc1 = make_idesc_f16(p.Npad), idesc2 = merged ? make_idesc_f16(2 * p.Npad) : 0u;
+            const int ksteps = (int)((p.K + 15) / 16);              // k-steps that hold data (the rest of the last chunk is zero)
+            int it = 0;
+            for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+                const int st = it & 1;
+                const uint32_t ph = (uint32_t)((it >> 1) & 1);
+                mbar_wait(t_empty(st), ph ^ 1u);                    // the epilogue has drained this accumulator set
+                mbar_wait(a_full(st), ph);
+                tc_fence_after();
+                const uint32_t d = tmem_d + (uint32_t)st * acc_cols;
+                uint32_t first = 1;
+                for (int c = 0; c < NC; ++c) {
+                    const uint32_t a_hi0 = a0 + st * a_stage + (uint32_t)c * 2u * A_PLANE;
+                    const uint64_t a_hi = make_desc_k_sw128(a_hi0), a_lo = make_desc_k_sw128(a_hi0 + A_PLANE);
+                    const uint64_t b_hi = make_desc_k_sw128(b0 + (uint32_t)c * 2u * b_plane);
+                    const uint64_t b_lo = make_desc_k_sw128(b0 + (uint32_t)c * 2u * b_plane + b_plane);
+                    for (int ks = 0; ks < KC / 16 && c * (KC / 16) + ks < ksteps; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        if (merged) {
+                            tc_mma_f16(d, a_hi + adv, b_hi + adv, idesc2, first ? 0u : 1u);
+                        } else {
+                            tc_mma_f16(d, a_hi + adv, b_hi + adv, idesc1, first ? 0u : 1u);
+                            tc_mma_f16(d + npad, a_hi + adv, b_lo + adv, idesc1, first ? 0u : 1u);
+                        }
+                        tc_mma_f16(d + npad, a_lo + adv, b_hi + adv, idesc1, 1u);
+                        first = 0;
+                    }
+                }
+                tc_commit(a_empty(st));
+                tc_commit(t_full(st));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue (4 warps: warp % 4 = TMEM lane quarter)
+        const int q = warp & 3;
+        const float inv = inv_scale_of(p.amax_a) * inv_scale_of(p.amax_b);
+        const int groups = p.Npad / 16;
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+            const int st = it & 1;
+            const int64_t m0 = tile * p.rows_per_tile;
+            const int64_t m_end = min(p.M, m0 + p.rows_per_tile);
+            const int64_t m = m0 + 32 * q + lane;
+            mbar_wait(t_full(st), (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            const uint32_t lane_base = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)st * acc_cols;
+            for (int g = 0; g < groups; ++g) {
+                uint32_t r0[16], r1[16];
+                tc_ld16(lane_base + (uint32_t)(16 * g), r0);
+                tc_ld16(lane_base + (uint32_t)(p.Npad + 16 * g), r1);
+                tc_ld_wait();
+                if (m < m_end) {
+                    float* dst = p.C + m * p.ldc + 16 * g;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) o[e] = (__uint_as_float(r1[4 * c4 + e]) + __uint_as_float(r0[4 * c4 + e])) * inv;
+                        const int n = 16 * g + 4 * c4;
+                        if (n + 3 < p.N) {
+                            *reinterpret_cast<float4*>(dst + 4 * c4) = make_float4(o[0], o[1], o[2], o[3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (n + e < p.N) dst[4 * c4 + e] = o[e];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty(st));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == SK_PROD_WARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(p.tmem_cols) : "memory");
+    }
+}
+
 // B[K x N] row-major (ldb) -> [batch][chunk][plane][Npad][64 fp16] with the 128B swizzle applied (16-byte unit u of row
 // n stored at unit u ^ (n & 7)); hi = fp16(s b), lo = fp16(s b - hi); rows n >= N and k >= K are zero.  One thread per
 // 16-byte piece (8 consecutive k of one column n); consecutive threads take consecutive n (coalesced reads of B rows).
@@ -1063,6 +1280,42 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
         const int64_t per = (int64_t)nchunks * npad * 8;
         dim3 grid((unsigned)((per + 255) / 256), (unsigned)(batch * kgroups));
         FCB_LAUNCH("pack_b_h", st, th::k_pack_b_h<<<grid, 256, 0, st>>>(B, Bp, K, N, npad, ldb, nchunks, sb, bp_stride, amax_b));
+    }
+    // short K (TangentLin): persistent kernel with a resident B operand and two accumulator sets (k_gemm_h_nn_small).
+    // FIELDCONV_B200_GEMM_SMALL=0 keeps the general kernel (A/B switch).
+    static const bool small_on = [] { const char* e = getenv("FIELDCONV_B200_GEMM_SMALL"); return !e || atoi(e) != 0; }();
+    if (small_on && !a_packed && nchunks <= 2 && batch == 1 && kgroups == 1 && split_k == 1 && !epi && !sa_gx && npad <= 128 &&
+        M > th::BM) {
+        th::ParamsSK q;
+        q.A = A; q.Bp = Bp; q.C = C; q.amax_a = amax_a; q.amax_b = amax_b;
+        q.M = M; q.K = K; q.lda = lda; q.ldc = ldc;
+        q.N = N; q.Npad = npad; q.nchunks = nchunks;
+        q.wide = ((lda % 8) == 0 && (reinterpret_cast<uintptr_t>(A) & 31u) == 0) ? 1 : 0;
+        // equal row tiles that give every CTA of the persistent grid the same number of tiles
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t tiles128 = (M + th::BM - 1) / th::BM;
+        const int64_t ctas = tiles128 < sms ? tiles128 : sms;
+        const int64_t rounds = (tiles128 + ctas - 1) / ctas;
+        int64_t rpt = ((M + rounds * ctas - 1) / (rounds * ctas) + 7) / 8 * 8;
+        if (rpt > th::BM) rpt = th::BM;
+        q.rows_per_tile = (int)rpt;
+        q.tiles = (M + rpt - 1) / rpt;
+        uint32_t cols = 32;
+        while ((int)cols < 4 * npad) cols <<= 1;                    // two [main | cross] sets
+        q.tmem_cols = cols;
+        const size_t smem = (size_t)nchunks * 2 * npad * 128 + 2 * (size_t)nchunks * 2 * th::A_PLANE + 1024 + 8 * 10 + 64;
+        static std::atomic<bool> sk_attr_dev[64];
+        if (!(dev >= 0 && dev < 64 && sk_attr_dev[dev].load(std::memory_order_acquire))) {
+            if (cudaFuncSetAttribute(th::k_gemm_h_nn_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+                set_error("gemm_h: cudaFuncSetAttribute failed");
+                return FCB_E_CUDA;
+            }
+            if (dev >= 0 && dev < 64) sk_attr_dev[dev].store(true, std::memory_order_release);
+        }
+        const unsigned grid = (unsigned)(q.tiles < ctas ? q.tiles : ctas);
+        FCB_LAUNCH("gemm_h_nn_small", st, (th::k_gemm_h_nn_small<<<grid, th::SK_THREADS, smem, st>>>(q)));
+        return FCB_OK;
     }
     th::Params p;
     p.A = A; p.Bp = Bp; p.C = C;
