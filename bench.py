@@ -381,7 +381,9 @@ def run_ours(args):
     # ---- end-to-end leg: pinned host buffers -> H2D -> device plan build -> fwd+bwd+step -> D2H loss.
     #      A loader stream stages step k+1 (H2D copies + plan build) while step k computes — every step's copies and
     #      plan build are still inside the timed region, the first step's included.
-    loader = torch.cuda.Stream(device=dev)
+    # high priority: the staging work is many small kernels (plan build) next to the step's SM-filling ones — at equal priority
+    # two boxes ran them only at the step's kernel boundaries (35-38 ms per step instead of 18 when the plan is rebuilt every step)
+    loader = torch.cuda.Stream(device=dev, priority=-1)
     plan_cache = {}                       # mesh-batch id -> device plan (+ the device copies of its static attributes)
 
     def stage(batch_id, cached):
