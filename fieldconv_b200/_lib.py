@@ -140,14 +140,14 @@ def ptr(t):
 
 class Bounds(ctypes.Structure):
     """struct fcb_bounds of the header: optional operand bounds (device pointers to one float, 0 = not available)."""
-    _fields_ = [("x", ctypes.c_void_p), ("gy", ctypes.c_void_p), ("act", ctypes.c_void_p)]
+    _fields_ = [("x", ctypes.c_void_p), ("gy", ctypes.c_void_p), ("act", ctypes.c_void_p), ("w", ctypes.c_void_p)]
 
 
-def bounds(x=None, gy=None, act=None):
+def bounds(x=None, gy=None, act=None, w=None):
     """-> argument for a `const fcb_bounds*` parameter (None when nothing is known: the library then computes what it needs)."""
-    if x is None and gy is None and act is None:
+    if x is None and gy is None and act is None and w is None:
         return None
-    return ctypes.byref(Bounds(ptr(x) or None, ptr(gy) or None, ptr(act) or None))
+    return ctypes.byref(Bounds(ptr(x) or None, ptr(gy) or None, ptr(act) or None, ptr(w) or None))
 
 
 def stream_ptr():

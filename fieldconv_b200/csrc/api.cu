@@ -466,18 +466,28 @@ static int apply_epilogue(const Dims& d, float* y, const GemmEpilogue* epi, cuda
 // epi (optional): y receives z = contraction (+ res), epi->act = modReLU(z, bias) — fused into the 2xFP16 kernel's epilogue
 // when the product is a single un-split launch, else applied by k_res_modrelu right after
 static int contract_fwd(const Dims& d, const float* contrib, const float* amax, const float* W, float* y, void* ws,
-                        size_t ws_bytes, int flags, cudaStream_t st, const GemmEpilogue* epi = nullptr) {
+                        size_t ws_bytes, int flags, cudaStream_t st, const GemmEpilogue* epi = nullptr, const float* w_bound = nullptr) {
     FCB_REQUIRE(ws_bytes >= fwd_ws(d), FCB_E_WORKSPACE, "fwd: workspace too small");
     Arena ar(ws, ws_bytes);
     ar.take<char>(256);      // the max|contrib| slot (fwd_amax_slot)
     float* Bw = ar.take<float>((size_t)(4 * d.K * d.Co));
     const int64_t tot = d.K * d.Co;
-    FCB_LAUNCH("pack_w_fwd", st, k_pack_w_fwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bw, d.Ci, d.Co, d.R, d.M));
     const size_t tcb = fwd_gemm_ws(d);
     void* tcw = ar.take<char>(tcb);
     int fused = 0;
-    int rc = launch_gemm(contrib, Bw, y, d.N, 2 * d.Co, 2 * d.K, 2 * d.K, 2 * d.Co, 2 * d.Co, 0, 1, 0, 0, 0, 1, tcw, tcb, flags, amax, st,
-                         epi, &fused);
+    int rc;
+    if (gemm_h_single_launch(2 * d.Co, 2 * d.K, flags)) {
+        // one launch: W -> packed fp16 (hi, lo) operand in the contraction's workspace (no fp32 embedding, no separate max / pack)
+        rc = launch_pack_w_h(W, 0, d.Ci, d.Co, d.R, d.M, w_bound, tcw, tcb, st);
+        if (rc) return rc;
+        rc = launch_gemm(contrib, nullptr, y, d.N, 2 * d.Co, 2 * d.K, 2 * d.K, 2 * d.Co, 2 * d.Co, 0, 1, 0, 0, 0, 1, tcw, tcb,
+                         flags | FCB_FLAG_B_PREPACKED, amax, st, epi, &fused);
+        if (rc || !epi || fused) return rc;
+        return apply_epilogue(d, y, epi, st);
+    }
+    FCB_LAUNCH("pack_w_fwd", st, k_pack_w_fwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bw, d.Ci, d.Co, d.R, d.M));
+    rc = launch_gemm(contrib, Bw, y, d.N, 2 * d.Co, 2 * d.K, 2 * d.K, 2 * d.Co, 2 * d.Co, 0, 1, 0, 0, 0, 1, tcw, tcb, flags, amax, st,
+                     epi, &fused);
     if (rc || !epi || fused) return rc;
     return apply_epilogue(d, y, epi, st);
 }
@@ -489,7 +499,7 @@ template <typename GatherT>
 static int backward_common(const Dims& d, const float* x, const float* W, const float* gy, const float* contrib,
                            const float* contrib_amax, float* g_amax, GatherT&& gather_transpose, float* gx, float* gW,
                            Arena& ar, int flags, cudaStream_t st, bool contrib_packed = false, bool g_packed = false,
-                           const float* x_bound = nullptr) {
+                           const float* x_bound = nullptr, const float* w_bound = nullptr) {
     float* Bt = ar.take<float>((size_t)(4 * d.K * d.Co));
     float* P = ar.take<float>((size_t)(4 * d.K * d.Co));
     const bool from_g = gW && !contrib;
@@ -520,16 +530,26 @@ static int backward_common(const Dims& d, const float* x, const float* W, const 
     }
     if (gx) {
         // K5b: gxh[:, m, :] = G[:, m, :] @ conj(W)[m]  (one real GEMM per m, batched)
-        FCB_LAUNCH("pack_w_bwd", st, k_pack_w_bwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bt, d.Ci, d.Co, d.R, d.M));
         const int64_t Q2 = 2 * (int64_t)d.R * d.Co;
         const size_t tcb = gx_gemm_ws(d);
         void* tcw = ar.take<char>(tcb);
         FCB_REQUIRE(ar.ok(), FCB_E_WORKSPACE, "bwd: workspace too small");
         int grouped = 0;     // all m in one pass over G (one long-K tensor-core pipeline) when the plan allows
+        // the grouped 2xFP16 product takes conj(W) packed straight from W (one launch) when it is certain to run
+        const bool pre = (flags & FCB_GEMM_MASK) == FCB_GEMM_TC_2XF16 && gemm_pk_grouped_ok(2 * d.Ci, Q2, d.M) &&
+                         tcb >= gemm_h_ws_bytes(2 * d.Ci, Q2, d.M) && aligned16(G) && aligned16(gxh);
+        int rc;
+        if (pre) {
+            rc = launch_pack_w_h(W, 1, d.Ci, d.Co, d.R, d.M, w_bound, tcw, tcb, st);
+            if (rc) return rc;
+        } else {
+            FCB_LAUNCH("pack_w_bwd", st, k_pack_w_bwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(W), Bt, d.Ci, d.Co, d.R, d.M));
+        }
         // 2xFP16 grouped product: the softAngle chain rule runs in its epilogue (grouped == 2) — gxhat never reaches memory
-        int rc = launch_gemm_grouped(G, Bt, gxh, d.N, 2 * d.Ci, Q2, d.M, flags | (g_packed ? FCB_FLAG_A_PACKED : 0), g_amax, tcw, tcb,
-                                     &grouped, st, x, gx);
+        rc = launch_gemm_grouped(G, pre ? nullptr : Bt, gxh, d.N, 2 * d.Ci, Q2, d.M,
+                                 flags | (g_packed ? FCB_FLAG_A_PACKED : 0) | (pre ? FCB_FLAG_B_PREPACKED : 0), g_amax, tcw, tcb, &grouped, st, x, gx);
         if (rc) return rc;
+        FCB_REQUIRE(grouped || !pre, FCB_E_ARG, "bwd: pre-packed filter but the grouped contraction did not run");
         FCB_REQUIRE(grouped || !g_packed, FCB_E_ARG, "bwd: packed G but the grouped contraction did not run");
         if (!grouped) {
             rc = launch_gemm(G, Bt, gxh, d.N, 2 * d.Ci, Q2, (int64_t)d.M * Q2, 2 * d.Ci, (int64_t)d.M * 2 * d.Ci, 0, d.M, Q2,
@@ -675,7 +695,7 @@ extern "C" int fcb_bwd_workspace_bytes(int64_t N, int Ci, int Co, int band_limit
 
 static int fwd_impl(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt, float* y,
                     float* contrib, float* contrib_absmax, int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws,
-                    size_t ws_bytes, void* stream, const GemmEpilogue* epi) {
+                    size_t ws_bytes, void* stream, const GemmEpilogue* epi, const float* w_bound = nullptr) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Dims d;
     int rc = check_dims("fwd", N, Ci, Co, band_limit, R, &d);
@@ -690,7 +710,7 @@ static int fwd_impl(const float* x, const float* W, const int32_t* rowptr_tgt, c
     FCB_REQUIRE(amax, FCB_E_CUDA, "fwd: cudaMemsetAsync failed");
     rc = launch_aggregate(x, rowptr_tgt, rec_tgt, rot_tgt, contrib, N, Ci, band_limit, R, 0, amax, st);
     if (rc) return rc;
-    return contract_fwd(d, contrib, amax, W, y, ws, ws_bytes, flags, st, epi);
+    return contract_fwd(d, contrib, amax, W, y, ws, ws_bytes, flags, st, epi, w_bound);
 }
 
 extern "C" int fcb_fwd_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
@@ -723,7 +743,7 @@ extern "C" int fcb_fwd_act_f32(const float* x, const float* W, const int32_t* ro
     int rc = make_epilogue(res, bias, act, Co, bounds, static_cast<cudaStream_t>(stream), &e);
     if (rc) return rc;
     return fwd_impl(x, W, rowptr_tgt, rec_tgt, rot_tgt, y, contrib, contrib_absmax, N, Ci, Co, band_limit, R, flags, ws, ws_bytes,
-                    stream, &e);
+                    stream, &e, bounds ? bounds->w : nullptr);
 }
 
 extern "C" int fcb_bwd_f32(const float* x, const float* W, const float* gy, const float* contrib,
@@ -756,7 +776,7 @@ extern "C" int fcb_bwd_f32(const float* x, const float* W, const float* gy, cons
         return launch_aggregate(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, g_amax, st);
     };
     return backward_common(d, x, W, gy, contrib, contrib_absmax, slots + 64, gather, gx, gW, ar, flags, st, false, false,
-                           bounds ? bounds->x : nullptr);
+                           bounds ? bounds->x : nullptr, bounds ? bounds->w : nullptr);
 }
 
 // ------------------------------------------------------------------ packed-operand (PK) variants
@@ -777,7 +797,7 @@ extern "C" int fcb_pk_contrib_bytes(int64_t N, int Ci, int band_limit, int R, si
 static int fwd_pk_impl(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt, const float* rot_tgt,
                        const float* norm_tgt, float* y, void* contrib_pk, float* contrib_scale, int64_t N, int Ci, int Co,
                        int band_limit, int R, int flags, void* ws, size_t ws_bytes, void* stream, const GemmEpilogue* epi,
-                       const float* x_bound) {
+                       const float* x_bound, const float* w_bound = nullptr) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Dims d;
     int rc = check_dims("fwd_pk", N, Ci, Co, band_limit, R, &d);
@@ -797,7 +817,8 @@ static int fwd_pk_impl(const float* x, const float* W, const int32_t* rowptr_tgt
     }
     rc = launch_aggregate_packed(x, rowptr_tgt, rec_tgt, rot_tgt, contrib_pk, N, Ci, band_limit, R, 0, x_amax, norm_tgt, contrib_scale, st);
     if (rc) return rc;
-    return contract_fwd(d, static_cast<const float*>(contrib_pk), contrib_scale, W, y, ws, ws_bytes, flags | FCB_FLAG_A_PACKED, st, epi);
+    return contract_fwd(d, static_cast<const float*>(contrib_pk), contrib_scale, W, y, ws, ws_bytes, flags | FCB_FLAG_A_PACKED, st, epi,
+                        w_bound);
 }
 
 extern "C" int fcb_fwd_pk_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
@@ -805,7 +826,7 @@ extern "C" int fcb_fwd_pk_f32(const float* x, const float* W, const int32_t* row
                               const fcb_bounds* bounds, int64_t N, int Ci, int Co, int band_limit, int R, int flags, void* ws,
                               size_t ws_bytes, void* stream) {
     return fwd_pk_impl(x, W, rowptr_tgt, rec_tgt, rot_tgt, norm_tgt, y, contrib_pk, contrib_scale, N, Ci, Co, band_limit, R, flags, ws,
-                       ws_bytes, stream, nullptr, bounds ? bounds->x : nullptr);
+                       ws_bytes, stream, nullptr, bounds ? bounds->x : nullptr, bounds ? bounds->w : nullptr);
 }
 
 extern "C" int fcb_fwd_act_pk_f32(const float* x, const float* W, const int32_t* rowptr_tgt, const void* rec_tgt,
@@ -816,7 +837,7 @@ extern "C" int fcb_fwd_act_pk_f32(const float* x, const float* W, const int32_t*
     int rc = make_epilogue(res, bias, act, Co, bounds, static_cast<cudaStream_t>(stream), &e);
     if (rc) return rc;
     return fwd_pk_impl(x, W, rowptr_tgt, rec_tgt, rot_tgt, norm_tgt, y, contrib_pk, contrib_scale, N, Ci, Co, band_limit, R, flags, ws,
-                       ws_bytes, stream, &e, bounds ? bounds->x : nullptr);
+                       ws_bytes, stream, &e, bounds ? bounds->x : nullptr, bounds ? bounds->w : nullptr);
 }
 
 extern "C" int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, const void* contrib_pk,
@@ -862,7 +883,7 @@ extern "C" int fcb_bwd_pk_f32(const float* x, const float* W, const float* gy, c
         return launch_aggregate_packed(gy, rowptr_src, rec_src, rot_src, G, N, Co, band_limit, R, 1, gy_amax, norm_src, g_amax, st);
     };
     return backward_common(d, x, W, gy, contrib, contrib_scale, slots + 64, gather, gx, gW, ar, flags, st, !from_g, g_pk,
-                           bounds ? bounds->x : nullptr);
+                           bounds ? bounds->x : nullptr, bounds ? bounds->w : nullptr);
 }
 
 // ------------------------------------------------------------------ fused forward (band_limit <= 1)

@@ -61,6 +61,7 @@ struct Arena {
 };
 
 constexpr int FCB_FLAG_A_PACKED = 0x10000;    // internal (launch_gemm / launch_gemm_grouped): A operand is a PK buffer
+constexpr int FCB_FLAG_B_PREPACKED = 0x20000; // internal: the B side of the 2xFP16 workspace is already filled (launch_pack_w_h)
 
 constexpr int NBR_BITS = 27;
 constexpr uint32_t NBR_MASK = (1u << NBR_BITS) - 1u;
@@ -145,7 +146,14 @@ int launch_absmax_f32(const float* p, int64_t rows, int cols, int64_t ld, int ba
 int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int n_pairs, int kgroups,
                      const float* amax_a, void* ws, size_t ws_bytes, int a_packed, cudaStream_t st, int split_k = 1,
-                     float* parts = nullptr, const GemmEpilogue* epi = nullptr, const float* sa_x = nullptr, float* sa_gx = nullptr);
+                     float* parts = nullptr, const GemmEpilogue* epi = nullptr, const float* sa_x = nullptr, float* sa_gx = nullptr,
+                     int b_prepacked = 0, const float* b_bound = nullptr);
+// folded filter W (Co,Ci,R,M) -> the B side (scale slot + packed operand) of a launch_gemm_h_nn workspace in one launch
+int launch_pack_w_h(const float* W, int dir, int Ci, int Co, int R, int M, const float* w_bound, void* ws, size_t ws_bytes,
+                    cudaStream_t st);
+// whether launch_gemm / launch_gemm_grouped would run this NN product as ONE 2xFP16 launch_gemm_h_nn call over all N columns
+// (the condition under which FCB_FLAG_B_PREPACKED may be passed)
+bool gemm_h_single_launch(int N, int64_t K, int flags);
 int launch_gemm_h_tn(const float* A, const float* B, float* C, int64_t Mr, int N, int64_t Kv, int64_t lda, int64_t ldb,
                      int64_t ldc, int split, int64_t k_per_split, float* parts, int n_main, const float* amax_a, void* bp_ws,
                      size_t bp_bytes, int a_packed, cudaStream_t st, const float* b_bound = nullptr);

@@ -285,7 +285,7 @@ int launch_gemm_grouped(const float* A, const float* Bm, float* C, int64_t M, in
         const bool packed = (flags & FCB_FLAG_A_PACKED) != 0;
         if (Kg % 64 != 0 || N > 128 || npad * groups > 512 || mmas_h > TC_MAX_ACC_MMAS_GROUPED || ((groups * (int64_t)N) % 4) != 0 ||
             ((groups * Kg) % 4) != 0 || !aligned16(A) || !aligned16(C) || ws_bytes < gemm_h_ws_bytes(N, Kg, groups)) {
-            FCB_REQUIRE(!packed, FCB_E_ARG, "gemm_grouped: packed A operand with an infeasible grouped shape");
+            FCB_REQUIRE(!packed && !(flags & FCB_FLAG_B_PREPACKED), FCB_E_ARG, "gemm_grouped: packed operand with an infeasible grouped shape");
             return FCB_OK;
         }
         FCB_REQUIRE(!packed || a_amax, FCB_E_ARG, "gemm_grouped: a packed A operand needs its scale");
@@ -297,7 +297,8 @@ int launch_gemm_grouped(const float* A, const float* Bm, float* C, int64_t M, in
         }
         const bool sa = sa_gx && sa_x && groups >= 3 && groups <= 7 && (groups & 1) && (N % 8) == 0 && aligned16(sa_x) && aligned16(sa_gx);
         int rc = launch_gemm_h_nn(A, Bm, C, M, N, Kg, groups * Kg, N, groups * (int64_t)N, 1, 0, Kg * N, 0, 1, groups, a_amax, ws,
-                                  ws_bytes, packed ? 1 : 0, st, 1, nullptr, nullptr, sa ? sa_x : nullptr, sa ? sa_gx : nullptr);
+                                  ws_bytes, packed ? 1 : 0, st, 1, nullptr, nullptr, sa ? sa_x : nullptr, sa ? sa_gx : nullptr,
+                                  (flags & FCB_FLAG_B_PREPACKED) ? 1 : 0);
         if (rc == FCB_OK) *done = sa ? 2 : 1;
         return rc;
     }
@@ -316,7 +317,8 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
                 int64_t ldc, int trans_a, int batch, int64_t sa, int64_t sb, int64_t sc, int split_k, void* ws,
                 size_t ws_bytes, int flags, const float* a_amax, cudaStream_t st, const GemmEpilogue* epi, int* epi_fused,
                 const float* b_amax) {
-    FCB_REQUIRE(A && Bm && C, FCB_E_ARG, "gemm: null pointer");
+    const bool b_pre = (flags & FCB_FLAG_B_PREPACKED) != 0;
+    FCB_REQUIRE(A && (Bm || b_pre) && C, FCB_E_ARG, "gemm: null pointer");
     if (epi_fused) *epi_fused = 0;
     FCB_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 1 && split_k >= 1, FCB_E_ARG, "gemm: bad sizes");
     const int mode = flags & FCB_GEMM_MASK;
@@ -347,19 +349,22 @@ int launch_gemm(const float* A, const float* Bm, float* C, int64_t M, int N, int
                 a_amax = slot;
             }
         }
+        FCB_REQUIRE(!b_pre || (h && chunk >= N && batch == 1), FCB_E_ARG, "gemm: pre-packed B needs the single-launch 2xFP16 path");
         // the block epilogue rides along when the product is ONE un-split 2xFP16 launch
         const bool fuse_epi = h && epi && chunk >= N && h_split == 1 && batch == 1;
         if (fuse_epi && epi_fused) *epi_fused = 1;
         for (int n0 = 0; n0 < N; n0 += chunk) {      // column chunks (one unless N is wide): same A, offset B and C
             const int nc = N - n0 < chunk ? N - n0 : chunk;
-            int rc = h ? launch_gemm_h_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, n_main, 1, a_amax, ws, ws_bytes,
-                                          packed ? 1 : 0, st, h_split, h_parts, fuse_epi ? epi : nullptr)
+            int rc = h ? launch_gemm_h_nn(A, b_pre ? nullptr : Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, n_main, 1, a_amax,
+                                          ws, ws_bytes, packed ? 1 : 0, st, h_split, h_parts, fuse_epi ? epi : nullptr, nullptr, nullptr,
+                                          b_pre ? 1 : 0, chunk >= N ? b_amax : nullptr)
                        : launch_gemm_tc_nn(A, Bm + n0, C + n0, M, nc, K, lda, ldb, ldc, batch, sa, sb, sc, mode, n_main, 1, ws,
                                            ws_bytes, st);
             if (rc) return rc;
         }
         return FCB_OK;
     }
+    FCB_REQUIRE(!b_pre, FCB_E_ARG, "gemm: pre-packed B reached a path that does not take it");
     float* partials = static_cast<float*>(ws);
     if (use_tc(N, K, trans_a, batch, split_k, flags) && trans_a && (lda % 4) == 0 && aligned16(A)) {
         const size_t parts_bytes = split_k > 1 ? align_up((size_t)split_k * M * N * 4, 256) : 0;
@@ -445,6 +450,12 @@ bool gemm_pk_nn_ok(int N, int64_t K) {
 }
 bool gemm_pk_tn_ok(int64_t Mr, int N, int64_t Kv, int split) {
     return (Mr % 64) == 0 && use_tc(N, Kv, 1, 1, split < 1 ? 1 : split, FCB_GEMM_TC_2XF16);
+}
+bool gemm_h_single_launch(int N, int64_t K, int flags) {
+    const int mode = flags & FCB_GEMM_MASK;
+    if (mode != FCB_GEMM_TC_2XF16 || !use_tc(N, K, 0, 1, 1, flags)) return false;
+    int n_main = 1, h_split = 1;
+    return tc_plan(N, tc_ksteps(K, 0, 1, mode), mode, 0, &n_main, &h_split) >= N;
 }
 bool gemm_pk_grouped_ok(int N, int64_t Kg, int groups) {
     const int npad = (N + 15) / 16 * 16;

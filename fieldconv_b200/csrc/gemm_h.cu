@@ -823,6 +823,55 @@ __global__ void k_pack_b_h(const float* __restrict__ B, __half* __restrict__ Bp,
     *reinterpret_cast<uint4*>(dst + (int64_t)Npad * KC) = lo;
 }
 
+// The folded filter W (Co,Ci,R,M) complex straight into the packed B operand of the 2xFP16 NN kernels — what k_pack_w_fwd /
+// k_pack_w_bwd (real embedding, api.cu) followed by k_absmax and k_pack_b_h produce, in ONE launch:
+//   forward  (BWD = false): B[2k+a][2o+b], k = (r M + m) Ci + c:   a=0: (w.x, w.y)[b];   a=1: (-w.y, w.x)[b]
+//   backward (BWD = true):  group m, B_m[2q+a][2c+b], q = r Co + o: a=0: (w.x, -w.y)[b];  a=1: (w.y, w.x)[b]   (conj(W))
+// One thread per 16-byte piece (8 consecutive rows k2 of one column n).  amax: bound of max|W| (largest |component|; the
+// complex modulus is fine); thread 0 copies it into the workspace's scale slot the contraction kernel reads.
+template <bool BWD>
+__global__ void k_pack_w_h(const float2* __restrict__ W, __half* __restrict__ Bp, int Ci, int Co, int R, int M, int Npad, int nchunks,
+                           int64_t bp_group_stride, const float* __restrict__ amax, float* __restrict__ amax_slot) {
+    const int64_t per = (int64_t)nchunks * Npad * 8;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int grp = blockIdx.y;                          // BWD: frequency m; forward: 0
+    if (i == 0 && grp == 0 && amax_slot != amax) *amax_slot = __ldg(amax);
+    if (i >= per) return;
+    const int n = (int)(i % Npad);
+    const int u = (int)((i / Npad) & 7);
+    const int64_t c = i / ((int64_t)Npad * 8);
+    const float s = scale_of(amax);
+    const int N = BWD ? 2 * Ci : 2 * Co;
+    const int64_t K2 = BWD ? 2 * (int64_t)R * Co : 2 * (int64_t)R * M * Ci;
+    F8 x;
+    zero8(x);
+    if (n < N) {
+        const int b = n & 1, nn = n >> 1;                // forward: nn = o; backward: nn = c
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int64_t k2 = c * KC + 8 * u + e;
+            if (k2 >= K2) continue;
+            const int a = (int)(k2 & 1);
+            const int64_t k = k2 >> 1;
+            float2 w;
+            if (BWD) {
+                const int o = (int)(k % Co), r = (int)(k / Co);
+                w = W[(((int64_t)o * Ci + nn) * R + r) * M + grp];
+                x.v[e] = a == 0 ? (b == 0 ? w.x : -w.y) : (b == 0 ? w.y : w.x);
+            } else {
+                const int ch = (int)(k % Ci), m = (int)((k / Ci) % M), r = (int)(k / ((int64_t)M * Ci));
+                w = W[(((int64_t)nn * Ci + ch) * R + r) * M + m];
+                x.v[e] = a == 0 ? (b == 0 ? w.x : w.y) : (b == 0 ? -w.y : w.x);
+            }
+        }
+    }
+    uint4 hi, lo;
+    split8(x, s, hi, lo);
+    __half* dst = Bp + grp * bp_group_stride + (c * 2) * (int64_t)Npad * KC + (int64_t)n * KC + ((u ^ (n & 7)) << 3);
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + (int64_t)Npad * KC) = lo;
+}
+
 // ------------------------------------------------------------------------------------------------------------ TN
 // P[Mr x N] = A^T B with A = [Kv x Mr] and B = [Kv x N] row-major: both operands MN-major.  A stage holds 64 vertices:
 // A planes = 8 K-groups x 2 atoms (64 columns each) x 1 KB, B planes = 8 K-groups x nb_atoms x 1 KB.
@@ -1248,11 +1297,38 @@ int launch_bound_modulus(const float* z, int64_t n, float* out, cudaStream_t st)
     return FCB_OK;
 }
 
+// Fills the B side of a launch_gemm_h_nn workspace (scale slot + packed operand) from the folded filter: dir 0 = forward
+// operand [2K x 2Co], dir 1 = the M grouped backward operands [2RCo x 2Ci].  w_bound (nullable): device float >= max|W|.
+int launch_pack_w_h(const float* W, int dir, int Ci, int Co, int R, int M, const float* w_bound, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
+    const int N = dir ? 2 * Ci : 2 * Co;
+    const int64_t K = dir ? 2 * (int64_t)R * Co : 2 * (int64_t)R * M * Ci;
+    const int groups = dir ? M : 1;
+    FCB_REQUIRE(W && ws && ws_bytes >= gemm_h_ws_bytes(N, K, groups), FCB_E_WORKSPACE, "pack_w_h: workspace too small");
+    const int npad = (N + 15) / 16 * 16;
+    const int nchunks = (int)((K + th::KC - 1) / th::KC);
+    float* slot = static_cast<float*>(ws);
+    __half* Bp = reinterpret_cast<__half*>(static_cast<char*>(ws) + 256);
+    const float* amax = w_bound;
+    if (!amax) {
+        int rc = th::launch_absmax(W, (int64_t)Co * Ci * R * M, 2, 2, 1, 0, slot, st);
+        if (rc) return rc;
+        amax = slot;
+    }
+    const int64_t per = (int64_t)nchunks * npad * 8;
+    dim3 grid((unsigned)((per + 255) / 256), (unsigned)groups);
+    const int64_t stride = (int64_t)nchunks * 2 * npad * th::KC;
+    const float2* W2 = reinterpret_cast<const float2*>(W);
+    if (dir) FCB_LAUNCH("pack_w_h", st, (th::k_pack_w_h<true><<<grid, 256, 0, st>>>(W2, Bp, Ci, Co, R, M, npad, nchunks, stride, amax, slot)));
+    else FCB_LAUNCH("pack_w_h", st, (th::k_pack_w_h<false><<<grid, 256, 0, st>>>(W2, Bp, Ci, Co, R, M, npad, nchunks, stride, amax, slot)));
+    return FCB_OK;
+}
+
 int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int batch, int64_t sa, int64_t sb, int64_t sc, int n_pairs, int kgroups,
                      const float* amax_a, void* ws, size_t ws_bytes, int a_packed, cudaStream_t st, int split_k, float* parts,
-                     const GemmEpilogue* epi, const float* sa_x, float* sa_gx) {
-    FCB_REQUIRE(A && B && C && ws && amax_a, FCB_E_ARG, "gemm_h: null pointer");
+                     const GemmEpilogue* epi, const float* sa_x, float* sa_gx, int b_prepacked, const float* b_bound) {
+    FCB_REQUIRE(A && (B || b_prepacked) && C && ws && amax_a, FCB_E_ARG, "gemm_h: null pointer");
     FCB_REQUIRE(M >= 0 && N > 0 && K > 0 && batch >= 1 && batch <= 65535, FCB_E_ARG, "gemm_h: bad sizes");
     FCB_REQUIRE(N <= 256, FCB_E_UNSUPPORTED, "gemm_h: N=%d > 256 not supported by one accumulator pair", N);
     FCB_REQUIRE(split_k >= 1 && split_k <= 65535 && (split_k == 1 || (parts && kgroups == 1)), FCB_E_ARG, "gemm_h: bad split-K arguments");
@@ -1268,15 +1344,19 @@ int launch_gemm_h_nn(const float* A, const float* B, float* C, int64_t M, int N,
     if (M == 0) return FCB_OK;
     const int npad = (N + 15) / 16 * 16;
     const int nchunks = (int)((K + th::KC - 1) / th::KC);
-    float* amax_b = static_cast<float*>(ws);
+    const float* amax_b = static_cast<float*>(ws);
     __half* Bp = reinterpret_cast<__half*>(static_cast<char*>(ws) + 256);
     const int64_t bp_stride = (int64_t)nchunks * 2 * npad * th::KC;
-    {
-        // one common scale for all batches / k-groups of B
-        const bool contiguous = (ldb == N) && (batch * kgroups == 1 || sb == K * (int64_t)N);
-        int rc = contiguous ? th::launch_absmax(B, (int64_t)batch * kgroups * K, N, N, 1, 0, amax_b, st)
-                            : th::launch_absmax(B, K, N, ldb, batch * kgroups, sb, amax_b, st);
-        if (rc) return rc;
+    if (!b_prepacked) {      // b_prepacked: launch_pack_w_h already filled the scale slot and Bp of this workspace
+        // one common scale for all batches / k-groups of B: the caller's bound, else a pass over B
+        if (b_bound) {
+            amax_b = b_bound;
+        } else {
+            const bool contiguous = (ldb == N) && (batch * kgroups == 1 || sb == K * (int64_t)N);
+            int rc = contiguous ? th::launch_absmax(B, (int64_t)batch * kgroups * K, N, N, 1, 0, static_cast<float*>(ws), st)
+                                : th::launch_absmax(B, K, N, ldb, batch * kgroups, sb, static_cast<float*>(ws), st);
+            if (rc) return rc;
+        }
         const int64_t per = (int64_t)nchunks * npad * 8;
         dim3 grid((unsigned)((per + 255) / 256), (unsigned)(batch * kgroups));
         FCB_LAUNCH("pack_b_h", st, th::k_pack_b_h<<<grid, 256, 0, st>>>(B, Bp, K, N, npad, ldb, nchunks, sb, bp_stride, amax_b));

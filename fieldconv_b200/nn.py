@@ -157,7 +157,11 @@ def prefold(module):
             continue
         w = fold_weights(torch.stack([m.zonal for m in layers]), torch.stack([m.spherical for m in layers]),
                          torch.stack([m.phase for m in layers]), ftype, band_limit)
-        for m, wi in zip(layers, w.unbind(0)):
+        # max|W| of every layer from ONE reduction: the operand scale of the packed filter (struct fcb_bounds, field w)
+        wb = w.detach().abs().flatten(1).amax(dim=1) if (ops.BOUNDS and w.is_cuda) else None
+        for i, (m, wi) in enumerate(zip(layers, w.unbind(0))):
+            if wb is not None:
+                ops.set_bound(wi, wb[i:i + 1])
             m._prefolded = (wi, _param_versions(m))       # valid only while the parameters are unchanged
     lins = {}
     for m in module.modules():
@@ -166,7 +170,10 @@ def prefold(module):
     for layers in lins.values():
         if len(layers) > 1:
             emb = _lin_embedding(torch.stack([m.Re for m in layers]), torch.stack([m.Im for m in layers]))
-            for m, e in zip(layers, emb.unbind(0)):
+            eb = emb.detach().abs().flatten(1).amax(dim=1) if (ops.BOUNDS and emb.is_cuda) else None
+            for i, (m, e) in enumerate(zip(layers, emb.unbind(0))):
+                if eb is not None:
+                    ops.set_bound(e, eb[i:i + 1])
                 m._preemb = (e, (m.Re._version, m.Im._version))
 
 
@@ -306,7 +313,8 @@ class TangentLin(nn.Module):
         if ci % 2 == 0 and co % 2 == 0 and x.is_cuda and x.dtype == torch.complex64:
             x = x.contiguous()
             xb = ops.bound_of(x) if ops._uses_bounds(self.gemm_flags) else None     # the A-operand scale; shared with the conv
-            return ops.tangent_lin(x, emb.contiguous(), self.gemm_flags, xb)
+            emb = emb.contiguous()
+            return ops.tangent_lin(x, emb, self.gemm_flags, xb, ops.peek_bound(emb) if xb is not None else None)
         xr = torch.view_as_real(x.contiguous()).reshape(x.shape[0], 2 * ci)
         if (2 * ci) % 4 or (2 * co) % 4:                         # GEMM wants 16-byte rows
             pad_i, pad_o = (2 * ci) % 4, (2 * co) % 4

@@ -91,7 +91,7 @@ def _padded_rows(n):
 @torch.library.custom_op("fieldconv_b200::fc_fwd", mutates_args=())
 def fc_fwd(x: Tensor, W: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: Tensor, rowptr_src: Tensor,
            rec_src: Tensor, rot_src: Tensor, norms: Tensor, band_limit: int, n_rings: int, flags: int,
-           keep_contrib: bool, x_bound: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+           keep_contrib: bool, x_bound: Optional[Tensor] = None, w_bound: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
     # the by-source plan tensors are unused here; they are inputs so autograd can hand them to fc_bwd
     _check(x, "x")
     _check(W, "W")
@@ -120,7 +120,12 @@ def fc_fwd(x: Tensor, W: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: T
         if packed:
             _lib.call("fcb_fwd_pk_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
                       rot_tgt.data_ptr(), norms.data_ptr(), _real(y).data_ptr(), _real(contrib).data_ptr(), cmax.data_ptr(),
-                      _lib.bounds(x=x_bound), n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes, _lib.stream_ptr())
+                      _lib.bounds(x=x_bound, w=w_bound), n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes,
+                      _lib.stream_ptr())
+        elif w_bound is not None:     # fcb_fwd_f32 with the filter bound: the epilogue-less form of fcb_fwd_act_f32
+            _lib.call("fcb_fwd_act_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
+                      rot_tgt.data_ptr(), _real(y).data_ptr(), _real(contrib).data_ptr(), cmax.data_ptr(), None, None, None,
+                      _lib.bounds(w=w_bound), n, ci, co, band_limit, n_rings, cflags, ws.data_ptr(), nbytes, _lib.stream_ptr())
         else:
             _lib.call("fcb_fwd_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
                       rot_tgt.data_ptr(), _real(y).data_ptr(), _real(contrib).data_ptr(), cmax.data_ptr(), n, ci, co,
@@ -132,7 +137,7 @@ def fc_fwd(x: Tensor, W: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: T
 
 @fc_fwd.register_fake
 def _(x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, keep_contrib,
-      x_bound=None):
+      x_bound=None, w_bound=None):
     n, ci = x.shape
     k = n_rings * ci * (2 * band_limit + 1)
     return (x.new_empty(n, W.shape[0]), x.new_empty((_padded_rows(n), k) if keep_contrib else (0,)),
@@ -142,7 +147,8 @@ def _(x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, b
 @torch.library.custom_op("fieldconv_b200::fc_bwd", mutates_args=())
 def fc_bwd(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, cmax: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: Tensor,
            rowptr_src: Tensor, rec_src: Tensor, rot_src: Tensor, norms: Tensor, band_limit: int, n_rings: int, flags: int,
-           need_gx: bool, need_gw: bool, x_bound: Optional[Tensor] = None, gy_bound: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+           need_gx: bool, need_gw: bool, x_bound: Optional[Tensor] = None, gy_bound: Optional[Tensor] = None,
+           w_bound: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     _check(gy, "grad_output")
     x, W, gy = x.contiguous(), W.contiguous(), gy.contiguous()
     n, ci = x.shape
@@ -157,7 +163,7 @@ def fc_bwd(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, cmax: Tensor, rowp
     nbytes = _lib.query_bytes("fcb_bwd_workspace_bytes", n, ci, co, band_limit, n_rings,
                               cflags | (_lib.FLAG_HAVE_CONTRIB if have_contrib else 0))
     ws = _ws(nbytes, x.device)
-    bnd = _lib.bounds(x=x_bound, gy=gy_bound)
+    bnd = _lib.bounds(x=x_bound, gy=gy_bound, w=w_bound)
     with torch.cuda.device(x.device):
         if packed:
             _lib.call("fcb_bwd_pk_f32", _real(x).data_ptr(), _real(W).data_ptr(), _real(gy).data_ptr(),
@@ -178,29 +184,30 @@ def fc_bwd(x: Tensor, W: Tensor, gy: Tensor, contrib: Tensor, cmax: Tensor, rowp
 
 @fc_bwd.register_fake
 def _(x, W, gy, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags,
-      need_gx, need_gw, x_bound=None, gy_bound=None):
+      need_gx, need_gw, x_bound=None, gy_bound=None, w_bound=None):
     return (torch.empty_like(x) if need_gx else x.new_empty(0)), (torch.empty_like(W) if need_gw else W.new_empty(0))
 
 
 def _fc_setup(ctx, inputs, output):
-    x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, keep, x_bound = inputs
+    (x, W, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, keep, x_bound,
+     w_bound) = inputs
     _, contrib, cmax = output
     ctx.save_for_backward(x, W, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms)
-    ctx.x_bound = x_bound            # a 1-element device scalar, not part of the graph
+    ctx.x_bound, ctx.w_bound = x_bound, w_bound      # 1-element device scalars, not part of the graph
     ctx.cfg = (band_limit, n_rings, flags)
     ctx.set_materialize_grads(False)      # no N*K zero tensor for the unused contrib output
 
 
 def _fc_backward(ctx, gy, _gcontrib, _gcmax):
     if gy is None:
-        return (None,) * 14
+        return (None,) * 15
     x, W, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms = ctx.saved_tensors
     band_limit, n_rings, flags = ctx.cfg
     gy = gy.contiguous()
     gx, gw = fc_bwd(x, W, gy, contrib, cmax, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit,
                     n_rings, flags, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.x_bound,
-                    peek_bound(gy) if _uses_bounds(flags) else None)
-    return (gx if ctx.needs_input_grad[0] else None, gw if ctx.needs_input_grad[1] else None) + (None,) * 12
+                    peek_bound(gy) if _uses_bounds(flags) else None, ctx.w_bound)
+    return (gx if ctx.needs_input_grad[0] else None, gw if ctx.needs_input_grad[1] else None) + (None,) * 13
 
 
 fc_fwd.register_autograd(_fc_backward, setup_context=_fc_setup)
@@ -210,7 +217,7 @@ fc_fwd.register_autograd(_fc_backward, setup_context=_fc_setup)
 @torch.library.custom_op("fieldconv_b200::fc_fwd_act", mutates_args=())
 def fc_fwd_act(x: Tensor, W: Tensor, res: Tensor, bias: Tensor, rowptr_tgt: Tensor, rec_tgt: Tensor, rot_tgt: Tensor,
                rowptr_src: Tensor, rec_src: Tensor, rot_src: Tensor, norms: Tensor, band_limit: int, n_rings: int, flags: int,
-               has_res: bool, x_bound: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+               has_res: bool, x_bound: Optional[Tensor] = None, w_bound: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
     """(act, z, bound) with z = FieldConv(x) (+ res) and act = modReLU(z, bias): nn/fc_resnet_block.py:84-88 with the
     TangentNonLin (and the residual add) applied in the contraction kernel's epilogue (fcb_fwd_act_f32 / fcb_fwd_act_pk_f32);
     bound = max_i |act_i|, reported by that epilogue.  Nothing of size N x K is kept: the backward is modrelu_bwd + fc_bwd with
@@ -236,7 +243,7 @@ def fc_fwd_act(x: Tensor, W: Tensor, res: Tensor, bias: Tensor, rowptr_tgt: Tens
     act_bound = torch.empty(1, dtype=torch.float32, device=x.device)
     nbytes = _lib.query_bytes("fcb_fwd_workspace_bytes", n, ci, co, band_limit, n_rings, cflags)
     ws = _ws(nbytes, x.device)
-    bnd = _lib.bounds(x=x_bound, act=act_bound)
+    bnd = _lib.bounds(x=x_bound, act=act_bound, w=w_bound)
     with torch.cuda.device(x.device):
         if packed:
             _lib.call("fcb_fwd_act_pk_f32", _real(x).data_ptr(), _real(W).data_ptr(), rowptr_tgt.data_ptr(), rec_tgt.data_ptr(),
@@ -252,15 +259,15 @@ def fc_fwd_act(x: Tensor, W: Tensor, res: Tensor, bias: Tensor, rowptr_tgt: Tens
 
 @fc_fwd_act.register_fake
 def _(x, W, res, bias, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, has_res,
-      x_bound=None):
+      x_bound=None, w_bound=None):
     return x.new_empty(x.shape[0], W.shape[0]), x.new_empty(x.shape[0], W.shape[0]), x.new_empty(1, dtype=torch.float32)
 
 
 def _fa_setup(ctx, inputs, output):
     (x, W, res, bias, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings, flags, has_res,
-     x_bound) = inputs
+     x_bound, w_bound) = inputs
     ctx.save_for_backward(x, W, bias, output[1], rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms)
-    ctx.x_bound = x_bound
+    ctx.x_bound, ctx.w_bound = x_bound, w_bound
     ctx.cfg = (band_limit, n_rings, flags, has_res)
     ctx.set_materialize_grads(False)
 
@@ -269,7 +276,7 @@ def _fa_backward(ctx, g_act, g_z, _g_bound):
     x, W, bias, z, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms = ctx.saved_tensors
     band_limit, n_rings, flags, has_res = ctx.cfg
     if g_act is None and g_z is None:
-        return (None,) * 16
+        return (None,) * 17
     gb = None
     gz = g_z
     gz_bound = None
@@ -285,9 +292,9 @@ def _fa_backward(ctx, g_act, g_z, _g_bound):
     cm = torch.zeros(1, dtype=torch.float32, device=x.device)
     gx, gw = fc_bwd(x, W, gz, empty, cm, rowptr_tgt, rec_tgt, rot_tgt, rowptr_src, rec_src, rot_src, norms, band_limit, n_rings,
                     flags & ~_lib.FLAG_FUSED, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.x_bound,
-                    gz_bound if _uses_bounds(flags) else None)
+                    gz_bound if _uses_bounds(flags) else None, ctx.w_bound)
     return (gx if ctx.needs_input_grad[0] else None, gw if ctx.needs_input_grad[1] else None,
-            gz if (has_res and ctx.needs_input_grad[2]) else None, gb if ctx.needs_input_grad[3] else None) + (None,) * 12
+            gz if (has_res and ctx.needs_input_grad[2]) else None, gb if ctx.needs_input_grad[3] else None) + (None,) * 13
 
 
 fc_fwd_act.register_autograd(_fa_backward, setup_context=_fa_setup)
@@ -306,8 +313,17 @@ def field_conv_act(x, W, plan, band_limit, bias, res=None, flags=0):
         res = torch.empty(0, dtype=torch.complex64, device=x.device)
     x = x.contiguous()
     act, _, act_bound = fc_fwd_act(x, W, res, bias, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src,
-                                   plan.rot_src, norms, band_limit, plan.n_rings, flags, has_res, _x_bound_for(x, W, flags))
+                                   plan.rot_src, norms, band_limit, plan.n_rings, flags, has_res, _x_bound_for(x, W, flags),
+                                   _w_bound_for(W, flags))
     return set_bound(act, act_bound)
+
+
+def _w_bound_for(W, flags):
+    """Bound of max|W| of the folded filter: attached by prefold() for a whole network at once, else one pass shared by the
+    forward and the backward of this layer."""
+    if not _uses_bounds(flags):
+        return None
+    return bound_of(W)
 
 
 def _x_bound_for(x, W, flags):
@@ -332,7 +348,7 @@ def field_conv(x, W, plan, band_limit, flags=0, keep_contrib=None):
         norms = torch.zeros(2, dtype=torch.float32, device=x.device)
     x = x.contiguous()
     y, _, _ = fc_fwd(x, W, plan.rowptr_tgt, plan.rec_tgt, plan.rot_tgt, plan.rowptr_src, plan.rec_src, plan.rot_src, norms,
-                     band_limit, plan.n_rings, flags, bool(keep_contrib), _x_bound_for(x, W, flags))
+                     band_limit, plan.n_rings, flags, bool(keep_contrib), _x_bound_for(x, W, flags), _w_bound_for(W, flags))
     return y
 
 
@@ -526,7 +542,8 @@ gemm.register_autograd(_gemm_backward, setup_context=_gemm_setup)
 
 # --------------------------------------------------------------------------- TangentLin on complex tensors
 @torch.library.custom_op("fieldconv_b200::tangent_lin", mutates_args=())
-def tangent_lin(x: Tensor, emb: Tensor, flags: int, x_bound: Optional[Tensor] = None) -> Tensor:
+def tangent_lin(x: Tensor, emb: Tensor, flags: int, x_bound: Optional[Tensor] = None,
+                emb_bound: Optional[Tensor] = None) -> Tensor:
     """y = x @ (Re + i Im)^T (nn/tangent_lin.py:27-29) as ONE real GEMM on the interleaved storage: [x_re, x_im] @ emb with emb
     the (2Ci, 2Co) real embedding of the weight.  Ci and Co even (16-byte rows).  Taking and returning the complex tensors
     themselves lets the backward see the very gradient tensor its producer attached a bound to (set_bound)."""
@@ -534,19 +551,19 @@ def tangent_lin(x: Tensor, emb: Tensor, flags: int, x_bound: Optional[Tensor] = 
     _check(emb, "emb", torch.float32)
     x = x.contiguous()
     n, ci = x.shape
-    yr = _gemm_call(_real(x).reshape(n, 2 * ci), emb, False, flags, x_bound, None)
+    yr = _gemm_call(_real(x).reshape(n, 2 * ci), emb, False, flags, x_bound, emb_bound)
     return torch.view_as_complex(yr.reshape(n, emb.shape[1] // 2, 2))
 
 
 @tangent_lin.register_fake
-def _(x, emb, flags, x_bound=None):
+def _(x, emb, flags, x_bound=None, emb_bound=None):
     return x.new_empty(x.shape[0], emb.shape[1] // 2)
 
 
 def _tl_setup(ctx, inputs, output):
-    x, emb, flags, x_bound = inputs
+    x, emb, flags, x_bound, emb_bound = inputs
     ctx.save_for_backward(x, emb)
-    ctx.flags, ctx.x_bound = flags, x_bound
+    ctx.flags, ctx.x_bound, ctx.emb_bound = flags, x_bound, emb_bound
 
 
 def _tl_backward(ctx, gy):
@@ -558,11 +575,11 @@ def _tl_backward(ctx, gy):
     gyr = _real(gy).reshape(n, 2 * co)
     gx = gemb = None
     if ctx.needs_input_grad[0]:
-        gxr = _gemm_call(gyr, emb.t().contiguous(), False, ctx.flags, gyb, None)
+        gxr = _gemm_call(gyr, emb.t().contiguous(), False, ctx.flags, gyb, ctx.emb_bound)     # the transpose has the same entries
         gx = torch.view_as_complex(gxr.reshape(n, ci, 2))
     if ctx.needs_input_grad[1]:
         gemb = _gemm_call(_real(x.contiguous()).reshape(n, 2 * ci), gyr, True, ctx.flags, ctx.x_bound, gyb)
-    return gx, gemb, None, None
+    return gx, gemb, None, None, None
 
 
 tangent_lin.register_autograd(_tl_backward, setup_context=_tl_setup)

@@ -119,11 +119,14 @@ int fcb_precomp_expand_f32(const int64_t* edges_ji, const float* log_mag, const 
  *   x    in : >= max_i |x_i|, complex modulus, over every row of x the call may gather
  *   gy   in : >= the largest |real or imaginary part| of gy
  *   act  out: max_i |act_i| (modulus) of the activation fcb_fwd_act_* writes — the `x` bound of the next layer
+ *   w    in : >= max |W| of the folded filter (a caller that folds the filters of a whole network in one batch gets all
+ *             their maxima from one reduction); with it the filter goes from W to the packed tensor-core operand in ONE launch
  * fcb_bound_f32 computes the modulus bound of n complex numbers (what a caller uses when no producer reported one). */
 typedef struct fcb_bounds {
     const float* x;
     const float* gy;
     float* act;
+    const float* w;
 } fcb_bounds;
 int fcb_bound_f32(const float* z, int64_t n_complex, float* bound_out, void* stream);
 
