@@ -279,7 +279,7 @@ int fcb_aggregate_f32(const float* feat, const int32_t* rowptr, const void* rec,
  * the FP32-FMA kernel or a tcgen05 tensor-core kernel (3xTF32 / TF32 / 2xFP16) when its accumulation plan fits.
  * The workspace size comes from fcb_gemm_workspace_bytes with the same arguments.
  * a_bound / b_bound (device floats, may be NULL): upper bounds of max|A|, max|B| for the 2xFP16 operand scales (see
- * fcb_bounds); used for the operands the kernel would otherwise take a pass over (A; B of a transposed product). */
+ * fcb_bounds); each one given saves the pass the library would otherwise take over that operand. */
 int fcb_gemm_workspace_bytes(int64_t M, int N, int64_t K, int trans_a, int batch, int split_k, int flags,
                              size_t* bytes);
 /* 1 if fcb_gemm_f32 with these flags would run on the tensor cores inside the fp32 parity budget (the
