@@ -29,6 +29,46 @@ def test_binding_covers_header():
     assert set(header_symbols()) <= bound
 
 
+def header_prototypes():
+    """name -> list of parameter declarations of every `int fcb_*(...)` prototype in the header"""
+    src = open(os.path.join(ROOT, "include", "fieldconv_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|const char\*|unsigned long long)\s+(fcb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        params = [a.strip() for a in m.group(2).split(",")]
+        out[m.group(1)] = [] if params in (["void"], [""]) else params
+    return out
+
+
+def _kind(decl):
+    """pointer / i64 / int / float / size of one C parameter declaration, as the ctypes binding has to mirror it"""
+    if "*" in decl:
+        return "ptr"
+    if "int64_t" in decl:
+        return "i64"
+    if "size_t" in decl:
+        return "size"
+    if "float" in decl:
+        return "float"
+    return "int"
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every binding in _lib.SIGNATURES has the argument count and the argument kinds (pointer / int64 / int / float / size_t)
+    of its prototype: a signature changed in the header but not in the binding shifts every later argument silently."""
+    kinds = {_lib._P: "ptr", _lib._PSZ: "ptr", ctypes.c_char_p: "ptr", ctypes.POINTER(ctypes.c_float): "ptr", ctypes.POINTER(ctypes.c_int): "ptr",
+             _lib._I64: "i64", _lib._I: "int", _lib._F: "float", _lib._SZ: "size"}
+    protos = header_prototypes()
+    checked = 0
+    for name, argtypes in _lib.SIGNATURES.items():
+        assert name in protos, name + " is bound but not declared in the header"
+        want = [_kind(d) for d in protos[name]]
+        got = [kinds[a] for a in argtypes]
+        assert got == want, "%s: binding %s, header %s" % (name, got, want)
+        checked += 1
+    assert checked >= 30
+
+
 def test_version_and_counter():
     lib = _lib.load()
     assert lib.fcb_version() >= 100
