@@ -582,13 +582,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_h_nn(const Params p) {
 // per-CTA fixed costs of k_gemm_h_nn (barrier set-up, TMEM allocation, the first B fetch, an un-overlapped epilogue) would be
 // most of its time.  Persistent form: one CTA per SM walks over row tiles; the packed B operand (<= 2 chunks) is fetched ONCE
 // and stays in shared memory; two operand stages and TWO accumulator sets in TMEM, so that
-//   warps 0-7   (producers) load / split / store the fp32 rows of tile t+1,
-//   warp  8     (one thread) issues the MMAs of tile t+1 as soon as its stage is full and an accumulator set is free,
-//   warps 9-12  (epilogue, one per TMEM lane quarter) drain tile t — all at the same time.
-constexpr int SK_PROD_WARPS = 8;
+//   warps 0-15  (producers) load / split / store the fp32 rows of tile t+1,
+//   warp  16    (one thread) issues the MMAs of tile t+1 as soon as its stage is full and an accumulator set is free,
+//   warps 17-20 (epilogue, one per TMEM lane quarter) drain tile t — all at the same time.
+constexpr int SK_PROD_WARPS = 16;
 constexpr int SK_PROD = SK_PROD_WARPS * 32;
 constexpr int SK_THREADS = (SK_PROD_WARPS + 1 + 4) * 32;
-constexpr int SK_UNITS = 4;          // 16-byte output units per producer thread and chunk (128 rows x 8 units / 256 threads)
+constexpr int SK_UNITS = 2;          // 16-byte output units per producer thread and chunk (128 rows x 8 units / 512 threads)
 
 struct ParamsSK {
     const float* A;
