@@ -7,6 +7,6 @@ from .partition import MeshPartition, allreduce_gradients, partition_mesh  # noq
 from .transforms import FCPrecomp, SupportGraph, farthest_point_sample, radius_graph  # noqa: F401
 from .echo import ECHO, ECHOBlock  # noqa: F401
 from .lift import LiftBlock, TransField  # noqa: F401
-from .nn import FCResNetBlock, FieldConv, TangentLin, TangentNonLin, fold_weights, prefold  # noqa: F401
+from .nn import FCResNetBlock, FieldConv, TangentLin, TangentNonLin, TangentPerceptron, fold_weights, prefold  # noqa: F401
 
 __version__ = "0.1.0"

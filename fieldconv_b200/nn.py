@@ -335,6 +335,19 @@ class TangentNonLin(nn.Module):
         return ops.modrelu(x, self.bias)
 
 
+class TangentPerceptron(nn.Module):
+    """nn/tangent_perceptron.py:7-25 — nonlin(lin(x)): the complex fully-connected layer + modReLU of the reference nets'
+    'meta' residual connections (correspondence.ipynb / feature_matching.ipynb `Net.res*`)."""
+
+    def __init__(self, in_channels, out_channels, *, precision="auto"):
+        super().__init__()
+        self.lin = TangentLin(in_channels, out_channels, precision=precision)
+        self.nonlin = TangentNonLin(out_channels)
+
+    def forward(self, x):
+        return self.nonlin(self.lin(x))
+
+
 class FCResNetBlock(nn.Module):
     """nn/fc_resnet_block.py:43-88 — nonlin2(res(x) + conv2(nonlin1(conv1(x))))."""
 

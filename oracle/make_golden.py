@@ -171,12 +171,98 @@ def make_echo(name, n_side, deg, c, n_bins, B, R, seed):
     print(name, "N", d.num_nodes, "E", e.shape[0], "hdim", echo.hdim, "|y|max", float(y.abs().max()))
 
 
+def build_net(ns, B, R, ftype, n_classes, n_des, n_bins):
+    """The reference notebooks' network shape in small: correspondence.ipynb `Net` (JSON lines of `class Net`: LiftBlock ->
+    FCResNetBlocks with TangentPerceptron 'meta' residuals, one frontloaded block -> ECHOBlock), here with 4 / 8 channels.
+    `ns` supplies the module classes: the unmodified reference (this script) or fieldconv_b200 (tests/test_gpu_net.py)."""
+    import torch.nn as tnn
+
+    class Net(tnn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lift = ns.LiftBlock(3, 4, n_rings=R, ftype=ftype)
+            self.resnet1 = ns.FCResNetBlock(4, 8, band_limit=B, n_rings=R, ftype=ftype)
+            self.resnet2 = ns.FCResNetBlock(8, 8, band_limit=B, n_rings=R, ftype=ftype)
+            self.resnet3 = ns.FCResNetBlock(8, n_des, band_limit=B, n_rings=R, ftype=ftype, frontload=True)
+            self.res1 = ns.TangentPerceptron(4, 8)
+            self.res2 = ns.TangentPerceptron(8, n_des)
+            self.echo = ns.ECHOBlock(n_des, n_classes, n_des=n_des, n_bins=n_bins, band_limit=B, n_rings=R, ftype=ftype)
+            self.band_limit = B
+
+        def forward(self, pos, supp_edges, supp_sten, ln, wxp):
+            b = self.band_limit
+            x1 = self.lift(pos, supp_edges, supp_sten[..., b:(b + 2)])
+            x = self.resnet1(x1, supp_edges, supp_sten)
+            x2 = self.resnet2(x, supp_edges, supp_sten) + self.res1(x1)
+            x = self.resnet3(x2, supp_edges, supp_sten) + self.res2(x2)
+            return self.echo(x, supp_edges, supp_sten, ln, wxp)
+
+    return Net()
+
+
+def make_net(name="net_b2r6", seed=21):
+    """A whole network of the reference's modules, forward + cross-entropy + backward, by the unmodified reference:
+    logits, loss and the gradient of EVERY parameter (LiftBlock, FCResNetBlock incl. frontload, TangentPerceptron, ECHOBlock)."""
+    ns = ref_loader.load()
+    B, R, ftype, n_classes, n_des, n_bins = 2, 6, 1, 5, 4, 2
+    d = syn.torus_mesh(9, deg=14.0, seed=seed, tile=4)
+    g = torch.Generator().manual_seed(seed)
+    e, sten, ln, wxp = ns.FCPrecomp(B, R, float(d.epsilon))(d)
+    pos = torch.randn(d.num_nodes, 3, generator=g)
+    labels = torch.randint(0, n_classes, (d.num_nodes,), generator=g)
+    torch.manual_seed(seed)
+    net = build_net(ns, B, R, ftype, n_classes, n_des, n_bins)
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if k.endswith("nonlin.bias") or ".nonlin1.bias" in k or ".nonlin2.bias" in k:
+                p.uniform_(-0.2, 0.2)
+    logits = net(pos, e, sten, ln, wxp)
+    loss = torch.nn.functional.cross_entropy(logits, labels)
+    loss.backward()
+    out = dict(n=np.int64(d.num_nodes), B=np.int64(B), R=np.int64(R), ftype=np.int64(ftype), n_classes=np.int64(n_classes),
+               n_des=np.int64(n_des), n_bins=np.int64(n_bins), epsilon=np.float64(d.epsilon), raw_edges=_np(d.supp_edges),
+               logMag=_np(d.logMag), logAng=_np(d.logAng), xp=_np(d.xp), w=_np(d.w), supp_edges=_np(e), supp_sten=_np(sten),
+               ln=_np(ln), wxp=_np(wxp), pos=_np(pos), labels=_np(labels), logits=_np(logits), loss=np.float64(loss.item()))
+    for k, v in net.state_dict().items():
+        out["p." + k] = _np(v)
+    for k, v in net.named_parameters():
+        out["g." + k] = _np(v.grad)
+    # The reference's OWN fp32 sensitivity to the summation order of scatter_add (nn/field_conv.py:134, nn/echo.py:143-147):
+    # the same network on the same inputs with the edge list permuted.  Logits move by ~2e-7, but parameter gradients by up
+    # to 1.5e-4 normwise (the deep chain through modReLU thresholds and ECHO's floor/ceil binning is ill-conditioned in
+    # fp32), so a gradient tolerance below that would test rounding luck, not parity: "noise.<param>" = the largest
+    # normwise deviation over 4 permutations, the yardstick tests/test_gpu_net.py scales its gradient tolerance by.
+    noise = {k: 0.0 for k, _ in net.named_parameters()}
+    noise_logits = 0.0
+    state = {k: v.clone() for k, v in net.state_dict().items()}
+
+    def dev(a, b):
+        return max(float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)),
+                   float(torch.linalg.vector_norm((a - b).reshape(-1)) / torch.linalg.vector_norm(b.reshape(-1)).clamp_min(1e-30)))
+
+    for t in range(4):
+        perm = torch.randperm(e.shape[0], generator=g)
+        net2 = build_net(ns, B, R, ftype, n_classes, n_des, n_bins)
+        net2.load_state_dict(state)
+        lg = net2(pos, e[perm], sten[perm], ln[perm], wxp[perm])
+        torch.nn.functional.cross_entropy(lg, labels).backward()
+        noise_logits = max(noise_logits, dev(lg.detach(), logits.detach()))
+        for (k, p2), (_, p1) in zip(net2.named_parameters(), net.named_parameters()):
+            noise[k] = max(noise[k], dev(p2.grad, p1.grad))
+    out["noise_logits"] = np.float64(noise_logits)
+    for k, v in noise.items():
+        out["noise." + k] = np.float64(v)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+    print(name, "N", d.num_nodes, "E", e.shape[0], "params", sum(p.numel() for p in net.parameters()), "loss", loss.item(),
+          "order noise: logits %.1e, gradients up to %.1e" % (noise_logits, max(noise.values())))
+
+
 def main():
     import sys
     if not ref_loader.available():
         raise SystemExit("reference tree not present; golden vectors can only be generated in the build container")
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
-    only = sys.argv[1] if len(sys.argv) > 1 else "all"      # "all" | "fc" | "lift" | "echo"
+    only = sys.argv[1] if len(sys.argv) > 1 else "all"      # "all" | "fc" | "lift" | "echo" | "net"
     if only in ("all", "fc"):
         for i, c in enumerate(CASES):
             make_case(*c, seed=100 + i)
@@ -187,6 +273,8 @@ def main():
     if only in ("all", "echo"):
         for i, c in enumerate(ECHO_CASES):
             make_echo(*c, seed=300 + i)
+    if only in ("all", "net"):
+        make_net()
 
 
 if __name__ == "__main__":

@@ -87,6 +87,7 @@ def load():
         LiftBlock=ref_nn.LiftBlock,
         ECHO=ref_nn.ECHO,
         ECHOBlock=ref_nn.ECHOBlock,
+        TangentPerceptron=ref_nn.TangentPerceptron,
     )
     _cache["ns"] = ns
     return ns

@@ -40,6 +40,21 @@ def test_reference_state_dict_loads():
     assert not missing and not unexpected
 
 
+def test_reference_network_state_dict_loads():
+    """The whole notebook-style network (LiftBlock, FCResNetBlock incl. frontload, TangentPerceptron, ECHOBlock) built from
+    this package's modules takes the reference network's state_dict as is: same keys, same shapes (net_b2r6 golden)."""
+    from oracle.make_golden import build_net
+    g = load_golden("net_b2r6")
+    net = build_net(fcb, g["B"], g["R"], g["ftype"], g["n_classes"], g["n_des"], g["n_bins"])
+    sd = {k[2:]: v for k, v in g.items() if k.startswith("p.")}
+    assert set(sd) == set(net.state_dict())
+    missing, unexpected = net.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    assert {k for k, _ in net.named_parameters()} == {k[2:] for k in g if k.startswith("g.")}
+    with pytest.raises(RuntimeError):          # no CPU path anywhere in the network
+        net(g["pos"], g["supp_edges"], g["supp_sten"], g["ln"], g["wxp"])
+
+
 def test_no_cpu_fallback():
     m = fcb.FieldConv(4, 4)
     x = torch.zeros(5, 4, dtype=torch.complex64)

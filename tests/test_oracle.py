@@ -132,3 +132,18 @@ def test_echo_restatement_matches_reference(name):
     assert dim == g["hdim"] and torch.equal(d_map, g["dMap"])
     assert float((y.detach() - g["y"]).abs().max()) <= 2e-6 * float(g["y"].abs().max())
     assert float((x.grad - g["gx"]).abs().max()) <= 2e-6 * float(g["gx"].abs().max())
+
+
+def test_network_restatement_matches_reference():
+    """oracle/restate.py notebook_net — LiftBlock, FCResNetBlocks (one frontloaded), TangentPerceptron residuals, ECHOBlock —
+    against logits, loss and every parameter gradient of the unmodified reference (net_b2r6).  Gradients are held to
+    max(1e-5, 10 x the reference's own summation-order noise for that parameter), see oracle/make_golden.py make_net."""
+    g = load_golden("net_b2r6")
+    p = {k[2:]: v.clone().requires_grad_(v.is_floating_point()) for k, v in g.items() if k.startswith("p.")}
+    logits = restate.notebook_net(g["pos"], g["supp_edges"], g["supp_sten"], g["ln"], g["wxp"], p, g["B"], g["n_bins"], g["ftype"])
+    loss = torch.nn.functional.cross_entropy(logits, g["labels"])
+    loss.backward()
+    assert_close_normwise(logits, g["logits"], 1e-5, "logits")
+    assert abs(loss.item() - g["loss"]) <= 1e-5 * abs(g["loss"])
+    for k in (k[2:] for k in g if k.startswith("g.")):
+        assert_close_normwise(p[k].grad, g["g." + k], max(1e-5, 10.0 * g["noise." + k]), "grad " + k)
