@@ -95,9 +95,15 @@ __device__ __forceinline__ void fold_amax(uint32_t* amax, float mx) {
 // producer warps at all.  `row_base` = block of (row tile, chunk 0, hi) + r*128; kk = real column of the m = -B entry,
 // kk_m = columns between consecutive m.  A lane's 4 reals (two complex channels) are one 8-byte half of a 16-byte unit:
 // two adjacent lanes fill a unit, the lanes of a row cover consecutive 8-byte pieces -> full-sector stores.
-template <int M>
+// FASTM: the columns of consecutive m are a whole number of 64-column chunks apart (kk_m % 64 == 0: 2*R*C for the
+// transposed layout, 2*C for the forward one — cfg 1, cfg 2 transposed, cfg 4), so chunk offset and swizzle are those of
+// m = -B and every further m is one pointer increment instead of the full address arithmetic (~10 of ~30 instructions
+// per stored (ring, m); the packed store is a quarter of the transposed kernel's instruction stream at cfg 2).
+template <int M, bool FASTM>
 __device__ __forceinline__ void store_ring_packed(uint8_t* __restrict__ row_base, uint32_t rsw, const float2 (&acc)[2][M],
                                                   uint32_t kk, uint32_t kk_m) {
+    uint8_t* p = row_base + (size_t)(kk >> 6) * PK_BLOCK_BYTES + ((((kk >> 3) & 7u) ^ rsw) << 4) + (((kk >> 2) & 1u) << 3);
+    const size_t step = (size_t)(kk_m >> 6) * PK_BLOCK_BYTES;
 #pragma unroll
     for (int m = 0; m < M; ++m, kk += kk_m) {
         // the accumulators already carry the operand scale (folded into wxp when the plan records are decoded)
@@ -105,10 +111,11 @@ __device__ __forceinline__ void store_ring_packed(uint8_t* __restrict__ row_base
         const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
         const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
-        uint8_t* p = row_base + (size_t)(kk >> 6) * PK_BLOCK_BYTES + ((((kk >> 3) & 7u) ^ rsw) << 4) + (((kk >> 2) & 1u) << 3);
+        if (!FASTM) p = row_base + (size_t)(kk >> 6) * PK_BLOCK_BYTES + ((((kk >> 3) & 7u) ^ rsw) << 4) + (((kk >> 2) & 1u) << 3);
         *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
         *reinterpret_cast<uint2*>(p + PK_PLANE_BYTES) =
             make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+        if (FASTM) p += step;
     }
 }
 
@@ -134,7 +141,7 @@ constexpr int AGG_CAP = 768;           // plan records staged per CTA and chunk 
 // 0.386 / 0.319 ms; 1M vertices x C=32: 2.74 / 2.53 -> 2.43 / 2.10 ms.  Deeper feature prefetch (two edges ahead in
 // registers, or a four-deep cp.async ring in shared memory) measured 2-4 % slower: after staging the kernel is bound by
 // instruction issue and the FMA pipe (ncu r02b: issue-active 70 %, FMA pipe 59 %), not by gather latency.
-template <int B, bool TRANSPOSE, bool PACK, int MINB>
+template <int B, bool TRANSPOSE, bool PACK, int MINB, bool FASTM = false>
 __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restrict__ feat, const int32_t* __restrict__ rowptr,
                                                       const int4* __restrict__ rec, const float2* __restrict__ rot,
                                                       float4* __restrict__ out, int64_t N, int C, int R,
@@ -148,8 +155,12 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
     const int cp = (int)(lane_id - row * P);
     const bool valid = row < N;
     float mx = 0.f;
-    __shared__ int4 s_a[AGG_CAP];        // {nbr | f << 27, weight of the even ring set, weight of the odd ring set, -}
-    __shared__ float4 s_b[AGG_CAP];      // {wxp, q0}: conjugated for the transposed operator, operand scale folded into wxp
+    // decoded records, two 16-byte halves AGG_CAP entries apart (one 32-bit shared address walks both):
+    //   [i]           {nbr * P (float4 index of the neighbour's row), weight of the even ring set, weight of the odd ring set, ring floor f}
+    //   [AGG_CAP + i] {wxp, q0}: conjugated for the transposed operator, operand scale folded into wxp
+    __shared__ int4 s_rec[2 * AGG_CAP];
+    int4* const s_a = s_rec;
+    float4* const s_b = reinterpret_cast<float4*>(s_rec + AGG_CAP);
 
     // PK addressing of this lane: first byte of its row inside (row tile, chunk 0, hi plane); real column of (ring 0, m = -B)
     uint8_t* pk_row = nullptr;
@@ -170,7 +181,7 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
             float2 z[2][M];
 #pragma unroll
             for (int m = 0; m < M; ++m) z[0][m] = z[1][m] = make_float2(0.f, 0.f);
-            for (int ring = 0; ring < R; ++ring) store_ring_packed<M>(pk_row, pk_rsw, z, pk_kk + ring * pk_kk_ring, pk_kk_m);
+            for (int ring = 0; ring < R; ++ring) store_ring_packed<M, FASTM>(pk_row, pk_rsw, z, pk_kk + ring * pk_kk_ring, pk_kk_m);
         }
     }
 
@@ -189,12 +200,12 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
     // ring fcur is complete: write it once and clear its accumulator set (it becomes ring fcur + 2)
     auto retire = [&](int ring) {
         if (ring & 1) {
-            if (PACK) store_ring_packed<M>(pk_row, pk_rsw, acc1, pk_kk, pk_kk_m);
+            if (PACK) store_ring_packed<M, FASTM>(pk_row, pk_rsw, acc1, pk_kk, pk_kk_m);
             else store_ring<M>(dst, acc1, m_stride, mx);
 #pragma unroll
             for (int m = 0; m < M; ++m) acc1[0][m] = acc1[1][m] = make_float2(0.f, 0.f);
         } else {
-            if (PACK) store_ring_packed<M>(pk_row, pk_rsw, acc0, pk_kk, pk_kk_m);
+            if (PACK) store_ring_packed<M, FASTM>(pk_row, pk_rsw, acc0, pk_kk, pk_kk_m);
             else store_ring<M>(dst, acc0, m_stride, mx);
 #pragma unroll
             for (int m = 0; m < M; ++m) acc0[0][m] = acc0[1][m] = make_float2(0.f, 0.f);
@@ -224,22 +235,35 @@ __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restric
             const bool odd = ((uint32_t)rc.x >> NBR_BITS) & 1u;
             const float wx = __int_as_float(rc.z) * pk_s, wy = (TRANSPOSE ? -__int_as_float(rc.w) : __int_as_float(rc.w)) * pk_s;
             const float qx = rt.x, qy = TRANSPOSE ? -rt.y : rt.y;
-            s_a[i] = make_int4(rc.x, __float_as_int(odd ? t : omt), __float_as_int(odd ? omt : t), 0);
+            s_a[i] = make_int4((int)(((uint32_t)rc.x & NBR_MASK) * (uint32_t)P), __float_as_int(odd ? t : omt), __float_as_int(odd ? omt : t),
+                               (int)((uint32_t)rc.x >> NBR_BITS));
             s_b[i] = make_float4(wx, wy, qx, qy);
         }
         __syncthreads();
         const int a = max(p0, lo) - lo, b = min(p1, hi) - lo;      // this lane's edges inside the chunk
         if (a < b) {
             const int last = b - 1;
-            auto row_of = [&](int i) { return fbase + ((uint32_t)s_a[i].x & NBR_MASK) * (uint32_t)P; };
-            float4 vA = __ldg(row_of(a));
+            // explicit shared-window addressing: one register walks the records (the generic form recomputed the window
+            // base every iteration: 5 of ~70 instructions per edge)
+            uint32_t sp = (uint32_t)__cvta_generic_to_shared(s_rec + a);
+            const uint32_t sp_last = sp + 16u * (uint32_t)(last - a);
+            auto lds_nbr = [](uint32_t addr) {
+                uint32_t v;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+                return v;
+            };
+            float4 vA = __ldg(fbase + lds_nbr(sp));
 #pragma unroll 2
-            for (int i = a; i <= last; ++i) {
+            for (; sp <= sp_last; sp += 16u) {
                 const float4 v = vA;
-                vA = __ldg(row_of(min(i + 1, last)));
-                const int4 ra = s_a[i];
-                const float4 rb = s_b[i];
-                const int f = (int)((uint32_t)ra.x >> NBR_BITS);
+                vA = __ldg(fbase + lds_nbr(min(sp + 16u, sp_last)));
+                int4 ra;
+                float4 rb;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ra.x), "=r"(ra.y), "=r"(ra.z), "=r"(ra.w) : "r"(sp));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                             : "=f"(rb.x), "=f"(rb.y), "=f"(rb.z), "=f"(rb.w)
+                             : "r"(sp), "n"(AGG_CAP * 16));
+                const int f = ra.w;
                 while (fcur < f) retire(fcur++);
                 const float2 w00 = bc2(__int_as_float(ra.y)), w11 = bc2(__int_as_float(ra.z));
 #pragma unroll
@@ -276,6 +300,12 @@ static int dispatch_aggregate(const float* feat, const int32_t* rowptr, const vo
     prof_begin(PACK ? (TRANSPOSE ? "aggregate_T_pk" : "aggregate_pk") : (TRANSPOSE ? "aggregate_T" : "aggregate"), st);
 #define FCB_AGG_ARGS <<<blocks, 256, 0, st>>>(f4, rowptr, r4, rt, o4, N, C, R, am, pk_feat_amax, pk_norm, pk_bound)
     // resident CTAs per SM: 3 (<= 85 registers) up to band limit 2, 2 beyond (the accumulators alone take 56+ registers)
+    // packed output whose per-m column step is a whole number of chunks: the pointer-increment store (store_ring_packed)
+    const bool fastm = PACK && ((TRANSPOSE ? 2 * R * C : 2 * C) % (int)PK_COLS) == 0 && B >= 1 && B <= 2;
+    if (fastm) {
+        if (B == 1) k_aggregate<1, TRANSPOSE, PACK, 3, PACK> FCB_AGG_ARGS;
+        else k_aggregate<2, TRANSPOSE, PACK, 3, PACK> FCB_AGG_ARGS;
+    } else
     switch (B) {
         case 0: k_aggregate<0, TRANSPOSE, PACK, 3> FCB_AGG_ARGS; break;
         case 1: k_aggregate<1, TRANSPOSE, PACK, 3> FCB_AGG_ARGS; break;

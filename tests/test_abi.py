@@ -161,12 +161,13 @@ def test_default_aggregation_variants_are_compiled_without_heavy_spills():
     lines = out.splitlines()
     usage = {}
     for i, l in enumerate(lines):
-        m = re.search(r"Function _ZN3fcb11k_aggregateILi(\d)ELb(\d)ELb(\d)ELi(\d)EEEv", l)
+        m = re.search(r"Function _ZN3fcb11k_aggregateILi(\d)ELb(\d)ELb(\d)ELi(\d)ELb(\d)EEEv", l)
         if m and i + 1 < len(lines):
             u = re.search(r"REG:(\d+) STACK:(\d+)", lines[i + 1])
             usage[tuple(int(x) for x in m.groups())] = (int(u.group(1)), int(u.group(2)))
-    # (band limit, transpose, packed, resident CTAs) — the dispatcher of aggregate_kernel.cuh
-    defaults = [(b, t, pk, 3 if b <= 2 else 2) for b in (0, 1, 2, 3) for t in (0, 1) for pk in (0, 1)]
+    # (band limit, transpose, packed, resident CTAs, pointer-increment packed store) — the dispatcher of aggregate_kernel.cuh
+    defaults = [(b, t, pk, 3 if b <= 2 else 2, 0) for b in (0, 1, 2, 3) for t in (0, 1) for pk in (0, 1)]
+    defaults += [(b, t, 1, 3, 1) for b in (1, 2) for t in (0, 1)]
     for key in defaults:
         assert key in usage, "missing kernel variant %s" % (key,)
         regs, stack = usage[key]
