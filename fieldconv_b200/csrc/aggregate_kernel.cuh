@@ -127,20 +127,22 @@ constexpr int AGG_CAP = 768;           // plan records staged per CTA and chunk 
 // the operand scale comes from the a-priori bound  max|out| <= max|feat| * max_row sum_e |wxp_e|  (pk_feat_amax,
 // pk_norm: device floats; block 0 publishes the product in *pk_bound for the GEMM's epilogue), and the lanes of the
 // rows N .. pk_rows_padded(N)-1 zero-fill the tail of the last row tile (the weight-gradient GEMM reduces over rows).
-// MINB: minimum resident CTAs per SM the register allocation is held to (3 for band limits <= 2: 80 registers).
+// MINB: minimum resident CTAs per SM the register allocation is held to (4 at band limit 1: 64 registers; 3 at band
+// limits 0 and 2: 80 registers; 2 beyond).  FASTM: the pointer-increment packed store (store_ring_packed).
 //
 // Records: the CTA's plan records (one contiguous CSR range, ~11 rows x 40 edges at C = 48) are copied into shared
-// memory with coalesced loads first and DECODED once per record instead of once per lane and edge (ring weights of the
-// even / odd accumulator set, conjugation of the transposed operator, the packed path's operand scale folded into
-// wxp); in the edge loop a record is two LDS.128 and the neighbour
-// id of the next edge is known without a global load, so the feature gather never waits on a record.  Ranges longer than
-// AGG_CAP records are staged chunk by chunk (any vertex degree).  The feature row of edge p+1 is in flight in registers
-// while edge p is accumulated.
-// Measured on B200 (profiles/r02a_, r02b_aggregate_variants.jsonl), cfg-2 layer forward / transposed: round-1 kernel
-// (records through registers, product arithmetic) 0.473 / 0.412 ms -> staged + decoded + recurrence arithmetic
-// 0.386 / 0.319 ms; 1M vertices x C=32: 2.74 / 2.53 -> 2.43 / 2.10 ms.  Deeper feature prefetch (two edges ahead in
-// registers, or a four-deep cp.async ring in shared memory) measured 2-4 % slower: after staging the kernel is bound by
-// instruction issue and the FMA pipe (ncu r02b: issue-active 70 %, FMA pipe 59 %), not by gather latency.
+// memory with coalesced loads first and DECODED once per record instead of once per lane and edge (gather offset
+// nbr * P, ring floor, ring weights of the even / odd accumulator set, conjugation of the transposed operator, the
+// packed path's operand scale folded into wxp); in the edge loop a record is two LDS.128 through one 32-bit
+// shared-window pointer and the gather offset of the next edge one LDS.32, so the feature gather never waits on a
+// record.  Ranges longer than AGG_CAP records are staged chunk by chunk (any vertex degree).  The feature row of edge
+// p+1 is in flight in registers while edge p is accumulated.
+// Measured on B200, cfg-2 layer forward / transposed: round-1 kernel (records through registers, product arithmetic)
+// 0.473 / 0.412 ms -> staged + decoded + recurrence arithmetic 0.386 / 0.319 ms (fp32 G; 0.371 with PK G)
+// (profiles/r02a_, r02b_aggregate_variants.jsonl) -> overhead instructions trimmed (100 -> 87 per edge and lane forward,
+// 71.5 -> 58 transposed; profiles/r04d, r04e) 0.358 / 0.326 ms (PK G).  Deeper feature prefetch (two edges ahead in
+// registers, a four-deep cp.async ring in shared memory, an L1 prefetch hint) measured 1-5 % slower each time.  ncu (r04e):
+// FMA pipe 60 %, issue-active 63-67 %, largest stall long_scoreboard (the gather).
 template <int B, bool TRANSPOSE, bool PACK, int MINB, bool FASTM = false>
 __global__ void __launch_bounds__(256, MINB) k_aggregate(const float4* __restrict__ feat, const int32_t* __restrict__ rowptr,
                                                       const int4* __restrict__ rec, const float2* __restrict__ rot,
