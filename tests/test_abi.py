@@ -222,3 +222,31 @@ def test_aggregation_edge_loop_instruction_budget():
         assert c["LDG"] == 2 and c["LDS"] == 6, (name, dict(c))            # one gather, two record halves + the next offset per edge
         assert c["LDL"] == 0 and c["STL"] == 0, (name, dict(c))            # no spill traffic inside the loop
         assert sum(c.values()) <= budget, (name, sum(c.values()), dict(c))
+
+
+def test_contraction_kernels_carry_tcgen05_and_bulk_copy_sass():
+    """The 2xFP16 / 3xTF32 contraction kernels and the fused forward really are tcgen05 kernels: their SASS holds UTCHMMA
+    (tcgen05.mma), LDTM (tcgen05.ld from TMEM), UBLKCP (cp.async.bulk) and SYNCS (mbarrier); the aggregation kernels hold
+    packed FFMA2.  Static check on the built library (profiles/r04_sass_summary.txt is the same listing per kernel)."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    per_fn, fn = {}, None
+    for l in out.splitlines():
+        m = re.search(r"Function : (\S+)", l)
+        if m:
+            fn = m.group(1)
+            per_fn[fn] = {"UTCHMMA": 0, "LDTM": 0, "UBLKCP": 0, "SYNCS": 0, "FFMA2": 0}
+            continue
+        if fn:
+            for k in per_fn[fn]:
+                if re.search(r"\b%s\b" % k, l):
+                    per_fn[fn][k] += 1
+    def total(pattern, key):
+        return sum(c[key] for f, c in per_fn.items() if pattern in f)
+    for kernel in ("k_gemm_h_nn", "k_gemm_h_tn", "k_gemm_h_nn_small", "k_gemm_tc_nn", "k_gemm_tc_tn", "k_fused_fwd"):
+        assert total(kernel, "UTCHMMA") > 0 and total(kernel, "LDTM") > 0 and total(kernel, "SYNCS") > 0, kernel
+    assert total("k_gemm_h_nn", "UBLKCP") > 0 and total("k_gemm_h_tn", "UBLKCP") > 0
+    assert total("k_aggregate", "FFMA2") > 0 and total("k_aggregate", "UTCHMMA") == 0
